@@ -1,0 +1,220 @@
+/*
+ * paged_attn.h -- C ABI of libpaged_attn.so: a B200 (sm_100a) paged KV-cache attention path
+ * that drops in behind the C interface of mx60s/llm.c-paged.
+ *
+ * Plain C (no CUDA headers needed by the including translation unit).  Two groups:
+ *
+ *   1. COMPAT: the reference's own names, argument order and error behaviour
+ *      (block_manager.c:25-201, paged_infer.c:163-240 and :505-573).  The reference has
+ *      no FFI/plugin layer -- integration is `#include "block_manager.c"`
+ *      (paged_infer.c:10) -- so the boundary is these source-level signatures.
+ *      A host translation unit replaces that include with `#include "paged_attn.h"`.
+ *
+ *   2. EXTENDED (pa_*): what the reference API cannot express -- run-time geometry,
+ *      many sequences per step, many layers per manager, device-resident q/out, streams.
+ *
+ * Error convention: compat calls return NULL / -1 and print to stderr exactly where the
+ * reference does (block_manager.c:116-119,138-141,148-151,166-169); pa_* calls return 0 or a
+ * negative pa_status and never exit(); pa_last_error() holds the message.
+ * There is NO CPU fallback: compute entry points fail loudly when no CUDA device is usable.
+ */
+#ifndef PAGED_ATTN_H
+#define PAGED_ATTN_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PA_API __attribute__((visibility("default")))
+#else
+#define PA_API
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Types.  Field names and meaning follow block_manager.c:9-23; arrays the reference sizes with
+ * the MAX_* macros (block_manager.c:4-6) are run-time sized here.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pa_handle pa_handle;
+
+typedef struct KVBlock {      /* block_manager.c:9-15 -- one page */
+    float* keys;              /* DEVICE pointer: pool_k + index*block_size*C   ([slot][C] fp32, layer 0) */
+    float* values;            /* DEVICE pointer: pool_v + index*block_size*C */
+    int filled;               /* valid rows */
+    int prompt_id;            /* owner, -1 = free */
+    int lru_counter;
+} KVBlock;
+
+typedef struct BlockManager { /* block_manager.c:17-23 */
+    int C;
+    KVBlock* blocks;              /* [max_blocks]                      (ref: KVBlock blocks[MAX_BLOCKS]) */
+    int** prompt_block_list;      /* [max_prompts] rows of block_table (ref: int [MAX_PROMPTS][MAX_BLOCKS]) */
+    int* prompt_block_count;      /* [max_prompts] */
+    int lru_epoch;
+    /* --- extensions (not in the reference) --- */
+    int block_size;               /* BLOCK_SIZE  (block_manager.c:6)  */
+    int max_blocks;               /* MAX_BLOCKS  (block_manager.c:5)  */
+    int max_prompts;              /* MAX_PROMPTS (block_manager.c:4)  */
+    int table_stride;             /* ints per block-table row */
+    int* block_table;             /* flat [max_prompts][table_stride]; this is what is mirrored to HBM */
+    pa_handle* pa;                /* owning handle (pool, streams); never NULL */
+} BlockManager;
+
+typedef enum pa_status {
+    PA_OK = 0,
+    PA_ERR_INVALID = -1,     /* bad argument / geometry */
+    PA_ERR_NOMEM = -2,       /* host or device allocation failed */
+    PA_ERR_CUDA = -3,        /* CUDA runtime error (message in pa_last_error) */
+    PA_ERR_NO_DEVICE = -4,   /* compute call on a host-only handle, or no GPU present */
+    PA_ERR_NO_BLOCKS = -5,   /* request_block failed ("No blocks available.") */
+    PA_ERR_UNSUPPORTED = -6  /* shape outside every kernel's domain */
+} pa_status;
+
+/* ------------------------------------------------------------------------------------------
+ * 1. COMPAT API -- same names / arguments as the reference.
+ * ---------------------------------------------------------------------------------------- */
+
+/* block_manager.c:38-52.  Geometry = reference macros (32/100/100) unless overridden by
+ * pa_set_default_geometry() or the env vars PA_BLOCK_SIZE / PA_MAX_BLOCKS / PA_MAX_PROMPTS.
+ * Allocates ONE device pool (K and V, 1 layer) instead of a malloc per page.  Unlike the
+ * reference it zero-initialises lru_epoch / filled / lru_counter.  NULL + stderr on failure. */
+PA_API BlockManager* create_block_manager(int channels);
+/* The reference free()s the manager (block_manager_test.c:53); here that would leak the pool. */
+PA_API void destroy_block_manager(BlockManager* manager);
+
+PA_API void print_state(BlockManager* manager, int prompt);                         /* :25-36  */
+PA_API int get_next_block_id(BlockManager* manager, int prompt, int block_id);      /* :54-63  */
+PA_API KVBlock* get_current_block(BlockManager* manager, int prompt_id);            /* :65-76  (silent) */
+PA_API void free_blocks_for_prompt(BlockManager* manager, int prompt_id);           /* :78-90  */
+PA_API int find_least_recently_used_block(BlockManager* manager);                   /* :92-102 */
+PA_API void page_out_lru_block(BlockManager* manager);                              /* :104-113 */
+PA_API KVBlock* request_block(BlockManager* manager, int prompt_id);                /* :115-162 */
+/* :165-201.  Returns malloc'd kv[0][i]=keys, kv[1][i]=values (device pointers) of the prompt's
+ * pages in table order; caller frees kv[0], kv[1], kv.  NULL if none / bad id. */
+PA_API float*** collect_kv_blocks(BlockManager* manager, int prompt_id, int* num_blocks);
+
+/* paged_infer.c:505-573.  qkv is (B,T,3C) fp32, HOST or DEVICE memory; appends K,V of the last
+ * n_tail rows of batch row 0 to prompt 0's current page (new page if none/full, else LRU touch),
+ * through the KV-append kernel.  Like the reference it does not cross a page boundary. */
+PA_API void add_to_cache(BlockManager* manager, float* qkv, int B, int T, int C, int n_tail);
+
+/* paged_infer.c:163-240.  out (B,T,C) and inp (B,T,3C) are HOST or DEVICE memory; key_blocks /
+ * value_blocks are the arrays collect_kv_blocks returned (host arrays of device page pointers).
+ * Row t attends cached tokens [offset, offset+t].  preatt/att ((B,NH,T,T) scratch, needed only
+ * by a backward pass the reference does not have) are NOT materialised and may be NULL. */
+PA_API void attention_paged(float* out, float* preatt, float* att, float* inp,
+                            float** key_blocks, float** value_blocks,
+                            int B, int T, int C, int NH, int offset);
+
+/* geometry used by the next create_block_manager() (<=0 keeps the current value) */
+PA_API void pa_set_default_geometry(int block_size, int max_blocks, int max_prompts);
+PA_API int pa_default_block_size(void);
+#ifdef PA_COMPAT_MACROS          /* for callers that loop over the reference's macros */
+#define BLOCK_SIZE (pa_default_block_size())
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * 2. EXTENDED API
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pa_config {
+    int block_size;          /* tokens per page                                  (BLOCK_SIZE)  */
+    int max_blocks;          /* pages in the pool, shared by all sequences        (MAX_BLOCKS)  */
+    int max_seqs;            /* sequence ids 0..max_seqs-1                        (MAX_PROMPTS) */
+    int max_blocks_per_seq;  /* block-table row stride; 0 -> max_blocks (as the reference) */
+    int n_layers;            /* KV pools behind one block table (reference: 1) */
+    int n_heads;             /* NH */
+    int head_dim;            /* hs; C = n_heads*head_dim */
+    int device;              /* CUDA ordinal; PA_HOST_ONLY = integer tables only (no pool, no compute) */
+    int max_batch_tokens;    /* most new tokens in one step over all sequences; 0 -> max_seqs */
+} pa_config;
+#define PA_HOST_ONLY (-1)
+
+PA_API int pa_create(const pa_config* cfg, pa_handle** out);
+PA_API void pa_destroy(pa_handle* h);
+PA_API BlockManager* pa_manager(pa_handle* h);
+PA_API const char* pa_last_error(void);
+PA_API const char* pa_version(void);
+
+/* ---- per-step host scheduling (integer; no device work) ---------------------------------- */
+/* Sequence seq_ids[i] receives n_new[i] tokens.  For each token run the page choice of
+ * add_to_cache (paged_infer.c:518-529: current page, new page if none/full, else LRU touch),
+ * crossing page boundaries when needed (extension), and record slot = page*block_size + row.
+ * Builds the step tables (context lengths, page prefix sums, slot mapping, block-table rows). */
+PA_API int pa_step_begin(pa_handle* h, const int* seq_ids, const int* n_new, int nseq);
+/* Optional sliding window: row i attends cached tokens [kv_start[i], ctx) (reference `offset`). */
+PA_API int pa_step_set_kv_start(pa_handle* h, const int* kv_start);
+/* The same tables without appending anything (attention over what is cached). */
+PA_API int pa_step_begin_readonly(pa_handle* h, const int* seq_ids, int nseq);
+PA_API const int* pa_step_slot_mapping(pa_handle* h, int* n_tokens);
+PA_API const int* pa_step_context_lens(pa_handle* h, int* nseq);
+PA_API const int* pa_step_block_table(pa_handle* h, int* nseq, int* stride);
+/* Mirror the step tables to HBM: ONE cudaMemcpyAsync from pinned memory. */
+PA_API int pa_step_upload(pa_handle* h, void* stream);
+
+/* ---- kernels (device pointers, caller's stream; NULL stream = the handle's own) ----------- */
+/* KV append: token j of the step (order of pa_step_begin) has K at k+j*row_stride, V likewise. */
+PA_API int pa_append(pa_handle* h, int layer, const float* k, const float* v, int row_stride, void* stream);
+/* Decode: one query per sequence (row i at q+i*q_stride, head hd at +hd*head_dim) attends
+ * cached tokens [kv_start, ctx) of its sequence; out row i at out+i*out_stride. */
+PA_API int pa_decode(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream);
+/* Causal rows: the n_new[i] new tokens of each sequence are the queries (packed in step order);
+ * row j of sequence i attends [kv_start, ctx_before + j].  fp32 SIMT. */
+PA_API int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream);
+
+/* ---- whole step with HOST buffers (the end-to-end entry: H2D, append, decode, D2H, sync) -- */
+/* qkv_host: (nseq, 3C) rows of the step's sequences [q | k | v]; out_host: (nseq, C). */
+PA_API int pa_decode_step_host(pa_handle* h, int layer, const float* qkv_host, float* out_host);
+
+/* ---- sequence bookkeeping ----------------------------------------------------------------- */
+PA_API int pa_seq_len(pa_handle* h, int seq_id);                 /* cached tokens */
+PA_API int pa_seq_truncate(pa_handle* h, int seq_id, int new_len); /* roll back (frees emptied pages) */
+PA_API int pa_seq_free(pa_handle* h, int seq_id);                /* = free_blocks_for_prompt */
+/* Install an externally built block table (e.g. a shuffled / fragmented layout for benchmarks):
+ * the sequence must be empty and the pages free. */
+PA_API int pa_seq_adopt(pa_handle* h, int seq_id, const int* blocks, int n_blocks, int n_tokens);
+
+/* ---- pool access (tests, benchmarks, checkpointing) --------------------------------------- */
+PA_API float* pa_pool_k(pa_handle* h, int layer);                /* device, [max_blocks][bs][C] */
+PA_API float* pa_pool_v(pa_handle* h, int layer);
+PA_API size_t pa_pool_bytes(pa_handle* h);                       /* K+V, all layers */
+PA_API int pa_device(pa_handle* h);
+PA_API int pa_sm_count(pa_handle* h);
+
+/* ---- tuning knobs (benchmarks/tests select a kernel or a tile shape) ----------------------- */
+typedef enum pa_tune_key {
+    PA_TUNE_DECODE_PATH = 0,   /* 0 auto, 1 stream (TMA/mbarrier) kernel, 2 generic SIMT kernel */
+    PA_TUNE_HEADS_PER_TILE = 1,/* 0 auto */
+    PA_TUNE_STAGES = 2,        /* 0 auto */
+    PA_TUNE_GRID = 3,          /* 0 auto (CTAs) */
+    PA_TUNE_COUNT_LAUNCHES = 4,/* read-only counter of kernels launched by this handle */
+    PA_TUNE_MAX
+} pa_tune_key;
+PA_API int pa_tune_set(pa_handle* h, int key, int value);
+PA_API int pa_tune_get(pa_handle* h, int key);
+
+/* ---- thin CUDA plumbing for plain-C hosts (no cuda_runtime.h needed) ----------------------- */
+PA_API int pa_device_count(void);
+PA_API void* pa_dev_alloc(size_t bytes);
+PA_API void pa_dev_free(void* p);
+PA_API void* pa_host_alloc(size_t bytes);                        /* pinned */
+PA_API void pa_host_free(void* p);
+PA_API int pa_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
+PA_API int pa_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
+PA_API int pa_memset(void* dst, int value, size_t bytes, void* stream);
+PA_API void* pa_stream_create(void);
+PA_API void pa_stream_destroy(void* stream);
+PA_API int pa_stream_sync(void* stream);
+PA_API int pa_device_sync(void);
+PA_API void* pa_event_create(void);
+PA_API void pa_event_destroy(void* ev);
+PA_API int pa_event_record(void* ev, void* stream);
+PA_API float pa_event_elapsed_ms(void* start, void* stop);       /* syncs on stop */
+/* write `bytes` of device scratch (> L2) to evict the L2 between timed iterations */
+PA_API int pa_flush_l2(void* scratch, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAGED_ATTN_H */

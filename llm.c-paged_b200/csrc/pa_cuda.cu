@@ -1,0 +1,257 @@
+/*
+ * pa_cuda.cu -- the thin C-ABI layer over the CUDA runtime: device selection, the KV page pool,
+ * pinned step-table ring + its single-copy mirror, staging for the host-buffer entry points and
+ * the small plumbing calls a plain-C host needs (no cuda_runtime.h on the host side).
+ *
+ * No PyTorch, no CPU fallback: every compute entry fails with PA_ERR_NO_DEVICE / PA_ERR_CUDA.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "pa_internal.h"
+
+#define CU_CHECK(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            pa_set_error("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return PA_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+namespace {
+struct StepRing {
+    static const int N = 4;
+    int* buf[N];
+    size_t cap[N];
+    cudaEvent_t ev[N];
+    bool pending[N];
+    int next;
+    int cur;
+    bool pinned;
+};
+}  // namespace
+
+extern "C" {
+
+int pa_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pa_cu_init(pa_handle* h) {
+    int n = pa_device_count();
+    if (n <= 0) {
+        pa_set_error("no CUDA device visible: libpaged_attn has no CPU fallback");
+        return PA_ERR_NO_DEVICE;
+    }
+    if (h->cfg.device < 0 || h->cfg.device >= n) {
+        pa_set_error("device %d out of range (%d visible)", h->cfg.device, n);
+        return PA_ERR_INVALID;
+    }
+    CU_CHECK(cudaSetDevice(h->cfg.device));
+    cudaDeviceProp prop;
+    CU_CHECK(cudaGetDeviceProperties(&prop, h->cfg.device));
+    if (prop.major < 10) {
+        pa_set_error("device %d is sm_%d%d; this library is built for sm_100a only", h->cfg.device, prop.major, prop.minor);
+        return PA_ERR_NO_DEVICE;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    cudaStream_t s;
+    CU_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    h->stream = (void*)s;
+    return PA_OK;
+}
+
+int pa_cu_alloc_pool(pa_handle* h) {
+    CU_CHECK(cudaSetDevice(h->cfg.device));
+    size_t bytes = (size_t)h->cfg.n_layers * h->layer_stride * sizeof(float);
+    cudaError_t e = cudaMalloc((void**)&h->pool_k, bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->pool_v, bytes);
+    if (e != cudaSuccess) {
+        pa_set_error("KV pool: cudaMalloc of 2 x %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return PA_ERR_NOMEM;
+    }
+    CU_CHECK(cudaMemsetAsync(h->pool_k, 0, bytes, (cudaStream_t)h->stream));
+    CU_CHECK(cudaMemsetAsync(h->pool_v, 0, bytes, (cudaStream_t)h->stream));
+    /* split-decode workspace: (max CTAs + max_seqs) partial slots of (C + 2*NH) floats, and one
+     * arrival counter per (sequence, head) -- see pa_decode_stream_kernel */
+    size_t max_ctas = (size_t)h->sm_count * 8;
+    if (h->max_heads < h->cfg.n_heads) h->max_heads = h->cfg.n_heads;
+    h->ws_floats = (max_ctas + (size_t)h->cfg.max_seqs) * ((size_t)h->C + 2 * (size_t)h->max_heads + 8);
+    h->n_counters = (size_t)h->cfg.max_seqs * h->max_heads;
+    CU_CHECK(cudaMalloc((void**)&h->d_ws, h->ws_floats * sizeof(float)));
+    CU_CHECK(cudaMalloc((void**)&h->d_counters, h->n_counters * sizeof(int)));
+    CU_CHECK(cudaMemsetAsync(h->d_counters, 0, h->n_counters * sizeof(int), (cudaStream_t)h->stream));
+    CU_CHECK(cudaStreamSynchronize((cudaStream_t)h->stream));
+    return PA_OK;
+}
+
+void pa_cu_release(pa_handle* h) {
+    StepRing* r = (StepRing*)h->step_ring;
+    if (!h->host_only && h->stream) {
+        cudaSetDevice(h->cfg.device);
+        cudaStreamSynchronize((cudaStream_t)h->stream);
+    }
+    if (r) {
+        for (int i = 0; i < StepRing::N; i++) {
+            if (r->buf[i]) { if (r->pinned) cudaFreeHost(r->buf[i]); else free(r->buf[i]); }
+            if (r->pinned && r->ev[i]) cudaEventDestroy(r->ev[i]);
+        }
+        delete r;
+        h->step_ring = NULL;
+    }
+    if (h->host_only) return;
+    cudaFree(h->pool_k); cudaFree(h->pool_v);
+    cudaFree(h->d_step); cudaFree(h->d_ws); cudaFree(h->d_counters);
+    cudaFree(h->d_stage);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->stream) cudaStreamDestroy((cudaStream_t)h->stream);
+    h->pool_k = h->pool_v = NULL;
+}
+
+int* pa_cu_step_host_buffer(pa_handle* h, size_t ints) {
+    StepRing* r = (StepRing*)h->step_ring;
+    if (!r) {
+        r = new StepRing();
+        memset(r, 0, sizeof(*r));
+        r->pinned = !h->host_only;
+        h->step_ring = r;
+    }
+    if (r->pinned) cudaSetDevice(h->cfg.device);
+    int i = r->next;
+    r->next = (r->next + 1) % StepRing::N;
+    if (r->pinned && r->pending[i]) {     /* the upload that last used this buffer must be done */
+        cudaEventSynchronize(r->ev[i]);
+        r->pending[i] = false;
+    }
+    if (r->cap[i] < ints) {
+        size_t cap = ints + ints / 2 + 1024;
+        if (r->buf[i]) { if (r->pinned) cudaFreeHost(r->buf[i]); else free(r->buf[i]); r->buf[i] = NULL; }
+        if (r->pinned) {
+            if (cudaMallocHost((void**)&r->buf[i], cap * sizeof(int)) != cudaSuccess) {
+                cudaGetLastError();
+                pa_set_error("pinned step buffer: cudaMallocHost(%zu) failed", cap * sizeof(int));
+                r->cap[i] = 0;
+                return NULL;
+            }
+            if (!r->ev[i]) cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming);
+        } else {
+            r->buf[i] = (int*)malloc(cap * sizeof(int));
+            if (!r->buf[i]) { pa_set_error("step buffer: out of host memory"); r->cap[i] = 0; return NULL; }
+        }
+        r->cap[i] = cap;
+    }
+    r->cur = i;
+    h->step.uploaded = 0;
+    return r->buf[i];
+}
+
+int pa_cu_step_upload(pa_handle* h, void* stream) {
+    StepRing* r = (StepRing*)h->step_ring;
+    if (!r || !h->h_step) { pa_set_error("pa_step_upload: no step tables"); return PA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)h->stream;
+    size_t ints = (size_t)h->step.total_ints;
+    if (h->d_step_cap_ints < ints) {
+        /* growing the mirror is rare; make sure nothing still reads the old one */
+        CU_CHECK(cudaDeviceSynchronize());
+        cudaFree(h->d_step);
+        h->d_step = NULL;
+        size_t cap = ints + ints / 2 + 1024;
+        CU_CHECK(cudaMalloc((void**)&h->d_step, cap * sizeof(int)));
+        h->d_step_cap_ints = cap;
+    }
+    CU_CHECK(cudaMemcpyAsync(h->d_step, h->h_step, ints * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU_CHECK(cudaEventRecord(r->ev[r->cur], s));
+    r->pending[r->cur] = true;
+    h->step.uploaded = 1;
+    return PA_OK;
+}
+
+int pa_cu_ensure_stage(pa_handle* h, size_t floats) {
+    if (h->stage_floats >= floats) return PA_OK;
+    CU_CHECK(cudaSetDevice(h->cfg.device));
+    CU_CHECK(cudaStreamSynchronize((cudaStream_t)h->stream));
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    cudaFree(h->d_stage);
+    h->h_stage = NULL; h->d_stage = NULL; h->stage_floats = 0;
+    size_t cap = floats + floats / 4;
+    CU_CHECK(cudaMallocHost((void**)&h->h_stage, cap * sizeof(float)));
+    CU_CHECK(cudaMalloc((void**)&h->d_stage, cap * sizeof(float)));
+    h->stage_floats = cap;
+    return PA_OK;
+}
+
+int pa_cu_is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+/* ---- plumbing for plain-C hosts ------------------------------------------------------------ */
+void* pa_dev_alloc(size_t bytes) {
+    void* p = NULL;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        pa_set_error("pa_dev_alloc(%zu): %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return NULL;
+    }
+    return p;
+}
+void pa_dev_free(void* p) { if (p) cudaFree(p); }
+void* pa_host_alloc(size_t bytes) {
+    void* p = NULL;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        pa_set_error("pa_host_alloc(%zu): %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return NULL;
+    }
+    return p;
+}
+void pa_host_free(void* p) { if (p) cudaFreeHost(p); }
+int pa_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+    CU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    if (!stream) CU_CHECK(cudaStreamSynchronize(0));
+    return PA_OK;
+}
+int pa_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+    CU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    if (!stream) CU_CHECK(cudaStreamSynchronize(0));
+    return PA_OK;
+}
+int pa_memset(void* dst, int value, size_t bytes, void* stream) {
+    CU_CHECK(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream));
+    return PA_OK;
+}
+void* pa_stream_create(void) {
+    cudaStream_t s;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return NULL; }
+    return (void*)s;
+}
+void pa_stream_destroy(void* stream) { if (stream) cudaStreamDestroy((cudaStream_t)stream); }
+int pa_stream_sync(void* stream) { CU_CHECK(cudaStreamSynchronize((cudaStream_t)stream)); return PA_OK; }
+int pa_device_sync(void) { CU_CHECK(cudaDeviceSynchronize()); return PA_OK; }
+void* pa_event_create(void) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return NULL; }
+    return (void*)e;
+}
+void pa_event_destroy(void* ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
+int pa_event_record(void* ev, void* stream) { CU_CHECK(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream)); return PA_OK; }
+float pa_event_elapsed_ms(void* start, void* stop) {
+    float ms = -1.0f;
+    if (cudaEventSynchronize((cudaEvent_t)stop) != cudaSuccess) { cudaGetLastError(); return -1.0f; }
+    if (cudaEventElapsedTime(&ms, (cudaEvent_t)start, (cudaEvent_t)stop) != cudaSuccess) { cudaGetLastError(); return -1.0f; }
+    return ms;
+}
+int pa_flush_l2(void* scratch, size_t bytes, void* stream) {
+    CU_CHECK(cudaMemsetAsync(scratch, 0, bytes, (cudaStream_t)stream));
+    return PA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+/* pa_internal.h -- shared between the plain-C host side (pa_block_manager.c, pa_step.c,
+ * pa_compat.c) and the CUDA side (pa_cuda.cu, pa_kernels.cu).  Not installed. */
+#ifndef PA_INTERNAL_H
+#define PA_INTERNAL_H
+
+#include "paged_attn.h"
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* step tables: ONE pinned int32 buffer mirrored with ONE cudaMemcpyAsync (pa_step_upload).
+ * Offsets are in ints from the start of the buffer. */
+typedef struct pa_step_layout {
+    int nseq;          /* batch rows */
+    int ntok;          /* new tokens in this step (rows of slot_mapping) */
+    int tstride;       /* ints per block-table row in the mirror (pages actually used, padded) */
+    int total_pages;   /* cum_pages[nseq] */
+    int max_q;         /* max new tokens of one sequence */
+    int off_kv_end;    /* [nseq]   cached tokens visible to the LAST query row (= context length) */
+    int off_kv_start;  /* [nseq]   first visible token (sliding window; 0 by default) */
+    int off_cum_pages; /* [nseq+1] prefix sum of pages in [kv_start/bs, ceil(kv_end/bs)) */
+    int off_q_row0;    /* [nseq+1] prefix sum of n_new (first query row of each sequence) */
+    int off_slot;      /* [ntok]   slot_mapping */
+    int off_table;     /* [nseq][tstride] block-table rows */
+    int total_ints;
+    int uploaded;      /* device copy is current */
+} pa_step_layout;
+
+struct pa_handle {
+    pa_config cfg;
+    int C;
+    BlockManager* mgr;
+    int host_only;
+    int compat;                   /* created by create_block_manager(): NH unknown until attention_paged */
+    /* device pool: [n_layers][max_blocks][block_size][C] fp32, K and V */
+    float* pool_k;
+    float* pool_v;
+    size_t layer_stride;          /* floats between layers */
+    /* step tables: h_step points into a small ring of pinned buffers so the host can build
+     * step n+1 while the copy of step n is still in flight (plain malloc when host_only) */
+    int* h_step;
+    int* d_step;
+    size_t d_step_cap_ints;
+    void* step_ring;              /* opaque, owned by pa_cuda.cu */
+    pa_step_layout step;
+    int* step_seq_ids;            /* host [max_seqs] */
+    int* step_n_new;              /* host [max_seqs] */
+    int* slot_scratch;            /* host [max_batch_tokens] */
+    /* decode split workspace */
+    float* d_ws;
+    size_t ws_floats;
+    int* d_counters;
+    size_t n_counters;
+    /* staging for the host-buffer entry points */
+    float* h_stage;               /* pinned */
+    float* d_stage;
+    size_t stage_floats;
+    void* stream;                 /* handle-owned stream */
+    int sm_count;
+    int smem_optin;
+    int tune[8];
+    long launches;
+    void* decode_attr_fn;         /* kernel whose dynamic-smem attribute has been raised */
+    int max_heads;                /* heads the split workspace was sized for */
+};
+
+void pa_set_error(const char* fmt, ...);
+
+/* ---- implemented in pa_block_manager.c (plain C, integer only) ------------------------- */
+BlockManager* pa_bm_create(pa_handle* owner, int channels, int block_size, int max_blocks,
+                           int max_prompts, int table_stride);
+void pa_bm_destroy(BlockManager* m);
+/* page choice of add_to_cache (paged_infer.c:518-529); returns page index or -1 */
+int pa_bm_choose_page(BlockManager* m, int prompt_id);
+int pa_bm_context_len(const BlockManager* m, int prompt_id);
+
+/* ---- implemented in pa_step.c ------------------------------------------------------------- */
+int pa_create_compat(const pa_config* cfg, pa_handle** out);
+/* step tables from explicit rows (compat attention_paged gets page pointers, not prompt ids):
+ * row i has n_pages[i] page indices at tables[i], sees tokens [kv_start[i], kv_end[i]) from its
+ * last query row and carries n_q[i] query rows. */
+int pa_step_begin_raw(pa_handle* h, int nseq, const int* const* tables, const int* n_pages,
+                      const int* kv_start, const int* kv_end, const int* n_q);
+
+/* ---- implemented in pa_cuda.cu (the thin C-ABI layer over the CUDA runtime) ------------- */
+int pa_cu_init(pa_handle* h);                 /* select device, query SMs/smem, create stream */
+int pa_cu_alloc_pool(pa_handle* h);
+void pa_cu_release(pa_handle* h);
+int pa_cu_ensure_stage(pa_handle* h, size_t floats);
+/* next pinned buffer of the ring with room for `ints` (waits for its previous upload) */
+int* pa_cu_step_host_buffer(pa_handle* h, size_t ints);
+int pa_cu_step_upload(pa_handle* h, void* stream);
+int pa_cu_is_device_ptr(const void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,783 @@
+/*
+ * pa_kernels.cu -- hand-written sm_100a kernels of the paged KV-cache path and their launchers.
+ *
+ *   pa_append_kernel          KV append: scatter new K/V rows into their page slots
+ *                             (semantics: add_to_cache copy loop, paged_infer.c:548-566)
+ *   pa_decode_stream_kernel   paged decode attention, HBM-bound streaming design:
+ *                             flat page stream split evenly over a persistent grid ("stream-K over
+ *                             pages"), K/V page tiles staged in shared memory by the TMA bulk-copy
+ *                             engine (cp.async.bulk + mbarrier ring, one producer warp), fp32 SIMT
+ *                             QK^T / online softmax / PV with warp-shuffle reductions, split
+ *                             partials merged in-kernel by the last-arriving CTA
+ *                             (semantics: row t=T-1 of attention_paged, paged_infer.c:182-236)
+ *   pa_attn_rows_kernel       generic fp32 SIMT causal attention through the block table: any
+ *                             head size / block size / alignment, any number of query rows per
+ *                             sequence (prefill; fallback decode)
+ *                             (semantics: attention_paged, paged_infer.c:163-240)
+ *
+ * Arithmetic notes for parity: running max starts at -10000.0f
+ * (paged_infer.c:187); 1/sum with sum==0 -> 0 (:213); scale = (float)(1.0/sqrtf(hs)) is computed
+ * on the host (:174); expf, never __expf; no fast-math.
+ */
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+
+#include "pa_internal.h"
+
+#define CU_CHECK(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            pa_set_error("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return PA_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+namespace {
+
+constexpr float kMaxInit = -10000.0f;   // paged_infer.c:187
+
+// =============================================================================================
+// KV append
+// =============================================================================================
+// One CTA row per new token; threads copy 16-byte chunks of the K row and the V row to
+// pool[slot][0..C).  slot = page*block_size + row_in_page comes from the mirrored slot mapping.
+template <bool kVec4>
+__global__ void __launch_bounds__(256)
+pa_append_kernel(const float* __restrict__ k_src, const float* __restrict__ v_src, int src_stride,
+                 float* __restrict__ pool_k, float* __restrict__ pool_v,
+                 const int* __restrict__ slot_mapping, int n_tokens, int C) {
+    for (int tok = blockIdx.y; tok < n_tokens; tok += gridDim.y) {
+        const size_t dst = (size_t)slot_mapping[tok] * C;
+        const size_t src = (size_t)tok * src_stride;
+        if (kVec4) {
+            const int n4 = C >> 2;
+            const float4* ks = reinterpret_cast<const float4*>(k_src + src);
+            const float4* vs = reinterpret_cast<const float4*>(v_src + src);
+            float4* kd = reinterpret_cast<float4*>(pool_k + dst);
+            float4* vd = reinterpret_cast<float4*>(pool_v + dst);
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+                kd[i] = __ldg(ks + i);
+                vd[i] = __ldg(vs + i);
+            }
+        } else {
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) {
+                pool_k[dst + i] = k_src[src + i];
+                pool_v[dst + i] = v_src[src + i];
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// mbarrier / TMA bulk-copy primitives (inline PTX; SASS: SYNCS.*, UBLKCP)
+// =============================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "PA_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra PA_DONE;\n"
+        "bra PA_WAIT;\n"
+        "PA_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy executed by the TMA engine; completion is signalled on `bar` as
+// `bytes` transaction bytes.  bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// =============================================================================================
+// decode: flat page-stream kernel
+// =============================================================================================
+struct DecodeParams {
+    const float* pool_k;      // layer base, [max_blocks][BS][C]
+    const float* pool_v;
+    const float* q;           // (B, q_stride)
+    float* out;               // (B, out_stride)
+    const int* kv_end;        // [B]
+    const int* kv_start;      // [B]
+    const int* cum_pages;     // [B+1]
+    const int* table;         // [B][tstride]
+    float* ws;                // partial slots
+    int* counters;            // [n_hg*B] arrival counters (self-resetting)
+    long long U;              // work units = n_hg * P
+    int B, C, hpg, n_hg, W;   // W = hpg*HS floats per tile row
+    int tstride, q_stride, out_stride;
+    int P;                    // total pages of the batch
+    int n_stages;
+    int n_cons;               // consumer threads (multiple of 32)
+    int slot_floats;          // floats per partial slot
+    float scale;
+};
+
+constexpr int kFlagFirst = 1;   // first page of a (sequence, head-group) segment in this CTA
+constexpr int kFlagLast = 2;    // last page of the segment in this CTA
+
+// Transposed butterfly: N per-token partial sums per lane, reduced over the 2*D lanes that share
+// a head.  Each step the lanes trade half of their values, so the whole reduction costs ~N
+// shuffles instead of N*log2(lanes).  Afterwards the lane holds max(1, N0/lanes) finished sums,
+// the first of them for token `tok`.
+template <int N, int D>
+struct XReduce {
+    template <int BS>
+    static __device__ __forceinline__ void run(float (&v)[BS], int gl, int& tok) {
+        if constexpr (D >= 1) {
+            if constexpr (N > 1) {
+                const bool upper = (gl & D) != 0;
+#pragma unroll
+                for (int i = 0; i < N / 2; ++i) {
+                    const float send = upper ? v[i] : v[i + N / 2];
+                    const float keep = upper ? v[i + N / 2] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, D);
+                }
+                tok += upper ? N / 2 : 0;
+                XReduce<N / 2, D / 2>::run(v, gl, tok);
+            } else {
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], D);
+                XReduce<1, D / 2>::run(v, gl, tok);
+            }
+        }
+    }
+};
+
+template <int LPH>
+__device__ __forceinline__ float group_max(float x) {
+#pragma unroll
+    for (int d = LPH / 2; d >= 1; d >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, d));
+    return x;
+}
+template <int LPH>
+__device__ __forceinline__ float group_sum(float x) {
+#pragma unroll
+    for (int d = LPH / 2; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    return x;
+}
+
+// Which CTA owns flat unit x when U units are dealt as [c*U/G, (c+1)*U/G).
+__device__ __forceinline__ int cta_of_unit(long long x, long long U, int G) {
+    return (int)(((x + 1) * (long long)G - 1) / U);
+}
+
+template <int HS, int BS>
+__global__ void __launch_bounds__(288, 1)
+pa_decode_stream_kernel(const DecodeParams p) {
+    constexpr int LPH = HS / 4;                       // lanes per head (one float4 column each)
+    constexpr int NV = (BS >= LPH) ? BS / LPH : 1;    // finished scores per lane after the reduce
+    constexpr int REP = (BS >= LPH) ? 1 : LPH / BS;   // lanes holding the same token's score
+    static_assert(LPH == 16 || LPH == 32, "head size 64 or 128");
+    static_assert(BS >= 4 && BS <= 32 && (BS & (BS - 1)) == 0, "block size 4..32, power of two");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int W = p.W;
+    const int W4 = W >> 2;
+    const int tile_floats = BS * W;
+    float* tiles = reinterpret_cast<float*>(smem_raw);                          // [n_stages][BS*W]
+    float* qbuf = tiles + (size_t)p.n_stages * tile_floats;                      // [n_stages][W]
+    float* psm = qbuf + (size_t)p.n_stages * W;                                  // [n_cons/LPH][BS]
+    int4* meta = reinterpret_cast<int4*>(psm + (p.n_cons / LPH) * BS);           // [n_stages][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * p.n_stages);         // full[], empty[]
+    int* s_flag = reinterpret_cast<int*>(bars + 2 * p.n_stages);
+
+    const int tid = threadIdx.x;
+    const int G = gridDim.x;
+    const int cta = blockIdx.x;
+    const long long U = p.U;
+    const long long u_begin = (long long)cta * U / G;
+    const long long u_end = (long long)(cta + 1) * U / G;
+    const int n_units = (int)(u_end - u_begin);
+    const int n_cons_warps = p.n_cons >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.n_stages; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);                          // full: producer's expect_tx arrive
+            mbar_init(smem_u32(&bars[p.n_stages + s]), n_cons_warps);  // empty: one arrive per consumer warp
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (tid >= p.n_cons) {
+        // =================================== producer warp ===================================
+        const int lane = tid & 31;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int base = 0; base < n_units; base += 32) {
+            // every lane resolves one page of the batch: sequence, page, block id, bounds
+            const long long u = u_begin + base + lane;
+            int row = 0, hg = 0, blk = 0, lo = 0, hi = 0, flags = 0, c_first = 0, nsegs = 1;
+            if (base + lane < n_units) {
+                hg = (int)(u / p.P);
+                const int f = (int)(u - (long long)hg * p.P);
+                int a = 0, b = p.B;                       // largest row with cum_pages[row] <= f
+                while (b - a > 1) {
+                    const int mid = (a + b) >> 1;
+                    if (__ldg(p.cum_pages + mid) <= f) a = mid; else b = mid;
+                }
+                row = a;
+                const int cum0 = __ldg(p.cum_pages + row), cum1 = __ldg(p.cum_pages + row + 1);
+                const int start = __ldg(p.kv_start + row), end = __ldg(p.kv_end + row);
+                const int pg = start / BS + (f - cum0);
+                blk = __ldg(p.table + (size_t)row * p.tstride + pg);
+                lo = (f == cum0) ? start % BS : 0;
+                hi = min(BS, end - pg * BS);
+                if (f == cum0 || base + lane == 0) flags |= kFlagFirst;
+                if (f == cum1 - 1 || base + lane == n_units - 1) flags |= kFlagLast;
+                const long long seg0 = (long long)hg * p.P + cum0;
+                const long long seg1 = (long long)hg * p.P + cum1 - 1;
+                c_first = cta_of_unit(seg0, U, G);
+                nsegs = cta_of_unit(seg1, U, G) - c_first + 1;
+            }
+            const int cnt = min(32, n_units - base);
+            for (int j = 0; j < cnt; ++j) {
+                const int j_row = __shfl_sync(0xffffffffu, row, j);
+                const int j_hg = __shfl_sync(0xffffffffu, hg, j);
+                const int j_blk = __shfl_sync(0xffffffffu, blk, j);
+                const int j_lo = __shfl_sync(0xffffffffu, lo, j);
+                const int j_hi = __shfl_sync(0xffffffffu, hi, j);
+                const int j_flags = __shfl_sync(0xffffffffu, flags, j);
+                const int j_cfirst = __shfl_sync(0xffffffffu, c_first, j);
+                const int j_nsegs = __shfl_sync(0xffffffffu, nsegs, j);
+                const size_t page_off = (size_t)j_blk * BS * p.C + (size_t)j_hg * W;
+                const bool first = (j_flags & kFlagFirst) != 0;
+#pragma unroll
+                for (int kv = 0; kv < 2; ++kv) {
+                    const uint32_t full = smem_u32(&bars[stage]);
+                    const uint32_t dst = smem_u32(tiles + (size_t)stage * tile_floats);
+                    const float* src = (kv == 0 ? p.pool_k : p.pool_v) + page_off;
+                    if (lane == 0) {
+                        mbar_wait(smem_u32(&bars[p.n_stages + stage]), phase ^ 1);   // slot free
+                        if (kv == 0) {
+                            meta[2 * stage] = make_int4(j_row, j_hg, j_lo | (j_hi << 8), j_flags);
+                            meta[2 * stage + 1] = make_int4(j_cfirst, j_nsegs, 0, 0);
+                        }
+                        uint32_t bytes = (uint32_t)j_hi * W * 4u;
+                        if (kv == 0 && first) bytes += W * 4u;
+                        mbar_arrive_expect_tx(full, bytes);
+                    }
+                    __syncwarp();
+                    if (W == p.C) {            // whole rows: the valid part of the page is contiguous
+                        if (lane == 0) tma_bulk_g2s(dst, src, (uint32_t)j_hi * W * 4u, full);
+                    } else if (lane < j_hi) {  // a column slice: one bulk copy per row
+                        tma_bulk_g2s(dst + lane * W * 4u, src + (size_t)lane * p.C, W * 4u, full);
+                    }
+                    if (kv == 0 && first && lane == 0)
+                        tma_bulk_g2s(smem_u32(qbuf + (size_t)stage * W),
+                                     p.q + (size_t)j_row * p.q_stride + (size_t)j_hg * W, W * 4u, full);
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ======================================= consumers =======================================
+    // rows of the batch that own no page at all produce zeros (paged_infer.c never hits this:
+    // T >= 1 always sees at least its own key)
+    for (int r = cta; r < p.B; r += G) {
+        if (__ldg(p.cum_pages + r + 1) == __ldg(p.cum_pages + r))
+            for (int c = tid; c < p.C; c += p.n_cons) p.out[(size_t)r * p.out_stride + c] = 0.0f;
+    }
+
+    const int lane = tid & 31;
+    const bool col_valid = tid < W4;
+    const int c4 = col_valid ? tid : W4 - 1;     // padded lanes shadow the last column
+    const int hl = tid / LPH;                    // head within the tile
+    const int hl_r = col_valid ? hl : 0;         // padded lanes read head 0's (m, l) in the merge
+    const int gl = tid % LPH;                    // lane within the head
+    float* my_p = psm + hl * BS;
+
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float m_run = kMaxInit, l_run = 0.0f;
+    int stage = 0;
+    uint32_t phase = 0;
+
+    for (int it = 0; it < n_units; ++it) {
+        // ------------------------------- K tile: scores -------------------------------------
+        mbar_wait(smem_u32(&bars[stage]), phase);
+        const int4 mt0 = meta[2 * stage];
+        const int4 mt1 = meta[2 * stage + 1];
+        const int lo = mt0.z & 0xff, hi = (mt0.z >> 8) & 0xff, flags = mt0.w;
+        if (flags & kFlagFirst) {
+            qv = reinterpret_cast<const float4*>(qbuf + (size_t)stage * W)[c4];
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            m_run = kMaxInit;
+            l_run = 0.0f;
+        }
+        float part[BS];
+        {
+            const float4* kt = reinterpret_cast<const float4*>(tiles + (size_t)stage * tile_floats) + c4;
+#pragma unroll
+            for (int t = 0; t < BS; ++t) {
+                const float4 k4 = kt[t * W4];
+                part[t] = fmaf(qv.w, k4.w, fmaf(qv.z, k4.z, fmaf(qv.y, k4.y, qv.x * k4.x)));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[p.n_stages + stage]));     // K slot free again
+        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+
+        int tok = 0;
+        XReduce<BS, LPH / 2>::run(part, gl, tok);
+        float s[NV];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int t = tok + v;
+            s[v] = (t >= lo && t < hi) ? part[v] * p.scale : -INFINITY;
+            mx = fmaxf(mx, s[v]);
+        }
+        mx = group_max<LPH>(mx);
+        const float m_new = fmaxf(m_run, mx);
+        const float alpha = expf(m_run - m_new);
+        float psum = 0.0f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float e = expf(s[v] - m_new);
+            my_p[tok + v] = e;
+            psum += e;
+        }
+        if (REP > 1 && (gl % REP) != 0) psum = 0.0f;     // replicated lanes count once
+        psum = group_sum<LPH>(psum);
+        l_run = l_run * alpha + psum;
+        m_run = m_new;
+        acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha;
+        __syncwarp();                                    // my_p visible to the head's lanes
+
+        // ------------------------------- V tile: weighted sum -------------------------------
+        mbar_wait(smem_u32(&bars[stage]), phase);
+        {
+            const float4* vt = reinterpret_cast<const float4*>(tiles + (size_t)stage * tile_floats) + c4;
+            const float4* p4 = reinterpret_cast<const float4*>(my_p);
+#pragma unroll
+            for (int t4 = 0; t4 < BS / 4; ++t4) {
+                const float4 pw = p4[t4];
+                const float pj[4] = {pw.x, pw.y, pw.z, pw.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = t4 * 4 + j;
+                    if (t < hi) {            // rows >= hi were never written by the copy
+                        const float4 v4 = vt[t * W4];
+                        acc.x = fmaf(pj[j], v4.x, acc.x);
+                        acc.y = fmaf(pj[j], v4.y, acc.y);
+                        acc.z = fmaf(pj[j], v4.z, acc.z);
+                        acc.w = fmaf(pj[j], v4.w, acc.w);
+                    }
+                }
+            }
+        }
+        __syncwarp();                                    // everyone done with my_p and the V tile
+        if (lane == 0) mbar_arrive(smem_u32(&bars[p.n_stages + stage]));
+        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+
+        // ------------------------------- end of a segment -----------------------------------
+        if (flags & kFlagLast) {
+            const int row = mt0.x, hg = mt0.y, c_first = mt1.x, nsegs = mt1.y;
+            float* out_ptr = p.out + (size_t)row * p.out_stride + (size_t)hg * W + c4 * 4;
+            if (nsegs == 1) {
+                const float inv = (l_run == 0.0f) ? 0.0f : 1.0f / l_run;
+                if (col_valid)
+                    *reinterpret_cast<float4*>(out_ptr) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+            } else {
+                // partial (m, l, unnormalised o) to this CTA's slot; the CTA that arrives last merges
+                float* slot = p.ws + (size_t)(cta + hg * p.B + row) * p.slot_floats;
+                if (col_valid) {
+                    __stcg(reinterpret_cast<float4*>(slot) + c4, acc);
+                    if (gl == 0) __stcg(reinterpret_cast<float2*>(slot + W) + hl, make_float2(m_run, l_run));
+                }
+                __threadfence();
+                named_bar_sync(1, p.n_cons);
+                if (tid == 0) {
+                    const int old = atomicAdd(p.counters + hg * p.B + row, 1);
+                    *s_flag = (old == nsegs - 1);
+                }
+                named_bar_sync(1, p.n_cons);
+                const bool merge = *s_flag != 0;
+                named_bar_sync(1, p.n_cons);             // s_flag may be rewritten by the next segment
+                if (merge) {
+                    __threadfence();
+                    float M = kMaxInit;
+                    for (int i = 0; i < nsegs; ++i) {
+                        const float* sl = p.ws + (size_t)(c_first + i + hg * p.B + row) * p.slot_floats;
+                        M = fmaxf(M, __ldcg(reinterpret_cast<const float2*>(sl + W) + hl_r).x);
+                    }
+                    float Lsum = 0.0f;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < nsegs; ++i) {
+                        const float* sl = p.ws + (size_t)(c_first + i + hg * p.B + row) * p.slot_floats;
+                        const float2 ml = __ldcg(reinterpret_cast<const float2*>(sl + W) + hl_r);
+                        const float w = expf(ml.x - M);
+                        const float4 oi = __ldcg(reinterpret_cast<const float4*>(sl) + c4);
+                        Lsum = fmaf(ml.y, w, Lsum);
+                        o.x = fmaf(oi.x, w, o.x); o.y = fmaf(oi.y, w, o.y);
+                        o.z = fmaf(oi.z, w, o.z); o.w = fmaf(oi.w, w, o.w);
+                    }
+                    const float inv = (Lsum == 0.0f) ? 0.0f : 1.0f / Lsum;
+                    if (col_valid)
+                        *reinterpret_cast<float4*>(out_ptr) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
+                    if (tid == 0) p.counters[hg * p.B + row] = 0;    // ready for the next launch
+                }
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// generic causal rows (prefill; fallback decode): one warp per (query row, head)
+// =============================================================================================
+struct RowsParams {
+    const float* pool_k;
+    const float* pool_v;
+    const float* q;
+    float* out;
+    const int* kv_end;      // [B] keys visible to the LAST query row of the sequence
+    const int* kv_start;    // [B]
+    const int* q_row0;      // [B+1] first packed query row of each sequence (NULL: one row per sequence)
+    const int* table;
+    int B, C, NH, hs, bs, tstride, q_stride, out_stride;
+    int n_rows;             // total query rows
+    float scale;
+};
+
+constexpr int kMaxHsPerLane = 8;   // hs <= 256
+
+__global__ void __launch_bounds__(128)
+pa_attn_rows_kernel(const RowsParams p) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= p.n_rows * p.NH) return;
+    const int row = warp / p.NH;
+    const int h = warp - row * p.NH;
+    // sequence of this row
+    int seq = row, j = 0, nq = 1;
+    if (p.q_row0) {
+        int a = 0, b = p.B;
+        while (b - a > 1) {
+            const int mid = (a + b) >> 1;
+            if (p.q_row0[mid] <= row) a = mid; else b = mid;
+        }
+        seq = a;
+        j = row - p.q_row0[seq];
+        nq = p.q_row0[seq + 1] - p.q_row0[seq];
+    }
+    const int first = p.kv_start[seq];
+    const int last = p.kv_end[seq] - (nq - 1 - j);     // row j sees keys [first, last)
+    const int* tbl = p.table + (size_t)seq * p.tstride;
+    const float* qh = p.q + (size_t)row * p.q_stride + h * p.hs;
+    float* oh = p.out + (size_t)row * p.out_stride + h * p.hs;
+
+    float o[kMaxHsPerLane];
+#pragma unroll
+    for (int i = 0; i < kMaxHsPerLane; ++i) o[i] = 0.0f;
+    float m_run = kMaxInit, l_run = 0.0f;
+
+    for (int g0 = first; g0 < last; g0 += 32) {
+        const int g = g0 + lane;
+        float s = -INFINITY;
+        const float* vrow = nullptr;
+        if (g < last) {
+            const size_t off = ((size_t)tbl[g / p.bs] * p.bs + (g % p.bs)) * p.C + h * p.hs;
+            const float* krow = p.pool_k + off;
+            vrow = p.pool_v + off;
+            float dot = 0.0f;
+            for (int i = 0; i < p.hs; ++i) dot = fmaf(qh[i], krow[i], dot);
+            s = dot * p.scale;
+        }
+        float mx = s;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        const float m_new = fmaxf(m_run, mx);
+        const float alpha = expf(m_run - m_new);
+        const float e = expf(s - m_new);
+        float esum = e;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, d);
+        l_run = l_run * alpha + esum;
+        m_run = m_new;
+#pragma unroll
+        for (int i = 0; i < kMaxHsPerLane; ++i) o[i] *= alpha;
+        const int cnt = min(32, last - g0);
+        for (int t = 0; t < cnt; ++t) {
+            const float et = __shfl_sync(0xffffffffu, e, t);
+            const float* vt = reinterpret_cast<const float*>(
+                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(vrow), t));
+#pragma unroll
+            for (int i = 0; i < kMaxHsPerLane; ++i) {
+                const int d = lane + 32 * i;
+                if (d < p.hs) o[i] = fmaf(et, vt[d], o[i]);
+            }
+        }
+    }
+    const float inv = (l_run == 0.0f) ? 0.0f : 1.0f / l_run;
+#pragma unroll
+    for (int i = 0; i < kMaxHsPerLane; ++i) {
+        const int d = lane + 32 * i;
+        if (d < p.hs) oh[d] = o[i] * inv;
+    }
+}
+
+// =============================================================================================
+// launch helpers
+// =============================================================================================
+typedef void (*decode_fn_t)(const DecodeParams);
+
+decode_fn_t pick_decode(int hs, int bs) {
+#define PA_CASE(H, Bk) if (hs == H && bs == Bk) return pa_decode_stream_kernel<H, Bk>;
+    PA_CASE(64, 4) PA_CASE(64, 8) PA_CASE(64, 16) PA_CASE(64, 32)
+    PA_CASE(128, 4) PA_CASE(128, 8) PA_CASE(128, 16) PA_CASE(128, 32)
+#undef PA_CASE
+    return nullptr;
+}
+
+struct DecodePlan {
+    int hpg, n_hg, W, n_stages, n_cons, grid, slot_floats;
+    size_t smem;
+};
+
+size_t decode_smem_bytes(int bs, int W, int n_stages, int n_cons, int lph) {
+    size_t b = (size_t)n_stages * bs * W * 4;          // tiles
+    b += (size_t)n_stages * W * 4;                     // q slots
+    b += (size_t)(n_cons / lph) * bs * 4;              // probabilities
+    b += (size_t)n_stages * 2 * sizeof(int4);          // meta
+    b += (size_t)n_stages * 2 * sizeof(uint64_t);      // barriers
+    b += 16;                                           // flag
+    return b;
+}
+
+// Choose heads per tile, stage count and grid for this step: the largest tile (whole pages when
+// C*block_size fits) that leaves a ring of >= 4 stages and still gives every SM a unit of work;
+// when the batch is too small for that, the smallest tile (most parallelism).
+bool plan_decode(const pa_handle* h, int total_pages, DecodePlan* plan) {
+    const int hs = h->cfg.head_dim, bs = h->cfg.block_size, NH = h->cfg.n_heads;
+    const int lph = hs / 4;
+    const int smem_cap = h->smem_optin - 1024;
+    const int want_hpg = h->tune[PA_TUNE_HEADS_PER_TILE];
+    int max_stages = h->tune[PA_TUNE_STAGES] > 0 ? h->tune[PA_TUNE_STAGES] : 8;
+    int best = 0, best_stages = 0;
+    for (int min_stages = 4; min_stages >= 2 && best == 0; --min_stages) {
+        for (int hpg = NH; hpg >= 1; --hpg) {
+            if (NH % hpg) continue;
+            if (want_hpg > 0 && hpg != want_hpg) continue;
+            const int W = hpg * hs;
+            const int n_cons = ((W / 4) + 31) & ~31;
+            if (n_cons > 256) continue;
+            const size_t per_stage = (size_t)bs * W * 4 + (size_t)W * 4 + 2 * sizeof(int4) + 16;
+            const size_t fixed = (size_t)(n_cons / lph) * bs * 4 + 64;
+            int stages = (int)((smem_cap - fixed) / per_stage);
+            if (stages > max_stages) stages = max_stages;
+            if (stages < min_stages && !(want_hpg > 0 && stages >= 2)) continue;
+            best = hpg;
+            best_stages = stages;
+            if ((long long)(NH / hpg) * total_pages >= h->sm_count) break;   // enough units: keep the big tile
+        }
+    }
+    if (best == 0) return false;
+    plan->hpg = best;
+    plan->n_hg = NH / best;
+    plan->W = best * hs;
+    plan->n_cons = ((plan->W / 4) + 31) & ~31;
+    plan->n_stages = best_stages;
+    plan->smem = decode_smem_bytes(bs, plan->W, best_stages, plan->n_cons, lph);
+    // CTAs: one per SM when the tile ring takes most of the shared memory, more when it is small
+    int per_sm = (int)((size_t)h->smem_optin / (plan->smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    const long long units = (long long)plan->n_hg * total_pages;
+    long long grid = (long long)h->sm_count * per_sm;
+    if (h->tune[PA_TUNE_GRID] > 0) grid = h->tune[PA_TUNE_GRID];
+    if (grid > (long long)h->sm_count * 8) grid = (long long)h->sm_count * 8;
+    if (grid > units) grid = units;
+    if (grid < 1) grid = 1;
+    plan->grid = (int)grid;
+    plan->slot_floats = (plan->W + 2 * plan->hpg + 3) & ~3;
+    return true;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int launch_rows(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride,
+                bool all_new_rows, cudaStream_t s) {
+    const pa_step_layout& L = h->step;
+    if (h->cfg.head_dim > 32 * kMaxHsPerLane) {
+        pa_set_error("head_dim %d > %d unsupported", h->cfg.head_dim, 32 * kMaxHsPerLane);
+        return PA_ERR_UNSUPPORTED;
+    }
+    RowsParams rp;
+    rp.pool_k = h->pool_k + (size_t)layer * h->layer_stride;
+    rp.pool_v = h->pool_v + (size_t)layer * h->layer_stride;
+    rp.q = q; rp.out = out;
+    rp.kv_end = h->d_step + L.off_kv_end;
+    rp.kv_start = h->d_step + L.off_kv_start;
+    rp.q_row0 = all_new_rows ? h->d_step + L.off_q_row0 : nullptr;
+    rp.table = h->d_step + L.off_table;
+    rp.B = L.nseq; rp.C = h->C; rp.NH = h->cfg.n_heads; rp.hs = h->cfg.head_dim; rp.bs = h->cfg.block_size;
+    rp.tstride = L.tstride; rp.q_stride = q_stride; rp.out_stride = out_stride;
+    rp.n_rows = all_new_rows ? L.ntok : L.nseq;
+    rp.scale = (float)(1.0 / sqrtf((float)h->cfg.head_dim));
+    if (rp.n_rows == 0) return PA_OK;
+    const long long warps = (long long)rp.n_rows * rp.NH;
+    const int threads = 128;
+    const long long blocks = (warps * 32 + threads - 1) / threads;
+    pa_attn_rows_kernel<<<(unsigned)blocks, threads, 0, s>>>(rp);
+    CU_CHECK(cudaGetLastError());
+    h->launches++;
+    return PA_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+static int check_compute(pa_handle* h, int layer, const char* who) {
+    if (!h) { pa_set_error("%s: NULL handle", who); return PA_ERR_INVALID; }
+    if (h->host_only || !h->pool_k) {
+        pa_set_error("%s: handle has no device (host-only); there is no CPU fallback", who);
+        return PA_ERR_NO_DEVICE;
+    }
+    if (layer < 0 || layer >= h->cfg.n_layers) { pa_set_error("%s: layer %d out of range", who, layer); return PA_ERR_INVALID; }
+    if (h->step.nseq < 1) { pa_set_error("%s: no step (call pa_step_begin)", who); return PA_ERR_INVALID; }
+    if (!h->step.uploaded) { pa_set_error("%s: step tables not uploaded (call pa_step_upload)", who); return PA_ERR_INVALID; }
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess) { pa_set_error("%s: cudaSetDevice failed", who); return PA_ERR_CUDA; }
+    return PA_OK;
+}
+
+int pa_append(pa_handle* h, int layer, const float* k, const float* v, int row_stride, void* stream) {
+    int rc = check_compute(h, layer, "pa_append");
+    if (rc != PA_OK) return rc;
+    const pa_step_layout& L = h->step;
+    if (L.ntok == 0) return PA_OK;
+    if (!k || !v || row_stride < h->C) { pa_set_error("pa_append: bad source"); return PA_ERR_INVALID; }
+    cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)h->stream;
+    float* pk = h->pool_k + (size_t)layer * h->layer_stride;
+    float* pv = h->pool_v + (size_t)layer * h->layer_stride;
+    const int* slots = h->d_step + L.off_slot;
+    const bool vec = (h->C % 4 == 0) && (row_stride % 4 == 0) && aligned16(k) && aligned16(v);
+    const int per_row = vec ? h->C / 4 : h->C;
+    dim3 grid((per_row + 255) / 256, L.ntok > 65535 ? 65535 : L.ntok);
+    if (vec) pa_append_kernel<true><<<grid, 256, 0, s>>>(k, v, row_stride, pk, pv, slots, L.ntok, h->C);
+    else pa_append_kernel<false><<<grid, 256, 0, s>>>(k, v, row_stride, pk, pv, slots, L.ntok, h->C);
+    CU_CHECK(cudaGetLastError());
+    h->launches++;
+    return PA_OK;
+}
+
+int pa_decode(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream) {
+    int rc = check_compute(h, layer, "pa_decode");
+    if (rc != PA_OK) return rc;
+    if (!q || !out || q_stride < h->C || out_stride < h->C) { pa_set_error("pa_decode: bad q/out"); return PA_ERR_INVALID; }
+    cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)h->stream;
+    const pa_step_layout& L = h->step;
+    const int hs = h->cfg.head_dim, bs = h->cfg.block_size;
+    const int path = h->tune[PA_TUNE_DECODE_PATH];
+    decode_fn_t fn = pick_decode(hs, bs);
+    const bool stream_ok = fn != nullptr && (q_stride % 4 == 0) && (out_stride % 4 == 0) && aligned16(q) && aligned16(out);
+    if (path == 1 && !stream_ok) {
+        pa_set_error("pa_decode: stream kernel needs head_dim 64/128, block_size 4/8/16/32 and 16-byte aligned q/out");
+        return PA_ERR_UNSUPPORTED;
+    }
+    DecodePlan plan;
+    if (path != 2 && stream_ok && plan_decode(h, L.total_pages, &plan)) {
+        DecodeParams dp;
+        dp.pool_k = h->pool_k + (size_t)layer * h->layer_stride;
+        dp.pool_v = h->pool_v + (size_t)layer * h->layer_stride;
+        dp.q = q; dp.out = out;
+        dp.kv_end = h->d_step + L.off_kv_end;
+        dp.kv_start = h->d_step + L.off_kv_start;
+        dp.cum_pages = h->d_step + L.off_cum_pages;
+        dp.table = h->d_step + L.off_table;
+        dp.ws = h->d_ws; dp.counters = h->d_counters;
+        dp.P = L.total_pages;
+        dp.U = (long long)plan.n_hg * L.total_pages;
+        dp.B = L.nseq; dp.C = h->C; dp.hpg = plan.hpg; dp.n_hg = plan.n_hg; dp.W = plan.W;
+        dp.tstride = L.tstride; dp.q_stride = q_stride; dp.out_stride = out_stride;
+        dp.n_stages = plan.n_stages; dp.n_cons = plan.n_cons; dp.slot_floats = plan.slot_floats;
+        dp.scale = (float)(1.0 / sqrtf((float)hs));          // paged_infer.c:174
+        if ((size_t)(plan.grid + plan.n_hg * L.nseq) * plan.slot_floats > h->ws_floats) {
+            pa_set_error("pa_decode: split workspace too small");
+            return PA_ERR_INVALID;
+        }
+        if (h->decode_attr_fn != (void*)fn) {      // once per handle (one geometry per handle)
+            CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+            h->decode_attr_fn = (void*)fn;
+        }
+        if (L.total_pages == 0) { dp.P = 1; plan.grid = 1; }   // nothing cached anywhere: zero-fill only (U == 0)
+        fn<<<plan.grid, plan.n_cons + 32, plan.smem, s>>>(dp);
+        CU_CHECK(cudaGetLastError());
+        h->launches++;
+        return PA_OK;
+    }
+    return launch_rows(h, layer, q, q_stride, out, out_stride, false, s);
+}
+
+int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream) {
+    int rc = check_compute(h, layer, "pa_prefill");
+    if (rc != PA_OK) return rc;
+    if (!q || !out || q_stride < h->C || out_stride < h->C) { pa_set_error("pa_prefill: bad q/out"); return PA_ERR_INVALID; }
+    cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)h->stream;
+    return launch_rows(h, layer, q, q_stride, out, out_stride, true, s);
+}
+
+int pa_decode_step_host(pa_handle* h, int layer, const float* qkv_host, float* out_host) {
+    if (!h || h->host_only) { pa_set_error("pa_decode_step_host: no device; there is no CPU fallback"); return PA_ERR_NO_DEVICE; }
+    if (!qkv_host || !out_host) { pa_set_error("pa_decode_step_host: NULL buffer"); return PA_ERR_INVALID; }
+    const pa_step_layout& L = h->step;
+    if (L.nseq < 1 || L.ntok != L.nseq) { pa_set_error("pa_decode_step_host: needs a step with one new token per sequence"); return PA_ERR_INVALID; }
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess) return PA_ERR_CUDA;
+    const size_t C = h->C, n = L.nseq;
+    int rc = pa_cu_ensure_stage(h, n * 4 * C);
+    if (rc != PA_OK) return rc;
+    cudaStream_t s = (cudaStream_t)h->stream;
+    if (!h->step.uploaded) { rc = pa_cu_step_upload(h, s); if (rc != PA_OK) return rc; }
+    float* d_qkv = h->d_stage;
+    float* d_out = h->d_stage + n * 3 * C;
+    /* pageable host memory is staged through the pinned buffer; pinned memory goes straight */
+    cudaPointerAttributes a;
+    bool pinned = cudaPointerGetAttributes(&a, qkv_host) == cudaSuccess && a.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const float* src = qkv_host;
+    if (!pinned) { memcpy(h->h_stage, qkv_host, n * 3 * C * sizeof(float)); src = h->h_stage; }
+    CU_CHECK(cudaMemcpyAsync(d_qkv, src, n * 3 * C * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = pa_append(h, layer, d_qkv + C, d_qkv + 2 * C, (int)(3 * C), s);
+    if (rc != PA_OK) return rc;
+    rc = pa_decode(h, layer, d_qkv, (int)(3 * C), d_out, (int)C, s);
+    if (rc != PA_OK) return rc;
+    bool out_pinned = cudaPointerGetAttributes(&a, out_host) == cudaSuccess && a.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    float* dst = out_pinned ? out_host : h->h_stage + n * 3 * C;
+    CU_CHECK(cudaMemcpyAsync(dst, d_out, n * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU_CHECK(cudaStreamSynchronize(s));
+    if (!out_pinned) memcpy(out_host, dst, n * C * sizeof(float));
+    return PA_OK;
+}
+
+}  // extern "C"

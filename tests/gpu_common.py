@@ -1,0 +1,107 @@
+"""Shared helpers for the -m gpu parity tests: build a device pool + block tables through the
+C ABI, mirror the same logical K/V content into the CPU oracle, compare."""
+import numpy as np
+
+import __graft_entry__ as ge
+import oracle_api as oa
+
+pa = ge.load_binding()
+
+# Tolerance for fp32 attention outputs (north_star: "max relative error 1e-5"):
+#   max|a-b| / max|ref| <= 1e-5   and   allclose(rtol=1e-5, atol=1e-6)
+REL_TOL = 1e-5
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def assert_close(got, want, what=""):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert np.isfinite(got).all(), f"{what}: non-finite output"
+    scale = max(np.abs(want).max(), 1e-30)
+    err = np.abs(got - want).max() / scale
+    assert err <= REL_TOL, f"{what}: max|a-b|/max|ref| = {err:.3e} > {REL_TOL}"
+    bad = np.abs(got - want) > ATOL + RTOL * np.abs(want)
+    assert not bad.any(), f"{what}: {bad.sum()} elements outside allclose(rtol={RTOL}, atol={ATOL}); worst {np.abs(got - want).max():.3e}"
+    return err
+
+
+class Scenario:
+    """A batch of sequences with given context lengths on one engine + the oracle twin."""
+
+    def __init__(self, NH, hs, bs, ctx, n_layers=1, layer=0, seed=1234, shuffle=False, extra_blocks=8,
+                 dist="normal", device=0):
+        self.NH, self.hs, self.bs, self.C = NH, hs, bs, NH * hs
+        self.ctx = list(ctx)
+        self.B = len(ctx)
+        self.layer = layer
+        pages = [(c + bs - 1) // bs for c in ctx]
+        self.max_blocks = sum(pages) + extra_blocks + self.B
+        self.eng = pa.PagedAttn(bs, self.max_blocks, self.B, NH, hs, n_layers=n_layers, device=device,
+                                max_batch_tokens=max(max(ctx), self.B) + 8)
+        self.orc = oa.OrcManager(self.C, bs, self.max_blocks, self.B)
+        rng = np.random.default_rng(seed)
+        # whole pool content in one upload
+        shape = (self.max_blocks * bs, self.C)
+        if dist == "normal":
+            pool_k = oa.normal(shape, seed=seed)
+            pool_v = oa.normal(shape, seed=seed + 1)
+        else:   # the reference test's value range, test_paged_attn.c:201
+            pool_k = oa.uniform(shape, 0.0, 100.0, seed=seed)
+            pool_v = oa.uniform(shape, 0.0, 100.0, seed=seed + 1)
+        self.pool_k, self.pool_v = pool_k, pool_v
+        lib = self.eng.lib
+        pa.check(lib.pa_memcpy_h2d(self.eng.pool_k(layer), pool_k.ctypes.data, pool_k.nbytes, None), "h2d")
+        pa.check(lib.pa_memcpy_h2d(self.eng.pool_v(layer), pool_v.ctypes.data, pool_v.nbytes, None), "h2d")
+        # block tables: allocator order, or a seeded permutation dealt round-robin (fragmented)
+        if shuffle:
+            perm = rng.permutation(self.max_blocks)
+            cur = 0
+            for s in range(self.B):
+                if ctx[s] == 0:
+                    continue
+                blocks = perm[cur:cur + pages[s]]
+                cur += pages[s]
+                assert self.eng.seq_adopt(s, blocks, ctx[s]) == 0, pa.last_error()
+        else:
+            for s in range(self.B):
+                if ctx[s] > 0:
+                    assert self.eng.step_begin([s], [ctx[s]]) == 0, pa.last_error()
+        # oracle twin: same logical content
+        for s in range(self.B):
+            tbl = self.eng.table(s)
+            for j, idx in enumerate(tbl):
+                oidx = self.orc.request_block(s)
+                k, v = self.orc.page_arrays(oidx)
+                n = min(bs, ctx[s] - j * bs)
+                k[:n] = pool_k[idx * bs: idx * bs + n]
+                v[:n] = pool_v[idx * bs: idx * bs + n]
+                self.orc.set_filled(oidx, n)
+        self.seq_ids = list(range(self.B))
+
+    def close(self):
+        self.eng.close()
+        self.orc.close()
+
+    def decode(self, q, kv_start=None, path=0, hpg=0, stages=0, grid=0):
+        """Run pa_decode over all sequences (read-only step) and return (B, C)."""
+        eng = self.eng
+        eng.tune(pa.PA_TUNE_DECODE_PATH, path)
+        eng.tune(pa.PA_TUNE_HEADS_PER_TILE, hpg)
+        eng.tune(pa.PA_TUNE_STAGES, stages)
+        eng.tune(pa.PA_TUNE_GRID, grid)
+        assert eng.step_begin_readonly(self.seq_ids) == 0, pa.last_error()
+        if kv_start is not None:
+            assert eng.step_set_kv_start(kv_start) == 0, pa.last_error()
+        pa.check(eng.upload(), "upload")
+        d_q = pa.DevBuf.from_numpy(q)
+        d_out = pa.DevBuf(self.B * self.C * 4)
+        pa.check(eng.lib.pa_memset(d_out.ptr, 0xff, self.B * self.C * 4, None), "memset")   # NaN canary
+        pa.check(eng.decode(self.layer, d_q.ptr, q.shape[1], d_out.ptr, self.C), "decode")
+        eng.sync()
+        out = d_out.download((self.B, self.C))
+        d_q.free(); d_out.free()
+        return out
+
+    def oracle_decode(self, q, kv_start=None):
+        return self.orc.decode_batch(self.seq_ids, self.NH, q[:, :self.C], kv_start=kv_start)

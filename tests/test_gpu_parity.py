@@ -1,0 +1,371 @@
+"""-m gpu parity tests proper: every call goes through the C ABI of libpaged_attn.so; the checker
+is the CPU oracle (pinned to the compiled reference by test_oracle_pinned.py) and, where the
+reference itself was built (oracle/_ref), the reference's own attention_paged."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_api as oa
+from gpu_common import Scenario, assert_close, pa
+
+pytestmark = pytest.mark.gpu
+
+
+# --------------------------------------------------------------------------------- KV append
+@pytest.mark.parametrize("NH,hs,bs", [(12, 64, 16), (25, 64, 16), (4, 128, 32), (2, 5, 2)])
+def test_append_bit_exact(NH, hs, bs):
+    Cc = NH * hs
+    B = 7
+    eng = pa.PagedAttn(bs, 64, B, NH, hs, n_layers=2, max_batch_tokens=256)
+    orc = oa.OrcManager(Cc, bs, 64, B)
+    try:
+        rng = np.random.default_rng(0)
+        for step in range(6):
+            seqs = rng.permutation(B)[: int(rng.integers(1, B + 1))].astype(np.int32)
+            n_new = (rng.integers(1, 2 * bs, size=len(seqs)) if step == 0 else np.ones(len(seqs))).astype(np.int32)
+            ntok = int(n_new.sum())
+            qkv = oa.normal((ntok, 3 * Cc), seed=10 + step)
+            assert eng.step_begin(seqs, n_new) == 0, pa.last_error()
+            pa.check(eng.upload(), "upload")
+            d = pa.DevBuf.from_numpy(qkv)
+            pa.check(eng.append(1, d.ptr + Cc * 4, d.ptr + 2 * Cc * 4, 3 * Cc), "append")
+            eng.sync()
+            slots = eng.slot_mapping()
+            k, v = eng.read_pool_rows(1, slots)
+            assert np.array_equal(k.view(np.uint32), qkv[:, Cc:2 * Cc].view(np.uint32))
+            assert np.array_equal(v.view(np.uint32), qkv[:, 2 * Cc:].view(np.uint32))
+            # same bytes at the same logical positions as the oracle's add_to_cache
+            row = 0
+            for s, n in zip(seqs, n_new):
+                for _ in range(int(n)):
+                    orc.add_to_cache(qkv[row][None, None, :], 1, 1, 1, prompt=int(s))
+                    row += 1
+            for s in seqs:
+                L = orc.context_len(int(s))
+                assert L == eng.seq_len(int(s))
+                pos = L - 1
+                ok, ov = orc.page_arrays(orc.table(int(s))[pos // bs])
+                gk, gv = eng.read_pool_rows(1, [eng.table(int(s))[pos // bs] * bs + pos % bs])
+                assert np.array_equal(gk[0], ok[pos % bs]) and np.array_equal(gv[0], ov[pos % bs])
+            d.free()
+        # layer 0 untouched
+        k0, _ = eng.read_pool_rows(0, eng.slot_mapping())
+        assert not k0.any()
+    finally:
+        eng.close(); orc.close()
+
+
+# --------------------------------------------------------------------------------- decode
+RAGGED = [1, 2, 15, 16, 17, 31, 32, 33, 47, 48, 49, 100, 255, 256, 257, 333]
+
+DECODE_CASES = [
+    # NH, hs, bs, ctx, shuffle
+    pytest.param(12, 64, 16, [256], False, id="cfg1-b1-ctx256"),
+    pytest.param(12, 64, 16, RAGGED, True, id="ragged-bs16-shuffled"),
+    pytest.param(12, 64, 32, RAGGED, False, id="ragged-bs32-refdefault"),
+    pytest.param(12, 64, 8, RAGGED, True, id="ragged-bs8"),
+    pytest.param(12, 64, 4, [1, 3, 4, 5, 64, 65], True, id="bs4"),
+    pytest.param(25, 64, 16, [128, 1024, 77, 513], True, id="xl-25heads"),
+    pytest.param(4, 128, 16, [1, 17, 300, 2048], True, id="hs128"),
+    pytest.param(4, 128, 32, [5, 64, 700], False, id="hs128-bs32"),
+    pytest.param(8, 128, 8, [9, 130], True, id="hs128-bs8"),
+    pytest.param(12, 64, 16, [0, 5, 0, 40], False, id="empty-sequences"),
+]
+
+
+@pytest.mark.parametrize("NH,hs,bs,ctx,shuffle", DECODE_CASES)
+@pytest.mark.parametrize("path", [1, 2], ids=["stream", "generic"])
+def test_decode_matches_oracle(NH, hs, bs, ctx, shuffle, path):
+    sc = Scenario(NH, hs, bs, ctx, shuffle=shuffle, seed=77)
+    try:
+        q = oa.normal((sc.B, sc.C), seed=5)
+        want = sc.oracle_decode(q)
+        got = sc.decode(q, path=path)
+        assert_close(got, want, f"decode path={path}")
+    finally:
+        sc.close()
+
+
+@pytest.mark.parametrize("hpg,stages,grid", [(1, 0, 0), (2, 2, 0), (3, 3, 7), (4, 0, 1), (6, 0, 0), (12, 2, 0),
+                                             (12, 4, 148), (12, 0, 1184), (0, 0, 5)])
+def test_decode_tile_shapes_and_splits(hpg, stages, grid):
+    """Every tile shape / ring depth / split count must give the same answer (split partials are
+    merged in-kernel by the last-arriving CTA)."""
+    sc = Scenario(12, 64, 16, [700, 3, 129, 64, 1000, 17], shuffle=True, seed=3)
+    try:
+        q = oa.normal((sc.B, sc.C), seed=6)
+        want = sc.oracle_decode(q)
+        for rep in range(3):      # repeated launches: the arrival counters must self-reset
+            got = sc.decode(q, path=1, hpg=hpg, stages=stages, grid=grid)
+            assert_close(got, want, f"hpg={hpg} stages={stages} grid={grid} rep={rep}")
+    finally:
+        sc.close()
+
+
+def test_decode_sliding_window():
+    """Reference `offset` (paged_infer.c:190,1057): row attends cached tokens [kv_start, ctx)."""
+    sc = Scenario(12, 64, 16, [100, 64, 33, 500], shuffle=True, seed=9)
+    try:
+        q = oa.normal((sc.B, sc.C), seed=2)
+        for kv_start in ([0, 0, 0, 0], [1, 16, 32, 17], [99, 63, 0, 255], [37, 5, 31, 499]):
+            want = sc.oracle_decode(q, kv_start=kv_start)
+            for path in (1, 2):
+                got = sc.decode(q, kv_start=kv_start, path=path)
+                assert_close(got, want, f"window {kv_start} path={path}")
+    finally:
+        sc.close()
+
+
+def test_decode_large_logits_reference_value_range():
+    """U[0,100) inputs as in test_paged_attn.c:201 -> logits of order 1e5: softmax is one-hot-ish
+    and the -10000 initial maximum never wins."""
+    sc = Scenario(2, 64, 16, [20, 70], seed=11, dist="uniform")
+    try:
+        q = oa.uniform((sc.B, sc.C), 0.0, 100.0, seed=4)
+        want = sc.oracle_decode(q)
+        for path in (1, 2):
+            assert_close(sc.decode(q, path=path), want, f"large logits path={path}")
+    finally:
+        sc.close()
+
+
+def test_decode_minus_10000_floor():
+    """Scores far below the reference's initial maximum (-10000.0f, paged_infer.c:187) underflow
+    to exp()=0 and the 0-sum guard (:213) yields zeros -- reproduce, do not 'fix'."""
+    sc = Scenario(2, 64, 16, [5, 40], seed=12)
+    try:
+        q = np.full((sc.B, sc.C), -3000.0, dtype=np.float32)
+        # make every key strongly positive so q.k*scale << -10000
+        sc.pool_k[:] = 10.0
+        lib = sc.eng.lib
+        pa.check(lib.pa_memcpy_h2d(sc.eng.pool_k(0), sc.pool_k.ctypes.data, sc.pool_k.nbytes, None), "h2d")
+        for s in range(sc.B):
+            for idx in sc.orc.table(s):
+                k, _ = sc.orc.page_arrays(idx)
+                k[:] = 10.0
+        want = sc.oracle_decode(q)
+        assert not want.any()
+        for path in (1, 2):
+            got = sc.decode(q, path=path)
+            assert np.array_equal(got, want)
+    finally:
+        sc.close()
+
+
+def test_decode_generic_odd_shapes():
+    """The reference test's own tiny shape (test_paged_attn.c:184-188: C=10, NH=2, block 2) and
+    other shapes outside the stream kernel's domain go to the generic SIMT kernel."""
+    for NH, hs, bs, ctx in [(2, 5, 2, [20, 1, 7]), (3, 48, 4, [33, 9]), (1, 200, 16, [50]), (5, 96, 32, [70, 31])]:
+        sc = Scenario(NH, hs, bs, ctx, shuffle=True, seed=21)
+        try:
+            q = oa.normal((sc.B, sc.C), seed=8)
+            assert_close(sc.decode(q, path=0), sc.oracle_decode(q), f"generic NH={NH} hs={hs} bs={bs}")
+            assert sc.eng.decode(0, None, sc.C, None, sc.C) == pa.PA_ERR_INVALID
+        finally:
+            sc.close()
+
+
+def test_decode_physical_placement_is_irrelevant():
+    """Size-independent property: where pages live in the pool (block-table permutation) must not
+    change a single bit -- the work split depends on logical pages only."""
+    ctx = [513, 64, 1000, 31]
+    a = Scenario(12, 64, 16, ctx, shuffle=False, seed=31)
+    b = Scenario(12, 64, 16, ctx, shuffle=True, seed=31)
+    try:
+        # same logical content in both: copy a's logical rows into b's physical slots
+        for s in range(len(ctx)):
+            ta, tb = a.eng.table(s), b.eng.table(s)
+            for ja, jb in zip(ta, tb):
+                b.pool_k[jb * 16:(jb + 1) * 16] = a.pool_k[ja * 16:(ja + 1) * 16]
+                b.pool_v[jb * 16:(jb + 1) * 16] = a.pool_v[ja * 16:(ja + 1) * 16]
+        lib = b.eng.lib
+        pa.check(lib.pa_memcpy_h2d(b.eng.pool_k(0), b.pool_k.ctypes.data, b.pool_k.nbytes, None), "h2d")
+        pa.check(lib.pa_memcpy_h2d(b.eng.pool_v(0), b.pool_v.ctypes.data, b.pool_v.nbytes, None), "h2d")
+        q = oa.normal((len(ctx), 768), seed=1)
+        ga, gb = a.decode(q, path=1), b.decode(q, path=1)
+        assert np.array_equal(ga.view(np.uint32), gb.view(np.uint32))
+    finally:
+        a.close(); b.close()
+
+
+def test_decode_constant_values_property():
+    """softmax weights sum to 1: with every V row equal to c the output is c."""
+    sc = Scenario(12, 64, 16, [1, 100, 1024], seed=41)
+    try:
+        c = oa.normal((sc.C,), seed=99)
+        sc.pool_v[:] = c
+        pa.check(sc.eng.lib.pa_memcpy_h2d(sc.eng.pool_v(0), sc.pool_v.ctypes.data, sc.pool_v.nbytes, None), "h2d")
+        q = oa.normal((sc.B, sc.C), seed=3)
+        got = sc.decode(q, path=1)
+        assert np.abs(got - c[None, :]).max() <= 2e-6 * np.abs(c).max() + 1e-6
+    finally:
+        sc.close()
+
+
+# --------------------------------------------------------------------------------- full step
+def test_decode_step_device_and_host_entry():
+    """append + decode of a real step (GPT-2 124M shape, 2 layers), device-resident and through
+    the host-buffer entry pa_decode_step_host; K/V written by the append kernel are what the
+    decode kernel then reads."""
+    NH, hs, bs, B = 12, 64, 16, 9
+    Cc = NH * hs
+    ctx0 = [0, 1, 15, 16, 31, 32, 100, 255, 256]
+    sc = Scenario(NH, hs, bs, ctx0, n_layers=2, layer=1, seed=51, shuffle=False, extra_blocks=32)
+    try:
+        eng, orc = sc.eng, sc.orc
+        for step in range(3):
+            qkv = oa.normal((B, 3 * Cc), seed=200 + step)
+            assert eng.step_begin(sc.seq_ids, [1] * B) == 0, pa.last_error()
+            for s in range(B):
+                orc.add_to_cache(qkv[s][None, None, :], 1, 1, 1, prompt=s)
+            want = orc.decode_batch(sc.seq_ids, NH, qkv[:, :Cc])
+            if step % 2 == 0:      # device-resident API
+                pa.check(eng.upload(), "upload")
+                d = pa.DevBuf.from_numpy(qkv)
+                o = pa.DevBuf(B * Cc * 4)
+                pa.check(eng.append(1, d.ptr + Cc * 4, d.ptr + 2 * Cc * 4, 3 * Cc), "append")
+                pa.check(eng.decode(1, d.ptr, 3 * Cc, o.ptr, Cc), "decode")
+                eng.sync()
+                got = o.download((B, Cc))
+            else:                  # host buffers in, host buffers out
+                got = np.zeros((B, Cc), dtype=np.float32)
+                pa.check(eng.decode_step_host(1, qkv.ctypes.data, got.ctypes.data), "decode_step_host")
+            assert_close(got, want, f"step {step}")
+    finally:
+        sc.close()
+
+
+# --------------------------------------------------------------------------------- prefill rows
+@pytest.mark.parametrize("NH,hs,bs", [(12, 64, 16), (2, 5, 2), (4, 128, 32)])
+def test_prefill_rows_match_oracle(NH, hs, bs):
+    """Causal rows through the block table: prompt prefill (ctx_before = 0) and chunked prefill
+    on top of cached tokens, mixed in one batch."""
+    Cc = NH * hs
+    before = [0, 5, 40, 0]
+    n_new = [33, 7, 1, 64]
+    sc = Scenario(NH, hs, bs, before, seed=61, extra_blocks=32)
+    try:
+        eng, orc = sc.eng, sc.orc
+        ntok = sum(n_new)
+        qkv = oa.normal((ntok, 3 * Cc), seed=62)
+        assert eng.step_begin(sc.seq_ids, n_new) == 0, pa.last_error()
+        pa.check(eng.upload(), "upload")
+        d = pa.DevBuf.from_numpy(qkv)
+        o = pa.DevBuf(ntok * Cc * 4)
+        pa.check(eng.append(0, d.ptr + Cc * 4, d.ptr + 2 * Cc * 4, 3 * Cc), "append")
+        pa.check(eng.prefill(0, d.ptr, 3 * Cc, o.ptr, Cc), "prefill")
+        eng.sync()
+        got = o.download((ntok, Cc))
+        row = 0
+        for s, n in enumerate(n_new):
+            for _ in range(n):
+                orc.add_to_cache(qkv[row][None, None, :], 1, 1, 1, prompt=s)
+                row += 1
+        want = orc.attend_rows(sc.seq_ids, [0] * 4, [b + 1 for b in before], n_new, NH, qkv[:, :Cc])
+        assert_close(got, want, "prefill rows")
+    finally:
+        sc.close()
+
+
+# --------------------------------------------------------------------------------- compat API
+def _compat_manager(lib, C_, bs, mb, mp):
+    lib.pa_set_default_geometry(bs, mb, mp)
+    m = lib.create_block_manager(C_)
+    assert m, "create_block_manager failed"
+    return m
+
+
+@pytest.mark.parametrize("device_buffers", [False, True], ids=["host-buffers", "device-buffers"])
+def test_compat_sliding_window_like_paged_infer_main(device_buffers):
+    """The reference call site (paged_infer.c:710-715) and main's pattern (:1055-1057): T=32,
+    first add_to_cache(n_tail=T), then n_tail=1 with offset=1..18, crossing into a second page.
+    Drop-in names, host buffers as in the reference."""
+    lib = pa.load()
+    bs, mb, mp, T, Cc, NH = 32, 100, 100, 32, 768, 12
+    m = _compat_manager(lib, Cc, bs, mb, mp)
+    orc = oa.OrcManager(Cc, bs, mb, mp)
+    ref = oa.RefManager(Cc, bs, mb, mp) if oa.have_ref(bs, mb, mp) else None
+    try:
+        stream = oa.normal((T + 18, 3 * Cc), seed=2024)
+        for step in range(19):
+            window = np.ascontiguousarray(stream[step:step + T][None])
+            n_tail = T if step == 0 else 1
+            out = np.zeros((1, T, Cc), dtype=np.float32)
+            if device_buffers:
+                d_in = pa.DevBuf.from_numpy(window)
+                d_out = pa.DevBuf(out.nbytes)
+                lib.add_to_cache(m, d_in.ptr, 1, T, Cc, n_tail)
+            else:
+                lib.add_to_cache(m, window.ctypes.data, 1, T, Cc, n_tail)
+            nb = C.c_int()
+            kv = lib.collect_kv_blocks(m, 0, C.byref(nb))
+            assert kv
+            if device_buffers:
+                lib.attention_paged(d_out.ptr, None, None, d_in.ptr, kv[0], kv[1], 1, T, Cc, NH, step)
+                out = d_out.download(out.shape)
+            else:
+                lib.attention_paged(out.ctypes.data, None, None, window.ctypes.data, kv[0], kv[1], 1, T, Cc, NH, step)
+            orc.add_to_cache(window, 1, T, n_tail)
+            _, want = orc.attend(0, window, 1, T, NH, step)
+            assert nb.value == len(orc.table(0))
+            assert_close(out, want, f"compat step {step}")
+            if ref is not None:
+                ref.add_to_cache(window, 1, T, n_tail)
+                _, rwant = ref.attend(0, window, 1, T, NH, step)
+                assert_close(out, rwant, f"compat vs compiled reference, step {step}")
+                assert ref.table(0) == pa.ManagerAdapter(m).table(0)
+                assert ref.epoch() == m.contents.lru_epoch
+        ad = pa.ManagerAdapter(m)
+        assert ad.table(0) == [0, 1]
+        assert [ad.block_info(i)[0] for i in (0, 1)] == [32, 18]
+        assert m.contents.lru_epoch == 19
+    finally:
+        lib.destroy_block_manager(m)
+        orc.close()
+        if ref is not None:
+            ref.close()
+        lib.pa_set_default_geometry(32, 100, 100)
+
+
+def test_compat_reference_unit_test_shape():
+    """test_paged_attn.c:184-188 (B=1,T=20,C=10,NH=2, 10 blocks of 2) on U[0,100) inputs, through
+    the compat names; block_manager_test.c's write/readback pattern on device pages."""
+    lib = pa.load()
+    bs, mb, mp, T, Cc, NH = 2, 64, 8, 20, 10, 2
+    m = _compat_manager(lib, Cc, bs, mb, mp)
+    orc = oa.OrcManager(Cc, bs, mb, mp)
+    try:
+        inp = oa.uniform((1, T, 3 * Cc), 0.0, 100.0, seed=42)
+        for t0 in range(0, T, bs):
+            blk = lib.request_block(m, 0)
+            assert blk
+            k_rows = np.ascontiguousarray(inp[0, t0:t0 + bs, Cc:2 * Cc])
+            v_rows = np.ascontiguousarray(inp[0, t0:t0 + bs, 2 * Cc:])
+            pa.check(lib.pa_memcpy_h2d(blk.contents.keys, k_rows.ctypes.data, k_rows.nbytes, None), "h2d")
+            pa.check(lib.pa_memcpy_h2d(blk.contents.values, v_rows.ctypes.data, v_rows.nbytes, None), "h2d")
+            blk.contents.filled = bs
+            back = np.zeros_like(k_rows)
+            pa.check(lib.pa_memcpy_d2h(back.ctypes.data, blk.contents.keys, back.nbytes, None), "d2h")
+            assert np.array_equal(back, k_rows)                      # block_manager_test.c:31-38
+            oidx = orc.request_block(0)
+            ok, ov = orc.page_arrays(oidx)
+            ok[:], ov[:] = k_rows, v_rows
+            orc.set_filled(oidx, bs)
+        nb = C.c_int()
+        kv = lib.collect_kv_blocks(m, 0, C.byref(nb))
+        assert nb.value == 10
+        out = np.zeros((1, T, Cc), dtype=np.float32)
+        lib.attention_paged(out.ctypes.data, None, None, inp.ctypes.data, kv[0], kv[1], 1, T, Cc, NH, 0)
+        _, want = orc.attend(0, inp, 1, T, NH, 0)
+        assert np.abs(out - want).max() <= 1e-2                      # the reference's own tolerance
+        assert_close(out, want, "compat test_paged_attn shape")
+        # error behaviour of the reference API
+        assert not lib.request_block(m, 100) and not lib.request_block(m, -1)
+        assert not lib.collect_kv_blocks(m, 5, C.byref(nb)) and nb.value == 0
+        lib.free_blocks_for_prompt(m, 0)
+        assert m.contents.prompt_block_count[0] == 0
+    finally:
+        lib.destroy_block_manager(m)
+        orc.close()
+        lib.pa_set_default_geometry(32, 100, 100)
