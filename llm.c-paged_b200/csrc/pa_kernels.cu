@@ -506,9 +506,11 @@ pa_attn_rows_kernel(const RowsParams p) {
             const size_t off = ((size_t)tbl[g / p.bs] * p.bs + (g % p.bs)) * p.C + h * p.hs;
             const float* krow = p.pool_k + off;
             vrow = p.pool_v + off;
+            // the reference's evaluation order, unfused (paged_infer.c:193-197): with large
+            // logits one ulp of the score already moves the softmax weights visibly
             float dot = 0.0f;
-            for (int i = 0; i < p.hs; ++i) dot = fmaf(qh[i], krow[i], dot);
-            s = dot * p.scale;
+            for (int i = 0; i < p.hs; ++i) dot = __fadd_rn(dot, __fmul_rn(qh[i], krow[i]));
+            s = __fmul_rn(dot, p.scale);
         }
         float mx = s;
 #pragma unroll

@@ -26,11 +26,25 @@ def assert_close(got, want, what=""):
     return err
 
 
+def assert_close_illconditioned(got, want32, want64, what="", floor=1e-2):
+    """Inputs in the reference test's range U[0,100) (test_paged_attn.c:201) give logits of order
+    1e4 whose fp32 ulp is ~1e-3, so ANY evaluation order moves the softmax weights by ~1e-3 and
+    the fp32 reference is itself only defined to about that.  Bar: no further from the fp64
+    truth than 4x the fp32 reference is, with the reference test's own absolute tolerance
+    (1e-2 on values in [0,100), test_paged_attn.c:8) as the floor."""
+    got = np.asarray(got, dtype=np.float64)
+    assert np.isfinite(got).all(), f"{what}: non-finite output"
+    ref_err = np.abs(np.asarray(want32, dtype=np.float64) - want64).max()
+    err = np.abs(got - want64).max()
+    assert err <= max(4 * ref_err, floor), f"{what}: |got-truth|={err:.3e}, |ref32-truth|={ref_err:.3e}"
+    return err
+
+
 class Scenario:
     """A batch of sequences with given context lengths on one engine + the oracle twin."""
 
     def __init__(self, NH, hs, bs, ctx, n_layers=1, layer=0, seed=1234, shuffle=False, extra_blocks=8,
-                 dist="normal", device=0):
+                 dist="normal", device=0, max_batch_tokens=0):
         self.NH, self.hs, self.bs, self.C = NH, hs, bs, NH * hs
         self.ctx = list(ctx)
         self.B = len(ctx)
@@ -38,7 +52,7 @@ class Scenario:
         pages = [(c + bs - 1) // bs for c in ctx]
         self.max_blocks = sum(pages) + extra_blocks + self.B
         self.eng = pa.PagedAttn(bs, self.max_blocks, self.B, NH, hs, n_layers=n_layers, device=device,
-                                max_batch_tokens=max(max(ctx), self.B) + 8)
+                                max_batch_tokens=max(max(ctx), self.B, max_batch_tokens) + 8)
         self.orc = oa.OrcManager(self.C, bs, self.max_blocks, self.B)
         rng = np.random.default_rng(seed)
         # whole pool content in one upload
@@ -102,6 +116,9 @@ class Scenario:
         out = d_out.download((self.B, self.C))
         d_q.free(); d_out.free()
         return out
+
+    def oracle_decode_f64(self, q, kv_start=None):
+        return self.orc.decode_batch_f64(self.seq_ids, self.NH, q[:, :self.C], kv_start=kv_start)
 
     def oracle_decode(self, q, kv_start=None):
         return self.orc.decode_batch(self.seq_ids, self.NH, q[:, :self.C], kv_start=kv_start)
