@@ -171,6 +171,9 @@ PA_API int pa_decode_step_host(pa_handle* h, int layer, const float* qkv_host, f
 PA_API int pa_seq_len(pa_handle* h, int seq_id);                 /* cached tokens */
 PA_API int pa_seq_truncate(pa_handle* h, int seq_id, int new_len); /* roll back (frees emptied pages) */
 PA_API int pa_seq_free(pa_handle* h, int seq_id);                /* = free_blocks_for_prompt */
+/* Undo the appends of the last pa_step_begin (speculative-decoding style roll back): every
+ * sequence of the step loses the n_new tokens it received; emptied pages return to the pool. */
+PA_API int pa_step_rollback(pa_handle* h);
 /* Install an externally built block table (e.g. a shuffled / fragmented layout for benchmarks):
  * the sequence must be empty and the pages free. */
 PA_API int pa_seq_adopt(pa_handle* h, int seq_id, const int* blocks, int n_blocks, int n_tokens);
@@ -180,6 +183,7 @@ PA_API float* pa_pool_k(pa_handle* h, int layer);                /* device, [max
 PA_API float* pa_pool_v(pa_handle* h, int layer);
 PA_API size_t pa_pool_bytes(pa_handle* h);                       /* K+V, all layers */
 PA_API int pa_device(pa_handle* h);
+PA_API void* pa_stream_of(pa_handle* h);                         /* the handle-owned stream (host-buffer entries run on it) */
 PA_API int pa_sm_count(pa_handle* h);
 
 /* ---- tuning knobs (benchmarks/tests select a kernel or a tile shape) ----------------------- */

@@ -89,6 +89,7 @@ float* pa_pool_k(pa_handle* h, int layer) { return (h && h->pool_k) ? h->pool_k 
 float* pa_pool_v(pa_handle* h, int layer) { return (h && h->pool_v) ? h->pool_v + (size_t)layer * h->layer_stride : NULL; }
 size_t pa_pool_bytes(pa_handle* h) { return h ? 2 * (size_t)h->cfg.n_layers * h->layer_stride * sizeof(float) : 0; }
 int pa_device(pa_handle* h) { return h ? h->cfg.device : PA_HOST_ONLY; }
+void* pa_stream_of(pa_handle* h) { return h ? h->stream : NULL; }
 int pa_sm_count(pa_handle* h) { return h ? h->sm_count : 0; }
 
 int pa_tune_set(pa_handle* h, int key, int value) {
@@ -359,6 +360,18 @@ int pa_seq_truncate(pa_handle* h, int seq_id, int new_len) {
     }
     m->prompt_block_count[seq_id] = keep;
     if (keep > 0) m->blocks[m->prompt_block_list[seq_id][keep - 1]].filled = new_len - (keep - 1) * bs;
+    return PA_OK;
+}
+
+int pa_step_rollback(pa_handle* h) {
+    if (!h || h->step.nseq < 1) { pa_set_error("pa_step_rollback: no step"); return PA_ERR_INVALID; }
+    for (int i = 0; i < h->step.nseq; i++) {
+        int p = h->step_seq_ids[i];
+        int len = pa_bm_context_len(h->mgr, p) - h->step_n_new[i];
+        int rc = pa_seq_truncate(h, p, len < 0 ? 0 : len);
+        if (rc != PA_OK) return rc;
+        h->step_n_new[i] = 0;
+    }
     return PA_OK;
 }
 

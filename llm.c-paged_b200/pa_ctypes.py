@@ -94,11 +94,13 @@ def load():
         "pa_seq_len": (C.c_int, [vp, C.c_int]),
         "pa_seq_truncate": (C.c_int, [vp, C.c_int, C.c_int]),
         "pa_seq_free": (C.c_int, [vp, C.c_int]),
+        "pa_step_rollback": (C.c_int, [vp]),
         "pa_seq_adopt": (C.c_int, [vp, C.c_int, c_int_p, C.c_int, C.c_int]),
         "pa_pool_k": (vp, [vp, C.c_int]),
         "pa_pool_v": (vp, [vp, C.c_int]),
         "pa_pool_bytes": (C.c_size_t, [vp]),
         "pa_device": (C.c_int, [vp]),
+        "pa_stream_of": (vp, [vp]),
         "pa_sm_count": (C.c_int, [vp]),
         "pa_tune_set": (C.c_int, [vp, C.c_int, C.c_int]),
         "pa_tune_get": (C.c_int, [vp, C.c_int]),
@@ -240,6 +242,9 @@ class PagedAttn:
 
     def seq_truncate(self, s, n):
         return self.lib.pa_seq_truncate(self.h, s, n)
+
+    def step_rollback(self):
+        return self.lib.pa_step_rollback(self.h)
 
     def seq_free(self, s):
         return self.lib.pa_seq_free(self.h, s)

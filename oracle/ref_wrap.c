@@ -117,11 +117,21 @@ REF_API int ref_attend_prompt(BlockManager* m, int prompt, float* out, float* pr
     free(kv[0]); free(kv[1]); free(kv);   /* the reference leaks these (paged_infer.c:713) */
     return nb;
 }
-/* wall clock exactly as the reference takes it (paged_infer.c:1019-1020,1085-1087) */
+/* wall clock exactly as the reference takes it (paged_infer.c:1019-1020,1085-1087).  The
+ * (B,NH,T,T) scratch is allocated once and reused, as gpt2_forward does (:598-637). */
+static float* g_scratch = NULL;
+static size_t g_scratch_floats = 0;
 REF_API double ref_time_attend_prompt(BlockManager* m, int prompt, float* out, float* inp,
                                       int B, int T, int C, int NH, int offset, int reps) {
-    float* preatt = (float*)malloc((size_t)B * NH * T * T * sizeof(float));
-    float* att = (float*)malloc((size_t)B * NH * T * T * sizeof(float));
+    size_t need = (size_t)B * NH * T * T;
+    if (g_scratch_floats < 2 * need) {
+        free(g_scratch);
+        g_scratch = (float*)malloc(2 * need * sizeof(float));
+        g_scratch_floats = 2 * need;
+        memset(g_scratch, 0, 2 * need * sizeof(float));   /* fault the pages in outside the clock */
+    }
+    float* preatt = g_scratch;
+    float* att = g_scratch + need;
     double best = 1e30;
     for (int r = 0; r < reps; r++) {
         struct timespec t0, t1;
@@ -135,7 +145,6 @@ REF_API double ref_time_attend_prompt(BlockManager* m, int prompt, float* out, f
         double dt = (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec) * 1e-9;
         if (dt < best) best = dt;
     }
-    free(preatt); free(att);
     return best;
 }
 

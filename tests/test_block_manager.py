@@ -148,6 +148,8 @@ def test_truncate_adopt_and_errors():
         assert eng.seq_truncate(0, 17) == 0 and eng.table(0) == [0, 1] and eng.seq_len(0) == 17
         assert eng.seq_truncate(0, 16) == 0 and eng.table(0) == [0] and eng.seq_len(0) == 16
         assert eng.seq_truncate(0, 99) == pa.PA_ERR_INVALID
+        assert eng.step_begin([0], [20]) == 0 and eng.seq_len(0) == 36 and eng.table(0) == [0, 1, 2]
+        assert eng.step_rollback() == 0 and eng.seq_len(0) == 16 and eng.table(0) == [0]
         assert eng.seq_adopt(1, [9, 3, 7], 33) == 0
         assert eng.table(1) == [9, 3, 7] and eng.seq_len(1) == 33
         assert eng.seq_adopt(2, [3], 5) == pa.PA_ERR_INVALID          # page in use
