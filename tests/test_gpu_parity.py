@@ -244,7 +244,7 @@ def test_prefill_rows_match_oracle(NH, hs, bs):
     Cc = NH * hs
     before = [0, 5, 40, 0]
     n_new = [33, 7, 1, 64]
-    sc = Scenario(NH, hs, bs, before, seed=61, extra_blocks=32, max_batch_tokens=sum(n_new))
+    sc = Scenario(NH, hs, bs, before, seed=61, extra_blocks=128, max_batch_tokens=sum(n_new))   # no eviction
     try:
         eng, orc = sc.eng, sc.orc
         ntok = sum(n_new)
