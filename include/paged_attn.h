@@ -159,6 +159,11 @@ PA_API int pa_append(pa_handle* h, int layer, const float* k, const float* v, in
 /* Decode: one query per sequence (row i at q+i*q_stride, head hd at +hd*head_dim) attends
  * cached tokens [kv_start, ctx) of its sequence; out row i at out+i*out_stride. */
 PA_API int pa_decode(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream);
+/* Decode with the KV append fused in (one launch per layer): the step must hold exactly one new
+ * token per sequence; row i of q, k, v (same row_stride, e.g. the (B,3C) qkv buffer) is that
+ * token.  The new K/V row is read straight from k/v, used, and stored to its page slot. */
+PA_API int pa_decode_append(pa_handle* h, int layer, const float* q, const float* k, const float* v, int row_stride,
+                            float* out, int out_stride, void* stream);
 /* Causal rows: the n_new[i] new tokens of each sequence are the queries (packed in step order);
  * row j of sequence i attends [kv_start, ctx_before + j].  fp32 SIMT. */
 PA_API int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream);
@@ -193,6 +198,8 @@ typedef enum pa_tune_key {
     PA_TUNE_STAGES = 2,        /* 0 auto */
     PA_TUNE_GRID = 3,          /* 0 auto (CTAs) */
     PA_TUNE_COUNT_LAUNCHES = 4,/* read-only counter of kernels launched by this handle */
+    PA_TUNE_STATIC_PCT = 5,    /* 0 auto: share of the page stream split statically (rest is claimed dynamically) */
+    PA_TUNE_DYN_UNITS = 6,     /* 0 auto: pages per dynamically claimed range */
     PA_TUNE_MAX
 } pa_tune_key;
 PA_API int pa_tune_set(pa_handle* h, int key, int value);

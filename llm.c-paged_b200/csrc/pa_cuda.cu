@@ -82,13 +82,14 @@ int pa_cu_alloc_pool(pa_handle* h) {
     CU_CHECK(cudaMemsetAsync(h->pool_v, 0, bytes, (cudaStream_t)h->stream));
     /* split-decode workspace: (max CTAs + max_seqs) partial slots of (C + 2*NH) floats, and one
      * arrival counter per (sequence, head) -- see pa_decode_stream_kernel */
-    size_t max_ctas = (size_t)h->sm_count * 8;
+    size_t max_ctas = (size_t)h->sm_count * 24;   /* static + dynamic ranges */
     if (h->max_heads < h->cfg.n_heads) h->max_heads = h->cfg.n_heads;
     h->ws_floats = (max_ctas + (size_t)h->cfg.max_seqs) * ((size_t)h->C + 2 * (size_t)h->max_heads + 8);
     h->n_counters = (size_t)h->cfg.max_seqs * h->max_heads;
     CU_CHECK(cudaMalloc((void**)&h->d_ws, h->ws_floats * sizeof(float)));
-    CU_CHECK(cudaMalloc((void**)&h->d_counters, h->n_counters * sizeof(int)));
-    CU_CHECK(cudaMemsetAsync(h->d_counters, 0, h->n_counters * sizeof(int), (cudaStream_t)h->stream));
+    /* + 2 scheduler words (next dynamic range, finished CTAs) */
+    CU_CHECK(cudaMalloc((void**)&h->d_counters, (h->n_counters + 2) * sizeof(int)));
+    CU_CHECK(cudaMemsetAsync(h->d_counters, 0, (h->n_counters + 2) * sizeof(int), (cudaStream_t)h->stream));
     CU_CHECK(cudaStreamSynchronize((cudaStream_t)h->stream));
     return PA_OK;
 }

@@ -116,29 +116,47 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // =============================================================================================
 // decode: flat page-stream kernel
 // =============================================================================================
+// Work decomposition ("stream-K over pages"): the pages of the whole batch, times the head
+// groups, form one flat list of U units.  The list is cut into RANGES, each owned by one virtual
+// CTA: the first Us units into Gs equal static ranges (range c is the first job of physical CTA
+// c), the tail U-Us into D small ranges that the physical CTAs claim with an atomic counter as
+// they run dry (tapered self-scheduling: SMs do not all stream at the same speed, and a static
+// split makes everyone wait for the slowest).  A range may start and end anywhere, also in the
+// middle of a sequence; every (sequence, head group) piece inside a range is a SEGMENT that
+// yields a partial (m, l, o).  Because both the range index and the row index grow
+// monotonically along the list, `range + hg*B + row` is a unique partial slot.
 struct DecodeParams {
-    const float* pool_k;      // layer base, [max_blocks][BS][C]
-    const float* pool_v;
+    float* pool_k;            // layer base, [max_blocks][BS][C]
+    float* pool_v;
     const float* q;           // (B, q_stride)
     float* out;               // (B, out_stride)
+    const float* k_new;       // fused append: this step's K row of sequence i at k_new + i*new_stride
+    const float* v_new;       //               (NULL: the rows are already in the pool)
     const int* kv_end;        // [B]
     const int* kv_start;      // [B]
     const int* cum_pages;     // [B+1]
     const int* table;         // [B][tstride]
     float* ws;                // partial slots
     int* counters;            // [n_hg*B] arrival counters (self-resetting)
+    int* sched;               // [0] next dynamic range, [1] finished CTAs (self-resetting)
     long long U;              // work units = n_hg * P
+    long long Us;             // units in the static part
+    int Gs;                   // static ranges (= physical CTAs that get one)
+    int D;                    // dynamic ranges
     int B, C, hpg, n_hg, W;   // W = hpg*HS floats per tile row
-    int tstride, q_stride, out_stride;
+    int tstride, q_stride, out_stride, new_stride;
     int P;                    // total pages of the batch
     int n_stages;
     int n_cons;               // consumer threads (multiple of 32)
     int slot_floats;          // floats per partial slot
+    int n_cum_smem;           // B+1 when the prefix sums are staged in shared memory, else 0
     float scale;
 };
 
-constexpr int kFlagFirst = 1;   // first page of a (sequence, head-group) segment in this CTA
-constexpr int kFlagLast = 2;    // last page of the segment in this CTA
+constexpr int kFlagFirst = 1;   // first page of a (sequence, head-group) segment in this range
+constexpr int kFlagLast = 2;    // last page of the segment in this range
+constexpr int kFlagNew = 4;     // last page of the sequence and its last row is this step's token
+constexpr int kFlagEnd = 8;     // no more work for this CTA
 
 // Transposed butterfly: N per-token partial sums per lane, reduced over the 2*D lanes that share
 // a head.  Each step the lanes trade half of their values, so the whole reduction costs ~N
@@ -180,9 +198,23 @@ __device__ __forceinline__ float group_sum(float x) {
     return x;
 }
 
-// Which CTA owns flat unit x when U units are dealt as [c*U/G, (c+1)*U/G).
-__device__ __forceinline__ int cta_of_unit(long long x, long long U, int G) {
-    return (int)(((x + 1) * (long long)G - 1) / U);
+// n units dealt to g ranges as [c*n/g, (c+1)*n/g): the range that owns unit x
+__device__ __forceinline__ int even_owner(long long x, long long n, int g) {
+    return (int)(((x + 1) * (long long)g - 1) / n);
+}
+__device__ __forceinline__ int range_of_unit(const DecodeParams& p, long long x) {
+    if (x < p.Us) return even_owner(x, p.Us, p.Gs);
+    return p.Gs + even_owner(x - p.Us, p.U - p.Us, p.D);
+}
+__device__ __forceinline__ void range_bounds(const DecodeParams& p, int r, long long& lo, long long& hi) {
+    if (r < p.Gs) {
+        lo = (long long)r * p.Us / p.Gs;
+        hi = (long long)(r + 1) * p.Us / p.Gs;
+    } else {
+        const long long n = p.U - p.Us;
+        lo = p.Us + (long long)(r - p.Gs) * n / p.D;
+        hi = p.Us + (long long)(r - p.Gs + 1) * n / p.D;
+    }
 }
 
 template <int HS, int BS>
@@ -203,15 +235,10 @@ pa_decode_stream_kernel(const DecodeParams p) {
     float* psm = qbuf + (size_t)p.n_stages * W;                                  // [n_cons/LPH][BS]
     int4* meta = reinterpret_cast<int4*>(psm + (p.n_cons / LPH) * BS);           // [n_stages][2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * p.n_stages);         // full[], empty[]
-    int* s_flag = reinterpret_cast<int*>(bars + 2 * p.n_stages);
+    int* s_flag = reinterpret_cast<int*>(bars + 2 * p.n_stages);                 // 4 ints
+    int* cum_sm = s_flag + 4;                                                    // [n_cum_smem]
 
     const int tid = threadIdx.x;
-    const int G = gridDim.x;
-    const int cta = blockIdx.x;
-    const long long U = p.U;
-    const long long u_begin = (long long)cta * U / G;
-    const long long u_end = (long long)(cta + 1) * U / G;
-    const int n_units = (int)(u_end - u_begin);
     const int n_cons_warps = p.n_cons >> 5;
 
     if (tid == 0) {
@@ -221,77 +248,112 @@ pa_decode_stream_kernel(const DecodeParams p) {
         }
         mbar_fence_init();
     }
+    for (int i = tid; i < p.n_cum_smem; i += blockDim.x) cum_sm[i] = __ldg(p.cum_pages + i);
     __syncthreads();
+    const int* cum = p.n_cum_smem ? cum_sm : p.cum_pages;
 
     if (tid >= p.n_cons) {
         // =================================== producer warp ===================================
         const int lane = tid & 31;
         int stage = 0;
         uint32_t phase = 0;
-        for (int base = 0; base < n_units; base += 32) {
-            // every lane resolves one page of the batch: sequence, page, block id, bounds
-            const long long u = u_begin + base + lane;
-            int row = 0, hg = 0, blk = 0, lo = 0, hi = 0, flags = 0, c_first = 0, nsegs = 1;
-            if (base + lane < n_units) {
-                hg = (int)(u / p.P);
-                const int f = (int)(u - (long long)hg * p.P);
-                int a = 0, b = p.B;                       // largest row with cum_pages[row] <= f
-                while (b - a > 1) {
-                    const int mid = (a + b) >> 1;
-                    if (__ldg(p.cum_pages + mid) <= f) a = mid; else b = mid;
+        int range = blockIdx.x;                     // first job: this CTA's static range
+        if (range >= p.Gs) {                        // (more CTAs than static ranges: go dynamic at once)
+            int r = 0;
+            if (lane == 0) r = atomicAdd(p.sched, 1);
+            range = p.Gs + __shfl_sync(0xffffffffu, r, 0);
+        }
+        while (range < p.Gs + p.D) {
+            long long u_begin, u_end;
+            range_bounds(p, range, u_begin, u_end);
+            const int n_units = (int)(u_end - u_begin);
+            for (int base = 0; base < n_units; base += 32) {
+                // every lane resolves one page of the batch: sequence, page, block id, bounds
+                const long long u = u_begin + base + lane;
+                int row = 0, hg = 0, blk = 0, lo = 0, hi = 0, flags = 0, r_first = 0, nsegs = 1;
+                if (base + lane < n_units) {
+                    hg = (int)(u / p.P);
+                    const int f = (int)(u - (long long)hg * p.P);
+                    int a = 0, b = p.B;                   // largest row with cum[row] <= f
+                    while (b - a > 1) {
+                        const int mid = (a + b) >> 1;
+                        if (cum[mid] <= f) a = mid; else b = mid;
+                    }
+                    row = a;
+                    const int cum0 = cum[row], cum1 = cum[row + 1];
+                    const int start = __ldg(p.kv_start + row), end = __ldg(p.kv_end + row);
+                    const int pg = start / BS + (f - cum0);
+                    blk = __ldg(p.table + (size_t)row * p.tstride + pg);
+                    lo = (f == cum0) ? start % BS : 0;
+                    hi = min(BS, end - pg * BS);
+                    if (f == cum0 || base + lane == 0) flags |= kFlagFirst;
+                    if (f == cum1 - 1 || base + lane == n_units - 1) flags |= kFlagLast;
+                    if (f == cum1 - 1 && p.k_new != nullptr) flags |= kFlagNew;
+                    const long long seg0 = (long long)hg * p.P + cum0;
+                    const long long seg1 = (long long)hg * p.P + cum1 - 1;
+                    r_first = range_of_unit(p, seg0);
+                    nsegs = range_of_unit(p, seg1) - r_first + 1;
                 }
-                row = a;
-                const int cum0 = __ldg(p.cum_pages + row), cum1 = __ldg(p.cum_pages + row + 1);
-                const int start = __ldg(p.kv_start + row), end = __ldg(p.kv_end + row);
-                const int pg = start / BS + (f - cum0);
-                blk = __ldg(p.table + (size_t)row * p.tstride + pg);
-                lo = (f == cum0) ? start % BS : 0;
-                hi = min(BS, end - pg * BS);
-                if (f == cum0 || base + lane == 0) flags |= kFlagFirst;
-                if (f == cum1 - 1 || base + lane == n_units - 1) flags |= kFlagLast;
-                const long long seg0 = (long long)hg * p.P + cum0;
-                const long long seg1 = (long long)hg * p.P + cum1 - 1;
-                c_first = cta_of_unit(seg0, U, G);
-                nsegs = cta_of_unit(seg1, U, G) - c_first + 1;
-            }
-            const int cnt = min(32, n_units - base);
-            for (int j = 0; j < cnt; ++j) {
-                const int j_row = __shfl_sync(0xffffffffu, row, j);
-                const int j_hg = __shfl_sync(0xffffffffu, hg, j);
-                const int j_blk = __shfl_sync(0xffffffffu, blk, j);
-                const int j_lo = __shfl_sync(0xffffffffu, lo, j);
-                const int j_hi = __shfl_sync(0xffffffffu, hi, j);
-                const int j_flags = __shfl_sync(0xffffffffu, flags, j);
-                const int j_cfirst = __shfl_sync(0xffffffffu, c_first, j);
-                const int j_nsegs = __shfl_sync(0xffffffffu, nsegs, j);
-                const size_t page_off = (size_t)j_blk * BS * p.C + (size_t)j_hg * W;
-                const bool first = (j_flags & kFlagFirst) != 0;
+                const int cnt = min(32, n_units - base);
+                for (int j = 0; j < cnt; ++j) {
+                    const int j_row = __shfl_sync(0xffffffffu, row, j);
+                    const int j_hg = __shfl_sync(0xffffffffu, hg, j);
+                    const int j_blk = __shfl_sync(0xffffffffu, blk, j);
+                    const int j_lo = __shfl_sync(0xffffffffu, lo, j);
+                    const int j_hi = __shfl_sync(0xffffffffu, hi, j);
+                    const int j_flags = __shfl_sync(0xffffffffu, flags, j);
+                    const int j_rfirst = __shfl_sync(0xffffffffu, r_first, j);
+                    const int j_nsegs = __shfl_sync(0xffffffffu, nsegs, j);
+                    const size_t page_off = (size_t)j_blk * BS * p.C + (size_t)j_hg * W;
+                    const bool first = (j_flags & kFlagFirst) != 0;
+                    // rows that come from the pool; with a fused append the sequence's newest row
+                    // comes straight from this step's k/v rows instead
+                    const int pool_rows = (j_flags & kFlagNew) ? j_hi - 1 : j_hi;
 #pragma unroll
-                for (int kv = 0; kv < 2; ++kv) {
-                    const uint32_t full = smem_u32(&bars[stage]);
-                    const uint32_t dst = smem_u32(tiles + (size_t)stage * tile_floats);
-                    const float* src = (kv == 0 ? p.pool_k : p.pool_v) + page_off;
-                    if (lane == 0) {
-                        mbar_wait(smem_u32(&bars[p.n_stages + stage]), phase ^ 1);   // slot free
-                        if (kv == 0) {
-                            meta[2 * stage] = make_int4(j_row, j_hg, j_lo | (j_hi << 8), j_flags);
-                            meta[2 * stage + 1] = make_int4(j_cfirst, j_nsegs, 0, 0);
+                    for (int kv = 0; kv < 2; ++kv) {
+                        const uint32_t full = smem_u32(&bars[stage]);
+                        const uint32_t dst = smem_u32(tiles + (size_t)stage * tile_floats);
+                        const float* src = (kv == 0 ? p.pool_k : p.pool_v) + page_off;
+                        if (lane == 0) {
+                            mbar_wait(smem_u32(&bars[p.n_stages + stage]), phase ^ 1);   // slot free
+                            if (kv == 0) {
+                                meta[2 * stage] = make_int4(j_row, j_hg, j_lo | (j_hi << 8), j_flags);
+                                meta[2 * stage + 1] = make_int4(j_rfirst, j_nsegs, range, j_blk);
+                            }
+                            uint32_t bytes = (uint32_t)j_hi * W * 4u;
+                            if (kv == 0 && first) bytes += W * 4u;
+                            mbar_arrive_expect_tx(full, bytes);
                         }
-                        uint32_t bytes = (uint32_t)j_hi * W * 4u;
-                        if (kv == 0 && first) bytes += W * 4u;
-                        mbar_arrive_expect_tx(full, bytes);
+                        __syncwarp();
+                        if (W == p.C) {            // whole rows: the valid part of the page is contiguous
+                            if (lane == 0 && pool_rows > 0) tma_bulk_g2s(dst, src, (uint32_t)pool_rows * W * 4u, full);
+                        } else if (lane < pool_rows) {   // a column slice: one bulk copy per row
+                            tma_bulk_g2s(dst + lane * W * 4u, src + (size_t)lane * p.C, W * 4u, full);
+                        }
+                        if ((j_flags & kFlagNew) && lane == 0)
+                            tma_bulk_g2s(dst + (uint32_t)(j_hi - 1) * W * 4u,
+                                         (kv == 0 ? p.k_new : p.v_new) + (size_t)j_row * p.new_stride + (size_t)j_hg * W,
+                                         W * 4u, full);
+                        if (kv == 0 && first && lane == 0)
+                            tma_bulk_g2s(smem_u32(qbuf + (size_t)stage * W),
+                                         p.q + (size_t)j_row * p.q_stride + (size_t)j_hg * W, W * 4u, full);
+                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (W == p.C) {            // whole rows: the valid part of the page is contiguous
-                        if (lane == 0) tma_bulk_g2s(dst, src, (uint32_t)j_hi * W * 4u, full);
-                    } else if (lane < j_hi) {  // a column slice: one bulk copy per row
-                        tma_bulk_g2s(dst + lane * W * 4u, src + (size_t)lane * p.C, W * 4u, full);
-                    }
-                    if (kv == 0 && first && lane == 0)
-                        tma_bulk_g2s(smem_u32(qbuf + (size_t)stage * W),
-                                     p.q + (size_t)j_row * p.q_stride + (size_t)j_hg * W, W * 4u, full);
-                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
+            }
+            int r = 0;
+            if (lane == 0) r = atomicAdd(p.sched, 1);
+            range = p.Gs + __shfl_sync(0xffffffffu, r, 0);
+        }
+        if (lane == 0) {
+            // tell the consumers there is nothing more, then take part in resetting the counters
+            mbar_wait(smem_u32(&bars[p.n_stages + stage]), phase ^ 1);
+            meta[2 * stage] = make_int4(0, 0, 0, kFlagEnd);
+            mbar_arrive(smem_u32(&bars[stage]));
+            const int done = atomicAdd(p.sched + 1, 1);
+            if (done == (int)gridDim.x - 1) {      // every CTA has made its last (failed) claim
+                p.sched[0] = 0;
+                p.sched[1] = 0;
             }
         }
         return;
@@ -300,8 +362,8 @@ pa_decode_stream_kernel(const DecodeParams p) {
     // ======================================= consumers =======================================
     // rows of the batch that own no page at all produce zeros (paged_infer.c never hits this:
     // T >= 1 always sees at least its own key)
-    for (int r = cta; r < p.B; r += G) {
-        if (__ldg(p.cum_pages + r + 1) == __ldg(p.cum_pages + r))
+    for (int r = blockIdx.x; r < p.B; r += gridDim.x) {
+        if (cum[r + 1] == cum[r])
             for (int c = tid; c < p.C; c += p.n_cons) p.out[(size_t)r * p.out_stride + c] = 0.0f;
     }
 
@@ -319,18 +381,22 @@ pa_decode_stream_kernel(const DecodeParams p) {
     int stage = 0;
     uint32_t phase = 0;
 
-    for (int it = 0; it < n_units; ++it) {
+    for (;;) {
         // ------------------------------- K tile: scores -------------------------------------
         mbar_wait(smem_u32(&bars[stage]), phase);
         const int4 mt0 = meta[2 * stage];
         const int4 mt1 = meta[2 * stage + 1];
         const int lo = mt0.z & 0xff, hi = (mt0.z >> 8) & 0xff, flags = mt0.w;
+        if (flags & kFlagEnd) break;
         if (flags & kFlagFirst) {
             qv = reinterpret_cast<const float4*>(qbuf + (size_t)stage * W)[c4];
             acc = make_float4(0.f, 0.f, 0.f, 0.f);
             m_run = kMaxInit;
             l_run = 0.0f;
         }
+        // fused append: the newest row sits in the tile (copied from this step's k row); store it
+        // to its page slot -- nobody reads it from the pool during this launch
+        const size_t new_off = ((size_t)mt1.w * BS + (hi - 1)) * p.C + (size_t)mt0.y * W + c4 * 4;
         float part[BS];
         {
             const float4* kt = reinterpret_cast<const float4*>(tiles + (size_t)stage * tile_floats) + c4;
@@ -339,6 +405,8 @@ pa_decode_stream_kernel(const DecodeParams p) {
                 const float4 k4 = kt[t * W4];
                 part[t] = fmaf(qv.w, k4.w, fmaf(qv.z, k4.z, fmaf(qv.y, k4.y, qv.x * k4.x)));
             }
+            if ((flags & kFlagNew) && col_valid)
+                *reinterpret_cast<float4*>(p.pool_k + new_off) = kt[(hi - 1) * W4];
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[p.n_stages + stage]));     // K slot free again
@@ -392,6 +460,8 @@ pa_decode_stream_kernel(const DecodeParams p) {
                     }
                 }
             }
+            if ((flags & kFlagNew) && col_valid)
+                *reinterpret_cast<float4*>(p.pool_v + new_off) = vt[(hi - 1) * W4];
         }
         __syncwarp();                                    // everyone done with my_p and the V tile
         if (lane == 0) mbar_arrive(smem_u32(&bars[p.n_stages + stage]));
@@ -399,15 +469,15 @@ pa_decode_stream_kernel(const DecodeParams p) {
 
         // ------------------------------- end of a segment -----------------------------------
         if (flags & kFlagLast) {
-            const int row = mt0.x, hg = mt0.y, c_first = mt1.x, nsegs = mt1.y;
+            const int row = mt0.x, hg = mt0.y, r_first = mt1.x, nsegs = mt1.y, range = mt1.z;
             float* out_ptr = p.out + (size_t)row * p.out_stride + (size_t)hg * W + c4 * 4;
             if (nsegs == 1) {
                 const float inv = (l_run == 0.0f) ? 0.0f : 1.0f / l_run;
                 if (col_valid)
                     *reinterpret_cast<float4*>(out_ptr) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
             } else {
-                // partial (m, l, unnormalised o) to this CTA's slot; the CTA that arrives last merges
-                float* slot = p.ws + (size_t)(cta + hg * p.B + row) * p.slot_floats;
+                // partial (m, l, unnormalised o) to this range's slot; the CTA that arrives last merges
+                float* slot = p.ws + (size_t)(range + hg * p.B + row) * p.slot_floats;
                 if (col_valid) {
                     __stcg(reinterpret_cast<float4*>(slot) + c4, acc);
                     if (gl == 0) __stcg(reinterpret_cast<float2*>(slot + W) + hl, make_float2(m_run, l_run));
@@ -425,13 +495,13 @@ pa_decode_stream_kernel(const DecodeParams p) {
                     __threadfence();
                     float M = kMaxInit;
                     for (int i = 0; i < nsegs; ++i) {
-                        const float* sl = p.ws + (size_t)(c_first + i + hg * p.B + row) * p.slot_floats;
+                        const float* sl = p.ws + (size_t)(r_first + i + hg * p.B + row) * p.slot_floats;
                         M = fmaxf(M, __ldcg(reinterpret_cast<const float2*>(sl + W) + hl_r).x);
                     }
                     float Lsum = 0.0f;
                     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                     for (int i = 0; i < nsegs; ++i) {
-                        const float* sl = p.ws + (size_t)(c_first + i + hg * p.B + row) * p.slot_floats;
+                        const float* sl = p.ws + (size_t)(r_first + i + hg * p.B + row) * p.slot_floats;
                         const float2 ml = __ldcg(reinterpret_cast<const float2*>(sl + W) + hl_r);
                         const float w = expf(ml.x - M);
                         const float4 oi = __ldcg(reinterpret_cast<const float4*>(sl) + c4);
@@ -560,26 +630,33 @@ decode_fn_t pick_decode(int hs, int bs) {
 
 struct DecodePlan {
     int hpg, n_hg, W, n_stages, n_cons, grid, slot_floats;
+    int Gs, D, n_cum_smem;
+    long long U, Us;
     size_t smem;
 };
 
-size_t decode_smem_bytes(int bs, int W, int n_stages, int n_cons, int lph) {
+constexpr int kMaxCumSmem = 4096;   // prefix sums staged in shared memory up to this many rows
+
+size_t decode_smem_bytes(int bs, int W, int n_stages, int n_cons, int lph, int n_cum) {
     size_t b = (size_t)n_stages * bs * W * 4;          // tiles
     b += (size_t)n_stages * W * 4;                     // q slots
     b += (size_t)(n_cons / lph) * bs * 4;              // probabilities
     b += (size_t)n_stages * 2 * sizeof(int4);          // meta
     b += (size_t)n_stages * 2 * sizeof(uint64_t);      // barriers
-    b += 16;                                           // flag
+    b += 16;                                           // flags
+    b += (size_t)n_cum * 4;                            // prefix sums of pages
     return b;
 }
 
-// Choose heads per tile, stage count and grid for this step: the largest tile (whole pages when
-// C*block_size fits) that leaves a ring of >= 4 stages and still gives every SM a unit of work;
-// when the batch is too small for that, the smallest tile (most parallelism).
-bool plan_decode(const pa_handle* h, int total_pages, DecodePlan* plan) {
+// Choose heads per tile, stage count, grid and the static/dynamic split for this step: the
+// largest tile (whole pages when C*block_size fits) that leaves a ring of >= 4 stages and still
+// gives every SM a unit of work; when the batch is too small for that, the smallest tile (most
+// parallelism).
+bool plan_decode(const pa_handle* h, int total_pages, int B, DecodePlan* plan) {
     const int hs = h->cfg.head_dim, bs = h->cfg.block_size, NH = h->cfg.n_heads;
     const int lph = hs / 4;
-    const int smem_cap = h->smem_optin - 1024;
+    const int n_cum = (B + 1 <= kMaxCumSmem) ? B + 1 : 0;
+    const int smem_cap = h->smem_optin - 1024 - n_cum * 4;
     const int want_hpg = h->tune[PA_TUNE_HEADS_PER_TILE];
     int max_stages = h->tune[PA_TUNE_STAGES] > 0 ? h->tune[PA_TUNE_STAGES] : 8;
     int best = 0, best_stages = 0;
@@ -606,7 +683,8 @@ bool plan_decode(const pa_handle* h, int total_pages, DecodePlan* plan) {
     plan->W = best * hs;
     plan->n_cons = ((plan->W / 4) + 31) & ~31;
     plan->n_stages = best_stages;
-    plan->smem = decode_smem_bytes(bs, plan->W, best_stages, plan->n_cons, lph);
+    plan->n_cum_smem = n_cum;
+    plan->smem = decode_smem_bytes(bs, plan->W, best_stages, plan->n_cons, lph, n_cum);
     // CTAs: one per SM when the tile ring takes most of the shared memory, more when it is small
     int per_sm = (int)((size_t)h->smem_optin / (plan->smem + 1024));
     if (per_sm < 1) per_sm = 1;
@@ -619,6 +697,20 @@ bool plan_decode(const pa_handle* h, int total_pages, DecodePlan* plan) {
     if (grid < 1) grid = 1;
     plan->grid = (int)grid;
     plan->slot_floats = (plan->W + 2 * plan->hpg + 3) & ~3;
+    // static part first, a tail of small ranges claimed dynamically
+    plan->U = units;
+    plan->Gs = (int)grid;
+    plan->Us = units;
+    plan->D = 0;
+    int pct = h->tune[PA_TUNE_STATIC_PCT] > 0 ? h->tune[PA_TUNE_STATIC_PCT] : 75;
+    int dyn_units = h->tune[PA_TUNE_DYN_UNITS] > 0 ? h->tune[PA_TUNE_DYN_UNITS] : 2;
+    if (pct < 100 && units >= 4 * grid) {
+        long long us = units * pct / 100;
+        long long d = (units - us + dyn_units - 1) / dyn_units;
+        const long long d_cap = (long long)h->sm_count * 15;
+        if (d > d_cap) d = d_cap;
+        if (d >= 1) { plan->Us = us; plan->D = (int)d; }
+    }
     return true;
 }
 
@@ -693,52 +785,75 @@ int pa_append(pa_handle* h, int layer, const float* k, const float* v, int row_s
     return PA_OK;
 }
 
-int pa_decode(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream) {
-    int rc = check_compute(h, layer, "pa_decode");
+static int decode_impl(pa_handle* h, int layer, const float* q, int q_stride, const float* k_new,
+                       const float* v_new, int new_stride, float* out, int out_stride, void* stream,
+                       const char* who) {
+    int rc = check_compute(h, layer, who);
     if (rc != PA_OK) return rc;
-    if (!q || !out || q_stride < h->C || out_stride < h->C) { pa_set_error("pa_decode: bad q/out"); return PA_ERR_INVALID; }
+    if (!q || !out || q_stride < h->C || out_stride < h->C) { pa_set_error("%s: bad q/out", who); return PA_ERR_INVALID; }
     cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)h->stream;
     const pa_step_layout& L = h->step;
+    const bool fused = k_new != nullptr;
+    if (fused && (!v_new || new_stride < h->C || L.ntok != L.nseq || L.max_q != 1)) {
+        pa_set_error("%s: fused append needs exactly one new token per sequence in the step", who);
+        return PA_ERR_INVALID;
+    }
     const int hs = h->cfg.head_dim, bs = h->cfg.block_size;
     const int path = h->tune[PA_TUNE_DECODE_PATH];
     decode_fn_t fn = pick_decode(hs, bs);
-    const bool stream_ok = fn != nullptr && (q_stride % 4 == 0) && (out_stride % 4 == 0) && aligned16(q) && aligned16(out);
+    bool stream_ok = fn != nullptr && (q_stride % 4 == 0) && (out_stride % 4 == 0) && aligned16(q) && aligned16(out);
+    if (fused) stream_ok = stream_ok && (new_stride % 4 == 0) && aligned16(k_new) && aligned16(v_new);
     if (path == 1 && !stream_ok) {
-        pa_set_error("pa_decode: stream kernel needs head_dim 64/128, block_size 4/8/16/32 and 16-byte aligned q/out");
+        pa_set_error("%s: stream kernel needs head_dim 64/128, block_size 4/8/16/32 and 16-byte aligned rows", who);
         return PA_ERR_UNSUPPORTED;
     }
     DecodePlan plan;
-    if (path != 2 && stream_ok && plan_decode(h, L.total_pages, &plan)) {
+    if (path != 2 && stream_ok && plan_decode(h, L.total_pages, L.nseq, &plan)) {
         DecodeParams dp;
         dp.pool_k = h->pool_k + (size_t)layer * h->layer_stride;
         dp.pool_v = h->pool_v + (size_t)layer * h->layer_stride;
         dp.q = q; dp.out = out;
+        dp.k_new = k_new; dp.v_new = v_new; dp.new_stride = new_stride;
         dp.kv_end = h->d_step + L.off_kv_end;
         dp.kv_start = h->d_step + L.off_kv_start;
         dp.cum_pages = h->d_step + L.off_cum_pages;
         dp.table = h->d_step + L.off_table;
-        dp.ws = h->d_ws; dp.counters = h->d_counters;
-        dp.P = L.total_pages;
-        dp.U = (long long)plan.n_hg * L.total_pages;
+        dp.ws = h->d_ws; dp.counters = h->d_counters; dp.sched = h->d_counters + h->n_counters;
+        dp.P = L.total_pages > 0 ? L.total_pages : 1;
+        dp.U = plan.U; dp.Us = plan.Us; dp.Gs = plan.Gs; dp.D = plan.D;
         dp.B = L.nseq; dp.C = h->C; dp.hpg = plan.hpg; dp.n_hg = plan.n_hg; dp.W = plan.W;
         dp.tstride = L.tstride; dp.q_stride = q_stride; dp.out_stride = out_stride;
         dp.n_stages = plan.n_stages; dp.n_cons = plan.n_cons; dp.slot_floats = plan.slot_floats;
+        dp.n_cum_smem = plan.n_cum_smem;
         dp.scale = (float)(1.0 / sqrtf((float)hs));          // paged_infer.c:174
-        if ((size_t)(plan.grid + plan.n_hg * L.nseq) * plan.slot_floats > h->ws_floats) {
-            pa_set_error("pa_decode: split workspace too small");
+        if ((size_t)(plan.Gs + plan.D + plan.n_hg * L.nseq) * plan.slot_floats > h->ws_floats) {
+            pa_set_error("%s: split workspace too small", who);
             return PA_ERR_INVALID;
         }
         if (h->decode_attr_fn != (void*)fn) {      // once per handle (one geometry per handle)
             CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
             h->decode_attr_fn = (void*)fn;
         }
-        if (L.total_pages == 0) { dp.P = 1; plan.grid = 1; }   // nothing cached anywhere: zero-fill only (U == 0)
         fn<<<plan.grid, plan.n_cons + 32, plan.smem, s>>>(dp);
         CU_CHECK(cudaGetLastError());
         h->launches++;
         return PA_OK;
     }
+    if (fused) {
+        rc = pa_append(h, layer, k_new, v_new, new_stride, s);
+        if (rc != PA_OK) return rc;
+    }
     return launch_rows(h, layer, q, q_stride, out, out_stride, false, s);
+}
+
+int pa_decode(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream) {
+    return decode_impl(h, layer, q, q_stride, nullptr, nullptr, 0, out, out_stride, stream, "pa_decode");
+}
+
+int pa_decode_append(pa_handle* h, int layer, const float* q, const float* k, const float* v, int row_stride,
+                     float* out, int out_stride, void* stream) {
+    if (!k || !v) { pa_set_error("pa_decode_append: NULL k/v"); return PA_ERR_INVALID; }
+    return decode_impl(h, layer, q, row_stride, k, v, row_stride, out, out_stride, stream, "pa_decode_append");
 }
 
 int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream) {
@@ -769,9 +884,7 @@ int pa_decode_step_host(pa_handle* h, int layer, const float* qkv_host, float* o
     const float* src = qkv_host;
     if (!pinned) { memcpy(h->h_stage, qkv_host, n * 3 * C * sizeof(float)); src = h->h_stage; }
     CU_CHECK(cudaMemcpyAsync(d_qkv, src, n * 3 * C * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = pa_append(h, layer, d_qkv + C, d_qkv + 2 * C, (int)(3 * C), s);
-    if (rc != PA_OK) return rc;
-    rc = pa_decode(h, layer, d_qkv, (int)(3 * C), d_out, (int)C, s);
+    rc = pa_decode_append(h, layer, d_qkv, d_qkv + C, d_qkv + 2 * C, (int)(3 * C), d_out, (int)C, s);
     if (rc != PA_OK) return rc;
     bool out_pinned = cudaPointerGetAttributes(&a, out_host) == cudaSuccess && a.type == cudaMemoryTypeHost;
     cudaGetLastError();

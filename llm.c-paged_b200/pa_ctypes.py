@@ -21,6 +21,7 @@ PA_HOST_ONLY = -1
 PA_OK = 0
 PA_ERR_INVALID, PA_ERR_NOMEM, PA_ERR_CUDA, PA_ERR_NO_DEVICE, PA_ERR_NO_BLOCKS, PA_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 PA_TUNE_DECODE_PATH, PA_TUNE_HEADS_PER_TILE, PA_TUNE_STAGES, PA_TUNE_GRID, PA_TUNE_COUNT_LAUNCHES = 0, 1, 2, 3, 4
+PA_TUNE_STATIC_PCT, PA_TUNE_DYN_UNITS = 5, 6
 
 
 class KVBlock(C.Structure):
@@ -90,6 +91,7 @@ def load():
         "pa_append": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp]),
         "pa_decode": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
         "pa_prefill": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
+        "pa_decode_append": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, vp]),
         "pa_decode_step_host": (C.c_int, [vp, C.c_int, vp, vp]),
         "pa_seq_len": (C.c_int, [vp, C.c_int]),
         "pa_seq_truncate": (C.c_int, [vp, C.c_int, C.c_int]),
@@ -266,6 +268,9 @@ class PagedAttn:
 
     def decode(self, layer, q_ptr, q_stride, out_ptr, out_stride, stream=None):
         return self.lib.pa_decode(self.h, layer, q_ptr, q_stride, out_ptr, out_stride, stream)
+
+    def decode_append(self, layer, q_ptr, k_ptr, v_ptr, row_stride, out_ptr, out_stride, stream=None):
+        return self.lib.pa_decode_append(self.h, layer, q_ptr, k_ptr, v_ptr, row_stride, out_ptr, out_stride, stream)
 
     def prefill(self, layer, q_ptr, q_stride, out_ptr, out_stride, stream=None):
         return self.lib.pa_prefill(self.h, layer, q_ptr, q_stride, out_ptr, out_stride, stream)

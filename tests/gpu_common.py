@@ -97,13 +97,15 @@ class Scenario:
         self.eng.close()
         self.orc.close()
 
-    def decode(self, q, kv_start=None, path=0, hpg=0, stages=0, grid=0):
+    def decode(self, q, kv_start=None, path=0, hpg=0, stages=0, grid=0, static_pct=0, dyn_units=0):
         """Run pa_decode over all sequences (read-only step) and return (B, C)."""
         eng = self.eng
         eng.tune(pa.PA_TUNE_DECODE_PATH, path)
         eng.tune(pa.PA_TUNE_HEADS_PER_TILE, hpg)
         eng.tune(pa.PA_TUNE_STAGES, stages)
         eng.tune(pa.PA_TUNE_GRID, grid)
+        eng.tune(pa.PA_TUNE_STATIC_PCT, static_pct)
+        eng.tune(pa.PA_TUNE_DYN_UNITS, dyn_units)
         assert eng.step_begin_readonly(self.seq_ids) == 0, pa.last_error()
         if kv_start is not None:
             assert eng.step_set_kv_start(kv_start) == 0, pa.last_error()

@@ -103,6 +103,58 @@ def test_decode_tile_shapes_and_splits(hpg, stages, grid):
         sc.close()
 
 
+@pytest.mark.parametrize("static_pct,dyn_units,grid", [(75, 2, 0), (50, 1, 0), (1, 1, 0), (90, 7, 0), (100, 0, 0),
+                                                       (60, 3, 37), (30, 2, 300)])
+def test_decode_dynamic_ranges(static_pct, dyn_units, grid):
+    """Static head + dynamically claimed tail of the page stream: any split must give the same
+    answer, launch after launch (the scheduler words and arrival counters reset themselves)."""
+    sc = Scenario(12, 64, 16, [1024, 900, 3, 129, 64, 1000, 17, 512, 700, 333, 1, 256], shuffle=True, seed=13)
+    try:
+        q = oa.normal((sc.B, sc.C), seed=6)
+        want = sc.oracle_decode(q)
+        for rep in range(3):
+            got = sc.decode(q, path=1, static_pct=static_pct, dyn_units=dyn_units, grid=grid)
+            assert_close(got, want, f"static_pct={static_pct} dyn_units={dyn_units} grid={grid} rep={rep}")
+    finally:
+        sc.close()
+
+
+@pytest.mark.parametrize("NH,hs,bs,hpg", [(12, 64, 16, 0), (12, 64, 16, 3), (25, 64, 16, 0), (4, 128, 32, 0), (12, 64, 8, 4),
+                                          (2, 5, 2, 0)])
+def test_decode_append_fused(NH, hs, bs, hpg):
+    """pa_decode_append = pa_append + pa_decode in one launch: the new token's K/V row is read
+    from the step's k/v rows, used, and stored to its slot (bit-exact copy); next step sees it."""
+    Cc = NH * hs
+    ctx0 = [0, 1, 15, 16, 17, 31, 32, 100, 255, 256, 700]      # page boundaries on both sides
+    B = len(ctx0)
+    sc = Scenario(NH, hs, bs, ctx0, n_layers=2, layer=1, seed=71, shuffle=True, extra_blocks=64)
+    try:
+        eng, orc = sc.eng, sc.orc
+        eng.tune(pa.PA_TUNE_HEADS_PER_TILE, hpg)
+        for step in range(4):
+            qkv = oa.normal((B, 3 * Cc), seed=300 + step)
+            assert eng.step_begin(sc.seq_ids, [1] * B) == 0, pa.last_error()
+            pa.check(eng.upload(), "upload")
+            for s in range(B):
+                orc.add_to_cache(qkv[s][None, None, :], 1, 1, 1, prompt=s)
+            want = orc.decode_batch(sc.seq_ids, NH, qkv[:, :Cc])
+            d = pa.DevBuf.from_numpy(qkv)
+            o = pa.DevBuf(B * Cc * 4)
+            pa.check(eng.decode_append(1, d.ptr, d.ptr + Cc * 4, d.ptr + 2 * Cc * 4, 3 * Cc, o.ptr, Cc), "decode_append")
+            eng.sync()
+            assert_close(o.download((B, Cc)), want, f"fused step {step}")
+            k, v = eng.read_pool_rows(1, eng.slot_mapping())
+            assert np.array_equal(k.view(np.uint32), qkv[:, Cc:2 * Cc].view(np.uint32))
+            assert np.array_equal(v.view(np.uint32), qkv[:, 2 * Cc:].view(np.uint32))
+            d.free(); o.free()
+        # a step with more than one new token per sequence cannot be fused
+        assert eng.step_begin([0], [2]) == 0
+        pa.check(eng.upload(), "upload")
+        assert eng.decode_append(1, 1, 1, 1, 3 * Cc, 1, Cc) == pa.PA_ERR_INVALID
+    finally:
+        sc.close()
+
+
 def test_decode_sliding_window():
     """Reference `offset` (paged_infer.c:190,1057): row attends cached tokens [kv_start, ctx)."""
     sc = Scenario(12, 64, 16, [100, 64, 33, 500], shuffle=True, seed=9)
