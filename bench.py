@@ -266,6 +266,8 @@ def main():
     ap.add_argument("--layers", type=int, default=0)
     ap.add_argument("--static-pct", type=int, default=0)
     ap.add_argument("--dyn-units", type=int, default=0)
+    ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--timeline", default="", help="write a per-CTA timeline of one decode launch to this file")
     ap.add_argument("--no-fuse", action="store_true", help="separate KV-append kernel instead of the fused decode+append")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -312,6 +314,7 @@ def main():
     eng.tune(pa.PA_TUNE_GRID, args.grid)
     eng.tune(pa.PA_TUNE_STATIC_PCT, args.static_pct)
     eng.tune(pa.PA_TUNE_DYN_UNITS, args.dyn_units)
+    eng.tune(pa.PA_TUNE_NO_PDL, 1 if args.no_pdl else 0)
 
     # ---- synthetic state: random-init K/V pools (seeded), shuffled block tables ------------
     rng = np.random.default_rng(1234 + rank)
@@ -351,30 +354,29 @@ def main():
     def rollback():
         pa.check(eng.step_rollback(), "rollback")
 
-    n_ev = 2 * L
-    evs = [lib.pa_event_create() for _ in range(n_ev)]
+    # kernel time: events around the L back-to-back decode launches of a step (no event between
+    # launches: that would serialise them and defeat programmatic dependent launch)
+    evs = [lib.pa_event_create() for _ in range(2)]
     dec_ms = []
 
     def step(timed_kernels=False):
         pa.check(eng.step_begin(seq_ids, ones), "step_begin")
         pa.check(eng.upload(stream), "upload")
+        if timed_kernels:
+            lib.pa_event_record(evs[0], stream)
         for layer in range(L):
             if args.no_fuse:
                 pa.check(eng.append(layer, d_qkv.ptr + C_ * 4, d_qkv.ptr + 2 * C_ * 4, 3 * C_, stream), "append")
-            if timed_kernels:
-                lib.pa_event_record(evs[2 * layer], stream)
-            if args.no_fuse:
                 pa.check(eng.decode(layer, d_qkv.ptr, 3 * C_, d_out.ptr, C_, stream), "decode")
             else:
                 pa.check(eng.decode_append(layer, d_qkv.ptr, d_qkv.ptr + C_ * 4, d_qkv.ptr + 2 * C_ * 4, 3 * C_,
                                            d_out.ptr, C_, stream), "decode_append")
-            if timed_kernels:
-                lib.pa_event_record(evs[2 * layer + 1], stream)
+        if timed_kernels:
+            lib.pa_event_record(evs[1], stream)
         rollback()
 
     def collect_kernel_times():
-        for layer in range(L):
-            dec_ms.append(lib.pa_event_elapsed_ms(evs[2 * layer], evs[2 * layer + 1]))
+        dec_ms.append(lib.pa_event_elapsed_ms(evs[0], evs[1]) / L)
 
     def barrier():
         pa.check(lib.pa_device_sync(), "sync")
@@ -396,8 +398,8 @@ def main():
     barrier()
     launches0 = eng.launches()
     e0, e1 = lib.pa_event_create(), lib.pa_event_create()
-    # the per-kernel events are recorded in every timed step and read back every 8th (reading
-    # needs a sync, which would serialise host and device if done each step)
+    # the kernel events are recorded in every timed step and read back every 8th (reading needs a
+    # sync, which would serialise host and device if done each step)
     lib.pa_event_record(e0, stream)
     for i in range(args.steps):
         step(timed_kernels=True)
@@ -414,6 +416,17 @@ def main():
         lib.pa_stream_sync(stream)
     barrier()
     clocks = sampler.stop() if sampler else None
+
+    if args.timeline and rank == 0:
+        eng.tune(pa.PA_TUNE_DEBUG_TIMELINE, 1)
+        step()
+        tl = eng.debug_timeline().astype(np.int64)
+        eng.tune(pa.PA_TUNE_DEBUG_TIMELINE, 0)
+        t0 = tl[:, 0].min()
+        with open(args.timeline, "w") as f:
+            f.write("cta,entry_ns,first_issue_ns,first_tile_ns,last_tile_ns,prod_wait_cyc,cons_wait_cyc,seg_cyc,tiles\n")
+            for i, r in enumerate(tl):
+                f.write(f"{i},{r[0]-t0},{r[1]-t0},{r[2]-t0},{r[3]-t0},{r[4]},{r[5]},{r[6]},{r[7]}\n")
 
     step_bytes = L * (decode_bytes(ctx, C_, bs) + append_bytes(B, C_))
     ms_per_step = ms_total / args.steps
@@ -459,7 +472,7 @@ def main():
 
     # ---- roofline of the dominant kernel ---------------------------------------------------
     peak, peak_src = peaks()
-    kbytes = decode_bytes(ctx, C_, bs) + (0 if args.no_fuse else append_bytes(B, C_))
+    kbytes = decode_bytes(ctx, C_, bs) + append_bytes(B, C_)      # per layer: append + decode
     kms = sum(dec_ms) / len(dec_ms)
     achieved = kbytes / (kms * 1e-3) / 1e9
     traffic = None
@@ -471,7 +484,8 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "kernel": "pa_decode_stream_kernel<64,16>" + ("" if args.no_fuse else " (KV append fused)"), "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": kbytes, "avg_launch_ms": kms, "launches_timed": len(dec_ms),
+                "algorithmic_bytes_per_launch": kbytes, "avg_launch_ms": kms, "launches_timed": len(dec_ms) * L,
+                "timing": f"CUDA events around the {L} back-to-back per-layer launches of a step, / {L}",
                 "frac_of_nominal_8TBps": achieved / 8000.0,
                 "kernel_share_of_step": kms * L / ms_per_step}
 

@@ -200,10 +200,17 @@ typedef enum pa_tune_key {
     PA_TUNE_COUNT_LAUNCHES = 4,/* read-only counter of kernels launched by this handle */
     PA_TUNE_STATIC_PCT = 5,    /* 0 auto: share of the page stream split statically (rest is claimed dynamically) */
     PA_TUNE_DYN_UNITS = 6,     /* 0 auto: pages per dynamically claimed range */
+    PA_TUNE_DEBUG_TIMELINE = 7,/* 1: the stream decode kernel records a per-CTA timeline (pa_debug_timeline) */
+    PA_TUNE_NO_PDL = 8,        /* 1: launch the decode kernel without programmatic dependent launch */
     PA_TUNE_MAX
 } pa_tune_key;
 PA_API int pa_tune_set(pa_handle* h, int key, int value);
 PA_API int pa_tune_get(pa_handle* h, int key);
+/* Per-CTA timeline of the last stream-decode launch, 8 words per CTA: [0] entry ns, [1] first
+ * TMA issue ns, [2] first tile landed ns, [3] last tile consumed ns (globaltimer), [4] producer
+ * cycles waiting for a free slot, [5] consumer cycles waiting for data, [6] consumer cycles in
+ * segment ends (partials, merges), [7] tiles.  Returns the number of CTAs written. */
+PA_API int pa_debug_timeline(pa_handle* h, unsigned long long* out, int max_ctas);
 
 /* ---- thin CUDA plumbing for plain-C hosts (no cuda_runtime.h needed) ----------------------- */
 PA_API int pa_device_count(void);

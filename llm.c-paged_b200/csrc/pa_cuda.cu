@@ -112,6 +112,7 @@ void pa_cu_release(pa_handle* h) {
     cudaFree(h->pool_k); cudaFree(h->pool_v);
     cudaFree(h->d_step); cudaFree(h->d_ws); cudaFree(h->d_counters);
     cudaFree(h->d_stage);
+    cudaFree(h->d_dbg);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->stream) cudaStreamDestroy((cudaStream_t)h->stream);
     h->pool_k = h->pool_v = NULL;

@@ -60,8 +60,10 @@ struct pa_handle {
     void* stream;                 /* handle-owned stream */
     int sm_count;
     int smem_optin;
-    int tune[8];
+    int tune[16];
     long launches;
+    void* d_dbg;                  /* optional per-CTA timeline of the last decode launch */
+    int dbg_ctas;
     void* decode_attr_fn;         /* kernel whose dynamic-smem attribute has been raised */
     int max_heads;                /* heads the split workspace was sized for */
 };

@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 
 #include "pa_internal.h"
 
@@ -139,6 +140,7 @@ struct DecodeParams {
     float* ws;                // partial slots
     int* counters;            // [n_hg*B] arrival counters (self-resetting)
     int* sched;               // [0] next dynamic range, [1] finished CTAs (self-resetting)
+    unsigned long long* dbg;  // optional per-CTA timeline (8 words per CTA), NULL normally
     long long U;              // work units = n_hg * P
     long long Us;             // units in the static part
     int Gs;                   // static ranges (= physical CTAs that get one)
@@ -157,6 +159,7 @@ constexpr int kFlagFirst = 1;   // first page of a (sequence, head-group) segmen
 constexpr int kFlagLast = 2;    // last page of the segment in this range
 constexpr int kFlagNew = 4;     // last page of the sequence and its last row is this step's token
 constexpr int kFlagEnd = 8;     // no more work for this CTA
+constexpr int kSegQ = 4;        // depth of the consumer -> merger queue of finished segments
 
 // Transposed butterfly: N per-token partial sums per lane, reduced over the 2*D lanes that share
 // a head.  Each step the lanes trade half of their values, so the whole reduction costs ~N
@@ -198,6 +201,12 @@ __device__ __forceinline__ float group_sum(float x) {
     return x;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // n units dealt to g ranges as [c*n/g, (c+1)*n/g): the range that owns unit x
 __device__ __forceinline__ int even_owner(long long x, long long n, int g) {
     return (int)(((x + 1) * (long long)g - 1) / n);
@@ -218,7 +227,7 @@ __device__ __forceinline__ void range_bounds(const DecodeParams& p, int r, long 
 }
 
 template <int HS, int BS>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(320, 1)
 pa_decode_stream_kernel(const DecodeParams p) {
     constexpr int LPH = HS / 4;                       // lanes per head (one float4 column each)
     constexpr int NV = (BS >= LPH) ? BS / LPH : 1;    // finished scores per lane after the reduce
@@ -234,122 +243,173 @@ pa_decode_stream_kernel(const DecodeParams p) {
     float* qbuf = tiles + (size_t)p.n_stages * tile_floats;                      // [n_stages][W]
     float* psm = qbuf + (size_t)p.n_stages * W;                                  // [n_cons/LPH][BS]
     int4* meta = reinterpret_cast<int4*>(psm + (p.n_cons / LPH) * BS);           // [n_stages][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * p.n_stages);         // full[], empty[]
-    int* s_flag = reinterpret_cast<int*>(bars + 2 * p.n_stages);                 // 4 ints
-    int* cum_sm = s_flag + 4;                                                    // [n_cum_smem]
+    int4* segdesc = meta + 2 * p.n_stages;                                       // [kSegQ][2] finished-segment queue
+    uint64_t* bars = reinterpret_cast<uint64_t*>(segdesc + 2 * kSegQ);           // full[], empty[], segq_full[], segq_empty[]
+    uint64_t* segq = bars + 2 * p.n_stages;
+    int* cum_sm = reinterpret_cast<int*>(segq + 2 * kSegQ);                      // [n_cum_smem] (+ kv_start, kv_end)
 
     const int tid = threadIdx.x;
     const int n_cons_warps = p.n_cons >> 5;
+    unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
 
     if (tid == 0) {
+        if (dbg) dbg[0] = global_ns();
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(smem_u32(&bars[s]), 1);                          // full: producer's expect_tx arrive
             mbar_init(smem_u32(&bars[p.n_stages + s]), n_cons_warps);  // empty: one arrive per consumer warp
         }
+        for (int s = 0; s < kSegQ; ++s) {
+            mbar_init(smem_u32(&segq[s]), n_cons_warps);               // segment posted by every consumer warp
+            mbar_init(smem_u32(&segq[kSegQ + s]), 1);                  // descriptor taken by the merger
+        }
         mbar_fence_init();
     }
+    // Let the next kernel in the stream start its own prologue as SMs drain (programmatic
+    // dependent launch); it blocks in griddepcontrol.wait until this grid has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // The step tables were mirrored by a copy that precedes the previous kernel in stream order,
+    // so they may be read before the dependency wait: stage the per-sequence prefix sums and
+    // bounds in shared memory (one round trip instead of a dependent chain per lookup).
     for (int i = tid; i < p.n_cum_smem; i += blockDim.x) cum_sm[i] = __ldg(p.cum_pages + i);
+    if (p.n_cum_smem) {
+        for (int i = tid; i < p.B; i += blockDim.x) {
+            cum_sm[p.n_cum_smem + i] = __ldg(p.kv_start + i);
+            cum_sm[p.n_cum_smem + p.B + i] = __ldg(p.kv_end + i);
+        }
+    }
     __syncthreads();
     const int* cum = p.n_cum_smem ? cum_sm : p.cum_pages;
+    const int* kvs = p.n_cum_smem ? cum_sm + p.n_cum_smem : p.kv_start;
+    const int* kve = p.n_cum_smem ? cum_sm + p.n_cum_smem + p.B : p.kv_end;
 
-    if (tid >= p.n_cons) {
+    if (tid >= p.n_cons && tid < p.n_cons + 32) {
         // =================================== producer warp ===================================
+        // Walks this CTA's ranges batch by batch (32 pages per batch, one page per lane).  The
+        // lookups of the NEXT batch (block ids) and the claim of the NEXT dynamic range are
+        // issued before the current batch's copies, so their latency hides behind the ring.
         const int lane = tid & 31;
         int stage = 0;
         uint32_t phase = 0;
-        int range = blockIdx.x;                     // first job: this CTA's static range
-        if (range >= p.Gs) {                        // (more CTAs than static ranges: go dynamic at once)
-            int r = 0;
-            if (lane == 0) r = atomicAdd(p.sched, 1);
-            range = p.Gs + __shfl_sync(0xffffffffu, r, 0);
-        }
-        while (range < p.Gs + p.D) {
+        long long t_empty = 0;
+        bool first_issue = true;
+        const int n_ranges = p.Gs + p.D;
+
+        struct Batch { int range, base, cnt, row, hg, blk, lo, hi, flags, r_first, nsegs; };
+        auto resolve = [&](int range, int base) {
+            Batch bt;
+            bt.range = range; bt.base = base; bt.cnt = 0;
+            bt.row = bt.hg = bt.blk = bt.lo = bt.hi = bt.flags = bt.r_first = 0; bt.nsegs = 1;
+            if (range >= n_ranges) return bt;
             long long u_begin, u_end;
             range_bounds(p, range, u_begin, u_end);
             const int n_units = (int)(u_end - u_begin);
-            for (int base = 0; base < n_units; base += 32) {
-                // every lane resolves one page of the batch: sequence, page, block id, bounds
+            bt.cnt = max(0, min(32, n_units - base));
+            if (base + lane < n_units) {
                 const long long u = u_begin + base + lane;
-                int row = 0, hg = 0, blk = 0, lo = 0, hi = 0, flags = 0, r_first = 0, nsegs = 1;
-                if (base + lane < n_units) {
-                    hg = (int)(u / p.P);
-                    const int f = (int)(u - (long long)hg * p.P);
-                    int a = 0, b = p.B;                   // largest row with cum[row] <= f
-                    while (b - a > 1) {
-                        const int mid = (a + b) >> 1;
-                        if (cum[mid] <= f) a = mid; else b = mid;
-                    }
-                    row = a;
-                    const int cum0 = cum[row], cum1 = cum[row + 1];
-                    const int start = __ldg(p.kv_start + row), end = __ldg(p.kv_end + row);
-                    const int pg = start / BS + (f - cum0);
-                    blk = __ldg(p.table + (size_t)row * p.tstride + pg);
-                    lo = (f == cum0) ? start % BS : 0;
-                    hi = min(BS, end - pg * BS);
-                    if (f == cum0 || base + lane == 0) flags |= kFlagFirst;
-                    if (f == cum1 - 1 || base + lane == n_units - 1) flags |= kFlagLast;
-                    if (f == cum1 - 1 && p.k_new != nullptr) flags |= kFlagNew;
-                    const long long seg0 = (long long)hg * p.P + cum0;
-                    const long long seg1 = (long long)hg * p.P + cum1 - 1;
-                    r_first = range_of_unit(p, seg0);
-                    nsegs = range_of_unit(p, seg1) - r_first + 1;
+                bt.hg = (int)(u / p.P);
+                const int f = (int)(u - (long long)bt.hg * p.P);
+                int a = 0, b = p.B;                   // largest row with cum[row] <= f
+                while (b - a > 1) {
+                    const int mid = (a + b) >> 1;
+                    if (cum[mid] <= f) a = mid; else b = mid;
                 }
-                const int cnt = min(32, n_units - base);
-                for (int j = 0; j < cnt; ++j) {
-                    const int j_row = __shfl_sync(0xffffffffu, row, j);
-                    const int j_hg = __shfl_sync(0xffffffffu, hg, j);
-                    const int j_blk = __shfl_sync(0xffffffffu, blk, j);
-                    const int j_lo = __shfl_sync(0xffffffffu, lo, j);
-                    const int j_hi = __shfl_sync(0xffffffffu, hi, j);
-                    const int j_flags = __shfl_sync(0xffffffffu, flags, j);
-                    const int j_rfirst = __shfl_sync(0xffffffffu, r_first, j);
-                    const int j_nsegs = __shfl_sync(0xffffffffu, nsegs, j);
-                    const size_t page_off = (size_t)j_blk * BS * p.C + (size_t)j_hg * W;
-                    const bool first = (j_flags & kFlagFirst) != 0;
-                    // rows that come from the pool; with a fused append the sequence's newest row
-                    // comes straight from this step's k/v rows instead
-                    const int pool_rows = (j_flags & kFlagNew) ? j_hi - 1 : j_hi;
+                bt.row = a;
+                const int cum0 = cum[a], cum1 = cum[a + 1];
+                const int start = kvs[a], end = kve[a];
+                const int pg = start / BS + (f - cum0);
+                bt.blk = __ldg(p.table + (size_t)a * p.tstride + pg);
+                bt.lo = (f == cum0) ? start % BS : 0;
+                bt.hi = min(BS, end - pg * BS);
+                if (f == cum0 || base + lane == 0) bt.flags |= kFlagFirst;
+                if (f == cum1 - 1 || base + lane == n_units - 1) bt.flags |= kFlagLast;
+                if (f == cum1 - 1 && p.k_new != nullptr) bt.flags |= kFlagNew;
+                const long long seg0 = (long long)bt.hg * p.P + cum0;
+                const long long seg1 = (long long)bt.hg * p.P + cum1 - 1;
+                bt.r_first = range_of_unit(p, seg0);
+                bt.nsegs = range_of_unit(p, seg1) - bt.r_first + 1;
+            }
+            return bt;
+        };
+        // where the batch after (range, base) starts; consumes the reserve claim at a range end
+        int claim = 0;                                  // lane 0: one dynamic range held in reserve
+        auto advance = [&](int range, int base, int& n_range, int& n_base) {
+            long long u_begin, u_end;
+            range_bounds(p, range, u_begin, u_end);
+            if (base + 32 < (int)(u_end - u_begin)) { n_range = range; n_base = base + 32; return; }
+            n_range = p.Gs + __shfl_sync(0xffffffffu, claim, 0);
+            n_base = 0;
+            if (n_range < n_ranges && lane == 0) claim = atomicAdd(p.sched, 1);   // refill the reserve
+        };
+
+        Batch cur = resolve(blockIdx.x, 0);             // first job: this CTA's static range
+        // q / k_new / v_new / out belong to the previous kernel until it has completed
+        // (and so do the scheduler words, the arrival counters and the partial slots)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (lane == 0) claim = atomicAdd(p.sched, 1);
+        while (cur.range < n_ranges) {
+            int n_range, n_base;
+            advance(cur.range, cur.base, n_range, n_base);
+            const Batch nxt = resolve(n_range, n_base);     // loads in flight during the copies below
+            for (int j = 0; j < cur.cnt; ++j) {
+                const int j_row = __shfl_sync(0xffffffffu, cur.row, j);
+                const int j_hg = __shfl_sync(0xffffffffu, cur.hg, j);
+                const int j_blk = __shfl_sync(0xffffffffu, cur.blk, j);
+                const int j_lo = __shfl_sync(0xffffffffu, cur.lo, j);
+                const int j_hi = __shfl_sync(0xffffffffu, cur.hi, j);
+                const int j_flags = __shfl_sync(0xffffffffu, cur.flags, j);
+                const int j_rfirst = __shfl_sync(0xffffffffu, cur.r_first, j);
+                const int j_nsegs = __shfl_sync(0xffffffffu, cur.nsegs, j);
+                const size_t page_off = (size_t)j_blk * BS * p.C + (size_t)j_hg * W;
+                const bool first = (j_flags & kFlagFirst) != 0;
+                // rows that come from the pool; with a fused append the sequence's newest row
+                // comes straight from this step's k/v rows instead
+                const int pool_rows = (j_flags & kFlagNew) ? j_hi - 1 : j_hi;
 #pragma unroll
-                    for (int kv = 0; kv < 2; ++kv) {
-                        const uint32_t full = smem_u32(&bars[stage]);
-                        const uint32_t dst = smem_u32(tiles + (size_t)stage * tile_floats);
-                        const float* src = (kv == 0 ? p.pool_k : p.pool_v) + page_off;
-                        if (lane == 0) {
+                for (int kv = 0; kv < 2; ++kv) {
+                    const uint32_t full = smem_u32(&bars[stage]);
+                    const uint32_t dst = smem_u32(tiles + (size_t)stage * tile_floats);
+                    const float* src = (kv == 0 ? p.pool_k : p.pool_v) + page_off;
+                    if (lane == 0) {
+                        if (dbg) {
+                            if (first_issue) { dbg[1] = global_ns(); first_issue = false; }
+                            const long long c0 = clock64();
+                            mbar_wait(smem_u32(&bars[p.n_stages + stage]), phase ^ 1);
+                            t_empty += clock64() - c0;
+                        } else {
                             mbar_wait(smem_u32(&bars[p.n_stages + stage]), phase ^ 1);   // slot free
-                            if (kv == 0) {
-                                meta[2 * stage] = make_int4(j_row, j_hg, j_lo | (j_hi << 8), j_flags);
-                                meta[2 * stage + 1] = make_int4(j_rfirst, j_nsegs, range, j_blk);
-                            }
-                            uint32_t bytes = (uint32_t)j_hi * W * 4u;
-                            if (kv == 0 && first) bytes += W * 4u;
-                            mbar_arrive_expect_tx(full, bytes);
                         }
-                        __syncwarp();
-                        if (W == p.C) {            // whole rows: the valid part of the page is contiguous
-                            if (lane == 0 && pool_rows > 0) tma_bulk_g2s(dst, src, (uint32_t)pool_rows * W * 4u, full);
-                        } else if (lane < pool_rows) {   // a column slice: one bulk copy per row
-                            tma_bulk_g2s(dst + lane * W * 4u, src + (size_t)lane * p.C, W * 4u, full);
+                        if (kv == 0) {
+                            meta[2 * stage] = make_int4(j_row, j_hg, j_lo | (j_hi << 8), j_flags);
+                            meta[2 * stage + 1] = make_int4(j_rfirst, j_nsegs, cur.range, j_blk);
                         }
-                        if ((j_flags & kFlagNew) && lane == 0)
-                            tma_bulk_g2s(dst + (uint32_t)(j_hi - 1) * W * 4u,
-                                         (kv == 0 ? p.k_new : p.v_new) + (size_t)j_row * p.new_stride + (size_t)j_hg * W,
-                                         W * 4u, full);
-                        if (kv == 0 && first && lane == 0)
-                            tma_bulk_g2s(smem_u32(qbuf + (size_t)stage * W),
-                                         p.q + (size_t)j_row * p.q_stride + (size_t)j_hg * W, W * 4u, full);
-                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                        uint32_t bytes = (uint32_t)j_hi * W * 4u;
+                        if (kv == 0 && first) bytes += W * 4u;
+                        mbar_arrive_expect_tx(full, bytes);
                     }
+                    __syncwarp();
+                    if (W == p.C) {            // whole rows: the valid part of the page is contiguous
+                        if (lane == 0 && pool_rows > 0) tma_bulk_g2s(dst, src, (uint32_t)pool_rows * W * 4u, full);
+                    } else if (lane < pool_rows) {   // a column slice: one bulk copy per row
+                        tma_bulk_g2s(dst + lane * W * 4u, src + (size_t)lane * p.C, W * 4u, full);
+                    }
+                    if ((j_flags & kFlagNew) && lane == 0)
+                        tma_bulk_g2s(dst + (uint32_t)(j_hi - 1) * W * 4u,
+                                     (kv == 0 ? p.k_new : p.v_new) + (size_t)j_row * p.new_stride + (size_t)j_hg * W,
+                                     W * 4u, full);
+                    if (kv == 0 && first && lane == 0)
+                        tma_bulk_g2s(smem_u32(qbuf + (size_t)stage * W),
+                                     p.q + (size_t)j_row * p.q_stride + (size_t)j_hg * W, W * 4u, full);
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
             }
-            int r = 0;
-            if (lane == 0) r = atomicAdd(p.sched, 1);
-            range = p.Gs + __shfl_sync(0xffffffffu, r, 0);
+            cur = nxt;
         }
         if (lane == 0) {
             // tell the consumers there is nothing more, then take part in resetting the counters
             mbar_wait(smem_u32(&bars[p.n_stages + stage]), phase ^ 1);
             meta[2 * stage] = make_int4(0, 0, 0, kFlagEnd);
             mbar_arrive(smem_u32(&bars[stage]));
+            if (dbg) dbg[4] = (unsigned long long)t_empty;
             const int done = atomicAdd(p.sched + 1, 1);
             if (done == (int)gridDim.x - 1) {      // every CTA has made its last (failed) claim
                 p.sched[0] = 0;
@@ -359,7 +419,86 @@ pa_decode_stream_kernel(const DecodeParams p) {
         return;
     }
 
+    if (tid >= p.n_cons + 32) {
+        // ==================================== merger warp ====================================
+        // Takes finished segments off the queue so the consumers never wait for a round trip:
+        // publishes the partial (fence + arrival count) and, when it is the last of its
+        // (sequence, head group), merges all partials into the output row.
+        const int lane = tid & 31;
+        int qs = 0;
+        uint32_t qph = 0;
+        for (;;) {
+            mbar_wait(smem_u32(&segq[qs]), qph);
+            const int4 d0 = segdesc[2 * qs];
+            const int4 d1 = segdesc[2 * qs + 1];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&segq[kSegQ + qs]));
+            if (++qs == kSegQ) { qs = 0; qph ^= 1; }
+            if (d1.y) break;                                   // end of this CTA's work
+            const int row = d0.x, hg = d0.y, r_first = d0.z, nsegs = d0.w;
+            int last = 0;
+            if (lane == 0) {
+                __threadfence();                               // partial stores before the arrival count
+                last = atomicAdd(p.counters + hg * p.B + row, 1) == nsegs - 1;
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (!last) continue;
+            __threadfence();
+            const float* base = p.ws + (size_t)(r_first + hg * p.B + row) * p.slot_floats;
+            // Online merge, one pass: every lane owns float4 columns lane, lane+32, ...; they are
+            // handled four at a time, and the (m, l, o) of four partials are loaded together, so
+            // a typical 3-4 way split costs two round trips to L2.
+            constexpr int kGrp = 4;
+            for (int c0 = 0; c0 < W4; c0 += 32 * kGrp) {
+                float4 o[kGrp];
+                float Ls[kGrp], M[kGrp];
+#pragma unroll
+                for (int k = 0; k < kGrp; ++k) { o[k] = make_float4(0.f, 0.f, 0.f, 0.f); Ls[k] = 0.0f; M[k] = kMaxInit; }
+                for (int i0 = 0; i0 < nsegs; i0 += 4) {
+                    float2 ml[4][kGrp];
+                    float4 oi[4][kGrp];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float* sl = base + (size_t)min(i0 + u, nsegs - 1) * p.slot_floats;
+#pragma unroll
+                        for (int k = 0; k < kGrp; ++k) {
+                            const int c = min(c0 + lane + 32 * k, W4 - 1);
+                            ml[u][k] = __ldcg(reinterpret_cast<const float2*>(sl + W) + c / LPH);
+                            oi[u][k] = __ldcg(reinterpret_cast<const float4*>(sl) + c);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (i0 + u < nsegs) {
+#pragma unroll
+                            for (int k = 0; k < kGrp; ++k) {
+                                const float m_new = fmaxf(M[k], ml[u][k].x);
+                                const float so = expf(M[k] - m_new), w = expf(ml[u][k].x - m_new);
+                                Ls[k] = fmaf(ml[u][k].y, w, Ls[k] * so);
+                                o[k].x = fmaf(oi[u][k].x, w, o[k].x * so); o[k].y = fmaf(oi[u][k].y, w, o[k].y * so);
+                                o[k].z = fmaf(oi[u][k].z, w, o[k].z * so); o[k].w = fmaf(oi[u][k].w, w, o[k].w * so);
+                                M[k] = m_new;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kGrp; ++k) {
+                    const int c = c0 + lane + 32 * k;
+                    if (c < W4) {
+                        const float inv = (Ls[k] == 0.0f) ? 0.0f : 1.0f / Ls[k];
+                        *reinterpret_cast<float4*>(p.out + (size_t)row * p.out_stride + (size_t)hg * W + c * 4) =
+                            make_float4(o[k].x * inv, o[k].y * inv, o[k].z * inv, o[k].w * inv);
+                    }
+                }
+            }
+            if (lane == 0) p.counters[hg * p.B + row] = 0;     // ready for the next launch
+        }
+        return;
+    }
+
     // ======================================= consumers =======================================
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // rows of the batch that own no page at all produce zeros (paged_infer.c never hits this:
     // T >= 1 always sees at least its own key)
     for (int r = blockIdx.x; r < p.B; r += gridDim.x) {
@@ -371,8 +510,7 @@ pa_decode_stream_kernel(const DecodeParams p) {
     const bool col_valid = tid < W4;
     const int c4 = col_valid ? tid : W4 - 1;     // padded lanes shadow the last column
     const int hl = tid / LPH;                    // head within the tile
-    const int hl_r = col_valid ? hl : 0;         // padded lanes read head 0's (m, l) in the merge
-    const int gl = tid % LPH;                    // lane within the head
+        const int gl = tid % LPH;                    // lane within the head
     float* my_p = psm + hl * BS;
 
     float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -380,10 +518,22 @@ pa_decode_stream_kernel(const DecodeParams p) {
     float m_run = kMaxInit, l_run = 0.0f;
     int stage = 0;
     uint32_t phase = 0;
+    long long t_full = 0, t_seg = 0;
+    unsigned long long n_tiles = 0;
+    int qs = 0;                                  // finished-segment queue position
+    uint32_t qph = 0;
 
     for (;;) {
         // ------------------------------- K tile: scores -------------------------------------
-        mbar_wait(smem_u32(&bars[stage]), phase);
+        if (dbg && tid == 0) {
+            const long long c0 = clock64();
+            mbar_wait(smem_u32(&bars[stage]), phase);
+            t_full += clock64() - c0;
+            if (n_tiles == 0) dbg[2] = global_ns();
+            n_tiles += 2;
+        } else {
+            mbar_wait(smem_u32(&bars[stage]), phase);
+        }
         const int4 mt0 = meta[2 * stage];
         const int4 mt1 = meta[2 * stage + 1];
         const int lo = mt0.z & 0xff, hi = (mt0.z >> 8) & 0xff, flags = mt0.w;
@@ -440,7 +590,13 @@ pa_decode_stream_kernel(const DecodeParams p) {
         __syncwarp();                                    // my_p visible to the head's lanes
 
         // ------------------------------- V tile: weighted sum -------------------------------
-        mbar_wait(smem_u32(&bars[stage]), phase);
+        if (dbg && tid == 0) {
+            const long long c0 = clock64();
+            mbar_wait(smem_u32(&bars[stage]), phase);
+            t_full += clock64() - c0;
+        } else {
+            mbar_wait(smem_u32(&bars[stage]), phase);
+        }
         {
             const float4* vt = reinterpret_cast<const float4*>(tiles + (size_t)stage * tile_floats) + c4;
             const float4* p4 = reinterpret_cast<const float4*>(my_p);
@@ -469,6 +625,7 @@ pa_decode_stream_kernel(const DecodeParams p) {
 
         // ------------------------------- end of a segment -----------------------------------
         if (flags & kFlagLast) {
+            const long long c_seg = dbg ? clock64() : 0;
             const int row = mt0.x, hg = mt0.y, r_first = mt1.x, nsegs = mt1.y, range = mt1.z;
             float* out_ptr = p.out + (size_t)row * p.out_stride + (size_t)hg * W + c4 * 4;
             if (nsegs == 1) {
@@ -476,46 +633,35 @@ pa_decode_stream_kernel(const DecodeParams p) {
                 if (col_valid)
                     *reinterpret_cast<float4*>(out_ptr) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
             } else {
-                // partial (m, l, unnormalised o) to this range's slot; the CTA that arrives last merges
+                // partial (m, l, unnormalised o) to this range's slot, then hand the segment to the
+                // merger warp and carry on with the next tile
+                mbar_wait(smem_u32(&segq[kSegQ + qs]), qph ^ 1);          // queue slot free
                 float* slot = p.ws + (size_t)(range + hg * p.B + row) * p.slot_floats;
                 if (col_valid) {
                     __stcg(reinterpret_cast<float4*>(slot) + c4, acc);
                     if (gl == 0) __stcg(reinterpret_cast<float2*>(slot + W) + hl, make_float2(m_run, l_run));
                 }
-                __threadfence();
-                named_bar_sync(1, p.n_cons);
                 if (tid == 0) {
-                    const int old = atomicAdd(p.counters + hg * p.B + row, 1);
-                    *s_flag = (old == nsegs - 1);
+                    segdesc[2 * qs] = make_int4(row, hg, r_first, nsegs);
+                    segdesc[2 * qs + 1] = make_int4(range, 0, 0, 0);
                 }
-                named_bar_sync(1, p.n_cons);
-                const bool merge = *s_flag != 0;
-                named_bar_sync(1, p.n_cons);             // s_flag may be rewritten by the next segment
-                if (merge) {
-                    __threadfence();
-                    float M = kMaxInit;
-                    for (int i = 0; i < nsegs; ++i) {
-                        const float* sl = p.ws + (size_t)(r_first + i + hg * p.B + row) * p.slot_floats;
-                        M = fmaxf(M, __ldcg(reinterpret_cast<const float2*>(sl + W) + hl_r).x);
-                    }
-                    float Lsum = 0.0f;
-                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int i = 0; i < nsegs; ++i) {
-                        const float* sl = p.ws + (size_t)(r_first + i + hg * p.B + row) * p.slot_floats;
-                        const float2 ml = __ldcg(reinterpret_cast<const float2*>(sl + W) + hl_r);
-                        const float w = expf(ml.x - M);
-                        const float4 oi = __ldcg(reinterpret_cast<const float4*>(sl) + c4);
-                        Lsum = fmaf(ml.y, w, Lsum);
-                        o.x = fmaf(oi.x, w, o.x); o.y = fmaf(oi.y, w, o.y);
-                        o.z = fmaf(oi.z, w, o.z); o.w = fmaf(oi.w, w, o.w);
-                    }
-                    const float inv = (Lsum == 0.0f) ? 0.0f : 1.0f / Lsum;
-                    if (col_valid)
-                        *reinterpret_cast<float4*>(out_ptr) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
-                    if (tid == 0) p.counters[hg * p.B + row] = 0;    // ready for the next launch
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&segq[qs]));
+                if (++qs == kSegQ) { qs = 0; qph ^= 1; }
             }
+            if (dbg) t_seg += clock64() - c_seg;
         }
+    }
+    // tell the merger warp to finish
+    mbar_wait(smem_u32(&segq[kSegQ + qs]), qph ^ 1);
+    if (tid == 0) segdesc[2 * qs + 1] = make_int4(0, 1, 0, 0);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&segq[qs]));
+    if (dbg && tid == 0) {
+        dbg[3] = global_ns();
+        dbg[5] = (unsigned long long)t_full;
+        dbg[6] = (unsigned long long)t_seg;
+        dbg[7] = n_tiles;
     }
 }
 
@@ -635,16 +781,15 @@ struct DecodePlan {
     size_t smem;
 };
 
-constexpr int kMaxCumSmem = 4096;   // prefix sums staged in shared memory up to this many rows
+constexpr int kMaxCumSmem = 1024;   // prefix sums + bounds staged in shared memory up to this many rows
 
 size_t decode_smem_bytes(int bs, int W, int n_stages, int n_cons, int lph, int n_cum) {
     size_t b = (size_t)n_stages * bs * W * 4;          // tiles
     b += (size_t)n_stages * W * 4;                     // q slots
     b += (size_t)(n_cons / lph) * bs * 4;              // probabilities
-    b += (size_t)n_stages * 2 * sizeof(int4);          // meta
-    b += (size_t)n_stages * 2 * sizeof(uint64_t);      // barriers
-    b += 16;                                           // flags
-    b += (size_t)n_cum * 4;                            // prefix sums of pages
+    b += (size_t)(n_stages + kSegQ) * 2 * sizeof(int4);      // tile meta + finished-segment queue
+    b += (size_t)(n_stages + kSegQ) * 2 * sizeof(uint64_t);  // barriers
+    b += (size_t)n_cum * 3 * 4;                        // prefix sums of pages, kv_start, kv_end
     return b;
 }
 
@@ -656,11 +801,14 @@ bool plan_decode(const pa_handle* h, int total_pages, int B, DecodePlan* plan) {
     const int hs = h->cfg.head_dim, bs = h->cfg.block_size, NH = h->cfg.n_heads;
     const int lph = hs / 4;
     const int n_cum = (B + 1 <= kMaxCumSmem) ? B + 1 : 0;
-    const int smem_cap = h->smem_optin - 1024 - n_cum * 4;
+    const int smem_cap = h->smem_optin - 1024 - n_cum * 12;
     const int want_hpg = h->tune[PA_TUNE_HEADS_PER_TILE];
-    int max_stages = h->tune[PA_TUNE_STAGES] > 0 ? h->tune[PA_TUNE_STAGES] : 8;
+    // ring depth: measured on B200, ~150 KB of bulk copies in flight per SM is the sweet spot
+    // (3 x 48 KB pages beat 4, 4 x 24 KB beat 8): more concurrent page streams cost DRAM locality
+    const bool stages_forced = h->tune[PA_TUNE_STAGES] > 0;
+    int max_stages = stages_forced ? h->tune[PA_TUNE_STAGES] : 8;
     int best = 0, best_stages = 0;
-    for (int min_stages = 4; min_stages >= 2 && best == 0; --min_stages) {
+    for (int min_stages = 3; min_stages >= 2 && best == 0; --min_stages) {
         for (int hpg = NH; hpg >= 1; --hpg) {
             if (NH % hpg) continue;
             if (want_hpg > 0 && hpg != want_hpg) continue;
@@ -668,9 +816,13 @@ bool plan_decode(const pa_handle* h, int total_pages, int B, DecodePlan* plan) {
             const int n_cons = ((W / 4) + 31) & ~31;
             if (n_cons > 256) continue;
             const size_t per_stage = (size_t)bs * W * 4 + (size_t)W * 4 + 2 * sizeof(int4) + 16;
-            const size_t fixed = (size_t)(n_cons / lph) * bs * 4 + 64;
+            const size_t fixed = (size_t)(n_cons / lph) * bs * 4 + 64 + kSegQ * 48;
             int stages = (int)((smem_cap - fixed) / per_stage);
             if (stages > max_stages) stages = max_stages;
+            if (!stages_forced) {
+                const int sweet = (int)((160 * 1024) / per_stage);
+                if (stages > sweet && sweet >= 3) stages = sweet;
+            }
             if (stages < min_stages && !(want_hpg > 0 && stages >= 2)) continue;
             best = hpg;
             best_stages = stages;
@@ -702,7 +854,10 @@ bool plan_decode(const pa_handle* h, int total_pages, int B, DecodePlan* plan) {
     plan->Gs = (int)grid;
     plan->Us = units;
     plan->D = 0;
-    int pct = h->tune[PA_TUNE_STATIC_PCT] > 0 ? h->tune[PA_TUNE_STATIC_PCT] : 75;
+    // default: all static.  The dynamic tail balances the SMs' streaming time, but every range is
+    // one more partial to merge, and the merges of the last sequences sit on the critical path
+    // (measured: slower than the static split for every setting tried; kept as a knob).
+    int pct = h->tune[PA_TUNE_STATIC_PCT] > 0 ? h->tune[PA_TUNE_STATIC_PCT] : 100;
     int dyn_units = h->tune[PA_TUNE_DYN_UNITS] > 0 ? h->tune[PA_TUNE_DYN_UNITS] : 2;
     if (pct < 100 && units >= 4 * grid) {
         long long us = units * pct / 100;
@@ -819,6 +974,15 @@ static int decode_impl(pa_handle* h, int layer, const float* q, int q_stride, co
         dp.cum_pages = h->d_step + L.off_cum_pages;
         dp.table = h->d_step + L.off_table;
         dp.ws = h->d_ws; dp.counters = h->d_counters; dp.sched = h->d_counters + h->n_counters;
+        dp.dbg = nullptr;
+        if (h->tune[PA_TUNE_DEBUG_TIMELINE]) {
+            if (!h->d_dbg) {
+                CU_CHECK(cudaMalloc((void**)&h->d_dbg, (size_t)h->sm_count * 8 * 8 * sizeof(unsigned long long)));
+            }
+            CU_CHECK(cudaMemsetAsync(h->d_dbg, 0, (size_t)h->sm_count * 8 * 8 * sizeof(unsigned long long), s));
+            dp.dbg = (unsigned long long*)h->d_dbg;
+            h->dbg_ctas = plan.grid;
+        }
         dp.P = L.total_pages > 0 ? L.total_pages : 1;
         dp.U = plan.U; dp.Us = plan.Us; dp.Gs = plan.Gs; dp.D = plan.D;
         dp.B = L.nseq; dp.C = h->C; dp.hpg = plan.hpg; dp.n_hg = plan.n_hg; dp.W = plan.W;
@@ -834,8 +998,18 @@ static int decode_impl(pa_handle* h, int layer, const float* q, int q_stride, co
             CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
             h->decode_attr_fn = (void*)fn;
         }
-        fn<<<plan.grid, plan.n_cons + 32, plan.smem, s>>>(dp);
-        CU_CHECK(cudaGetLastError());
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(plan.grid);
+        cfg.blockDim = dim3(plan.n_cons + 64);     // consumers + producer warp + merger warp
+        cfg.dynamicSmemBytes = plan.smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = h->tune[PA_TUNE_NO_PDL] ? 0 : 1;
+        CU_CHECK(cudaLaunchKernelEx(&cfg, fn, dp));
         h->launches++;
         return PA_OK;
     }
@@ -844,6 +1018,15 @@ static int decode_impl(pa_handle* h, int layer, const float* q, int q_stride, co
         if (rc != PA_OK) return rc;
     }
     return launch_rows(h, layer, q, q_stride, out, out_stride, false, s);
+}
+
+int pa_debug_timeline(pa_handle* h, unsigned long long* out, int max_ctas) {
+    if (!h || !h->d_dbg || !out) { pa_set_error("pa_debug_timeline: enable PA_TUNE_DEBUG_TIMELINE and run a decode first"); return PA_ERR_INVALID; }
+    int n = h->dbg_ctas < max_ctas ? h->dbg_ctas : max_ctas;
+    CU_CHECK(cudaSetDevice(h->cfg.device));
+    CU_CHECK(cudaDeviceSynchronize());
+    CU_CHECK(cudaMemcpy(out, h->d_dbg, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return n;
 }
 
 int pa_decode(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream) {

@@ -21,7 +21,7 @@ PA_HOST_ONLY = -1
 PA_OK = 0
 PA_ERR_INVALID, PA_ERR_NOMEM, PA_ERR_CUDA, PA_ERR_NO_DEVICE, PA_ERR_NO_BLOCKS, PA_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 PA_TUNE_DECODE_PATH, PA_TUNE_HEADS_PER_TILE, PA_TUNE_STAGES, PA_TUNE_GRID, PA_TUNE_COUNT_LAUNCHES = 0, 1, 2, 3, 4
-PA_TUNE_STATIC_PCT, PA_TUNE_DYN_UNITS = 5, 6
+PA_TUNE_STATIC_PCT, PA_TUNE_DYN_UNITS, PA_TUNE_DEBUG_TIMELINE, PA_TUNE_NO_PDL = 5, 6, 7, 8
 
 
 class KVBlock(C.Structure):
@@ -106,6 +106,7 @@ def load():
         "pa_sm_count": (C.c_int, [vp]),
         "pa_tune_set": (C.c_int, [vp, C.c_int, C.c_int]),
         "pa_tune_get": (C.c_int, [vp, C.c_int]),
+        "pa_debug_timeline": (C.c_int, [vp, C.POINTER(C.c_ulonglong), C.c_int]),
         "pa_device_count": (C.c_int, []),
         "pa_dev_alloc": (vp, [C.c_size_t]),
         "pa_dev_free": (None, [vp]),
@@ -286,6 +287,13 @@ class PagedAttn:
 
     def tune(self, key, value):
         return self.lib.pa_tune_set(self.h, key, value)
+
+    def debug_timeline(self):
+        buf = np.zeros((2048, 8), dtype=np.uint64)
+        n = self.lib.pa_debug_timeline(self.h, buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), 2048)
+        if n < 0:
+            raise PagedAttnError(last_error())
+        return buf[:n]
 
     def launches(self):
         return self.lib.pa_tune_get(self.h, PA_TUNE_COUNT_LAUNCHES)
