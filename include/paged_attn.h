@@ -169,7 +169,9 @@ PA_API int pa_decode_append(pa_handle* h, int layer, const float* q, const float
 PA_API int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream);
 
 /* ---- whole step with HOST buffers (the end-to-end entry: H2D, append, decode, D2H, sync) -- */
-/* qkv_host: (nseq, 3C) rows of the step's sequences [q | k | v]; out_host: (nseq, C). */
+/* qkv_host: (nseq, 3C) rows of the step's sequences [q | k | v]; out_host: (nseq, C).  Pinned
+ * buffers (pa_host_alloc) are read and written by the kernel directly over PCIe (zero-copy);
+ * pageable buffers are staged through pinned memory with cudaMemcpyAsync. */
 PA_API int pa_decode_step_host(pa_handle* h, int layer, const float* qkv_host, float* out_host);
 
 /* ---- sequence bookkeeping ----------------------------------------------------------------- */
@@ -202,6 +204,7 @@ typedef enum pa_tune_key {
     PA_TUNE_DYN_UNITS = 6,     /* 0 auto: pages per dynamically claimed range */
     PA_TUNE_DEBUG_TIMELINE = 7,/* 1: the stream decode kernel records a per-CTA timeline (pa_debug_timeline) */
     PA_TUNE_NO_PDL = 8,        /* 1: launch the decode kernel without programmatic dependent launch */
+    PA_TUNE_NO_ZEROCOPY = 9,   /* 1: pa_decode_step_host stages pinned buffers with copies instead of mapping them */
     PA_TUNE_MAX
 } pa_tune_key;
 PA_API int pa_tune_set(pa_handle* h, int key, int value);

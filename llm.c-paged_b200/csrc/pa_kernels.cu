@@ -1054,23 +1054,34 @@ int pa_decode_step_host(pa_handle* h, int layer, const float* qkv_host, float* o
     if (L.nseq < 1 || L.ntok != L.nseq) { pa_set_error("pa_decode_step_host: needs a step with one new token per sequence"); return PA_ERR_INVALID; }
     if (cudaSetDevice(h->cfg.device) != cudaSuccess) return PA_ERR_CUDA;
     const size_t C = h->C, n = L.nseq;
-    int rc = pa_cu_ensure_stage(h, n * 4 * C);
-    if (rc != PA_OK) return rc;
     cudaStream_t s = (cudaStream_t)h->stream;
+    int rc;
     if (!h->step.uploaded) { rc = pa_cu_step_upload(h, s); if (rc != PA_OK) return rc; }
+    cudaPointerAttributes a;
+    const bool in_pinned = cudaPointerGetAttributes(&a, qkv_host) == cudaSuccess && a.type == cudaMemoryTypeHost;
+    const float* in_alias = in_pinned ? (const float*)a.devicePointer : nullptr;
+    const bool out_pinned = cudaPointerGetAttributes(&a, out_host) == cudaSuccess && a.type == cudaMemoryTypeHost;
+    float* out_alias = out_pinned ? (float*)a.devicePointer : nullptr;
+    cudaGetLastError();
+    if (in_alias && out_alias && !h->tune[PA_TUNE_NO_ZEROCOPY]) {
+        /* Pinned host buffers are mapped into the device address space: the kernel's bulk copies
+         * pull the q / k / v rows over PCIe themselves (each row is read exactly once) and the
+         * output rows are stored straight to host memory -- no staging copies, one launch. */
+        rc = pa_decode_append(h, layer, in_alias, in_alias + C, in_alias + 2 * C, (int)(3 * C), out_alias, (int)C, s);
+        if (rc != PA_OK) return rc;
+        CU_CHECK(cudaStreamSynchronize(s));
+        return PA_OK;
+    }
+    rc = pa_cu_ensure_stage(h, n * 4 * C);
+    if (rc != PA_OK) return rc;
     float* d_qkv = h->d_stage;
     float* d_out = h->d_stage + n * 3 * C;
     /* pageable host memory is staged through the pinned buffer; pinned memory goes straight */
-    cudaPointerAttributes a;
-    bool pinned = cudaPointerGetAttributes(&a, qkv_host) == cudaSuccess && a.type == cudaMemoryTypeHost;
-    cudaGetLastError();
     const float* src = qkv_host;
-    if (!pinned) { memcpy(h->h_stage, qkv_host, n * 3 * C * sizeof(float)); src = h->h_stage; }
+    if (!in_pinned) { memcpy(h->h_stage, qkv_host, n * 3 * C * sizeof(float)); src = h->h_stage; }
     CU_CHECK(cudaMemcpyAsync(d_qkv, src, n * 3 * C * sizeof(float), cudaMemcpyHostToDevice, s));
     rc = pa_decode_append(h, layer, d_qkv, d_qkv + C, d_qkv + 2 * C, (int)(3 * C), d_out, (int)C, s);
     if (rc != PA_OK) return rc;
-    bool out_pinned = cudaPointerGetAttributes(&a, out_host) == cudaSuccess && a.type == cudaMemoryTypeHost;
-    cudaGetLastError();
     float* dst = out_pinned ? out_host : h->h_stage + n * 3 * C;
     CU_CHECK(cudaMemcpyAsync(dst, d_out, n * C * sizeof(float), cudaMemcpyDeviceToHost, s));
     CU_CHECK(cudaStreamSynchronize(s));

@@ -1,0 +1,60 @@
+"""The plain-C host example (examples/paged_decode_host.c: gcc only, reference call site
+paged_infer.c:710-715 unchanged + the batched API) runs on the GPU and matches the oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as ge
+import oracle_api as oa
+
+pytestmark = pytest.mark.gpu
+
+
+def checksum(x):
+    x = np.asarray(x, dtype=np.float64).ravel()
+    return float((x * ((np.arange(x.size) % 7) + 1)).sum())
+
+
+def test_plain_c_host_example():
+    exe = os.path.join(ge.ROOT, "examples", "paged_decode_host")
+    assert os.path.exists(exe), "build() should have produced the example"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    m1 = re.search(r"part1 blocks=(\d+) filled0=(\d+) filled1=(\d+) lru_epoch=(\d+) checksum=([-\d.]+)", r.stdout)
+    m2 = re.search(r"part2 ctx=(\d+) pages=(\d+) table0=\[(\d+) (\d+) (\d+)\] checksum=([-\d.]+)", r.stdout)
+    assert m1 and m2, r.stdout
+
+    # ---- part 1: the reference call site with main's sliding window
+    T, C_, NH, steps, bs = 32, 768, 12, 19, 32
+    stream = oa.uniform(((T + steps) * 3 * C_,), -1.0, 1.0, seed=1337).reshape(T + steps, 3 * C_)
+    orc = oa.OrcManager(C_, bs, 100, 100)
+    want = 0.0
+    for step in range(steps):
+        window = np.ascontiguousarray(stream[step:step + T][None])
+        orc.add_to_cache(window, 1, T, T if step == 0 else 1)
+        _, out = orc.attend(0, window, 1, T, NH, step)
+        want += checksum(out)
+    assert [int(m1.group(i)) for i in (1, 2, 3, 4)] == [2, 32, 18, 19]          # bit-exact integer state
+    assert len(orc.table(0)) == 2 and orc.epoch() == 19
+    assert abs(float(m1.group(5)) - want) <= 1e-5 * max(1.0, abs(want)) + 1e-3
+    orc.close()
+
+    # ---- part 2: batched decode, 8 sequences x 2 layers x 40 steps
+    B, L, bs = 8, 2, 16
+    data = oa.uniform((40 * L * B * 3 * C_,), -1.0, 1.0, seed=42).reshape(40, L, B, 3 * C_)
+    orcs = [oa.OrcManager(C_, bs, 256, B) for _ in range(L)]    # same allocator trace per layer
+    want = 0.0
+    for step in range(40):
+        for layer in range(L):
+            qkv = data[step, layer]
+            for s in range(B):
+                orcs[layer].add_to_cache(qkv[s][None, None, :], 1, 1, 1, prompt=s)
+            want += checksum(orcs[layer].decode_batch(list(range(B)), NH, qkv[:, :C_]))
+    assert int(m2.group(1)) == 40 and int(m2.group(2)) == 3
+    assert [int(m2.group(i)) for i in (3, 4, 5)] == orcs[0].table(0)           # interleaved first-fit: 0, 8, 16
+    assert abs(float(m2.group(6)) - want) <= 1e-5 * max(1.0, abs(want)) + 1e-3
+    for o in orcs:
+        o.close()

@@ -280,10 +280,31 @@ def test_decode_step_device_and_host_entry():
                 pa.check(eng.decode(1, d.ptr, 3 * Cc, o.ptr, Cc), "decode")
                 eng.sync()
                 got = o.download((B, Cc))
-            else:                  # host buffers in, host buffers out
+            elif step == 1:        # pageable host buffers in, host buffers out (staged copies)
                 got = np.zeros((B, Cc), dtype=np.float32)
                 pa.check(eng.decode_step_host(1, qkv.ctypes.data, got.ctypes.data), "decode_step_host")
             assert_close(got, want, f"step {step}")
+        # pinned host buffers: the kernel reads/writes them directly (zero-copy), and the staged
+        # variant of the same call
+        import ctypes as Ct
+        lib = eng.lib
+        hin, hout = lib.pa_host_alloc(B * 3 * Cc * 4), lib.pa_host_alloc(B * Cc * 4)
+        try:
+            for step, nozc in ((10, 0), (11, 1)):
+                qkv = oa.normal((B, 3 * Cc), seed=200 + step)
+                Ct.memmove(hin, qkv.ctypes.data, qkv.nbytes)
+                eng.tune(pa.PA_TUNE_NO_ZEROCOPY, nozc)
+                assert eng.step_begin(sc.seq_ids, [1] * B) == 0, pa.last_error()
+                for s in range(B):
+                    orc.add_to_cache(qkv[s][None, None, :], 1, 1, 1, prompt=s)
+                want = orc.decode_batch(sc.seq_ids, NH, qkv[:, :Cc])
+                pa.check(eng.decode_step_host(1, hin, hout), "decode_step_host pinned")
+                got = np.ctypeslib.as_array(Ct.cast(hout, Ct.POINTER(Ct.c_float)), (B, Cc)).copy()
+                assert_close(got, want, f"pinned host entry, zero-copy={'off' if nozc else 'on'}")
+                k, v = eng.read_pool_rows(1, eng.slot_mapping())
+                assert np.array_equal(k, qkv[:, Cc:2 * Cc]) and np.array_equal(v, qkv[:, 2 * Cc:])
+        finally:
+            lib.pa_host_free(hin); lib.pa_host_free(hout)
     finally:
         sc.close()
 
