@@ -43,6 +43,12 @@ WORKLOADS = {
     # BASELINE.json configs[2]
     "cfg3": dict(name="GPT-2 124M paged decode, batch 256, mixed ctx U{128..1024}, block 16, KV append + attention",
                  NH=12, hs=64, bs=16, L=12, B=256, ctx="uniform", ctx_lo=128, ctx_hi=1024),
+    # BASELINE.json configs[3], one GPU's shard at 8 GPUs (512/8 sequences); 4 of the 48 layers keep set-up short
+    "xl": dict(name="GPT-2 XL shape (25 heads, head_dim 64) paged decode, 64 sequences x 1024 ctx per GPU, block 16, 4 of 48 layers",
+               NH=25, hs=64, bs=16, L=4, B=64, ctx="fixed", ctx_len=1024),
+    # BASELINE.json configs[4], one GPU's share: 32k contexts, head_dim 128
+    "long": dict(name="long-context paged decode, 8 sequences x 32768 ctx, 32 heads x head_dim 128, block 16, 1 layer",
+                 NH=32, hs=128, bs=16, L=1, B=8, ctx="fixed", ctx_len=32768),
     # BASELINE.json configs[0] (L2-resident, latency-bound)
     "cfg1": dict(name="GPT-2 124M paged decode batch 1, block 16, ctx 256 (L2-resident)",
                  NH=12, hs=64, bs=16, L=12, B=1, ctx="fixed", ctx_len=256),
@@ -133,10 +139,13 @@ def reference_arm(args, w, quiet=False):
     decode step for ONE sequence and ONE layer of the workload per 'step': add_to_cache(n_tail=1)
     + collect_kv_blocks + attention_paged over the full T=ctx window, exactly what
     paged_infer.c:706-715 executes per generated token (the reference recomputes all T rows)."""
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread it can get
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     import oracle_api as oa
     NH, hs, bs = w["NH"], w["hs"], w["bs"]
     C_ = NH * hs
     T = w["ctx_len"] if w["ctx"] == "fixed" else (w["ctx_lo"] + w["ctx_hi"]) // 2
+    T = min(T, 2048)          # bounded sample: the as-written reference is O(T^2)
     geom = (16, 4352, 256)
     have = bs == 16 and oa.have_ref(*geom, "fast")
     rng = np.random.default_rng(1234)
@@ -491,7 +500,9 @@ def main():
                 "algorithmic_bytes_per_launch": kbytes, "avg_launch_ms": kms, "launches_timed": len(dec_ms) * L,
                 "timing": f"CUDA events around the {L} back-to-back per-layer launches of a step, / {L}",
                 "frac_of_nominal_8TBps": achieved / 8000.0,
-                "kernel_share_of_step": kms * L / ms_per_step}
+                "kernel_share_of_step": kms * L / ms_per_step,
+                "plan": {"heads_per_tile": lib.pa_tune_get(eng.h, 10), "ring_stages": lib.pa_tune_get(eng.h, 11),
+                         "ctas": lib.pa_tune_get(eng.h, 12)}}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

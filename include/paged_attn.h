@@ -205,6 +205,9 @@ typedef enum pa_tune_key {
     PA_TUNE_DEBUG_TIMELINE = 7,/* 1: the stream decode kernel records a per-CTA timeline (pa_debug_timeline) */
     PA_TUNE_NO_PDL = 8,        /* 1: launch the decode kernel without programmatic dependent launch */
     PA_TUNE_NO_ZEROCOPY = 9,   /* 1: pa_decode_step_host stages pinned buffers with copies instead of mapping them */
+    PA_TUNE_LAST_HPG = 10,     /* read-only: heads per tile, ring stages and CTAs of the last stream-decode launch */
+    PA_TUNE_LAST_STAGES = 11,  /*            (0 when the last decode ran on the generic kernel) */
+    PA_TUNE_LAST_GRID = 12,
     PA_TUNE_MAX
 } pa_tune_key;
 PA_API int pa_tune_set(pa_handle* h, int key, int value);

@@ -62,6 +62,7 @@ int pa_cu_init(pa_handle* h) {
     }
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     cudaStream_t s;
     CU_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     h->stream = (void*)s;

@@ -60,6 +60,7 @@ struct pa_handle {
     void* stream;                 /* handle-owned stream */
     int sm_count;
     int smem_optin;
+    int smem_per_sm;
     int tune[16];
     long launches;
     void* d_dbg;                  /* optional per-CTA timeline of the last decode launch */

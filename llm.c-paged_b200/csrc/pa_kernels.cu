@@ -793,41 +793,50 @@ size_t decode_smem_bytes(int bs, int W, int n_stages, int n_cons, int lph, int n
     return b;
 }
 
-// Choose heads per tile, stage count, grid and the static/dynamic split for this step: the
-// largest tile (whole pages when C*block_size fits) that leaves a ring of >= 4 stages and still
-// gives every SM a unit of work; when the batch is too small for that, the smallest tile (most
-// parallelism).
+// Choose heads per tile, ring depth and CTAs per SM for this step.  Measured on B200 (round 1,
+// profiles/r01_tile_sweep.txt):
+//  * a CTA turns over one (K,V) tile pair per ~0.9 us whatever the tile width (the consumer warps
+//    work on a tile in lock-step), so narrow tiles need several CTAs per SM to keep up with HBM:
+//    pairs >= 80 KB -> 1 CTA/SM, >= 36 KB -> 2, >= 18 KB -> 3, else 4;
+//  * 3 stages for tiles >= 40 KB, else 4: more bulk copies in flight cost DRAM locality
+//    (3 x 48 KB beat 4 x 48 KB; 2 CTAs x 4 x 20 KB beat 1 CTA x 8 x 20 KB by 1.5x);
+//  * the widest tile that still gives every CTA slot a unit of work; when the batch is too
+//    small for that, the narrowest tile (most parallelism).
 bool plan_decode(const pa_handle* h, int total_pages, int B, DecodePlan* plan) {
     const int hs = h->cfg.head_dim, bs = h->cfg.block_size, NH = h->cfg.n_heads;
     const int lph = hs / 4;
     const int n_cum = (B + 1 <= kMaxCumSmem) ? B + 1 : 0;
-    const int smem_cap = h->smem_optin - 1024 - n_cum * 12;
     const int want_hpg = h->tune[PA_TUNE_HEADS_PER_TILE];
-    // ring depth: measured on B200, ~150 KB of bulk copies in flight per SM is the sweet spot
-    // (3 x 48 KB pages beat 4, 4 x 24 KB beat 8): more concurrent page streams cost DRAM locality
-    const bool stages_forced = h->tune[PA_TUNE_STAGES] > 0;
-    int max_stages = stages_forced ? h->tune[PA_TUNE_STAGES] : 8;
-    int best = 0, best_stages = 0;
-    for (int min_stages = 3; min_stages >= 2 && best == 0; --min_stages) {
-        for (int hpg = NH; hpg >= 1; --hpg) {
-            if (NH % hpg) continue;
-            if (want_hpg > 0 && hpg != want_hpg) continue;
-            const int W = hpg * hs;
-            const int n_cons = ((W / 4) + 31) & ~31;
-            if (n_cons > 256) continue;
-            const size_t per_stage = (size_t)bs * W * 4 + (size_t)W * 4 + 2 * sizeof(int4) + 16;
-            const size_t fixed = (size_t)(n_cons / lph) * bs * 4 + 64 + kSegQ * 48;
-            int stages = (int)((smem_cap - fixed) / per_stage);
-            if (stages > max_stages) stages = max_stages;
-            if (!stages_forced) {
-                const int sweet = (int)((160 * 1024) / per_stage);
-                if (stages > sweet && sweet >= 3) stages = sweet;
-            }
-            if (stages < min_stages && !(want_hpg > 0 && stages >= 2)) continue;
-            best = hpg;
-            best_stages = stages;
-            if ((long long)(NH / hpg) * total_pages >= h->sm_count) break;   // enough units: keep the big tile
+    const int want_stages = h->tune[PA_TUNE_STAGES];
+    const int smem_sm = h->smem_per_sm > 0 ? h->smem_per_sm : h->smem_optin + 1024;
+    int best = 0, best_stages = 0, best_per_sm = 1;
+    for (int hpg = NH; hpg >= 1; --hpg) {
+        if (NH % hpg) continue;
+        if (want_hpg > 0 && hpg != want_hpg) continue;
+        const int W = hpg * hs;
+        const int n_cons = ((W / 4) + 31) & ~31;
+        if (n_cons > 256) continue;
+        const size_t tile = (size_t)bs * W * 4;
+        const size_t per_stage = tile + (size_t)W * 4 + 2 * sizeof(int4) + 16;
+        const size_t fixed = (size_t)(n_cons / lph) * bs * 4 + 64 + kSegQ * 48 + (size_t)n_cum * 12;
+        int per_sm = 2 * tile >= 80 * 1024 ? 1 : (2 * tile >= 36 * 1024 ? 2 : (2 * tile >= 18 * 1024 ? 3 : 4));
+        const int regs_limit = 65536 / (168 * (n_cons + 64));            // register file
+        if (per_sm > regs_limit) per_sm = regs_limit > 0 ? regs_limit : 1;
+        int stages = 0;
+        for (; per_sm >= 1; --per_sm) {
+            size_t budget = (size_t)smem_sm / per_sm - 1024;
+            if (budget > (size_t)h->smem_optin) budget = h->smem_optin;
+            if (budget <= fixed) continue;
+            stages = (int)((budget - fixed) / per_stage);
+            const int cap = want_stages > 0 ? want_stages : (tile >= 40 * 1024 ? 3 : 4);
+            if (stages > cap) stages = cap;
+            if (stages >= 2) break;
         }
+        if (stages < 2) continue;
+        best = hpg;
+        best_stages = stages;
+        best_per_sm = per_sm;
+        if ((long long)(NH / hpg) * total_pages >= (long long)h->sm_count * per_sm) break;   // enough units: keep the wide tile
     }
     if (best == 0) return false;
     plan->hpg = best;
@@ -837,12 +846,8 @@ bool plan_decode(const pa_handle* h, int total_pages, int B, DecodePlan* plan) {
     plan->n_stages = best_stages;
     plan->n_cum_smem = n_cum;
     plan->smem = decode_smem_bytes(bs, plan->W, best_stages, plan->n_cons, lph, n_cum);
-    // CTAs: one per SM when the tile ring takes most of the shared memory, more when it is small
-    int per_sm = (int)((size_t)h->smem_optin / (plan->smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
     const long long units = (long long)plan->n_hg * total_pages;
-    long long grid = (long long)h->sm_count * per_sm;
+    long long grid = (long long)h->sm_count * best_per_sm;
     if (h->tune[PA_TUNE_GRID] > 0) grid = h->tune[PA_TUNE_GRID];
     if (grid > (long long)h->sm_count * 8) grid = (long long)h->sm_count * 8;
     if (grid > units) grid = units;
@@ -1011,8 +1016,12 @@ static int decode_impl(pa_handle* h, int layer, const float* q, int q_stride, co
         cfg.numAttrs = h->tune[PA_TUNE_NO_PDL] ? 0 : 1;
         CU_CHECK(cudaLaunchKernelEx(&cfg, fn, dp));
         h->launches++;
+        h->tune[PA_TUNE_LAST_HPG] = plan.hpg;
+        h->tune[PA_TUNE_LAST_STAGES] = plan.n_stages;
+        h->tune[PA_TUNE_LAST_GRID] = plan.grid;
         return PA_OK;
     }
+    h->tune[PA_TUNE_LAST_HPG] = h->tune[PA_TUNE_LAST_STAGES] = h->tune[PA_TUNE_LAST_GRID] = 0;
     if (fused) {
         rc = pa_append(h, layer, k_new, v_new, new_stride, s);
         if (rc != PA_OK) return rc;
