@@ -208,6 +208,7 @@ typedef enum pa_tune_key {
     PA_TUNE_LAST_HPG = 10,     /* read-only: heads per tile, ring stages and CTAs of the last stream-decode launch */
     PA_TUNE_LAST_STAGES = 11,  /*            (0 when the last decode ran on the generic kernel) */
     PA_TUNE_LAST_GRID = 12,
+    PA_TUNE_PREFILL_PATH = 13, /* 0 auto (tiled fp32 SIMT), 1 tiled fp32 SIMT, 2 generic rows kernel, 3 tcgen05 TF32 (own tolerance) */
     PA_TUNE_MAX
 } pa_tune_key;
 PA_API int pa_tune_set(pa_handle* h, int key, int value);

@@ -97,6 +97,11 @@ int* pa_cu_step_host_buffer(pa_handle* h, size_t ints);
 int pa_cu_step_upload(pa_handle* h, void* stream);
 int pa_cu_is_device_ptr(const void* p);
 
+/* ---- implemented in pa_prefill.cu / pa_prefill_tc.cu ------------------------------------- */
+/* PA_OK = launched; PA_ERR_UNSUPPORTED = shape outside the kernel's domain (use the generic rows kernel) */
+int pa_cu_prefill_tiled(pa_handle* h, int layer, const float* q, int q_stride, float* out,
+                        int out_stride, int all_new_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

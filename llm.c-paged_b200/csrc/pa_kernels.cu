@@ -1053,6 +1053,12 @@ int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out
     if (rc != PA_OK) return rc;
     if (!q || !out || q_stride < h->C || out_stride < h->C) { pa_set_error("pa_prefill: bad q/out"); return PA_ERR_INVALID; }
     cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)h->stream;
+    const int path = h->tune[PA_TUNE_PREFILL_PATH];
+    if (path != 2) {
+        rc = pa_cu_prefill_tiled(h, layer, q, q_stride, out, out_stride, 1, (void*)s);
+        if (rc != PA_ERR_UNSUPPORTED) return rc;
+        if (path == 1) { pa_set_error("pa_prefill: tiled kernel needs head_dim 64/128 and 16-byte aligned rows"); return rc; }
+    }
     return launch_rows(h, layer, q, q_stride, out, out_stride, true, s);
 }
 

@@ -93,7 +93,8 @@ void* pa_stream_of(pa_handle* h) { return h ? h->stream : NULL; }
 int pa_sm_count(pa_handle* h) { return h ? h->sm_count : 0; }
 
 int pa_tune_set(pa_handle* h, int key, int value) {
-    if (!h || key < 0 || key >= PA_TUNE_MAX || key == PA_TUNE_COUNT_LAUNCHES || key >= PA_TUNE_LAST_HPG) return PA_ERR_INVALID;
+    if (!h || key < 0 || key >= PA_TUNE_MAX || key == PA_TUNE_COUNT_LAUNCHES ||
+        (key >= PA_TUNE_LAST_HPG && key <= PA_TUNE_LAST_GRID)) return PA_ERR_INVALID;
     h->tune[key] = value;
     return PA_OK;
 }

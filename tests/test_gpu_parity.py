@@ -310,22 +310,26 @@ def test_decode_step_device_and_host_entry():
 
 
 # --------------------------------------------------------------------------------- prefill rows
-@pytest.mark.parametrize("NH,hs,bs", [(12, 64, 16), (2, 5, 2), (4, 128, 32)])
-def test_prefill_rows_match_oracle(NH, hs, bs):
-    """Causal rows through the block table: prompt prefill (ctx_before = 0) and chunked prefill
-    on top of cached tokens, mixed in one batch."""
+def _run_prefill(NH, hs, bs, before, n_new, path, seed=61, kv_start=None, dist="normal", shuffle=False):
+    """Append + causal rows for a mixed batch; returns (got, want32, scenario-free copies)."""
     Cc = NH * hs
-    before = [0, 5, 40, 0]
-    n_new = [33, 7, 1, 64]
-    sc = Scenario(NH, hs, bs, before, seed=61, extra_blocks=128, max_batch_tokens=sum(n_new))   # no eviction
+    sc = Scenario(NH, hs, bs, before, seed=seed, extra_blocks=sum((n + bs - 1) // bs + 1 for n in n_new) + 8,
+                  max_batch_tokens=sum(n_new), dist=dist, shuffle=shuffle)   # no eviction
     try:
         eng, orc = sc.eng, sc.orc
         ntok = sum(n_new)
-        qkv = oa.normal((ntok, 3 * Cc), seed=62)
+        if dist == "normal":
+            qkv = oa.normal((ntok, 3 * Cc), seed=seed + 1)
+        else:
+            qkv = oa.uniform((ntok, 3 * Cc), 0.0, 100.0, seed=seed + 1)
+        eng.tune(pa.PA_TUNE_PREFILL_PATH, path)
         assert eng.step_begin(sc.seq_ids, n_new) == 0, pa.last_error()
+        if kv_start is not None:
+            assert eng.step_set_kv_start(kv_start) == 0, pa.last_error()
         pa.check(eng.upload(), "upload")
         d = pa.DevBuf.from_numpy(qkv)
         o = pa.DevBuf(ntok * Cc * 4)
+        pa.check(eng.lib.pa_memset(o.ptr, 0xff, ntok * Cc * 4, None), "memset")   # NaN canary
         pa.check(eng.append(0, d.ptr + Cc * 4, d.ptr + 2 * Cc * 4, 3 * Cc), "append")
         pa.check(eng.prefill(0, d.ptr, 3 * Cc, o.ptr, Cc), "prefill")
         eng.sync()
@@ -335,10 +339,50 @@ def test_prefill_rows_match_oracle(NH, hs, bs):
             for _ in range(n):
                 orc.add_to_cache(qkv[row][None, None, :], 1, 1, 1, prompt=s)
                 row += 1
-        want = orc.attend_rows(sc.seq_ids, [0] * 4, [b + 1 for b in before], n_new, NH, qkv[:, :Cc])
-        assert_close(got, want, "prefill rows")
+        ks = [0] * len(n_new) if kv_start is None else kv_start
+        want = orc.attend_rows(sc.seq_ids, ks, [b + 1 for b in before], n_new, NH, qkv[:, :Cc])
+        return got, want
     finally:
         sc.close()
+
+
+@pytest.mark.parametrize("path", [1, 2], ids=["tiled", "rows"])
+@pytest.mark.parametrize("NH,hs,bs", [(12, 64, 16), (2, 5, 2), (4, 128, 32)])
+def test_prefill_rows_match_oracle(NH, hs, bs, path):
+    """Causal rows through the block table: prompt prefill (ctx_before = 0) and chunked prefill
+    on top of cached tokens, mixed in one batch."""
+    if path == 1 and hs not in (64, 128):
+        pytest.skip("tiled kernel: head_dim 64/128")
+    got, want = _run_prefill(NH, hs, bs, [0, 5, 40, 0], [33, 7, 1, 64], path)
+    assert_close(got, want, "prefill rows")
+
+
+@pytest.mark.parametrize("NH,hs,bs,before,n_new", [
+    (3, 64, 16, [0, 100, 0, 17, 300], [300, 129, 128, 1, 257]),     # several q tiles, diagonal + tail tiles
+    (2, 128, 16, [0, 77, 0], [200, 65, 64]),
+    (2, 64, 4, [3, 0], [130, 70]),                                   # small pages
+    (2, 64, 3, [5, 0], [100, 64]),                                   # block size not a power of two
+    (1, 64, 32, [0], [1]),                                           # a single row
+])
+def test_prefill_tiled_shapes(NH, hs, bs, before, n_new):
+    got, want = _run_prefill(NH, hs, bs, before, n_new, 1, shuffle=True)
+    assert_close(got, want, "tiled prefill")
+
+
+def test_prefill_tiled_sliding_window():
+    """kv_start > 0 (the reference's `offset`): every row of the chunk sees [kv_start, its own token]."""
+    got, want = _run_prefill(2, 64, 16, [150, 70], [90, 140], 1, kv_start=[37, 64])
+    assert_close(got, want, "tiled prefill, window")
+
+
+def test_prefill_tiled_equals_rows_kernel_large_logits():
+    """Reference test value range U[0,100): the two kernels must agree with each other about as
+    well as either agrees with the fp32 reference (ill-conditioned softmax, see gpu_common)."""
+    got_t, want = _run_prefill(2, 64, 16, [0, 20], [70, 40], 1, dist="uniform")
+    got_r, _ = _run_prefill(2, 64, 16, [0, 20], [70, 40], 2, dist="uniform")
+    assert np.isfinite(got_t).all()
+    ref_gap = np.abs(got_r.astype(np.float64) - want).max()
+    assert np.abs(got_t.astype(np.float64) - want).max() <= max(4 * ref_gap, 1e-2)
 
 
 # --------------------------------------------------------------------------------- compat API
