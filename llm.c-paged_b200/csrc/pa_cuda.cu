@@ -110,6 +110,7 @@ void pa_cu_release(pa_handle* h) {
         h->step_ring = NULL;
     }
     if (h->host_only) return;
+    pa_cu_prefill_tc_release(h);
     cudaFree(h->pool_k); cudaFree(h->pool_v);
     cudaFree(h->d_step); cudaFree(h->d_ws); cudaFree(h->d_counters);
     cudaFree(h->d_stage);

@@ -67,6 +67,7 @@ struct pa_handle {
     int dbg_ctas;
     void* decode_attr_fn;         /* kernel whose dynamic-smem attribute has been raised */
     int max_heads;                /* heads the split workspace was sized for */
+    void* tc_state;               /* TMA tensor maps of the pool (pa_prefill_tc.cu), lazily built */
 };
 
 void pa_set_error(const char* fmt, ...);
@@ -101,6 +102,9 @@ int pa_cu_is_device_ptr(const void* p);
 /* PA_OK = launched; PA_ERR_UNSUPPORTED = shape outside the kernel's domain (use the generic rows kernel) */
 int pa_cu_prefill_tiled(pa_handle* h, int layer, const float* q, int q_stride, float* out,
                         int out_stride, int all_new_rows, void* stream);
+int pa_cu_prefill_tc(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride,
+                     void* stream);
+void pa_cu_prefill_tc_release(pa_handle* h);
 
 #ifdef __cplusplus
 }

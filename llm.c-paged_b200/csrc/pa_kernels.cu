@@ -1054,6 +1054,12 @@ int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out
     if (!q || !out || q_stride < h->C || out_stride < h->C) { pa_set_error("pa_prefill: bad q/out"); return PA_ERR_INVALID; }
     cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)h->stream;
     const int path = h->tune[PA_TUNE_PREFILL_PATH];
+    if (path == 3) {      // tensor-core TF32 variant: opt-in, own tolerance
+        rc = pa_cu_prefill_tc(h, layer, q, q_stride, out, out_stride, (void*)s);
+        if (rc == PA_ERR_UNSUPPORTED)
+            pa_set_error("pa_prefill: tcgen05 kernel needs head_dim 64/128, block_size 8..128 (power of two), 16-byte aligned rows");
+        return rc;
+    }
     if (path != 2) {
         rc = pa_cu_prefill_tiled(h, layer, q, q_stride, out, out_stride, 1, (void*)s);
         if (rc != PA_ERR_UNSUPPORTED) return rc;

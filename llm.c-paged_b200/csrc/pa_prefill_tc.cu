@@ -1,0 +1,636 @@
+/*
+ * pa_prefill_tc.cu -- tensor-core variant of the causal multi-row paged attention (prefill):
+ * tcgen05.mma kind::tf32 with accumulators in TMEM, K/V pages gathered by TMA tensor-map box
+ * copies (one box per page and 32-column block, 128-byte hardware swizzle) completing on
+ * mbarriers.  Used only where the contraction really is dense: many query rows per sequence.
+ *
+ * REDUCED PRECISION: Q, K, V and the probabilities enter the tensor cores as TF32 (10-bit
+ * mantissa, fp32 accumulate) and exp is ex2.approx.  This path is opt-in
+ * (PA_TUNE_PREFILL_PATH = 3) and has its own tolerance, stated in tests/gpu_common.py
+ * (TC_REL_TOL); the default prefill path is the fp32 SIMT kernel in pa_prefill.cu (1e-5).
+ *
+ * Semantics: attention_paged rows (paged_infer.c:163-240), as pa_prefill.cu.
+ *
+ * One CTA per (head, sequence, tile of 128 query rows) = one TMEM lane per query row:
+ *   warps 0..4*NWG-1  softmax warpgroups; warpgroup g owns key tiles g, g+NWG, ... with its own
+ *                     online-softmax state (m, l, o) -- the states are merged at the end, so the
+ *                     warpgroups never wait for each other.  A thread reads its row of S from
+ *                     TMEM (tcgen05.ld), writes P back over it (tcgen05.st) and accumulates the
+ *                     P.V tile from TMEM into registers.
+ *   warp 4*NWG        TMA producer (+ TMEM allocation)
+ *   warp 4*NWG+1      MMA issuer: S = Q.K^T (A, B from shared memory, both K-major) and
+ *                     O_tile = P.V (A = P from TMEM, B = V from shared memory, MN-major)
+ * Shared memory tiles are [32-column block][row][32 floats] with a 128-byte swizzle: for K that
+ * is the K-major SW128 layout (rows = keys = N, 16-byte chunks XOR row%8), for V the MN-major
+ * layout of a 32-bit operand (rows = keys = K, 32-byte chunks XOR row%4,
+ * CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): the same box shapes serve both, the tensor maps and
+ * descriptors differ.
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+#include "pa_internal.h"
+
+#define CU_CHECK(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            pa_set_error("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return PA_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+namespace {
+
+constexpr float kMaxInit = -10000.0f;   // paged_infer.c:187
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kBM = 128;                // query rows per CTA = TMEM lanes
+
+struct TcParams {
+    const float* q;
+    float* out;
+    const int* kv_end;
+    const int* kv_start;
+    const int* q_row0;
+    const int* table;
+    int B, C, NH, bs, tstride, q_stride, out_stride;
+    int n_tiles, layer;
+    int debug;              // 1: dump raw S of key tile 0 (first HS columns), 2: un-normalised o
+    float sl2;              // scale * log2(e): scores are handled in the exp2 domain
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "TC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra TC_DONE;\n"
+        "bra TC_WAIT;\n"
+        "TC_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// TMA: 3-D tensor-map box (columns, rows, layer) -> shared memory, completes on an mbarrier
+__device__ __forceinline__ void tma_box_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// 32 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Shared-memory matrix descriptor (sm_100 format): 128-byte swizzle, 8-row groups 1024 B apart.
+//   K-major  operand: rows = M or N index, 32 floats (128 B) of K per row; LBO unused
+//   MN-major operand: rows = K index, 32 floats (128 B) of M/N per row; LBO = bytes between
+//                     consecutive 32-column blocks
+// Layout types: 2 = SWIZZLE_128B (16-byte chunks XOR row%8; K-major operands), 1 = SWIZZLE_128B with
+// 32-byte chunks XOR row%4 -- the only layout tcgen05 accepts for an MN-major 32-bit operand
+// (rows = K index in groups of 4, SBO = bytes between groups).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3ffff) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+// Instruction descriptor: tf32 x tf32 -> f32, M x N, operand majors (0 = K-major, 1 = MN-major)
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// tile_lin -> (sequence, q tile): warp-parallel scan over ceil(nq/128)
+__device__ __forceinline__ void find_tile(const TcParams& p, int tile_lin, int& seq, int& qt, int& n_qt) {
+    const int lane = threadIdx.x & 31;
+    int run = 0;
+    seq = -1; qt = 0; n_qt = 0;
+    for (int c = 0; c < p.B; c += 32) {
+        const int i = c + lane;
+        int n = 0;
+        if (i < p.B) n = (p.q_row0[i + 1] - p.q_row0[i] + kBM - 1) / kBM;
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, run + incl > tile_lin);
+        if (hit) {
+            const int l = __ffs(hit) - 1;
+            const int excl = __shfl_sync(0xffffffffu, incl - n, l);
+            seq = c + l;
+            qt = tile_lin - run - excl;
+            n_qt = __shfl_sync(0xffffffffu, n, l);
+            return;
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+template <int HS, int BN, int NWG>
+struct TcCfg {
+    static constexpr int kThreads = NWG * 128 + 64;
+    static constexpr int kQBytes = kBM * HS * 4;
+    static constexpr int kKVBytes = BN * HS * 4;
+    static constexpr int kTileBytes = kQBytes + 2 * NWG * kKVBytes;
+    static constexpr int kBarBytes = 5 * NWG * 8 + 32;
+    static constexpr size_t kSmem = 1024 + kTileBytes + kBarBytes;     // 1024: manual alignment slack
+    static constexpr int kCols = NWG * (BN + HS);
+    static constexpr int kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
+    static_assert(NWG * BN + NWG * HS <= 512, "TMEM columns");
+    static_assert(NWG == 1 || kBM * (HS + 2) * 4 <= 2 * NWG * kKVBytes, "merge scratch must fit the K/V buffers");
+};
+
+template <int HS, int BN, int NWG>
+__global__ void __launch_bounds__(NWG * 128 + 64, (NWG == 1 && HS == 64) ? 2 : 1)
+pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const TcParams p) {
+    using Cfg = TcCfg<HS, BN, NWG>;
+    constexpr int DB = HS / 32;                         // 32-column blocks per row
+    constexpr uint32_t kIdescQK = instr_desc(kBM, BN, 0, 0);
+    constexpr uint32_t kIdescPV = instr_desc(kBM, HS, 0, 1);
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* Qs = base;                                          // [DB][128][128 B]
+    unsigned char* Ks = Qs + Cfg::kQBytes;                              // [NWG][DB][BN][128 B]
+    unsigned char* Vs = Ks + NWG * Cfg::kKVBytes;                       // [NWG][DB][BN][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + NWG * Cfg::kKVBytes);
+    uint64_t* k_full = bars;                 // TMA bytes of a K tile landed
+    uint64_t* v_full = bars + NWG;
+    uint64_t* s_full = bars + 2 * NWG;       // Q.K^T committed: S readable, K buffer free
+    uint64_t* p_ready = bars + 3 * NWG;      // the warpgroup wrote P over S
+    uint64_t* o_full = bars + 4 * NWG;       // P.V committed: O tile readable, V buffer free
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 * NWG);
+    int* s_unit = reinterpret_cast<int*>(tmem_slot + 1);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int kProducerWarp = NWG * 4, kMmaWarp = NWG * 4 + 1;
+
+    const int h = blockIdx.x / p.n_tiles;
+    const int tile_lin = blockIdx.x - h * p.n_tiles;
+    if (warp == 0) {
+        int seq, qt, n_qt;
+        find_tile(p, tile_lin, seq, qt, n_qt);
+        if (lane == 0) { s_unit[0] = seq; s_unit[1] = n_qt - 1 - qt; }     // heaviest q tile first
+    }
+    if (tid == 0) {
+        for (int b = 0; b < NWG; ++b) {
+            mbar_init(smem_u32(&k_full[b]), 1);
+            mbar_init(smem_u32(&v_full[b]), 1);
+            mbar_init(smem_u32(&s_full[b]), 1);
+            mbar_init(smem_u32(&p_ready[b]), 128);
+            mbar_init(smem_u32(&o_full[b]), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kProducerWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int seq = s_unit[0];
+    const int qt = s_unit[1];
+
+    int n_kt = 0, rows = 0, row0 = 0, nq = 0, kv_start = 0, kv_end = 0, j0 = 0, k_begin = 0;
+    if (seq >= 0) {
+        row0 = p.q_row0[seq];
+        nq = p.q_row0[seq + 1] - row0;
+        kv_start = p.kv_start[seq];
+        kv_end = p.kv_end[seq];
+        j0 = qt * kBM;
+        rows = min(kBM, nq - j0);
+        const int lim_last = kv_end - (nq - 1 - (j0 + rows - 1));
+        k_begin = (kv_start / BN) * BN;
+        n_kt = lim_last > k_begin ? (lim_last - k_begin + BN - 1) / BN : 0;
+    }
+
+    // ---- Q tile: cp.async with the 128-byte swizzle applied by hand --------------------------
+    if (warp < NWG * 4 && n_kt > 0) {
+        for (int i = tid; i < kBM * (HS / 4); i += NWG * 128) {
+            const int r = i / (HS / 4), c4 = i - r * (HS / 4);
+            const bool ok = r < rows;
+            const float* src = p.q + (size_t)(row0 + j0 + (ok ? r : 0)) * p.q_stride + h * HS + c4 * 4;
+            const int db = c4 >> 3, cc = c4 & 7;
+            cp_async16(smem_u32(Qs + db * (kBM * 128) + r * 128 + ((cc ^ (r & 7)) << 4)), src, ok ? 16 : 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA (async proxy)
+    }
+    __syncthreads();
+
+    if (warp == kProducerWarp) {
+        // ================================ TMA producer ========================================
+        if (n_kt > 0) {
+            const int* tbl = p.table + (size_t)seq * p.tstride;
+            const int n_pages = (kv_end + p.bs - 1) / p.bs;
+            const int ppt = BN / p.bs;                                   // pages per key tile
+            for (int it = 0; it < n_kt; ++it) {
+                const int b = it % NWG, j = it / NWG;
+                const int pg0 = (k_begin + it * BN) / p.bs;
+#pragma unroll
+                for (int kv = 0; kv < 2; ++kv) {
+                    // the buffer is free once the MMA that read its previous content has completed
+                    if (j > 0) mbar_wait(smem_u32(kv == 0 ? &s_full[b] : &o_full[b]), (j - 1) & 1);
+                    const uint32_t bar = smem_u32(kv == 0 ? &k_full[b] : &v_full[b]);
+                    if (lane == 0) mbar_arrive_expect_tx(bar, Cfg::kKVBytes);
+                    __syncwarp();
+                    unsigned char* dst0 = (kv == 0 ? Ks : Vs) + b * Cfg::kKVBytes;
+                    for (int pi = lane; pi < ppt; pi += 32) {
+                        // pages past the sequence's last one repeat it (their keys are masked)
+                        const int page = __ldg(tbl + min(pg0 + pi, n_pages - 1));
+#pragma unroll
+                        for (int db = 0; db < DB; ++db)
+                            tma_box_3d(smem_u32(dst0 + db * (BN * 128) + pi * p.bs * 128), kv == 0 ? &tm_k : &tm_v,
+                                       h * HS + db * 32, page * p.bs, p.layer, bar);
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ================================= MMA issuer =========================================
+        if (lane == 0 && n_kt > 0) {
+            const uint32_t q_addr = smem_u32(Qs);
+            auto issue_pv = [&](int it) {
+                const int b = it % NWG, j = it / NWG;
+                mbar_wait(smem_u32(&v_full[b]), j & 1);
+                mbar_wait(smem_u32(&p_ready[b]), j & 1);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(Vs + b * Cfg::kKVBytes);
+                const uint32_t p_tmem = tmem_base + b * BN;
+                const uint32_t o_tmem = tmem_base + NWG * BN + b * HS;
+#pragma unroll
+                for (int ks = 0; ks < BN / 8; ++ks) {        // 8 keys per instruction = one 1024-byte row group
+                    if (p.debug == 5)       // experiment: B read K-major (wrong maths, tests the A-from-TMEM path)
+                        mma_tf32_ts(o_tmem, p_tmem + ks * 8, smem_desc(v_addr + (ks & 3) * 32, 16, 1024), instr_desc(kBM, HS, 0, 0), ks > 0);
+                    else
+                        mma_tf32_ts(o_tmem, p_tmem + ks * 8, smem_desc(v_addr + ks * 1024, BN * 128, 512, 1), kIdescPV, ks > 0);
+                }
+                tc_commit(smem_u32(&o_full[b]));
+            };
+            for (int it = 0; it < n_kt; ++it) {
+                const int b = it % NWG, j = it / NWG;
+                mbar_wait(smem_u32(&k_full[b]), j & 1);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(Ks + b * Cfg::kKVBytes);
+                const uint32_t s_tmem = tmem_base + b * BN;
+#pragma unroll
+                for (int ks = 0; ks < HS / 8; ++ks) {        // 8 floats (32 B) of the head dimension per instruction
+                    const uint32_t koff = (ks >> 2) * (BN * 128) + (ks & 3) * 32;
+                    const uint32_t qoff = (ks >> 2) * (kBM * 128) + (ks & 3) * 32;
+                    mma_tf32_ss(s_tmem, smem_desc(q_addr + qoff, 16, 1024), smem_desc(k_addr + koff, 16, 1024), kIdescQK, ks > 0);
+                }
+                tc_commit(smem_u32(&s_full[b]));
+                if (it >= NWG - 1) issue_pv(it - (NWG - 1));
+            }
+            for (int it = max(0, n_kt - (NWG - 1)); it < n_kt; ++it) issue_pv(it);
+        }
+    } else {
+        // ============================== softmax warpgroups ====================================
+        const int g = warp >> 2;                         // warpgroup
+        const int wq = warp & 3;                         // TMEM lane quarter of this warp
+        const int r = wq * 32 + lane;                    // query row of the tile = TMEM lane
+        const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+        const int lim = kv_end - (nq - 1 - (j0 + r));    // this row sees keys [kv_start, lim)
+        const int lim_first = kv_end - (nq - 1 - j0);
+        float o[HS];
+#pragma unroll
+        for (int i = 0; i < HS; ++i) o[i] = 0.0f;
+        float m_run = kMaxInit * kLog2e, l_run = 0.0f;
+
+        for (int it = g; it < n_kt; it += NWG) {
+            const int j = it / NWG;
+            const int g0 = k_begin + it * BN;
+            const bool need_mask = (g0 < kv_start) || (g0 + BN > lim_first);
+            const uint32_t s_tmem = tmem_base + lane_off + g * BN;
+            mbar_wait(smem_u32(&s_full[g]), j & 1);
+            tc_fence_after();
+            // pass 1: row maximum
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < BN; c += 32) {
+                float v[32];
+                tmem_ld32(s_tmem + c, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float t = v[i] * p.sl2;
+                    if (need_mask) {
+                        const int key = g0 + c + i;
+                        if (key < kv_start || key >= lim) t = -INFINITY;
+                    }
+                    mx = fmaxf(mx, t);
+                }
+            }
+            if (p.debug == 1 && it == 0 && r < rows) {
+                float* dst = p.out + (size_t)(row0 + j0 + r) * p.out_stride + h * HS;
+#pragma unroll
+                for (int c = 0; c < HS; c += 32) {
+                    float v[32];
+                    tmem_ld32(s_tmem + c, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) dst[c + i] = v[i];
+                }
+            }
+            const float m_new = fmaxf(m_run, mx);
+            const float alpha = ex2(m_run - m_new);
+            // pass 2: probabilities, written back over S
+            float psum = 0.0f;
+#pragma unroll
+            for (int c = 0; c < BN; c += 32) {
+                float v[32];
+                tmem_ld32(s_tmem + c, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float t = fmaf(v[i], p.sl2, -m_new);
+                    if (need_mask) {
+                        const int key = g0 + c + i;
+                        if (key < kv_start || key >= lim) t = -INFINITY;
+                    }
+                    const float e = ex2(t);
+                    v[i] = e;
+                    psum += e;
+                }
+                tmem_st32(s_tmem + c, v);
+            }
+            tmem_wait_st();
+            if (p.debug == 3 && it == 0 && r < rows) {       // read P back from TMEM
+                float* dst = p.out + (size_t)(row0 + j0 + r) * p.out_stride + h * HS;
+#pragma unroll
+                for (int c = 0; c < HS; c += 32) {
+                    float v[32];
+                    tmem_ld32(s_tmem + c, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) dst[c + i] = v[i];
+                }
+                dst[HS - 1] = psum;
+            }
+            if (p.debug >= 4) {                                // sentinel in the O tile: tells a no-op MMA from zero products
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 7.0f;
+#pragma unroll
+                for (int c = 0; c < HS; c += 32) tmem_st32(tmem_base + lane_off + NWG * BN + g * HS + c, v);
+                tmem_wait_st();
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&p_ready[g]));
+            l_run = l_run * alpha + psum;
+            m_run = m_new;
+            // O tile of this key tile: o = o * alpha + P.V
+            mbar_wait(smem_u32(&o_full[g]), j & 1);
+            tc_fence_after();
+            const uint32_t o_tmem = tmem_base + lane_off + NWG * BN + g * HS;
+#pragma unroll
+            for (int c = 0; c < HS; c += 32) {
+                float v[32];
+                tmem_ld32(o_tmem + c, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha, v[i]);
+            }
+            tc_fence_before();
+        }
+
+        // ---- merge the warpgroups' states, normalise, store ----------------------------------
+        if (NWG > 1) {
+            // every MMA and copy this CTA issued has completed before a warpgroup leaves its loop
+            // with the LAST tile; the other may still be working, so meet first
+            asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
+            float* scratch = reinterpret_cast<float*>(Ks);               // [128][HS+2]
+            if (g == 1) {
+                float* dst = scratch + r * (HS + 2);
+#pragma unroll
+                for (int i = 0; i < HS; ++i) dst[i] = o[i];
+                dst[HS] = m_run;
+                dst[HS + 1] = l_run;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
+            if (g == 0) {
+                const float* src = scratch + r * (HS + 2);
+                const float m1 = src[HS], l1 = src[HS + 1];
+                const float m = fmaxf(m_run, m1);
+                const float w0 = ex2(m_run - m), w1 = ex2(m1 - m);
+                l_run = l_run * w0 + l1 * w1;
+#pragma unroll
+                for (int i = 0; i < HS; ++i) o[i] = o[i] * w0 + src[i] * w1;
+            }
+        }
+        if (g == 0 && r < rows && seq >= 0 && p.debug != 1 && p.debug != 3) {
+            const float inv = p.debug >= 2 ? 1.0f : ((l_run == 0.0f) ? 0.0f : 1.0f / l_run);
+            float* dst = p.out + (size_t)(row0 + j0 + r) * p.out_stride + h * HS;
+#pragma unroll
+            for (int i = 0; i < HS; i += 4)
+                *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kProducerWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcState {
+    CUtensorMap tm_k, tm_v;
+    bool ready;
+};
+
+encode_tiled_fn get_encode() {
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        fn = reinterpret_cast<encode_tiled_fn>(sym);
+    }
+    return fn;
+}
+
+// pool viewed as (layer, row = page*bs + slot, column) fp32; box = one page x 32 columns, 128-byte swizzle
+int make_pool_map(CUtensorMap* map, float* pool, const pa_handle* h, CUtensorMapSwizzle swizzle) {
+    encode_tiled_fn enc = get_encode();
+    if (!enc) { pa_set_error("cuTensorMapEncodeTiled not available from the driver"); return PA_ERR_CUDA; }
+    const cuuint64_t rows = (cuuint64_t)h->cfg.max_blocks * h->cfg.block_size;
+    cuuint64_t dims[3] = {(cuuint64_t)h->C, rows, (cuuint64_t)h->cfg.n_layers};
+    cuuint64_t strides[2] = {(cuuint64_t)h->C * 4, (cuuint64_t)h->layer_stride * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)h->cfg.block_size, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, pool, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { pa_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return PA_ERR_CUDA; }
+    return PA_OK;
+}
+
+template <int HS, int BN, int NWG>
+int launch_tc(const TcState* st, const TcParams& p, cudaStream_t s) {
+    using Cfg = TcCfg<HS, BN, NWG>;
+    auto fn = pa_prefill_tc_kernel<HS, BN, NWG>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+        attr_done = true;
+    }
+    fn<<<(unsigned)((long long)p.n_tiles * p.NH), Cfg::kThreads, Cfg::kSmem, s>>>(st->tm_k, st->tm_v, p);
+    CU_CHECK(cudaGetLastError());
+    return PA_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" void pa_cu_prefill_tc_release(pa_handle* h) {
+    free(h->tc_state);
+    h->tc_state = nullptr;
+}
+
+// PA_OK = launched; PA_ERR_UNSUPPORTED = outside the kernel's domain
+extern "C" int pa_cu_prefill_tc(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride,
+                                void* stream) {
+    const pa_step_layout& L = h->step;
+    const int hs = h->cfg.head_dim, bs = h->cfg.block_size;
+    if (!(hs == 64 || hs == 128)) return PA_ERR_UNSUPPORTED;
+    const int BN = hs == 64 ? 128 : 64;
+    // a page must be whole 8-row swizzle groups and divide the key tile
+    if (bs < 8 || (bs & (bs - 1)) || bs > BN) return PA_ERR_UNSUPPORTED;
+    if ((h->C % 4) || (q_stride % 4) || (out_stride % 4) || !aligned16(q) || !aligned16(out)) return PA_ERR_UNSUPPORTED;
+    TcState* st = (TcState*)h->tc_state;
+    if (!st) {
+        void* mem = nullptr;
+        if (posix_memalign(&mem, 64, sizeof(TcState)) != 0) { pa_set_error("out of host memory"); return PA_ERR_NOMEM; }
+        st = (TcState*)mem;
+        memset(st, 0, sizeof(*st));
+        h->tc_state = st;
+    }
+    if (!st->ready) {
+        // K is a K-major operand (16-byte swizzle chunks), V an MN-major one (32-byte chunks)
+        int rc = make_pool_map(&st->tm_k, h->pool_k, h, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc == PA_OK) rc = make_pool_map(&st->tm_v, h->pool_v, h, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc != PA_OK) return rc;
+        st->ready = true;
+    }
+    TcParams p;
+    p.q = q; p.out = out;
+    p.kv_end = h->d_step + L.off_kv_end;
+    p.kv_start = h->d_step + L.off_kv_start;
+    p.q_row0 = h->d_step + L.off_q_row0;
+    p.table = h->d_step + L.off_table;
+    p.B = L.nseq; p.C = h->C; p.NH = h->cfg.n_heads; p.bs = bs;
+    p.tstride = L.tstride; p.q_stride = q_stride; p.out_stride = out_stride;
+    p.layer = layer;
+    p.debug = h->tune[PA_TUNE_TC_DEBUG];
+    p.sl2 = (float)(1.0 / sqrtf((float)hs)) * kLog2e;
+    long long n_tiles = 0;
+    const int* qr = h->h_step + L.off_q_row0;
+    for (int i = 0; i < L.nseq; ++i) n_tiles += (qr[i + 1] - qr[i] + kBM - 1) / kBM;
+    if (n_tiles == 0) return PA_OK;
+    if (n_tiles * p.NH > 0x7fffffffLL) return PA_ERR_UNSUPPORTED;
+    p.n_tiles = (int)n_tiles;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nwg = h->tune[PA_TUNE_TC_WARPGROUPS] == 1 ? 1 : 2;
+    int rc;
+    if (hs == 64) rc = nwg == 1 ? launch_tc<64, 128, 1>(st, p, s) : launch_tc<64, 128, 2>(st, p, s);
+    else rc = nwg == 1 ? launch_tc<128, 64, 1>(st, p, s) : launch_tc<128, 64, 2>(st, p, s);
+    if (rc == PA_OK) h->launches++;
+    return rc;
+}

@@ -23,6 +23,8 @@ PA_ERR_INVALID, PA_ERR_NOMEM, PA_ERR_CUDA, PA_ERR_NO_DEVICE, PA_ERR_NO_BLOCKS, P
 PA_TUNE_DECODE_PATH, PA_TUNE_HEADS_PER_TILE, PA_TUNE_STAGES, PA_TUNE_GRID, PA_TUNE_COUNT_LAUNCHES = 0, 1, 2, 3, 4
 PA_TUNE_STATIC_PCT, PA_TUNE_DYN_UNITS, PA_TUNE_DEBUG_TIMELINE, PA_TUNE_NO_PDL, PA_TUNE_NO_ZEROCOPY = 5, 6, 7, 8, 9
 PA_TUNE_LAST_HPG, PA_TUNE_LAST_STAGES, PA_TUNE_LAST_GRID, PA_TUNE_PREFILL_PATH = 10, 11, 12, 13
+PA_TUNE_TC_WARPGROUPS = 14
+PA_TUNE_TC_DEBUG = 15
 
 
 class KVBlock(C.Structure):

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle_api as oa
-from gpu_common import Scenario, assert_close, assert_close_illconditioned, pa
+from gpu_common import assert_close_tc, Scenario, assert_close, assert_close_illconditioned, pa
 
 pytestmark = pytest.mark.gpu
 
@@ -310,7 +310,7 @@ def test_decode_step_device_and_host_entry():
 
 
 # --------------------------------------------------------------------------------- prefill rows
-def _run_prefill(NH, hs, bs, before, n_new, path, seed=61, kv_start=None, dist="normal", shuffle=False):
+def _run_prefill(NH, hs, bs, before, n_new, path, seed=61, kv_start=None, dist="normal", shuffle=False, nwg=0):
     """Append + causal rows for a mixed batch; returns (got, want32, scenario-free copies)."""
     Cc = NH * hs
     sc = Scenario(NH, hs, bs, before, seed=seed, extra_blocks=sum((n + bs - 1) // bs + 1 for n in n_new) + 8,
@@ -323,6 +323,7 @@ def _run_prefill(NH, hs, bs, before, n_new, path, seed=61, kv_start=None, dist="
         else:
             qkv = oa.uniform((ntok, 3 * Cc), 0.0, 100.0, seed=seed + 1)
         eng.tune(pa.PA_TUNE_PREFILL_PATH, path)
+        eng.tune(pa.PA_TUNE_TC_WARPGROUPS, nwg)
         assert eng.step_begin(sc.seq_ids, n_new) == 0, pa.last_error()
         if kv_start is not None:
             assert eng.step_set_kv_start(kv_start) == 0, pa.last_error()
@@ -367,6 +368,29 @@ def test_prefill_rows_match_oracle(NH, hs, bs, path):
 def test_prefill_tiled_shapes(NH, hs, bs, before, n_new):
     got, want = _run_prefill(NH, hs, bs, before, n_new, 1, shuffle=True)
     assert_close(got, want, "tiled prefill")
+
+
+@pytest.mark.parametrize("nwg", [1, 2])
+@pytest.mark.parametrize("NH,hs,bs,before,n_new", [
+    (3, 64, 16, [0, 100, 0, 17, 300], [300, 129, 128, 1, 257]),
+    (2, 128, 16, [0, 77, 0], [200, 65, 64]),
+    (2, 64, 8, [3, 0], [130, 70]),
+    (2, 64, 32, [0, 500], [1000, 3]),
+    (1, 128, 64, [0], [129]),
+])
+def test_prefill_tcgen05_tf32(NH, hs, bs, before, n_new, nwg):
+    """Opt-in tensor-core prefill (tcgen05 kind::tf32, TMEM accumulators, TMA page gather) against
+    the fp32 oracle at the TF32 tolerance stated in gpu_common.TC_REL_TOL."""
+    got, want = _run_prefill(NH, hs, bs, before, n_new, 3, shuffle=True, nwg=nwg)
+    err = assert_close_tc(got, want, "tcgen05 prefill")
+    print(f"tcgen05 tf32 prefill hs={hs} bs={bs} nwg={nwg}: max rel err {err:.2e}")
+
+
+def test_prefill_tcgen05_window_and_unsupported_shapes():
+    got, want = _run_prefill(2, 64, 16, [150, 70], [90, 140], 3, kv_start=[37, 64])
+    assert_close_tc(got, want, "tcgen05 prefill, window")
+    with pytest.raises(pa.PagedAttnError):          # block size 4 < one swizzle group: fails loudly, no silent fallback
+        _run_prefill(2, 64, 4, [0], [40], 3)
 
 
 def test_prefill_tiled_sliding_window():
