@@ -209,8 +209,8 @@ typedef enum pa_tune_key {
     PA_TUNE_LAST_STAGES = 11,  /*            (0 when the last decode ran on the generic kernel) */
     PA_TUNE_LAST_GRID = 12,
     PA_TUNE_PREFILL_PATH = 13, /* 0 auto (tiled fp32 SIMT), 1 tiled fp32 SIMT, 2 generic rows kernel, 3 tcgen05 TF32 (own tolerance) */
-    PA_TUNE_TC_WARPGROUPS = 14,/* tcgen05 prefill: softmax warpgroups per CTA, 0 auto (2), 1 or 2 */
-    PA_TUNE_TC_DEBUG = 15,     /* tcgen05 prefill debugging: 1 dumps raw S of key tile 0, 2 un-normalised outputs */
+    PA_TUNE_TC_WARPGROUPS = 14,/* tcgen05 prefill: softmax warpgroups per CTA, 0 auto, 1 or 2 */
+    PA_TUNE_TC_KEY_TILE = 15,  /* tcgen05 prefill, head_dim 64: keys per tile, 0 auto (128) or 64 */
     PA_TUNE_MAX
 } pa_tune_key;
 PA_API int pa_tune_set(pa_handle* h, int key, int value);

@@ -18,8 +18,8 @@
  *                     TMEM (tcgen05.ld), writes P back over it (tcgen05.st) and accumulates the
  *                     P.V tile from TMEM into registers.
  *   warp 4*NWG        TMA producer (+ TMEM allocation)
- *   warp 4*NWG+1      MMA issuer: S = Q.K^T (A, B from shared memory, both K-major) and
- *                     O_tile = P.V (A = P from TMEM, B = V from shared memory, MN-major)
+ *   warp 4*NWG+1      MMA issuer: S = Q.K^T (A = Q from TMEM, B = K from shared memory, K-major)
+ *                     and O += P.V (A = P from TMEM, B = V from shared memory, MN-major)
  * Shared memory tiles are [32-column block][row][32 floats] with a 128-byte swizzle: for K that
  * is the K-major SW128 layout (rows = keys = N, 16-byte chunks XOR row%8), for V the MN-major
  * layout of a 32-bit operand (rows = keys = K, 32-byte chunks XOR row%4,
@@ -33,6 +33,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "pa_internal.h"
 
@@ -60,7 +61,6 @@ struct TcParams {
     const int* table;
     int B, C, NH, bs, tstride, q_stride, out_stride;
     int n_tiles, layer;
-    int debug;              // 1: dump raw S of key tile 0 (first HS columns), 2: un-normalised o
     float sl2;              // scale * log2(e): scores are handled in the exp2 domain
 };
 
@@ -125,7 +125,7 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         : "memory");
 }
 // 32 consecutive columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -138,7 +138,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -213,17 +213,17 @@ struct TcCfg {
     static constexpr int kThreads = NWG * 128 + 64;
     static constexpr int kQBytes = kBM * HS * 4;
     static constexpr int kKVBytes = BN * HS * 4;
-    static constexpr int kTileBytes = kQBytes + 2 * NWG * kKVBytes;
+    static constexpr int kTileBytes = 2 * NWG * kKVBytes;
     static constexpr int kBarBytes = 5 * NWG * 8 + 32;
     static constexpr size_t kSmem = 1024 + kTileBytes + kBarBytes;     // 1024: manual alignment slack
-    static constexpr int kCols = NWG * (BN + HS);
+    static constexpr int kCols = HS + NWG * (BN + HS);      // Q | S[NWG] | O[NWG]
     static constexpr int kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
-    static_assert(NWG * BN + NWG * HS <= 512, "TMEM columns");
-    static_assert(NWG == 1 || kBM * (HS + 2) * 4 <= 2 * NWG * kKVBytes, "merge scratch must fit the K/V buffers");
+    static_assert(HS + NWG * BN + NWG * HS <= 512, "TMEM columns");
+    static_assert((NWG - 1) * kBM * (HS + 2) * 4 <= 2 * NWG * kKVBytes, "merge scratch must fit the K/V buffers");
 };
 
 template <int HS, int BN, int NWG>
-__global__ void __launch_bounds__(NWG * 128 + 64, (NWG == 1 && HS == 64) ? 2 : 1)
+__global__ void __launch_bounds__(NWG * 128 + 64, (NWG == 1 && HS == 64) ? 2 : 1)   // 1 warpgroup: two CTAs per SM overlap instead
 pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const TcParams p) {
     using Cfg = TcCfg<HS, BN, NWG>;
     constexpr int DB = HS / 32;                         // 32-column blocks per row
@@ -232,8 +232,7 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* Qs = base;                                          // [DB][128][128 B]
-    unsigned char* Ks = Qs + Cfg::kQBytes;                              // [NWG][DB][BN][128 B]
+    unsigned char* Ks = base;                                           // [NWG][DB][BN][128 B]
     unsigned char* Vs = Ks + NWG * Cfg::kKVBytes;                       // [NWG][DB][BN][128 B]
     uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + NWG * Cfg::kKVBytes);
     uint64_t* k_full = bars;                 // TMA bytes of a K tile landed
@@ -289,20 +288,30 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
         n_kt = lim_last > k_begin ? (lim_last - k_begin + BN - 1) / BN : 0;
     }
 
-    // ---- Q tile: cp.async with the 128-byte swizzle applied by hand --------------------------
+    // ---- Q tile -> TMEM columns [0, HS): thread = query row = TMEM lane.  Q is the A operand of
+    // every S = Q.K^T instruction; read from TMEM it costs no shared-memory bandwidth (from
+    // shared memory the 4 KB of A per 8-deep k-step would exceed what the SM can feed the MMA).
     if (warp < NWG * 4 && n_kt > 0) {
-        for (int i = tid; i < kBM * (HS / 4); i += NWG * 128) {
-            const int r = i / (HS / 4), c4 = i - r * (HS / 4);
-            const bool ok = r < rows;
-            const float* src = p.q + (size_t)(row0 + j0 + (ok ? r : 0)) * p.q_stride + h * HS + c4 * 4;
-            const int db = c4 >> 3, cc = c4 & 7;
-            cp_async16(smem_u32(Qs + db * (kBM * 128) + r * 128 + ((cc ^ (r & 7)) << 4)), src, ok ? 16 : 0);
+        const int g = warp >> 2, wq = warp & 3;
+        const int r = wq * 32 + lane;
+        constexpr int kColsPerWg = HS / NWG;             // each warpgroup stores its share of the columns
+        const bool ok = r < rows;
+        const float* src = p.q + (size_t)(row0 + j0 + (ok ? r : 0)) * p.q_stride + h * HS + g * kColsPerWg;
+#pragma unroll
+        for (int c = 0; c < kColsPerWg; c += 32) {
+            float qv[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(src + c + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                qv[i] = t.x; qv[i + 1] = t.y; qv[i + 2] = t.z; qv[i + 3] = t.w;
+            }
+            tmem_st32(tmem_base + ((uint32_t)(wq * 32) << 16) + g * kColsPerWg + c, qv);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA (async proxy)
+        tmem_wait_st();
     }
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
 
     if (warp == kProducerWarp) {
         // ================================ TMA producer ========================================
@@ -310,24 +319,30 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
             const int* tbl = p.table + (size_t)seq * p.tstride;
             const int n_pages = (kv_end + p.bs - 1) / p.bs;
             const int ppt = BN / p.bs;                                   // pages per key tile
+            // page ids of a tile: one lane each, fetched one tile ahead of their use
+            auto fetch_pages = [&](int it) {
+                const int pg = (k_begin + it * BN) / p.bs + lane;
+                return (lane < ppt && it < n_kt) ? __ldg(tbl + min(pg, n_pages - 1)) : 0;   // pages past the last one repeat it (their keys are masked)
+            };
+            int page_next = fetch_pages(0);
+            const uint32_t page_bytes = (uint32_t)p.bs * 128u;
             for (int it = 0; it < n_kt; ++it) {
                 const int b = it % NWG, j = it / NWG;
-                const int pg0 = (k_begin + it * BN) / p.bs;
+                const int row = page_next * p.bs;
+                page_next = fetch_pages(it + 1);
 #pragma unroll
                 for (int kv = 0; kv < 2; ++kv) {
                     // the buffer is free once the MMA that read its previous content has completed
                     if (j > 0) mbar_wait(smem_u32(kv == 0 ? &s_full[b] : &o_full[b]), (j - 1) & 1);
                     const uint32_t bar = smem_u32(kv == 0 ? &k_full[b] : &v_full[b]);
+                    const uint32_t dst0 = smem_u32((kv == 0 ? Ks : Vs) + b * Cfg::kKVBytes) + lane * page_bytes;
                     if (lane == 0) mbar_arrive_expect_tx(bar, Cfg::kKVBytes);
                     __syncwarp();
-                    unsigned char* dst0 = (kv == 0 ? Ks : Vs) + b * Cfg::kKVBytes;
-                    for (int pi = lane; pi < ppt; pi += 32) {
-                        // pages past the sequence's last one repeat it (their keys are masked)
-                        const int page = __ldg(tbl + min(pg0 + pi, n_pages - 1));
+                    // lane pi issues the boxes of page pi (measured faster than one lane issuing all)
+                    if (lane < ppt) {
 #pragma unroll
                         for (int db = 0; db < DB; ++db)
-                            tma_box_3d(smem_u32(dst0 + db * (BN * 128) + pi * p.bs * 128), kv == 0 ? &tm_k : &tm_v,
-                                       h * HS + db * 32, page * p.bs, p.layer, bar);
+                            tma_box_3d(dst0 + db * (BN * 128), kv == 0 ? &tm_k : &tm_v, h * HS + db * 32, row, p.layer, bar);
                     }
                 }
             }
@@ -335,22 +350,18 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
     } else if (warp == kMmaWarp) {
         // ================================= MMA issuer =========================================
         if (lane == 0 && n_kt > 0) {
-            const uint32_t q_addr = smem_u32(Qs);
             auto issue_pv = [&](int it) {
                 const int b = it % NWG, j = it / NWG;
                 mbar_wait(smem_u32(&v_full[b]), j & 1);
                 mbar_wait(smem_u32(&p_ready[b]), j & 1);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(Vs + b * Cfg::kKVBytes);
-                const uint32_t p_tmem = tmem_base + b * BN;
-                const uint32_t o_tmem = tmem_base + NWG * BN + b * HS;
+                const uint32_t p_tmem = tmem_base + HS + b * BN;
+                const uint32_t o_tmem = tmem_base + HS + NWG * BN + b * HS;
 #pragma unroll
-                for (int ks = 0; ks < BN / 8; ++ks) {        // 8 keys per instruction = one 1024-byte row group
-                    if (p.debug == 5)       // experiment: B read K-major (wrong maths, tests the A-from-TMEM path)
-                        mma_tf32_ts(o_tmem, p_tmem + ks * 8, smem_desc(v_addr + (ks & 3) * 32, 16, 1024), instr_desc(kBM, HS, 0, 0), ks > 0);
-                    else
-                        mma_tf32_ts(o_tmem, p_tmem + ks * 8, smem_desc(v_addr + ks * 1024, BN * 128, 512, 1), kIdescPV, ks > 0);
-                }
+                for (int ks = 0; ks < BN / 8; ++ks)          // 8 keys per instruction = two 4-row swizzle groups
+                    mma_tf32_ts(o_tmem, p_tmem + ks * 8, smem_desc(v_addr + ks * 1024, BN * 128, 512, 1), kIdescPV,
+                                (j > 0 || ks > 0) ? 1u : 0u);
                 tc_commit(smem_u32(&o_full[b]));
             };
             for (int it = 0; it < n_kt; ++it) {
@@ -358,12 +369,11 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
                 mbar_wait(smem_u32(&k_full[b]), j & 1);
                 tc_fence_after();
                 const uint32_t k_addr = smem_u32(Ks + b * Cfg::kKVBytes);
-                const uint32_t s_tmem = tmem_base + b * BN;
+                const uint32_t s_tmem = tmem_base + HS + b * BN;
 #pragma unroll
                 for (int ks = 0; ks < HS / 8; ++ks) {        // 8 floats (32 B) of the head dimension per instruction
                     const uint32_t koff = (ks >> 2) * (BN * 128) + (ks & 3) * 32;
-                    const uint32_t qoff = (ks >> 2) * (kBM * 128) + (ks & 3) * 32;
-                    mma_tf32_ss(s_tmem, smem_desc(q_addr + qoff, 16, 1024), smem_desc(k_addr + koff, 16, 1024), kIdescQK, ks > 0);
+                    mma_tf32_ts(s_tmem, tmem_base + ks * 8, smem_desc(k_addr + koff, 16, 1024), kIdescQK, ks > 0);
                 }
                 tc_commit(smem_u32(&s_full[b]));
                 if (it >= NWG - 1) issue_pv(it - (NWG - 1));
@@ -378,116 +388,101 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
         const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
         const int lim = kv_end - (nq - 1 - (j0 + r));    // this row sees keys [kv_start, lim)
         const int lim_first = kv_end - (nq - 1 - j0);
-        float o[HS];
-#pragma unroll
-        for (int i = 0; i < HS; ++i) o[i] = 0.0f;
+        const uint32_t s_tmem = tmem_base + lane_off + HS + g * BN;
+        const uint32_t o_tmem = tmem_base + lane_off + HS + NWG * BN + g * HS;
+        // exp2-domain online softmax.  The O accumulator stays in TMEM across this warpgroup's key
+        // tiles; it is rescaled only when the row maximum has grown by more than 2^8 since the
+        // maximum in use (probabilities stay <= 256, far inside fp32/tf32 range), so the common
+        // tile costs one TMEM read of S and one write of P per thread.
         float m_run = kMaxInit * kLog2e, l_run = 0.0f;
-
-        for (int it = g; it < n_kt; it += NWG) {
+        int n_mine = 0;
+        // One key tile of this warpgroup.  MASK is a compile-time flag and the two instances are
+        // reached through a real branch: only tiles that touch the window start or a row's causal
+        // limit pay for the per-element compares (as predicated code they would cost issue slots
+        // on every tile).
+        auto tile = [&](auto mask_tag, int it) {
+            constexpr bool MASK = decltype(mask_tag)::value;
             const int j = it / NWG;
             const int g0 = k_begin + it * BN;
-            const bool need_mask = (g0 < kv_start) || (g0 + BN > lim_first);
-            const uint32_t s_tmem = tmem_base + lane_off + g * BN;
             mbar_wait(smem_u32(&s_full[g]), j & 1);
             tc_fence_after();
-            // pass 1: row maximum
+            float sv[BN];
+#pragma unroll
+            for (int c = 0; c < BN; c += 32) tmem_ld32(s_tmem + c, sv + c);
+            tmem_wait_ld();
+            if (MASK) {
+#pragma unroll
+                for (int i = 0; i < BN; ++i) {
+                    const int key = g0 + i;
+                    if (key < kv_start || key >= lim) sv[i] = -INFINITY;
+                }
+            }
+            // the scale is positive, so the maximum can be taken on the raw scores
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < BN; c += 32) {
-                float v[32];
-                tmem_ld32(s_tmem + c, v);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float t = v[i] * p.sl2;
-                    if (need_mask) {
-                        const int key = g0 + c + i;
-                        if (key < kv_start || key >= lim) t = -INFINITY;
-                    }
-                    mx = fmaxf(mx, t);
-                }
-            }
-            if (p.debug == 1 && it == 0 && r < rows) {
-                float* dst = p.out + (size_t)(row0 + j0 + r) * p.out_stride + h * HS;
-#pragma unroll
-                for (int c = 0; c < HS; c += 32) {
-                    float v[32];
-                    tmem_ld32(s_tmem + c, v);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) dst[c + i] = v[i];
-                }
-            }
-            const float m_new = fmaxf(m_run, mx);
-            const float alpha = ex2(m_run - m_new);
-            // pass 2: probabilities, written back over S
+            for (int i = 0; i < BN; ++i) mx = fmaxf(mx, sv[i]);
+            const float m_new = fmaxf(m_run, mx * p.sl2);
+            const bool grow = (m_new - m_run) > 8.0f;
+            const float m_use = grow ? m_new : m_run;
+            const float neg_m = -m_use;
             float psum = 0.0f;
 #pragma unroll
-            for (int c = 0; c < BN; c += 32) {
-                float v[32];
-                tmem_ld32(s_tmem + c, v);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float t = fmaf(v[i], p.sl2, -m_new);
-                    if (need_mask) {
-                        const int key = g0 + c + i;
-                        if (key < kv_start || key >= lim) t = -INFINITY;
-                    }
-                    const float e = ex2(t);
-                    v[i] = e;
-                    psum += e;
-                }
-                tmem_st32(s_tmem + c, v);
+            for (int i = 0; i < BN; ++i) {
+                const float e = ex2(fmaf(sv[i], p.sl2, neg_m));
+                sv[i] = e;
+                psum += e;
             }
-            tmem_wait_st();
-            if (p.debug == 3 && it == 0 && r < rows) {       // read P back from TMEM
-                float* dst = p.out + (size_t)(row0 + j0 + r) * p.out_stride + h * HS;
+#pragma unroll
+            for (int c = 0; c < BN; c += 32) tmem_st32(s_tmem + c, sv + c);
+            const float alpha = grow ? ex2(m_run - m_new) : 1.0f;
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {
+                // rescale this warpgroup's O: its previous P.V must have completed, and the next one
+                // cannot start before p_ready below
+                mbar_wait(smem_u32(&o_full[g]), (j - 1) & 1);
+                tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < HS; c += 32) {
-                    float v[32];
-                    tmem_ld32(s_tmem + c, v);
+                    float ov[32];
+                    tmem_ld32(o_tmem + c, ov);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) dst[c + i] = v[i];
+                    for (int i = 0; i < 32; ++i) ov[i] *= alpha;
+                    tmem_st32(o_tmem + c, ov);
                 }
-                dst[HS - 1] = psum;
             }
-            if (p.debug >= 4) {                                // sentinel in the O tile: tells a no-op MMA from zero products
-                float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 7.0f;
-#pragma unroll
-                for (int c = 0; c < HS; c += 32) tmem_st32(tmem_base + lane_off + NWG * BN + g * HS + c, v);
-                tmem_wait_st();
-            }
+            l_run = l_run * alpha + psum;
+            m_run = m_use;
+            tmem_wait_st();
             tc_fence_before();
             mbar_arrive(smem_u32(&p_ready[g]));
-            l_run = l_run * alpha + psum;
-            m_run = m_new;
-            // O tile of this key tile: o = o * alpha + P.V
-            mbar_wait(smem_u32(&o_full[g]), j & 1);
-            tc_fence_after();
-            const uint32_t o_tmem = tmem_base + lane_off + NWG * BN + g * HS;
-#pragma unroll
-            for (int c = 0; c < HS; c += 32) {
-                float v[32];
-                tmem_ld32(o_tmem + c, v);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha, v[i]);
-            }
-            tc_fence_before();
+        };
+        for (int it = g; it < n_kt; it += NWG, ++n_mine) {
+            const int g0 = k_begin + it * BN;
+            if ((g0 < kv_start) || (g0 + BN > lim_first)) tile(std::true_type{}, it);
+            else tile(std::false_type{}, it);
         }
+        // ---- this warpgroup's O out of TMEM -----------------------------------------------------
+        float o[HS];
+        if (n_mine > 0) {
+            mbar_wait(smem_u32(&o_full[g]), (n_mine - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < HS; c += 32) tmem_ld32(o_tmem + c, o + c);
+            tmem_wait_ld();
+        } else {
+#pragma unroll
+            for (int i = 0; i < HS; ++i) o[i] = 0.0f;
+        }
+        tc_fence_before();
 
         // ---- merge the warpgroups' states, normalise, store ----------------------------------
         if (NWG > 1) {
-            // every MMA and copy this CTA issued has completed before a warpgroup leaves its loop
-            // with the LAST tile; the other may still be working, so meet first
+            // a warpgroup leaves its loop when ITS last P.V has completed; the other one may still
+            // be using the K/V buffers that double as merge scratch, so meet first
             asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
-            float* scratch = reinterpret_cast<float*>(Ks);               // [128][HS+2]
-            if (g == 1) {
-                float* dst = scratch + r * (HS + 2);
+            float* scratch = reinterpret_cast<float*>(Ks);               // [NWG-1][128][HS+2]
+            if (g > 0) {
+                float* dst = scratch + ((g - 1) * kBM + r) * (HS + 2);
 #pragma unroll
                 for (int i = 0; i < HS; ++i) dst[i] = o[i];
                 dst[HS] = m_run;
@@ -495,17 +490,21 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
             if (g == 0) {
-                const float* src = scratch + r * (HS + 2);
-                const float m1 = src[HS], l1 = src[HS + 1];
-                const float m = fmaxf(m_run, m1);
-                const float w0 = ex2(m_run - m), w1 = ex2(m1 - m);
-                l_run = l_run * w0 + l1 * w1;
+#pragma unroll 1
+                for (int og = 1; og < NWG; ++og) {
+                    const float* src = scratch + ((og - 1) * kBM + r) * (HS + 2);
+                    const float m1 = src[HS], l1 = src[HS + 1];
+                    const float m = fmaxf(m_run, m1);
+                    const float w0 = ex2(m_run - m), w1 = ex2(m1 - m);
+                    l_run = l_run * w0 + l1 * w1;
 #pragma unroll
-                for (int i = 0; i < HS; ++i) o[i] = o[i] * w0 + src[i] * w1;
+                    for (int i = 0; i < HS; ++i) o[i] = o[i] * w0 + src[i] * w1;
+                    m_run = m;
+                }
             }
         }
-        if (g == 0 && r < rows && seq >= 0 && p.debug != 1 && p.debug != 3) {
-            const float inv = p.debug >= 2 ? 1.0f : ((l_run == 0.0f) ? 0.0f : 1.0f / l_run);
+        if (g == 0 && r < rows && seq >= 0) {
+            const float inv = (l_run == 0.0f) ? 0.0f : 1.0f / l_run;
             float* dst = p.out + (size_t)(row0 + j0 + r) * p.out_stride + h * HS;
 #pragma unroll
             for (int i = 0; i < HS; i += 4)
@@ -590,7 +589,7 @@ extern "C" int pa_cu_prefill_tc(pa_handle* h, int layer, const float* q, int q_s
     const pa_step_layout& L = h->step;
     const int hs = h->cfg.head_dim, bs = h->cfg.block_size;
     if (!(hs == 64 || hs == 128)) return PA_ERR_UNSUPPORTED;
-    const int BN = hs == 64 ? 128 : 64;
+    const int BN = (hs == 64 && h->tune[PA_TUNE_TC_KEY_TILE] != 64) ? 128 : 64;     // keys per tile
     // a page must be whole 8-row swizzle groups and divide the key tile
     if (bs < 8 || (bs & (bs - 1)) || bs > BN) return PA_ERR_UNSUPPORTED;
     if ((h->C % 4) || (q_stride % 4) || (out_stride % 4) || !aligned16(q) || !aligned16(out)) return PA_ERR_UNSUPPORTED;
@@ -618,7 +617,6 @@ extern "C" int pa_cu_prefill_tc(pa_handle* h, int layer, const float* q, int q_s
     p.B = L.nseq; p.C = h->C; p.NH = h->cfg.n_heads; p.bs = bs;
     p.tstride = L.tstride; p.q_stride = q_stride; p.out_stride = out_stride;
     p.layer = layer;
-    p.debug = h->tune[PA_TUNE_TC_DEBUG];
     p.sl2 = (float)(1.0 / sqrtf((float)hs)) * kLog2e;
     long long n_tiles = 0;
     const int* qr = h->h_step + L.off_q_row0;
@@ -627,9 +625,13 @@ extern "C" int pa_cu_prefill_tc(pa_handle* h, int layer, const float* q, int q_s
     if (n_tiles * p.NH > 0x7fffffffLL) return PA_ERR_UNSUPPORTED;
     p.n_tiles = (int)n_tiles;
     cudaStream_t s = (cudaStream_t)stream;
-    const int nwg = h->tune[PA_TUNE_TC_WARPGROUPS] == 1 ? 1 : 2;
+    // measured (profiles/r01_prefill.md): head_dim 64 runs best as two 1-warpgroup CTAs per SM,
+    // head_dim 128 (one CTA per SM) with two warpgroups
+    const int want_wg = h->tune[PA_TUNE_TC_WARPGROUPS];
+    const int nwg = want_wg == 1 || want_wg == 2 ? want_wg : (hs == 64 ? 1 : 2);
     int rc;
-    if (hs == 64) rc = nwg == 1 ? launch_tc<64, 128, 1>(st, p, s) : launch_tc<64, 128, 2>(st, p, s);
+    if (hs == 64 && BN == 128) rc = nwg == 1 ? launch_tc<64, 128, 1>(st, p, s) : launch_tc<64, 128, 2>(st, p, s);
+    else if (hs == 64) rc = nwg == 1 ? launch_tc<64, 64, 1>(st, p, s) : launch_tc<64, 64, 2>(st, p, s);
     else rc = nwg == 1 ? launch_tc<128, 64, 1>(st, p, s) : launch_tc<128, 64, 2>(st, p, s);
     if (rc == PA_OK) h->launches++;
     return rc;

@@ -24,7 +24,7 @@ PA_TUNE_DECODE_PATH, PA_TUNE_HEADS_PER_TILE, PA_TUNE_STAGES, PA_TUNE_GRID, PA_TU
 PA_TUNE_STATIC_PCT, PA_TUNE_DYN_UNITS, PA_TUNE_DEBUG_TIMELINE, PA_TUNE_NO_PDL, PA_TUNE_NO_ZEROCOPY = 5, 6, 7, 8, 9
 PA_TUNE_LAST_HPG, PA_TUNE_LAST_STAGES, PA_TUNE_LAST_GRID, PA_TUNE_PREFILL_PATH = 10, 11, 12, 13
 PA_TUNE_TC_WARPGROUPS = 14
-PA_TUNE_TC_DEBUG = 15
+PA_TUNE_TC_KEY_TILE = 15
 
 
 class KVBlock(C.Structure):

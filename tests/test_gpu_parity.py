@@ -310,7 +310,7 @@ def test_decode_step_device_and_host_entry():
 
 
 # --------------------------------------------------------------------------------- prefill rows
-def _run_prefill(NH, hs, bs, before, n_new, path, seed=61, kv_start=None, dist="normal", shuffle=False, nwg=0):
+def _run_prefill(NH, hs, bs, before, n_new, path, seed=61, kv_start=None, dist="normal", shuffle=False, nwg=0, bn=0):
     """Append + causal rows for a mixed batch; returns (got, want32, scenario-free copies)."""
     Cc = NH * hs
     sc = Scenario(NH, hs, bs, before, seed=seed, extra_blocks=sum((n + bs - 1) // bs + 1 for n in n_new) + 8,
@@ -324,6 +324,7 @@ def _run_prefill(NH, hs, bs, before, n_new, path, seed=61, kv_start=None, dist="
             qkv = oa.uniform((ntok, 3 * Cc), 0.0, 100.0, seed=seed + 1)
         eng.tune(pa.PA_TUNE_PREFILL_PATH, path)
         eng.tune(pa.PA_TUNE_TC_WARPGROUPS, nwg)
+        eng.tune(pa.PA_TUNE_TC_KEY_TILE, bn)
         assert eng.step_begin(sc.seq_ids, n_new) == 0, pa.last_error()
         if kv_start is not None:
             assert eng.step_set_kv_start(kv_start) == 0, pa.last_error()
@@ -370,7 +371,7 @@ def test_prefill_tiled_shapes(NH, hs, bs, before, n_new):
     assert_close(got, want, "tiled prefill")
 
 
-@pytest.mark.parametrize("nwg", [1, 2])
+@pytest.mark.parametrize("nwg,bn", [(1, 0), (2, 0), (1, 64), (2, 64)])
 @pytest.mark.parametrize("NH,hs,bs,before,n_new", [
     (3, 64, 16, [0, 100, 0, 17, 300], [300, 129, 128, 1, 257]),
     (2, 128, 16, [0, 77, 0], [200, 65, 64]),
@@ -378,12 +379,14 @@ def test_prefill_tiled_shapes(NH, hs, bs, before, n_new):
     (2, 64, 32, [0, 500], [1000, 3]),
     (1, 128, 64, [0], [129]),
 ])
-def test_prefill_tcgen05_tf32(NH, hs, bs, before, n_new, nwg):
+def test_prefill_tcgen05_tf32(NH, hs, bs, before, n_new, nwg, bn):
     """Opt-in tensor-core prefill (tcgen05 kind::tf32, TMEM accumulators, TMA page gather) against
     the fp32 oracle at the TF32 tolerance stated in gpu_common.TC_REL_TOL."""
-    got, want = _run_prefill(NH, hs, bs, before, n_new, 3, shuffle=True, nwg=nwg)
+    if bn == 64 and hs != 64:
+        pytest.skip("key-tile knob applies to head_dim 64")
+    got, want = _run_prefill(NH, hs, bs, before, n_new, 3, shuffle=True, nwg=nwg, bn=bn)
     err = assert_close_tc(got, want, "tcgen05 prefill")
-    print(f"tcgen05 tf32 prefill hs={hs} bs={bs} nwg={nwg}: max rel err {err:.2e}")
+    print(f"tcgen05 tf32 prefill hs={hs} bs={bs} nwg={nwg} bn={bn}: max rel err {err:.2e}")
 
 
 def test_prefill_tcgen05_window_and_unsupported_shapes():

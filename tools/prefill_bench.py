@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--bs", type=int, default=16)
     ap.add_argument("--path", type=int, default=0)
     ap.add_argument("--nwg", type=int, default=0, help="tcgen05 path: softmax warpgroups per CTA")
+    ap.add_argument("--bn", type=int, default=0, help="tcgen05 path, head_dim 64: keys per tile (64/128)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--check", action="store_true", help="compare against the rows kernel (path 2) on the same inputs")
@@ -65,6 +66,7 @@ def main():
     e0, e1 = lib.pa_event_create(), lib.pa_event_create()
     eng.tune(pa.PA_TUNE_PREFILL_PATH, args.path)
     eng.tune(pa.PA_TUNE_TC_WARPGROUPS, args.nwg)
+    eng.tune(pa.PA_TUNE_TC_KEY_TILE, args.bn)
 
     def one_pass(timed):
         assert eng.step_begin(list(range(B)), [T] * B) == 0, pa.last_error()
@@ -87,7 +89,7 @@ def main():
     keys_seen = B * sum(args.before + j + 1 for j in range(T))
     flops = 4.0 * hs * NH * keys_seen
     line = {"tool": "prefill_bench", "shape": args.shape, "NH": NH, "hs": hs, "B": B, "T": T, "before": args.before,
-            "bs": bs, "path": PATH_NAMES[args.path], "nwg": args.nwg, "ms": t * 1e3, "tflops": flops / t / 1e12,
+            "bs": bs, "path": PATH_NAMES[args.path], "nwg": args.nwg, "bn": args.bn, "ms": t * 1e3, "tflops": flops / t / 1e12,
             "tokens_per_s": ntok / t, "ms_all": [round(x, 4) for x in ms]}
     if args.check:
         got = o.download((ntok, C_))
