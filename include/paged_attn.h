@@ -108,6 +108,12 @@ PA_API void attention_paged(float* out, float* preatt, float* att, float* inp,
                             float** key_blocks, float** value_blocks,
                             int B, int T, int C, int NH, int offset);
 
+/* The step before the path (paged_infer.c:92-160, call sites :703-706): fp32 GEMM with bias,
+ * out (B,T,OC) = inp (B,T,C) . weight (OC,C)^T + bias; matmul_cached computes Q for every window
+ * row and K, V only for the last row of each batch entry.  HOST or DEVICE pointers. */
+PA_API void matmul_forward(float* out, float* inp, float* weight, float* bias, int B, int T, int C, int OC);
+PA_API void matmul_cached(float* out, float* inp, float* weight, float* bias, int B, int T, int C, int OC);
+
 /* geometry used by the next create_block_manager() (<=0 keeps the current value) */
 PA_API void pa_set_default_geometry(int block_size, int max_blocks, int max_prompts);
 PA_API int pa_default_block_size(void);
@@ -167,6 +173,15 @@ PA_API int pa_decode_append(pa_handle* h, int layer, const float* q, const float
 /* Causal rows: the n_new[i] new tokens of each sequence are the queries (packed in step order);
  * row j of sequence i attends [kv_start, ctx_before + j].  fp32 SIMT. */
 PA_API int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream);
+
+/* QKV projection of the step's new tokens with the KV append fused into its epilogue
+ * (matmul_cached + add_to_cache in one kernel): x (ntok, C) rows in step order, w (3C, C), bias (3C)
+ * or NULL.  Q goes to q_out (ntok, C); K and V go straight to each token's page slot. */
+PA_API int pa_qkv_append(pa_handle* h, int layer, const float* x, int x_stride, const float* w, const float* bias,
+                         float* q_out, int q_stride, void* stream);
+/* plain fp32 GEMM with bias on device pointers: out (M,N) = x (M,K) . w (N,K)^T + bias */
+PA_API int pa_matmul_bias(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
+                          int M, int N, int K, void* stream);
 
 /* ---- whole step with HOST buffers (the end-to-end entry: H2D, append, decode, D2H, sync) -- */
 /* qkv_host: (nseq, 3C) rows of the step's sequences [q | k | v]; out_host: (nseq, C).  Pinned

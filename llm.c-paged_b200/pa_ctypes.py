@@ -96,6 +96,10 @@ def load():
         "pa_prefill": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
         "pa_decode_append": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, vp]),
         "pa_decode_step_host": (C.c_int, [vp, C.c_int, vp, vp]),
+        "pa_qkv_append": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, vp]),
+        "pa_matmul_bias": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+        "matmul_forward": (None, [vp, vp, vp, vp] + [C.c_int] * 4),
+        "matmul_cached": (None, [vp, vp, vp, vp] + [C.c_int] * 4),
         "pa_seq_len": (C.c_int, [vp, C.c_int]),
         "pa_seq_truncate": (C.c_int, [vp, C.c_int, C.c_int]),
         "pa_seq_free": (C.c_int, [vp, C.c_int]),
@@ -278,6 +282,9 @@ class PagedAttn:
 
     def prefill(self, layer, q_ptr, q_stride, out_ptr, out_stride, stream=None):
         return self.lib.pa_prefill(self.h, layer, q_ptr, q_stride, out_ptr, out_stride, stream)
+
+    def qkv_append(self, layer, x_ptr, x_stride, w_ptr, bias_ptr, q_ptr, q_stride, stream=None):
+        return self.lib.pa_qkv_append(self.h, layer, x_ptr, x_stride, w_ptr, bias_ptr, q_ptr, q_stride, stream)
 
     def decode_step_host(self, layer, qkv_ptr, out_ptr):
         return self.lib.pa_decode_step_host(self.h, layer, qkv_ptr, out_ptr)

@@ -1,0 +1,130 @@
+"""-m gpu parity tests of the row next to the path: the QKV projection with the KV
+append fused into its epilogue (pa_qkv_append), and the reference-named matmul_forward /
+matmul_cached (paged_infer.c:92-160).  Checker: oracle/paged_oracle.c (orc_matmul_*, pinned
+bit-exact to the compiled reference by tests/test_oracle_pinned.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_api as oa
+from gpu_common import REL_TOL, Scenario, assert_close, pa
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_close_gemm(got, want, what=""):
+    """GEMM outputs: max|a-b| / max|ref| <= 1e-5 (north_star's bar).  The element-wise allclose of
+    gpu_common.assert_close (atol 1e-6) does not apply: a K-term fp32 dot product is itself only
+    defined to ~sqrt(K)*6e-8*|terms| (~1e-6 here) under a change of summation order, which both the
+    -Ofast reference and any tiled kernel make."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape and np.isfinite(got).all(), what
+    err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+    assert err <= REL_TOL, f"{what}: max|a-b|/max|ref| = {err:.3e} > {REL_TOL}"
+    return err
+
+
+def _oracle_matmul(x, w, bias, cached=False, T=1):
+    ol = oa.load_oracle()
+    rows, Cc = x.shape
+    OC = w.shape[0]
+    out = np.zeros((rows, OC), dtype=np.float32)
+    fn = ol.orc_matmul_cached if cached else ol.orc_matmul_forward
+    fn(oa.fptr(out), oa.fptr(x), oa.fptr(w), oa.fptr(bias) if bias is not None else None, rows // T, T, Cc, OC)
+    return out
+
+
+@pytest.mark.parametrize("NH,hs,bs,ctx", [
+    (12, 64, 16, [1, 16, 17, 100, 333, 64, 5]),
+    (25, 64, 16, [40, 1, 129]),
+    (4, 128, 32, [31, 32, 33, 200]),
+    (3, 20, 8, [9, 2]),                        # C = 60: not a multiple of the tile sizes
+])
+def test_qkv_append_then_decode_matches_oracle(NH, hs, bs, ctx):
+    """One decode step: x -> (q | k | v) with k, v written straight to the page slots by the GEMM
+    epilogue, then paged decode attention.  Oracle: matmul_forward (the single-row case of
+    matmul_cached) -> add_to_cache -> attention row."""
+    Cc = NH * hs
+    B = len(ctx)
+    before = [c - 1 for c in ctx]
+    sc = Scenario(NH, hs, bs, before, seed=71, extra_blocks=B + 8)
+    try:
+        eng, orc, lib = sc.eng, sc.orc, sc.eng.lib
+        x = oa.normal((B, Cc), seed=72)
+        w = (oa.normal((3 * Cc, Cc), seed=73) * np.float32(1.0 / np.sqrt(Cc))).astype(np.float32)
+        bias = oa.normal((3 * Cc,), seed=74)
+        want_qkv = _oracle_matmul(x, w, bias)
+        assert eng.step_begin(sc.seq_ids, [1] * B) == 0, pa.last_error()
+        pa.check(eng.upload(), "upload")
+        dx, dw, db = pa.DevBuf.from_numpy(x), pa.DevBuf.from_numpy(w), pa.DevBuf.from_numpy(bias)
+        dq, do = pa.DevBuf(B * Cc * 4), pa.DevBuf(B * Cc * 4)
+        pa.check(eng.qkv_append(0, dx.ptr, Cc, dw.ptr, db.ptr, dq.ptr, Cc), "qkv_append")
+        pa.check(eng.decode(0, dq.ptr, Cc, do.ptr, Cc), "decode")
+        eng.sync()
+        q = dq.download((B, Cc))
+        assert_close_gemm(q, want_qkv[:, :Cc], "q")
+        k, v = eng.read_pool_rows(0, eng.slot_mapping())
+        assert_close_gemm(k, want_qkv[:, Cc:2 * Cc], "k in the page slots")
+        assert_close_gemm(v, want_qkv[:, 2 * Cc:], "v in the page slots")
+        for s in range(B):
+            orc.add_to_cache(want_qkv[s][None, None, :], 1, 1, 1, prompt=s)
+        want = orc.decode_batch(sc.seq_ids, NH, want_qkv[:, :Cc])
+        assert_close_gemm(do.download((B, Cc)), want, "decode after fused qkv append")
+    finally:
+        sc.close()
+
+
+def test_qkv_append_prefill_chunk():
+    """Several new tokens per sequence (prompt chunk): every token's K/V lands in its own slot."""
+    NH, hs, bs = 4, 64, 16
+    Cc = NH * hs
+    before, n_new = [0, 30, 7], [40, 3, 25]
+    sc = Scenario(NH, hs, bs, before, seed=81, extra_blocks=16, max_batch_tokens=sum(n_new))
+    try:
+        eng = sc.eng
+        ntok = sum(n_new)
+        x = oa.normal((ntok, Cc), seed=82)
+        w = (oa.normal((3 * Cc, Cc), seed=83) * np.float32(1.0 / np.sqrt(Cc))).astype(np.float32)
+        want = _oracle_matmul(x, w, None)
+        assert eng.step_begin(sc.seq_ids, n_new) == 0, pa.last_error()
+        pa.check(eng.upload(), "upload")
+        dx, dw = pa.DevBuf.from_numpy(x), pa.DevBuf.from_numpy(w)
+        dq = pa.DevBuf(ntok * Cc * 4)
+        pa.check(eng.qkv_append(0, dx.ptr, Cc, dw.ptr, None, dq.ptr, Cc), "qkv_append")
+        eng.sync()
+        assert_close_gemm(dq.download((ntok, Cc)), want[:, :Cc], "q")
+        k, v = eng.read_pool_rows(0, eng.slot_mapping())
+        assert_close_gemm(k, want[:, Cc:2 * Cc], "k")
+        assert_close_gemm(v, want[:, 2 * Cc:], "v")
+    finally:
+        sc.close()
+
+
+@pytest.mark.parametrize("device_buffers", [False, True], ids=["host-buffers", "device-buffers"])
+@pytest.mark.parametrize("B,T,Cc", [(2, 5, 24), (3, 64, 768), (1, 1, 100)])
+def test_compat_matmul_forward_and_cached(B, T, Cc, device_buffers):
+    """The reference's own names and (B,T,OC) layout; matmul_cached leaves the K/V columns of the
+    rows before the last one untouched (paged_infer.c:117-160)."""
+    lib = pa.load()
+    x = oa.normal((B * T, Cc), seed=91)
+    w = (oa.normal((3 * Cc, Cc), seed=92) * np.float32(1.0 / np.sqrt(Cc))).astype(np.float32)
+    bias = oa.normal((3 * Cc,), seed=93)
+    for name, cached in (("matmul_forward", False), ("matmul_cached", True)):
+        sentinel = np.float32(-7.25)
+        out = np.full((B * T, 3 * Cc), sentinel, dtype=np.float32)
+        if device_buffers:
+            bufs = [pa.DevBuf.from_numpy(a) for a in (out, x, w, bias)]
+            getattr(lib, name)(bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr, B, T, Cc, 3 * Cc)
+            got = bufs[0].download(out.shape)
+        else:
+            getattr(lib, name)(out.ctypes.data, x.ctypes.data, w.ctypes.data, bias.ctypes.data, B, T, Cc, 3 * Cc)
+            got = out
+        want = np.full((B * T, 3 * Cc), sentinel, dtype=np.float32)
+        ol = oa.load_oracle()
+        fn = ol.orc_matmul_cached if cached else ol.orc_matmul_forward
+        fn(oa.fptr(want), oa.fptr(x), oa.fptr(w), oa.fptr(bias), B, T, Cc, 3 * Cc)
+        untouched = want == sentinel
+        assert np.array_equal(got[untouched], want[untouched]), f"{name}: wrote outside its columns"
+        assert_close_gemm(got, want, name)
