@@ -1,0 +1,457 @@
+/*
+ * pa_gemm_tc.cu -- fp32-accurate tensor-core GEMM for the projections next to the attention path
+ * (SURVEY 8f.1/8f.2):   out[m][n] = bias[n] + sum_k x[m][k] * w[n][k]      (paged_infer.c:92-114)
+ *
+ * tcgen05.mma kind::tf32 with the 3xTF32 split: every fp32 operand a is used as
+ * a_hi (what the tensor core sees: the top 19 bits) and a_lo = a - a_hi, and
+ *      x.w  ~=  x_hi.w_hi + x_hi.w_lo + x_lo.w_hi          (the dropped x_lo.w_lo term is 2^-22 relative)
+ * That keeps the result inside the path's 1e-5 tolerance at a third of the TF32 tensor rate --
+ * still an order of magnitude above fp32 FFMA.  One more thing is needed for that: the tensor
+ * core's fp32 accumulate TRUNCATES (measured: results biased towards zero by ~3e-8 of the
+ * accumulator per MMA, coherently, i.e. 1.3e-5 at K=1600 if everything is summed in one TMEM
+ * accumulator).  So the leading term x_hi.w_hi is accumulated in TMEM only over chunks of 256
+ * floats of K, and the chunks are added in registers with round-to-nearest fp32 (the partial
+ * sums of different chunks have unrelated signs, so the bias no longer adds up); the two small
+ * terms go to a second TMEM accumulator whose truncation is 2^-11 further down.
+ *
+ * One CTA per (128 rows of x, BN columns of out):
+ *   warp 4       TMA producer: per 32-float k-slab one box of x (128 rows) and one of w (BN rows),
+ *                128-byte swizzle, 4-stage mbarrier ring
+ *   warps 0-3    splitter, then epilogue: thread r copies row r of the x slab into TMEM as the A
+ *                operand (raw = hi, and lo) and the warpgroup writes the w_lo slab next to the raw w
+ *                slab in shared memory (element-wise, so the swizzled layout is irrelevant)
+ *   warp 5       MMA issuer: 3 MMAs per 8-deep k-step, A from TMEM, B from shared memory
+ * Epilogue: thread r reads row r of the accumulator from TMEM, adds the bias and stores BN
+ * contiguous floats -- to the dense output row, or (fused KV append) to the token's page slot.
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+
+#include "pa_internal.h"
+
+#define CU_CHECK(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            pa_set_error("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return PA_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+namespace {
+
+constexpr int kBM = 128;          // rows per CTA = TMEM lanes
+constexpr int kBK = 32;           // floats per k-slab = one 128-byte swizzle row
+constexpr int kStages = 4;
+constexpr int kChunk = 8;          // k-slabs per main-accumulator chunk (256 floats of K)
+
+struct GemmTcParams {
+    const float* bias;       // (N) or NULL
+    float* out;              // dense destination, column n < n_dense of row m at out + m*out_stride + n
+    float* pool_k;           // destinations of columns >= n_dense (fused KV append), or NULL
+    float* pool_v;
+    const int* slots;        // [M] slot_mapping
+    int M, N, K;
+    int out_stride;
+    int n_dense;
+    int C;
+    int terms;               // 3: 3xTF32 (fp32-accurate), 1: plain TF32 (reduced precision)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "GT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra GT_DONE;\n"
+        "bra GT_WAIT;\n"
+        "GT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_box_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t smem_desc_k128(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3ffff) >> 4);
+    d |= (uint64_t)1 << 16;                    // LBO (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;          // SBO
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// the part of an fp32 value the TF32 datapath drops
+__device__ __forceinline__ float tf32_lo(float a) {
+    return a - __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+}
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kXBytes = kBM * 128;            // one k-slab of x: 128 rows x 128 B
+    static constexpr int kWBytes = BN * 128;
+    static constexpr int kStageBytes = kXBytes + 2 * kWBytes;     // x | w | w_lo
+    static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256;
+    static constexpr int kACols = 2 * kBK;               // A operand per stage: 32 raw + 32 lo columns
+    // TMEM columns: main accumulator (hi.hi) x2 (chunks alternate) | small-term accumulator | A slabs
+    static constexpr int kMain = 0, kSmall = 2 * BN, kA = 3 * BN;
+    static constexpr int kCols = 3 * BN + kStages * kACols;
+    static constexpr int kTmemCols = kCols <= 256 ? 256 : 512;
+    static_assert(kCols <= 512, "TMEM columns");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const GemmTcParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr uint32_t kIdesc = instr_desc_tf32(kBM, BN);
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + kStages * Cfg::kStageBytes);
+    uint64_t* full = bars;                       // TMA bytes of a stage landed
+    uint64_t* split = bars + kStages;            // A in TMEM and w_lo in shared memory are ready
+    uint64_t* empty = bars + 2 * kStages;        // the MMAs that read the stage have completed
+    uint64_t* done = bars + 3 * kStages;         // every MMA has completed
+    uint64_t* chunk_done = done + 1;             // [2] the chunk in main accumulator b is complete
+    uint64_t* chunk_free = done + 3;             // [2] the splitter threads have taken it into registers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 5);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+    const int n_slabs = (p.K + kBK - 1) / kBK;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&split[s]), 128);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        mbar_init(smem_u32(done), 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&chunk_done[b]), 1); mbar_init(smem_u32(&chunk_free[b]), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ================================ TMA producer ========================================
+        if (lane == 0) {
+            for (int s = 0; s < n_slabs; ++s) {
+                const int st = s % kStages, j = s / kStages;
+                if (j > 0) mbar_wait(smem_u32(&empty[st]), (j - 1) & 1);
+                unsigned char* stage = base + st * Cfg::kStageBytes;
+                const uint32_t bar = smem_u32(&full[st]);
+                mbar_arrive_expect_tx(bar, Cfg::kXBytes + Cfg::kWBytes);
+                tma_box_2d(smem_u32(stage), &tm_x, s * kBK, m0, bar);                   // rows/columns past the matrix read as zero
+                tma_box_2d(smem_u32(stage + Cfg::kXBytes), &tm_w, s * kBK, n0, bar);
+            }
+        }
+    } else if (warp == 5) {
+        // ================================= MMA issuer =========================================
+        if (lane == 0) {
+            for (int s = 0; s < n_slabs; ++s) {
+                const int st = s % kStages, j = s / kStages;
+                const int ch = s / kChunk, cb = ch & 1;
+                const bool chunk_start = (s % kChunk) == 0;
+                // main accumulator cb is reused every second chunk: the splitter threads must have read it
+                if (chunk_start && ch >= 2) { mbar_wait(smem_u32(&chunk_free[cb]), ((ch >> 1) - 1) & 1); }
+                mbar_wait(smem_u32(&split[st]), j & 1);
+                tc_fence_after();
+                const uint32_t w_addr = smem_u32(base + st * Cfg::kStageBytes + Cfg::kXBytes);
+                const uint32_t wlo_addr = w_addr + Cfg::kWBytes;
+                const uint32_t a_raw = tmem_base + Cfg::kA + st * Cfg::kACols;
+                const uint32_t a_lo = a_raw + kBK;
+                const uint32_t d_main = tmem_base + Cfg::kMain + cb * BN;
+                const uint32_t d_small = tmem_base + Cfg::kSmall;
+#pragma unroll
+                for (int ks = 0; ks < kBK / 8; ++ks) {
+                    mma_tf32_ts(d_main, a_raw + ks * 8, smem_desc_k128(w_addr + ks * 32), kIdesc, (chunk_start && ks == 0) ? 0u : 1u);
+                    if (p.terms == 3) {
+                        mma_tf32_ts(d_small, a_lo + ks * 8, smem_desc_k128(w_addr + ks * 32), kIdesc, (s > 0 || ks > 0) ? 1u : 0u);
+                        mma_tf32_ts(d_small, a_raw + ks * 8, smem_desc_k128(wlo_addr + ks * 32), kIdesc, 1u);
+                    }
+                }
+                tc_commit(smem_u32(&empty[st]));
+                if ((s % kChunk) == kChunk - 1 || s == n_slabs - 1) tc_commit(smem_u32(&chunk_done[cb]));
+            }
+            tc_commit(smem_u32(done));
+        }
+    } else {
+        // ============================ splitter, then epilogue ==================================
+        const int r = tid;                               // row of the tile = TMEM lane
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        float acc[BN];                                   // chunk sums of the leading term, round-to-nearest fp32
+#pragma unroll
+        for (int i = 0; i < BN; ++i) acc[i] = 0.0f;
+        const int n_chunks = (n_slabs + kChunk - 1) / kChunk;
+        int next_chunk = 0;                              // chunks are taken in order
+        auto take_chunk = [&](int ch) {                  // main accumulator of chunk ch -> registers
+            const int cb = ch & 1;
+            mbar_wait(smem_u32(&chunk_done[cb]), (ch >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < BN; c += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + lane_off + Cfg::kMain + cb * BN + c, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[c + i] += v[i];
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&chunk_free[cb]));
+        };
+        for (int s = 0; s < n_slabs; ++s) {
+            const int st = s % kStages, j = s / kStages;
+            // half a chunk later the MMAs of the previous chunk have long completed: no stall
+            if ((s % kChunk) == kChunk / 2 && s >= kChunk) take_chunk(next_chunk++);
+            mbar_wait(smem_u32(&full[st]), j & 1);
+            // the TMEM A slab of this stage is free once the MMAs of its previous use completed; the
+            // producer waited for exactly that before refilling the stage, and `full` comes after
+            tc_fence_after();
+            const unsigned char* xs = base + st * Cfg::kStageBytes;
+            float a[kBK];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {                // row r of the swizzled slab: chunk c sits at c ^ (r % 8)
+                const float4 v = *reinterpret_cast<const float4*>(xs + r * 128 + ((c ^ (r & 7)) << 4));
+                a[4 * c] = v.x; a[4 * c + 1] = v.y; a[4 * c + 2] = v.z; a[4 * c + 3] = v.w;
+            }
+            const uint32_t a_tmem = tmem_base + lane_off + Cfg::kA + st * Cfg::kACols;
+            tmem_st32(a_tmem, a);
+            if (p.terms == 3) {
+#pragma unroll
+                for (int i = 0; i < kBK; ++i) a[i] = tf32_lo(a[i]);
+                tmem_st32(a_tmem + kBK, a);
+                // w_lo slab: element-wise over the flat (swizzled) buffer
+                const float4* ws = reinterpret_cast<const float4*>(xs + Cfg::kXBytes);
+                float4* wl = reinterpret_cast<float4*>(const_cast<unsigned char*>(xs) + Cfg::kXBytes + Cfg::kWBytes);
+#pragma unroll
+                for (int i = 0; i < Cfg::kWBytes / 16 / 128; ++i) {
+                    const float4 v = ws[tid + i * 128];
+                    wl[tid + i * 128] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&split[st]));
+        }
+        // ---- epilogue ---------------------------------------------------------------------------
+        while (next_chunk < n_chunks) take_chunk(next_chunk++);      // the last one or two chunks
+        mbar_wait(smem_u32(done), 0);
+        tc_fence_after();
+        const int m = m0 + r;
+        const size_t slot_off = (p.slots && m < p.M) ? (size_t)p.slots[m] * p.C : 0;
+#pragma unroll
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            if (p.terms == 3) {
+                tmem_ld32(tmem_base + lane_off + Cfg::kSmall + c, v);
+                tmem_wait_ld();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+            }
+            if (m < p.M) {
+                const int n = n0 + c;
+                // a 32-column group lies entirely in one destination (Q | K | V boundaries are multiples of 32
+                // whenever this kernel is chosen)
+                float* dst;
+                if (n < p.n_dense) dst = p.out + (size_t)m * p.out_stride + n;
+                else if (n - p.n_dense < p.C) dst = p.pool_k + slot_off + (n - p.n_dense);
+                else dst = p.pool_v + slot_off + (n - p.n_dense - p.C);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (n + i < p.N) {
+                        float4 o = make_float4(acc[c + i] + v[i], acc[c + i + 1] + v[i + 1], acc[c + i + 2] + v[i + 2], acc[c + i + 3] + v[i + 3]);
+                        if (p.bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + i) = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_fn get_encode() {
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        fn = reinterpret_cast<encode_tiled_fn>(sym);
+    }
+    return fn;
+}
+// (rows, K) fp32 matrix with a row stride; box = 32 columns x box_rows rows, 128-byte swizzle, zero fill outside
+int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int row_stride, int box_rows) {
+    encode_tiled_fn enc = get_encode();
+    if (!enc) { pa_set_error("cuTensorMapEncodeTiled not available from the driver"); return PA_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_stride * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { pa_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return PA_ERR_CUDA; }
+    return PA_OK;
+}
+
+// small cache of encoded maps: the same weight matrices and activation buffers come back every step
+struct MapKey { const void* ptr; int rows, K, stride, box_rows; };
+struct MapCache {
+    static constexpr int N = 32;
+    MapKey key[N];
+    CUtensorMap map[N];
+    int used = 0, next = 0;
+    std::mutex mu;
+};
+MapCache g_maps;
+int get_map(CUtensorMap* out, const float* ptr, int rows, int K, int row_stride, int box_rows) {
+    std::lock_guard<std::mutex> lock(g_maps.mu);
+    for (int i = 0; i < g_maps.used; ++i) {
+        const MapKey& k = g_maps.key[i];
+        if (k.ptr == ptr && k.rows == rows && k.K == K && k.stride == row_stride && k.box_rows == box_rows) {
+            *out = g_maps.map[i];
+            return PA_OK;
+        }
+    }
+    int rc = make_map(out, ptr, rows, K, row_stride, box_rows);
+    if (rc != PA_OK) return rc;
+    const int i = g_maps.used < MapCache::N ? g_maps.used++ : (g_maps.next++ % MapCache::N);
+    g_maps.key[i] = MapKey{ptr, rows, K, row_stride, box_rows};
+    g_maps.map[i] = *out;
+    return PA_OK;
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams& p, cudaStream_t s) {
+    using Cfg = GemmCfg<BN>;
+    auto fn = pa_gemm3x_kernel<BN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+        attr_done = true;
+    }
+    dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM);
+    fn<<<grid, 192, Cfg::kSmem, s>>>(tx, tw, p);
+    CU_CHECK(cudaGetLastError());
+    return PA_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+/* out (M,N) = x (M,K) . w (N,K)^T + bias on the tensor cores; columns >= n_dense go to the page
+ * slots (fused KV append) when pool_k is given.  terms = 3 (3xTF32, fp32-accurate) or 1 (TF32).
+ * PA_ERR_UNSUPPORTED when the shape is outside the kernel's domain (caller falls back to SIMT). */
+extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
+                             int M, int N, int K, int n_dense, float* pool_k, float* pool_v, const int* slots, int C,
+                             int terms, void* stream) {
+    if (M <= 0 || N <= 0) return PA_OK;
+    if ((K & 3) || (x_stride & 3) || (out_stride & 3) || !aligned16(x) || !aligned16(w) || !aligned16(out) ||
+        (bias && !aligned16(bias)) || (N & 3))
+        return PA_ERR_UNSUPPORTED;
+    // a 32-column group of the epilogue must not straddle the Q | K | V boundaries
+    if (pool_k && ((n_dense & 31) || (C & 31))) return PA_ERR_UNSUPPORTED;
+    const int BN = 64;
+    CUtensorMap tx, tw;
+    int rc = get_map(&tx, x, M, K, x_stride, kBM);
+    if (rc == PA_OK) rc = get_map(&tw, w, N, K, K, BN);
+    if (rc != PA_OK) return rc;
+    GemmTcParams p;
+    p.bias = bias; p.out = out; p.pool_k = pool_k; p.pool_v = pool_v; p.slots = slots;
+    p.M = M; p.N = N; p.K = K; p.out_stride = out_stride; p.n_dense = pool_k ? n_dense : N; p.C = C;
+    p.terms = terms == 1 ? 1 : 3;
+    return launch_gemm<64>(tx, tw, p, (cudaStream_t)stream);
+}

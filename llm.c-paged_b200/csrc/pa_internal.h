@@ -61,7 +61,7 @@ struct pa_handle {
     int sm_count;
     int smem_optin;
     int smem_per_sm;
-    int tune[16];
+    int tune[32];
     long launches;
     void* d_dbg;                  /* optional per-CTA timeline of the last decode launch */
     int dbg_ctas;
@@ -105,6 +105,11 @@ int pa_cu_prefill_tiled(pa_handle* h, int layer, const float* q, int q_stride, f
 int pa_cu_prefill_tc(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride,
                      void* stream);
 void pa_cu_prefill_tc_release(pa_handle* h);
+
+/* ---- implemented in pa_gemm_tc.cu: fp32-accurate (3xTF32) tensor-core GEMM ---------------- */
+int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
+                  int M, int N, int K, int n_dense, float* pool_k, float* pool_v, const int* slots, int C,
+                  int terms, void* stream);
 
 #ifdef __cplusplus
 }

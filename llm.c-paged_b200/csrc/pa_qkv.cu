@@ -9,8 +9,10 @@
  * new K/V rows never make a round trip through a (B,T,3C) activation buffer and no separate
  * append kernel runs (the reference does matmul_cached -> add_to_cache, paged_infer.c:706-710).
  *
- * fp32 SIMT, register-tiled; both operands are K-contiguous.  The reference accumulates
- * sequentially from the bias (:105-110); this kernel accumulates per k-slab with FMA and adds
+ * Default: the 3xTF32 tensor-core GEMM in pa_gemm_tc.cu (fp32-accurate).  This file holds the
+ * fp32 SIMT kernel used for shapes outside that kernel's domain (unaligned rows, gathered input
+ * rows) and as the cross-check: register-tiled, both operands K-contiguous.  The reference
+ * accumulates sequentially from the bias (:105-110); both kernels accumulate in tiles and add
  * the bias last -- within the 1e-5 tolerance of the path (tests/test_gpu_qkv.py).
  *
  * Also exported with the reference's own names for the call at paged_infer.c:703-706:
@@ -179,7 +181,18 @@ int pa_qkv_append(pa_handle* h, int layer, const float* x, int x_stride, const f
     p.M = L.ntok; p.N = 3 * h->C; p.K = h->C;
     p.x_stride = x_stride; p.out_stride = q_stride;
     p.n_dense = h->C; p.C = h->C;
-    int rc = launch(p, stream ? (cudaStream_t)stream : (cudaStream_t)h->stream);
+    cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)h->stream;
+    const int path = h->tune[PA_TUNE_GEMM_PATH];
+    int rc = PA_ERR_UNSUPPORTED;
+    if (path != 1) {       // tensor cores: 3xTF32 keeps fp32 accuracy; plain TF32 only on request
+        rc = pa_cu_gemm_tc(x, x_stride, w, bias, q_out, q_stride, p.M, p.N, p.K, p.n_dense, p.pool_k, p.pool_v, p.slots,
+                           p.C, path == 3 ? 1 : 3, (void*)s);
+        if (rc == PA_ERR_UNSUPPORTED && path >= 2) {
+            pa_set_error("pa_qkv_append: tcgen05 GEMM needs C %% 32 == 0 and 16-byte aligned rows");
+            return rc;
+        }
+    }
+    if (rc == PA_ERR_UNSUPPORTED) rc = launch(p, s);
     if (rc == PA_OK) h->launches++;
     return rc;
 }
@@ -195,6 +208,8 @@ int pa_matmul_bias(const float* x, int x_stride, const float* w, const float* bi
     p.M = M; p.N = N; p.K = K;
     p.x_stride = x_stride; p.out_stride = out_stride;
     p.n_dense = N; p.C = 0;
+    int rc = pa_cu_gemm_tc(x, x_stride, w, bias, out, out_stride, M, N, K, N, nullptr, nullptr, nullptr, 0, 3, stream);
+    if (rc != PA_ERR_UNSUPPORTED) return rc;
     return launch(p, (cudaStream_t)stream);
 }
 

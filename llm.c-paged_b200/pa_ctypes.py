@@ -25,6 +25,7 @@ PA_TUNE_STATIC_PCT, PA_TUNE_DYN_UNITS, PA_TUNE_DEBUG_TIMELINE, PA_TUNE_NO_PDL, P
 PA_TUNE_LAST_HPG, PA_TUNE_LAST_STAGES, PA_TUNE_LAST_GRID, PA_TUNE_PREFILL_PATH = 10, 11, 12, 13
 PA_TUNE_TC_WARPGROUPS = 14
 PA_TUNE_TC_KEY_TILE = 15
+PA_TUNE_GEMM_PATH = 16
 
 
 class KVBlock(C.Structure):
