@@ -46,7 +46,9 @@ namespace {
 
 constexpr int kBM = 128;          // rows per CTA = TMEM lanes
 constexpr int kBK = 32;           // floats per k-slab = one 128-byte swizzle row
-constexpr int kStages = 4;
+constexpr int kStages = 6;        // shared-memory ring (32 KB per stage at BN = 64)
+constexpr int kAStages = 4;       // TMEM ring of A slabs
+constexpr int kMaxSplit = 4;      // CTAs of a cluster splitting K
 constexpr int kChunk = 8;          // k-slabs per main-accumulator chunk (256 floats of K)
 
 struct GemmTcParams {
@@ -158,14 +160,36 @@ struct GemmCfg {
     static constexpr int kWBytes = BN * 128;
     static constexpr int kStageBytes = kXBytes + 2 * kWBytes;     // x | w | w_lo
     static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256;
-    static constexpr int kACols = 2 * kBK;               // A operand per stage: 32 raw + 32 lo columns
-    // TMEM columns: main accumulator (hi.hi) x2 (chunks alternate) | small-term accumulator | A slabs
+    static constexpr int kACols = 2 * kBK;               // A operand per slab: 32 raw + 32 lo columns
+    // TMEM columns: main accumulator (hi.hi) x2 (chunks alternate) | small-term accumulator | A ring
     static constexpr int kMain = 0, kSmall = 2 * BN, kA = 3 * BN;
-    static constexpr int kCols = 3 * BN + kStages * kACols;
+    static constexpr int kCols = 3 * BN + kAStages * kACols;
     static constexpr int kTmemCols = kCols <= 256 ? 256 : 512;
     static_assert(kCols <= 512, "TMEM columns");
+    // split-K reduction scratch in the leader's (idle) stage buffers: [peer][float4 column][row]
+    static_assert((kMaxSplit - 1) * kBM * BN * 4 <= kStages * kStageBytes, "reduction scratch");
 };
 
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, const float4& v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// grid (N tiles, M tiles, n_split); the n_split CTAs of a cluster share an output tile and split K.
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const GemmTcParams p) {
@@ -184,7 +208,11 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
-    const int n_slabs = (p.K + kBK - 1) / kBK;
+    const int n_split = gridDim.z;
+    const int krank = n_split > 1 ? (int)cluster_rank() : 0;
+    const int total_slabs = (p.K + kBK - 1) / kBK;
+    const int slab0 = (int)((long long)krank * total_slabs / n_split);
+    const int n_slabs = (int)((long long)(krank + 1) * total_slabs / n_split) - slab0;     // >= 1: the host keeps n_split <= total_slabs
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -214,8 +242,8 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 unsigned char* stage = base + st * Cfg::kStageBytes;
                 const uint32_t bar = smem_u32(&full[st]);
                 mbar_arrive_expect_tx(bar, Cfg::kXBytes + Cfg::kWBytes);
-                tma_box_2d(smem_u32(stage), &tm_x, s * kBK, m0, bar);                   // rows/columns past the matrix read as zero
-                tma_box_2d(smem_u32(stage + Cfg::kXBytes), &tm_w, s * kBK, n0, bar);
+                tma_box_2d(smem_u32(stage), &tm_x, (slab0 + s) * kBK, m0, bar);          // rows/columns past the matrix read as zero
+                tma_box_2d(smem_u32(stage + Cfg::kXBytes), &tm_w, (slab0 + s) * kBK, n0, bar);
             }
         }
     } else if (warp == 5) {
@@ -231,7 +259,7 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 tc_fence_after();
                 const uint32_t w_addr = smem_u32(base + st * Cfg::kStageBytes + Cfg::kXBytes);
                 const uint32_t wlo_addr = w_addr + Cfg::kWBytes;
-                const uint32_t a_raw = tmem_base + Cfg::kA + st * Cfg::kACols;
+                const uint32_t a_raw = tmem_base + Cfg::kA + (s % kAStages) * Cfg::kACols;
                 const uint32_t a_lo = a_raw + kBK;
                 const uint32_t d_main = tmem_base + Cfg::kMain + cb * BN;
                 const uint32_t d_small = tmem_base + Cfg::kSmall;
@@ -248,16 +276,18 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             }
             tc_commit(smem_u32(done));
         }
-    } else {
+    }
+
+    float acc[BN];                                       // splitter threads: this CTA's share of the output row
+    const int r = tid;                                   // row of the tile = TMEM lane (threads 0..127)
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    if (warp < 4) {
         // ============================ splitter, then epilogue ==================================
-        const int r = tid;                               // row of the tile = TMEM lane
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-        float acc[BN];                                   // chunk sums of the leading term, round-to-nearest fp32
 #pragma unroll
         for (int i = 0; i < BN; ++i) acc[i] = 0.0f;
         const int n_chunks = (n_slabs + kChunk - 1) / kChunk;
         int next_chunk = 0;                              // chunks are taken in order
-        auto take_chunk = [&](int ch) {                  // main accumulator of chunk ch -> registers
+        auto take_chunk = [&](int ch) {                  // main accumulator of chunk ch -> registers (round-to-nearest adds)
             const int cb = ch & 1;
             mbar_wait(smem_u32(&chunk_done[cb]), (ch >> 1) & 1);
             tc_fence_after();
@@ -276,9 +306,13 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const int st = s % kStages, j = s / kStages;
             // half a chunk later the MMAs of the previous chunk have long completed: no stall
             if ((s % kChunk) == kChunk / 2 && s >= kChunk) take_chunk(next_chunk++);
+            // the A ring in TMEM is shorter than the stage ring: slab s reuses the columns of slab
+            // s - kAStages, whose MMAs signal the `empty` barrier of the stage that slab used
+            if (s >= kAStages) {
+                const int sp = s - kAStages;
+                mbar_wait(smem_u32(&empty[sp % kStages]), (sp / kStages) & 1);
+            }
             mbar_wait(smem_u32(&full[st]), j & 1);
-            // the TMEM A slab of this stage is free once the MMAs of its previous use completed; the
-            // producer waited for exactly that before refilling the stage, and `full` comes after
             tc_fence_after();
             const unsigned char* xs = base + st * Cfg::kStageBytes;
             float a[kBK];
@@ -287,7 +321,7 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 const float4 v = *reinterpret_cast<const float4*>(xs + r * 128 + ((c ^ (r & 7)) << 4));
                 a[4 * c] = v.x; a[4 * c + 1] = v.y; a[4 * c + 2] = v.z; a[4 * c + 3] = v.w;
             }
-            const uint32_t a_tmem = tmem_base + lane_off + Cfg::kA + st * Cfg::kACols;
+            const uint32_t a_tmem = tmem_base + lane_off + Cfg::kA + (s % kAStages) * Cfg::kACols;
             tmem_st32(a_tmem, a);
             if (p.terms == 3) {
 #pragma unroll
@@ -307,26 +341,56 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             tc_fence_before();
             mbar_arrive(smem_u32(&split[st]));
         }
-        // ---- epilogue ---------------------------------------------------------------------------
         while (next_chunk < n_chunks) take_chunk(next_chunk++);      // the last one or two chunks
         mbar_wait(smem_u32(done), 0);
         tc_fence_after();
-        const int m = m0 + r;
-        const size_t slot_off = (p.slots && m < p.M) ? (size_t)p.slots[m] * p.C : 0;
+        if (p.terms == 3) {
 #pragma unroll
-        for (int c = 0; c < BN; c += 32) {
-            float v[32];
-            if (p.terms == 3) {
+            for (int c = 0; c < BN; c += 32) {
+                float v[32];
                 tmem_ld32(tmem_base + lane_off + Cfg::kSmall + c, v);
                 tmem_wait_ld();
-            } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+                for (int i = 0; i < 32; ++i) acc[c + i] += v[i];
             }
-            if (m < p.M) {
+        }
+        tc_fence_before();
+    }
+
+    // ---- split-K: the peers hand their partial rows to the leader through distributed shared
+    // memory; the leader adds them in rank order (deterministic) ---------------------------------
+    __syncwarp();
+    if (n_split > 1) {
+        cluster_sync_all();                              // the leader's stage buffers are idle from here on
+        if (warp < 4 && krank > 0) {
+            const uint32_t dst = mapa(smem_u32(base + (size_t)(krank - 1) * kBM * BN * 4), 0);
+#pragma unroll
+            for (int c4 = 0; c4 < BN / 4; ++c4)
+                st_cluster_v4(dst + (uint32_t)(c4 * kBM + r) * 16u, make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]));
+        }
+        cluster_sync_all();
+        if (warp < 4 && krank == 0) {
+            for (int pr = 0; pr < n_split - 1; ++pr) {
+                const float4* src = reinterpret_cast<const float4*>(base + (size_t)pr * kBM * BN * 4);
+#pragma unroll
+                for (int c4 = 0; c4 < BN / 4; ++c4) {
+                    const float4 v = src[c4 * kBM + r];
+                    acc[4 * c4] += v.x; acc[4 * c4 + 1] += v.y; acc[4 * c4 + 2] += v.z; acc[4 * c4 + 3] += v.w;
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: bias, then the dense row or the token's page slot ------------------------------
+    if (warp < 4 && krank == 0) {
+        const int m = m0 + r;
+        if (m < p.M) {
+            const size_t slot_off = p.slots ? (size_t)p.slots[m] * p.C : 0;
+#pragma unroll
+            for (int c = 0; c < BN; c += 32) {
                 const int n = n0 + c;
-                // a 32-column group lies entirely in one destination (Q | K | V boundaries are multiples of 32
-                // whenever this kernel is chosen)
+                // a 32-column group lies entirely in one destination (the Q | K | V boundaries are multiples
+                // of 32 whenever this kernel is chosen)
                 float* dst;
                 if (n < p.n_dense) dst = p.out + (size_t)m * p.out_stride + n;
                 else if (n - p.n_dense < p.C) dst = p.pool_k + slot_off + (n - p.n_dense);
@@ -334,7 +398,7 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     if (n + i < p.N) {
-                        float4 o = make_float4(acc[c + i] + v[i], acc[c + i + 1] + v[i + 1], acc[c + i + 2] + v[i + 2], acc[c + i + 3] + v[i + 3]);
+                        float4 o = make_float4(acc[c + i], acc[c + i + 1], acc[c + i + 2], acc[c + i + 3]);
                         if (p.bias) {
                             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
                             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
@@ -414,7 +478,7 @@ int get_map(CUtensorMap* out, const float* ptr, int rows, int K, int row_stride,
 }
 
 template <int BN>
-int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams& p, cudaStream_t s) {
+int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams& p, int n_split, cudaStream_t s) {
     using Cfg = GemmCfg<BN>;
     auto fn = pa_gemm3x_kernel<BN>;
     static bool attr_done = false;
@@ -422,9 +486,20 @@ int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams
         CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
         attr_done = true;
     }
-    dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM);
-    fn<<<grid, 192, Cfg::kSmem, s>>>(tx, tw, p);
-    CU_CHECK(cudaGetLastError());
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, n_split);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = Cfg::kSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;     // the K splits of a tile form one cluster
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = n_split;
+    cfg.attrs = attr;
+    cfg.numAttrs = n_split > 1 ? 1 : 0;
+    CU_CHECK(cudaLaunchKernelEx(&cfg, fn, tx, tw, p));
     return PA_OK;
 }
 
@@ -437,7 +512,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
  * PA_ERR_UNSUPPORTED when the shape is outside the kernel's domain (caller falls back to SIMT). */
 extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
                              int M, int N, int K, int n_dense, float* pool_k, float* pool_v, const int* slots, int C,
-                             int terms, void* stream) {
+                             int terms, int n_split_override, void* stream) {
     if (M <= 0 || N <= 0) return PA_OK;
     if ((K & 3) || (x_stride & 3) || (out_stride & 3) || !aligned16(x) || !aligned16(w) || !aligned16(out) ||
         (bias && !aligned16(bias)) || (N & 3))
@@ -453,5 +528,19 @@ extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const
     p.bias = bias; p.out = out; p.pool_k = pool_k; p.pool_v = pool_v; p.slots = slots;
     p.M = M; p.N = N; p.K = K; p.out_stride = out_stride; p.n_dense = pool_k ? n_dense : N; p.C = C;
     p.terms = terms == 1 ? 1 : 3;
-    return launch_gemm<64>(tx, tw, p, (cudaStream_t)stream);
+    // Small M (decode): a handful of CTAs each walking all of K is latency-bound (one HBM round trip
+    // per ring refill), so K is split over a cluster until the grid covers the machine.
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (long long)((N + BN - 1) / BN) * ((M + kBM - 1) / kBM);
+    const int total_slabs = (K + kBK - 1) / kBK;
+    int n_split = 1;
+    while (n_split < kMaxSplit && tiles * n_split * 2 <= sms && total_slabs / (n_split * 2) >= 2) n_split *= 2;
+    if (n_split_override > 0) {
+        n_split = n_split_override > kMaxSplit ? kMaxSplit : n_split_override;
+        if (n_split == 3) n_split = 2;
+        while (n_split > 1 && total_slabs < n_split) n_split /= 2;
+    }
+    return launch_gemm<64>(tx, tw, p, n_split, (cudaStream_t)stream);
 }

@@ -109,7 +109,7 @@ void pa_cu_prefill_tc_release(pa_handle* h);
 /* ---- implemented in pa_gemm_tc.cu: fp32-accurate (3xTF32) tensor-core GEMM ---------------- */
 int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
                   int M, int N, int K, int n_dense, float* pool_k, float* pool_v, const int* slots, int C,
-                  int terms, void* stream);
+                  int terms, int n_split, void* stream);
 
 #ifdef __cplusplus
 }

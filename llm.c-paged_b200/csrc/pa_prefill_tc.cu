@@ -99,6 +99,15 @@ __device__ __forceinline__ void tma_box_3d(uint32_t dst, const CUtensorMap* map,
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
+// One lane of a CONVERGED warp.  tcgen05.mma / TMA instructions take their operands from uniform
+// registers: issued under a plain `lane == 0` test the compiler wraps each one in a per-lane
+// serialisation loop (~100 cycles per instruction, measured with tools/mma_bench.cu); under an
+// elect.sync predicate they are emitted straight and issue at the hardware rate.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -208,39 +217,43 @@ __device__ __forceinline__ void find_tile(const TcParams& p, int tile_lin, int& 
     }
 }
 
-template <int HS, int BN, int NWG>
+template <int HS, int BN, int NWG, int NST>
 struct TcCfg {
     static constexpr int kThreads = NWG * 128 + 64;
+    // two CTAs per SM when their tiles fit (one-warpgroup CTAs overlap through co-residency)
+    static constexpr int kMinBlocks = (NWG == 1 && 2 * (1024 + 2 * NST * BN * HS * 4 + 512) <= 227 * 1024 && 2 * (HS + BN + HS) <= 512) ? 2 : 1;
     static constexpr int kQBytes = kBM * HS * 4;
     static constexpr int kKVBytes = BN * HS * 4;
-    static constexpr int kTileBytes = 2 * NWG * kKVBytes;
-    static constexpr int kBarBytes = 5 * NWG * 8 + 32;
+    static constexpr int kTileBytes = 2 * NST * kKVBytes;      // NST-deep rings of K and V tiles
+    static constexpr int kBarBytes = (3 * NWG + 4 * NST) * 8 + 32;
     static constexpr size_t kSmem = 1024 + kTileBytes + kBarBytes;     // 1024: manual alignment slack
     static constexpr int kCols = HS + NWG * (BN + HS);      // Q | S[NWG] | O[NWG]
     static constexpr int kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
     static_assert(HS + NWG * BN + NWG * HS <= 512, "TMEM columns");
-    static_assert((NWG - 1) * kBM * (HS + 2) * 4 <= 2 * NWG * kKVBytes, "merge scratch must fit the K/V buffers");
+    static_assert((NWG - 1) * kBM * (HS + 2) * 4 <= 2 * NST * kKVBytes, "merge scratch must fit the K/V buffers");
 };
 
-template <int HS, int BN, int NWG>
-__global__ void __launch_bounds__(NWG * 128 + 64, (NWG == 1 && HS == 64) ? 2 : 1)   // 1 warpgroup: two CTAs per SM overlap instead
+template <int HS, int BN, int NWG, int NST>
+__global__ void __launch_bounds__(NWG * 128 + 64, (TcCfg<HS, BN, NWG, NST>::kMinBlocks))
 pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const TcParams p) {
-    using Cfg = TcCfg<HS, BN, NWG>;
+    using Cfg = TcCfg<HS, BN, NWG, NST>;
     constexpr int DB = HS / 32;                         // 32-column blocks per row
     constexpr uint32_t kIdescQK = instr_desc(kBM, BN, 0, 0);
     constexpr uint32_t kIdescPV = instr_desc(kBM, HS, 0, 1);
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* Ks = base;                                           // [NWG][DB][BN][128 B]
-    unsigned char* Vs = Ks + NWG * Cfg::kKVBytes;                       // [NWG][DB][BN][128 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + NWG * Cfg::kKVBytes);
-    uint64_t* k_full = bars;                 // TMA bytes of a K tile landed
-    uint64_t* v_full = bars + NWG;
-    uint64_t* s_full = bars + 2 * NWG;       // Q.K^T committed: S readable, K buffer free
-    uint64_t* p_ready = bars + 3 * NWG;      // the warpgroup wrote P over S
-    uint64_t* o_full = bars + 4 * NWG;       // P.V committed: O tile readable, V buffer free
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 * NWG);
+    unsigned char* Ks = base;                                           // [NST][DB][BN][128 B]
+    unsigned char* Vs = Ks + NST * Cfg::kKVBytes;                       // [NST][DB][BN][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + NST * Cfg::kKVBytes);
+    uint64_t* k_full = bars;                 // [NST] TMA bytes of a K tile landed
+    uint64_t* v_full = bars + NST;           // [NST]
+    uint64_t* k_empty = bars + 2 * NST;      // [NST] the Q.K^T that read the K tile has completed
+    uint64_t* v_empty = bars + 3 * NST;      // [NST] the P.V that read the V tile has completed
+    uint64_t* s_full = bars + 4 * NST;       // [NWG] Q.K^T committed: S readable
+    uint64_t* p_ready = s_full + NWG;        // [NWG] the warpgroup wrote P over S
+    uint64_t* o_full = s_full + 2 * NWG;     // [NWG] P.V committed: O holds this tile too
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3 * NWG);
     int* s_unit = reinterpret_cast<int*>(tmem_slot + 1);
 
     const int tid = threadIdx.x;
@@ -255,9 +268,13 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
         if (lane == 0) { s_unit[0] = seq; s_unit[1] = n_qt - 1 - qt; }     // heaviest q tile first
     }
     if (tid == 0) {
-        for (int b = 0; b < NWG; ++b) {
+        for (int b = 0; b < NST; ++b) {
             mbar_init(smem_u32(&k_full[b]), 1);
             mbar_init(smem_u32(&v_full[b]), 1);
+            mbar_init(smem_u32(&k_empty[b]), 1);
+            mbar_init(smem_u32(&v_empty[b]), 1);
+        }
+        for (int b = 0; b < NWG; ++b) {
             mbar_init(smem_u32(&s_full[b]), 1);
             mbar_init(smem_u32(&p_ready[b]), 128);
             mbar_init(smem_u32(&o_full[b]), 1);
@@ -326,56 +343,69 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
             };
             int page_next = fetch_pages(0);
             const uint32_t page_bytes = (uint32_t)p.bs * 128u;
+            const bool leader = elect_one();
             for (int it = 0; it < n_kt; ++it) {
-                const int b = it % NWG, j = it / NWG;
-                const int row = page_next * p.bs;
+                const int st = it % NST, j = it / NST;
+                const int page_cur = page_next;
                 page_next = fetch_pages(it + 1);
 #pragma unroll
                 for (int kv = 0; kv < 2; ++kv) {
-                    // the buffer is free once the MMA that read its previous content has completed
-                    if (j > 0) mbar_wait(smem_u32(kv == 0 ? &s_full[b] : &o_full[b]), (j - 1) & 1);
-                    const uint32_t bar = smem_u32(kv == 0 ? &k_full[b] : &v_full[b]);
-                    const uint32_t dst0 = smem_u32((kv == 0 ? Ks : Vs) + b * Cfg::kKVBytes) + lane * page_bytes;
-                    if (lane == 0) mbar_arrive_expect_tx(bar, Cfg::kKVBytes);
-                    __syncwarp();
-                    // lane pi issues the boxes of page pi (measured faster than one lane issuing all)
-                    if (lane < ppt) {
+                    // the ring slot is free once the MMA that read its previous content has completed
+                    if (j > 0) mbar_wait(smem_u32(kv == 0 ? &k_empty[st] : &v_empty[st]), (j - 1) & 1);
+                    const uint32_t bar = smem_u32(kv == 0 ? &k_full[st] : &v_full[st]);
+                    const uint32_t dst0 = smem_u32((kv == 0 ? Ks : Vs) + st * Cfg::kKVBytes);
+                    const CUtensorMap* map = kv == 0 ? &tm_k : &tm_v;
+                    if (leader) mbar_arrive_expect_tx(bar, Cfg::kKVBytes);
+                    for (int pi = 0; pi < ppt; ++pi) {
+                        const int row = __shfl_sync(0xffffffffu, page_cur, pi) * p.bs;
+                        if (leader) {
 #pragma unroll
-                        for (int db = 0; db < DB; ++db)
-                            tma_box_3d(dst0 + db * (BN * 128), kv == 0 ? &tm_k : &tm_v, h * HS + db * 32, row, p.layer, bar);
+                            for (int db = 0; db < DB; ++db)
+                                tma_box_3d(dst0 + db * (BN * 128) + pi * page_bytes, map, h * HS + db * 32, row, p.layer, bar);
+                        }
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == kMmaWarp) {
         // ================================= MMA issuer =========================================
-        if (lane == 0 && n_kt > 0) {
+        if (n_kt > 0) {
+            const bool leader = elect_one();
             auto issue_pv = [&](int it) {
-                const int b = it % NWG, j = it / NWG;
-                mbar_wait(smem_u32(&v_full[b]), j & 1);
+                const int b = it % NWG, j = it / NWG, st = it % NST;
+                mbar_wait(smem_u32(&v_full[st]), (it / NST) & 1);
                 mbar_wait(smem_u32(&p_ready[b]), j & 1);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(Vs + b * Cfg::kKVBytes);
+                const uint32_t v_addr = smem_u32(Vs + st * Cfg::kKVBytes);
                 const uint32_t p_tmem = tmem_base + HS + b * BN;
                 const uint32_t o_tmem = tmem_base + HS + NWG * BN + b * HS;
+                if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < BN / 8; ++ks)          // 8 keys per instruction = two 4-row swizzle groups
-                    mma_tf32_ts(o_tmem, p_tmem + ks * 8, smem_desc(v_addr + ks * 1024, BN * 128, 512, 1), kIdescPV,
-                                (j > 0 || ks > 0) ? 1u : 0u);
-                tc_commit(smem_u32(&o_full[b]));
+                    for (int ks = 0; ks < BN / 8; ++ks)          // 8 keys per instruction = two 4-row swizzle groups
+                        mma_tf32_ts(o_tmem, p_tmem + ks * 8, smem_desc(v_addr + ks * 1024, BN * 128, 512, 1), kIdescPV,
+                                    (j > 0 || ks > 0) ? 1u : 0u);
+                    tc_commit(smem_u32(&o_full[b]));
+                    tc_commit(smem_u32(&v_empty[st]));
+                }
+                __syncwarp();
             };
             for (int it = 0; it < n_kt; ++it) {
-                const int b = it % NWG, j = it / NWG;
-                mbar_wait(smem_u32(&k_full[b]), j & 1);
+                const int b = it % NWG, st = it % NST;
+                mbar_wait(smem_u32(&k_full[st]), (it / NST) & 1);
                 tc_fence_after();
-                const uint32_t k_addr = smem_u32(Ks + b * Cfg::kKVBytes);
+                const uint32_t k_addr = smem_u32(Ks + st * Cfg::kKVBytes);
                 const uint32_t s_tmem = tmem_base + HS + b * BN;
+                if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < HS / 8; ++ks) {        // 8 floats (32 B) of the head dimension per instruction
-                    const uint32_t koff = (ks >> 2) * (BN * 128) + (ks & 3) * 32;
-                    mma_tf32_ts(s_tmem, tmem_base + ks * 8, smem_desc(k_addr + koff, 16, 1024), kIdescQK, ks > 0);
+                    for (int ks = 0; ks < HS / 8; ++ks) {        // 8 floats (32 B) of the head dimension per instruction
+                        const uint32_t koff = (ks >> 2) * (BN * 128) + (ks & 3) * 32;
+                        mma_tf32_ts(s_tmem, tmem_base + ks * 8, smem_desc(k_addr + koff, 16, 1024), kIdescQK, ks > 0);
+                    }
+                    tc_commit(smem_u32(&s_full[b]));
+                    tc_commit(smem_u32(&k_empty[st]));
                 }
-                tc_commit(smem_u32(&s_full[b]));
+                __syncwarp();
                 if (it >= NWG - 1) issue_pv(it - (NWG - 1));
             }
             for (int it = max(0, n_kt - (NWG - 1)); it < n_kt; ++it) issue_pv(it);
@@ -560,10 +590,10 @@ int make_pool_map(CUtensorMap* map, float* pool, const pa_handle* h, CUtensorMap
     return PA_OK;
 }
 
-template <int HS, int BN, int NWG>
+template <int HS, int BN, int NWG, int NST>
 int launch_tc(const TcState* st, const TcParams& p, cudaStream_t s) {
-    using Cfg = TcCfg<HS, BN, NWG>;
-    auto fn = pa_prefill_tc_kernel<HS, BN, NWG>;
+    using Cfg = TcCfg<HS, BN, NWG, NST>;
+    auto fn = pa_prefill_tc_kernel<HS, BN, NWG, NST>;
     static bool attr_done = false;
     if (!attr_done) {
         CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
@@ -630,9 +660,11 @@ extern "C" int pa_cu_prefill_tc(pa_handle* h, int layer, const float* q, int q_s
     const int want_wg = h->tune[PA_TUNE_TC_WARPGROUPS];
     const int nwg = want_wg == 1 || want_wg == 2 ? want_wg : (hs == 64 ? 1 : 2);
     int rc;
-    if (hs == 64 && BN == 128) rc = nwg == 1 ? launch_tc<64, 128, 1>(st, p, s) : launch_tc<64, 128, 2>(st, p, s);
-    else if (hs == 64) rc = nwg == 1 ? launch_tc<64, 64, 1>(st, p, s) : launch_tc<64, 64, 2>(st, p, s);
-    else rc = nwg == 1 ? launch_tc<128, 64, 1>(st, p, s) : launch_tc<128, 64, 2>(st, p, s);
+    // K/V rings are 3 tiles deep (the load of tile i+3 starts when the MMAs of tile i have completed:
+    // with 2 the tensor pipe waited a full L2 round trip every other tile)
+    if (hs == 64 && BN == 128) rc = nwg == 1 ? launch_tc<64, 128, 1, 3>(st, p, s) : launch_tc<64, 128, 2, 3>(st, p, s);
+    else if (hs == 64) rc = nwg == 1 ? launch_tc<64, 64, 1, 3>(st, p, s) : launch_tc<64, 64, 2, 3>(st, p, s);
+    else rc = nwg == 1 ? launch_tc<128, 64, 1, 3>(st, p, s) : launch_tc<128, 64, 2, 3>(st, p, s);
     if (rc == PA_OK) h->launches++;
     return rc;
 }

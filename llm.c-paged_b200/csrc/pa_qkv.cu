@@ -186,7 +186,7 @@ int pa_qkv_append(pa_handle* h, int layer, const float* x, int x_stride, const f
     int rc = PA_ERR_UNSUPPORTED;
     if (path != 1) {       // tensor cores: 3xTF32 keeps fp32 accuracy; plain TF32 only on request
         rc = pa_cu_gemm_tc(x, x_stride, w, bias, q_out, q_stride, p.M, p.N, p.K, p.n_dense, p.pool_k, p.pool_v, p.slots,
-                           p.C, path == 3 ? 1 : 3, (void*)s);
+                           p.C, path == 3 ? 1 : 3, h->tune[PA_TUNE_GEMM_SPLIT_K], (void*)s);
         if (rc == PA_ERR_UNSUPPORTED && path >= 2) {
             pa_set_error("pa_qkv_append: tcgen05 GEMM needs C %% 32 == 0 and 16-byte aligned rows");
             return rc;
@@ -208,7 +208,7 @@ int pa_matmul_bias(const float* x, int x_stride, const float* w, const float* bi
     p.M = M; p.N = N; p.K = K;
     p.x_stride = x_stride; p.out_stride = out_stride;
     p.n_dense = N; p.C = 0;
-    int rc = pa_cu_gemm_tc(x, x_stride, w, bias, out, out_stride, M, N, K, N, nullptr, nullptr, nullptr, 0, 3, stream);
+    int rc = pa_cu_gemm_tc(x, x_stride, w, bias, out, out_stride, M, N, K, N, nullptr, nullptr, nullptr, 0, 3, 0, stream);
     if (rc != PA_ERR_UNSUPPORTED) return rc;
     return launch(p, (cudaStream_t)stream);
 }

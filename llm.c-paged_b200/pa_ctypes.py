@@ -26,6 +26,7 @@ PA_TUNE_LAST_HPG, PA_TUNE_LAST_STAGES, PA_TUNE_LAST_GRID, PA_TUNE_PREFILL_PATH =
 PA_TUNE_TC_WARPGROUPS = 14
 PA_TUNE_TC_KEY_TILE = 15
 PA_TUNE_GEMM_PATH = 16
+PA_TUNE_GEMM_SPLIT_K = 17
 
 
 class KVBlock(C.Structure):

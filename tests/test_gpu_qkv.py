@@ -80,6 +80,39 @@ def test_qkv_append_then_decode_matches_oracle(NH, hs, bs, ctx, path):
         sc.close()
 
 
+@pytest.mark.parametrize("split", [1, 2, 4])
+@pytest.mark.parametrize("B,NH,hs", [(70, 12, 64), (130, 25, 64), (3, 2, 64)])
+def test_qkv_append_split_k_clusters(B, NH, hs, split):
+    """Tensor-core GEMM with K split over a cluster of 1/2/4 CTAs (partial rows reduced through
+    distributed shared memory in rank order): same result within the path tolerance, and
+    bit-identical between two runs (deterministic reduction)."""
+    bs = 16
+    Cc = NH * hs
+    sc = Scenario(NH, hs, bs, [3] * B, seed=95, extra_blocks=B + 8)
+    try:
+        eng = sc.eng
+        x = oa.normal((B, Cc), seed=96)
+        w = (oa.normal((3 * Cc, Cc), seed=97) * np.float32(1.0 / np.sqrt(Cc))).astype(np.float32)
+        bias = oa.normal((3 * Cc,), seed=98)
+        want = _oracle_matmul(x, w, bias)
+        eng.tune(pa.PA_TUNE_GEMM_PATH, 2)
+        eng.tune(pa.PA_TUNE_GEMM_SPLIT_K, split)
+        dx, dw, db, dq = pa.DevBuf.from_numpy(x), pa.DevBuf.from_numpy(w), pa.DevBuf.from_numpy(bias), pa.DevBuf(B * Cc * 4)
+        runs = []
+        for _ in range(2):
+            assert eng.step_begin(sc.seq_ids, [1] * B) == 0, pa.last_error()
+            pa.check(eng.upload(), "upload")
+            pa.check(eng.qkv_append(0, dx.ptr, Cc, dw.ptr, db.ptr, dq.ptr, Cc), "qkv_append")
+            eng.sync()
+            k, v = eng.read_pool_rows(0, eng.slot_mapping())
+            runs.append(np.concatenate([dq.download((B, Cc)), k, v], axis=1))
+            pa.check(eng.step_rollback(), "rollback")
+        assert_close_gemm(runs[0], want, f"split-K {split}")
+        assert np.array_equal(runs[0].view(np.uint32), runs[1].view(np.uint32)), "split-K reduction is not deterministic"
+    finally:
+        sc.close()
+
+
 def test_qkv_append_plain_tf32_has_its_own_tolerance():
     """PA_TUNE_GEMM_PATH=3: one TF32 MMA per k-step (reduced precision, opt-in): ~1e-3 of max|ref|."""
     NH, hs, bs, B = 12, 64, 16, 70

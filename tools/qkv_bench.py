@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--bs", type=int, default=16)
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--split", type=int, default=0, help="tensor-core GEMM: K splits per cluster")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32, 3 tcgen05 TF32")
     args = ap.parse_args()
     pa = ge.build(quiet=True)
@@ -41,6 +42,7 @@ def main():
     pages = (ctx + bs - 1) // bs + 1
     eng = pa.PagedAttn(bs, B * pages + 8, B, NH, hs, n_layers=1, device=0, max_batch_tokens=B)
     eng.tune(pa.PA_TUNE_GEMM_PATH, args.path)
+    eng.tune(pa.PA_TUNE_GEMM_SPLIT_K, args.split)
     rng = np.random.default_rng(11)
     perm = rng.permutation(B * pages + 8)
     for s in range(B):
@@ -73,7 +75,7 @@ def main():
     ts = np.array([step() for _ in range(args.iters)])
     t_qkv, t_dec = np.median(ts[:, 0]) / 1e3, np.median(ts[:, 1]) / 1e3
     flops = 2.0 * B * 3 * C_ * C_
-    line = {"tool": "qkv_bench", "shape": args.shape, "B": B, "ctx": ctx, "C": C_, "path": args.path,
+    line = {"tool": "qkv_bench", "shape": args.shape, "B": B, "ctx": ctx, "C": C_, "path": args.path, "split": args.split,
             "qkv_append_us": t_qkv * 1e6, "qkv_tflops": flops / t_qkv / 1e12,
             "qkv_weight_gbs": 3 * C_ * C_ * 4 / t_qkv / 1e9,
             "decode_us": t_dec * 1e6, "qkv_share_of_layer": t_qkv / (t_qkv + t_dec)}
