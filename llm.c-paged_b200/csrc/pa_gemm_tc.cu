@@ -29,6 +29,8 @@
 
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "pa_internal.h"
@@ -62,6 +64,7 @@ struct GemmTcParams {
     int n_dense;
     int C;
     int terms;               // 3: 3xTF32 (fp32-accurate), 1: plain TF32 (reduced precision)
+    unsigned long long* dbg; // optional timeline of CTA (0,0,0) (PA_GEMM_DEBUG=1), NULL normally
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -93,6 +96,13 @@ __device__ __forceinline__ void tma_box_2d(uint32_t dst, const CUtensorMap* map,
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
+}
+// one lane of a CONVERGED warp: tcgen05.mma / TMA issued under an elect.sync predicate are emitted
+// straight; under a plain `lane == 0` test the compiler serialises each one (~100 cycles, tools/mma_bench.cu)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -159,7 +169,7 @@ struct GemmCfg {
     static constexpr int kXBytes = kBM * 128;            // one k-slab of x: 128 rows x 128 B
     static constexpr int kWBytes = BN * 128;
     static constexpr int kStageBytes = kXBytes + 2 * kWBytes;     // x | w | w_lo
-    static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256;
+    static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256 + BN * 4;
     static constexpr int kACols = 2 * kBK;               // A operand per slab: 32 raw + 32 lo columns
     // TMEM columns: main accumulator (hi.hi) x2 (chunks alternate) | small-term accumulator | A ring
     static constexpr int kMain = 0, kSmall = 2 * BN, kA = 3 * BN;
@@ -205,8 +215,12 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     uint64_t* chunk_done = done + 1;             // [2] the chunk in main accumulator b is complete
     uint64_t* chunk_free = done + 3;             // [2] the splitter threads have taken it into registers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 5);
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);      // [BN] this tile's bias, fetched while the pipeline fills
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+    auto stamp = [&](int i) { if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[i] = t; } };
+    stamp(0);
     const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
     const int n_split = gridDim.z;
     const int krank = n_split > 1 ? (int)cluster_rank() : 0;
@@ -224,6 +238,7 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&chunk_done[b]), 1); mbar_init(smem_u32(&chunk_free[b]), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid < BN) bias_s[tid] = (p.bias && n0 + tid < p.N) ? __ldg(p.bias + n0 + tid) : 0.0f;
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -232,37 +247,43 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    stamp(1);
+    // page slot of this thread's row (fused KV append), fetched long before the epilogue needs it
+    const int my_slot = (p.slots && warp < 4 && m0 + tid < p.M) ? __ldg(p.slots + m0 + tid) : 0;
 
     if (warp == 4) {
         // ================================ TMA producer ========================================
-        if (lane == 0) {
-            for (int s = 0; s < n_slabs; ++s) {
-                const int st = s % kStages, j = s / kStages;
-                if (j > 0) mbar_wait(smem_u32(&empty[st]), (j - 1) & 1);
-                unsigned char* stage = base + st * Cfg::kStageBytes;
-                const uint32_t bar = smem_u32(&full[st]);
+        const bool leader = elect_one();
+        for (int s = 0; s < n_slabs; ++s) {
+            const int st = s % kStages, j = s / kStages;
+            if (j > 0) mbar_wait(smem_u32(&empty[st]), (j - 1) & 1);
+            unsigned char* stage = base + st * Cfg::kStageBytes;
+            const uint32_t bar = smem_u32(&full[st]);
+            if (leader) {
                 mbar_arrive_expect_tx(bar, Cfg::kXBytes + Cfg::kWBytes);
                 tma_box_2d(smem_u32(stage), &tm_x, (slab0 + s) * kBK, m0, bar);          // rows/columns past the matrix read as zero
                 tma_box_2d(smem_u32(stage + Cfg::kXBytes), &tm_w, (slab0 + s) * kBK, n0, bar);
             }
+            __syncwarp();
         }
     } else if (warp == 5) {
         // ================================= MMA issuer =========================================
-        if (lane == 0) {
-            for (int s = 0; s < n_slabs; ++s) {
-                const int st = s % kStages, j = s / kStages;
-                const int ch = s / kChunk, cb = ch & 1;
-                const bool chunk_start = (s % kChunk) == 0;
-                // main accumulator cb is reused every second chunk: the splitter threads must have read it
-                if (chunk_start && ch >= 2) { mbar_wait(smem_u32(&chunk_free[cb]), ((ch >> 1) - 1) & 1); }
-                mbar_wait(smem_u32(&split[st]), j & 1);
-                tc_fence_after();
-                const uint32_t w_addr = smem_u32(base + st * Cfg::kStageBytes + Cfg::kXBytes);
-                const uint32_t wlo_addr = w_addr + Cfg::kWBytes;
-                const uint32_t a_raw = tmem_base + Cfg::kA + (s % kAStages) * Cfg::kACols;
-                const uint32_t a_lo = a_raw + kBK;
-                const uint32_t d_main = tmem_base + Cfg::kMain + cb * BN;
-                const uint32_t d_small = tmem_base + Cfg::kSmall;
+        const bool leader = elect_one();
+        for (int s = 0; s < n_slabs; ++s) {
+            const int st = s % kStages, j = s / kStages;
+            const int ch = s / kChunk, cb = ch & 1;
+            const bool chunk_start = (s % kChunk) == 0;
+            // main accumulator cb is reused every second chunk: the splitter threads must have read it
+            if (chunk_start && ch >= 2) { mbar_wait(smem_u32(&chunk_free[cb]), ((ch >> 1) - 1) & 1); }
+            mbar_wait(smem_u32(&split[st]), j & 1);
+            tc_fence_after();
+            const uint32_t w_addr = smem_u32(base + st * Cfg::kStageBytes + Cfg::kXBytes);
+            const uint32_t wlo_addr = w_addr + Cfg::kWBytes;
+            const uint32_t a_raw = tmem_base + Cfg::kA + (s % kAStages) * Cfg::kACols;
+            const uint32_t a_lo = a_raw + kBK;
+            const uint32_t d_main = tmem_base + Cfg::kMain + cb * BN;
+            const uint32_t d_small = tmem_base + Cfg::kSmall;
+            if (leader) {
 #pragma unroll
                 for (int ks = 0; ks < kBK / 8; ++ks) {
                     mma_tf32_ts(d_main, a_raw + ks * 8, smem_desc_k128(w_addr + ks * 32), kIdesc, (chunk_start && ks == 0) ? 0u : 1u);
@@ -274,8 +295,10 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 tc_commit(smem_u32(&empty[st]));
                 if ((s % kChunk) == kChunk - 1 || s == n_slabs - 1) tc_commit(smem_u32(&chunk_done[cb]));
             }
-            tc_commit(smem_u32(done));
+            __syncwarp();
         }
+        if (leader) tc_commit(smem_u32(done));
+        __syncwarp();
     }
 
     float acc[BN];                                       // splitter threads: this CTA's share of the output row
@@ -313,6 +336,7 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 mbar_wait(smem_u32(&empty[sp % kStages]), (sp / kStages) & 1);
             }
             mbar_wait(smem_u32(&full[st]), j & 1);
+            if (s == 0) stamp(2);
             tc_fence_after();
             const unsigned char* xs = base + st * Cfg::kStageBytes;
             float a[kBK];
@@ -341,8 +365,10 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             tc_fence_before();
             mbar_arrive(smem_u32(&split[st]));
         }
+        stamp(3);
         while (next_chunk < n_chunks) take_chunk(next_chunk++);      // the last one or two chunks
         mbar_wait(smem_u32(done), 0);
+        stamp(4);
         tc_fence_after();
         if (p.terms == 3) {
 #pragma unroll
@@ -381,11 +407,12 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
     }
 
+    stamp(5);
     // ---- epilogue: bias, then the dense row or the token's page slot ------------------------------
     if (warp < 4 && krank == 0) {
         const int m = m0 + r;
         if (m < p.M) {
-            const size_t slot_off = p.slots ? (size_t)p.slots[m] * p.C : 0;
+            const size_t slot_off = (size_t)my_slot * p.C;
 #pragma unroll
             for (int c = 0; c < BN; c += 32) {
                 const int n = n0 + c;
@@ -399,16 +426,15 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 for (int i = 0; i < 32; i += 4) {
                     if (n + i < p.N) {
                         float4 o = make_float4(acc[c + i], acc[c + i + 1], acc[c + i + 2], acc[c + i + 3]);
-                        if (p.bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                        }
+                        const float4 b = *reinterpret_cast<const float4*>(bias_s + c + i);
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                         *reinterpret_cast<float4*>(dst + i) = o;
                     }
                 }
             }
         }
     }
+    stamp(6);
     tc_fence_before();
     __syncthreads();
     if (warp == 4) {
@@ -528,6 +554,9 @@ extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const
     p.bias = bias; p.out = out; p.pool_k = pool_k; p.pool_v = pool_v; p.slots = slots;
     p.M = M; p.N = N; p.K = K; p.out_stride = out_stride; p.n_dense = pool_k ? n_dense : N; p.C = C;
     p.terms = terms == 1 ? 1 : 3;
+    static unsigned long long* d_dbg = nullptr;
+    p.dbg = nullptr;
+    if (getenv("PA_GEMM_DEBUG")) { if (!d_dbg) cudaMalloc((void**)&d_dbg, 64); p.dbg = d_dbg; }
     // Small M (decode): a handful of CTAs each walking all of K is latency-bound (one HBM round trip
     // per ring refill), so K is split over a cluster until the grid covers the machine.
     int dev = 0, sms = 148;
@@ -536,11 +565,23 @@ extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const
     const long long tiles = (long long)((N + BN - 1) / BN) * ((M + kBM - 1) / kBM);
     const int total_slabs = (K + kBK - 1) / kBK;
     int n_split = 1;
-    while (n_split < kMaxSplit && tiles * n_split * 2 <= sms && total_slabs / (n_split * 2) >= 2) n_split *= 2;
+    // clusters of 4 one-CTA-per-SM blocks fit 4 to a GPC (measured: 36 of them run in two waves), so
+    // 4-way splits only up to 32 tiles; 2-way while the grid still fits the machine in one wave
+    if (tiles * 4 <= (sms / 37) * 32 && total_slabs >= 16) n_split = 4;
+    else if (tiles * 2 <= sms && total_slabs >= 8) n_split = 2;
     if (n_split_override > 0) {
         n_split = n_split_override > kMaxSplit ? kMaxSplit : n_split_override;
         if (n_split == 3) n_split = 2;
         while (n_split > 1 && total_slabs < n_split) n_split /= 2;
     }
-    return launch_gemm<64>(tx, tw, p, n_split, (cudaStream_t)stream);
+    rc = launch_gemm<64>(tx, tw, p, n_split, (cudaStream_t)stream);
+    if (p.dbg) {      // ns since kernel entry: TMEM ready, first slab landed, splitter done, MMAs done, reduction done, stores issued
+        unsigned long long hst[8];
+        cudaDeviceSynchronize();
+        cudaMemcpy(hst, d_dbg, 56, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "gemm dbg split=%d:", n_split);
+        for (int i = 1; i < 7; ++i) fprintf(stderr, " t%d=%lld", i, (long long)(hst[i] - hst[0]));
+        fprintf(stderr, "\n");
+    }
+    return rc;
 }
