@@ -110,6 +110,14 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src_
                  ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// One lane of a CONVERGED warp.  Bulk-copy (UBLKCP) operands live in uniform registers: issued
+// under a per-lane test the compiler wraps every copy in a lane-serialisation loop (~100 cycles
+// each, tools/mma_bench.cu); under an elect.sync predicate they are emitted straight.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -288,6 +296,7 @@ pa_decode_stream_kernel(const DecodeParams p) {
         // lookups of the NEXT batch (block ids) and the claim of the NEXT dynamic range are
         // issued before the current batch's copies, so their latency hides behind the ring.
         const int lane = tid & 31;
+        const bool leader = elect_one();                // issues every copy and barrier operation
         int stage = 0;
         uint32_t phase = 0;
         long long t_empty = 0;
@@ -369,7 +378,7 @@ pa_decode_stream_kernel(const DecodeParams p) {
                     const uint32_t full = smem_u32(&bars[stage]);
                     const uint32_t dst = smem_u32(tiles + (size_t)stage * tile_floats);
                     const float* src = (kv == 0 ? p.pool_k : p.pool_v) + page_off;
-                    if (lane == 0) {
+                    if (leader) {
                         if (dbg) {
                             if (first_issue) { dbg[1] = global_ns(); first_issue = false; }
                             const long long c0 = clock64();
@@ -388,23 +397,25 @@ pa_decode_stream_kernel(const DecodeParams p) {
                     }
                     __syncwarp();
                     if (W == p.C) {            // whole rows: the valid part of the page is contiguous
-                        if (lane == 0 && pool_rows > 0) tma_bulk_g2s(dst, src, (uint32_t)pool_rows * W * 4u, full);
-                    } else if (lane < pool_rows) {   // a column slice: one bulk copy per row
-                        tma_bulk_g2s(dst + lane * W * 4u, src + (size_t)lane * p.C, W * 4u, full);
+                        if (leader && pool_rows > 0) tma_bulk_g2s(dst, src, (uint32_t)pool_rows * W * 4u, full);
+                    } else {                   // a column slice: one bulk copy per row
+                        for (int r = 0; r < pool_rows; ++r)
+                            if (leader) tma_bulk_g2s(dst + r * W * 4u, src + (size_t)r * p.C, W * 4u, full);
                     }
-                    if ((j_flags & kFlagNew) && lane == 0)
+                    if ((j_flags & kFlagNew) && leader)
                         tma_bulk_g2s(dst + (uint32_t)(j_hi - 1) * W * 4u,
                                      (kv == 0 ? p.k_new : p.v_new) + (size_t)j_row * p.new_stride + (size_t)j_hg * W,
                                      W * 4u, full);
-                    if (kv == 0 && first && lane == 0)
+                    if (kv == 0 && first && leader)
                         tma_bulk_g2s(smem_u32(qbuf + (size_t)stage * W),
                                      p.q + (size_t)j_row * p.q_stride + (size_t)j_hg * W, W * 4u, full);
+                    __syncwarp();
                     if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
             }
             cur = nxt;
         }
-        if (lane == 0) {
+        if (leader) {
             // tell the consumers there is nothing more, then take part in resetting the counters
             mbar_wait(smem_u32(&bars[p.n_stages + stage]), phase ^ 1);
             meta[2 * stage] = make_int4(0, 0, 0, kFlagEnd);
