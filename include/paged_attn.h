@@ -183,6 +183,30 @@ PA_API int pa_qkv_append(pa_handle* h, int layer, const float* x, int x_stride, 
 PA_API int pa_matmul_bias(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
                           int M, int N, int K, void* stream);
 
+/* ---- the whole decode step of the model around the path ----------------------- */
+/* gpt2_forward (paged_infer.c:646-728) for one new token per sequence, over ALL layers (the
+ * reference fork stops at layer 0), on a handle created with n_layers KV pools.  Parameters: the
+ * checkpoint's 16 tensors in file order (paged_infer.c:441-488) in one buffer. */
+typedef struct pa_model pa_model;
+typedef struct pa_model_config {
+    int max_seq_len;   /* maxT: rows of wpe */
+    int vocab_size;    /* V */
+    int n_layers;      /* L  (== handle n_layers) */
+    int n_heads;       /* NH (== handle n_heads) */
+    int channels;      /* C  (== n_heads * head_dim of the handle) */
+} pa_model_config;
+PA_API size_t pa_model_param_count(const pa_model_config* cfg);
+/* params_host: pa_model_param_count floats, or NULL for synthetic random-init weights (seeded). */
+PA_API int pa_model_create(pa_handle* h, const pa_model_config* cfg, const float* params_host, unsigned long long seed,
+                           int max_batch, pa_model** out);
+PA_API void pa_model_destroy(pa_model* m);
+/* Sequence seq_ids[i] receives tokens[i] at its next position; next_tokens[i] is sampled from its
+ * logits with coins[i] in [0,1) as sample_mult does (paged_infer.c:838-848), or argmax if coins is NULL. */
+PA_API int pa_model_decode_step(pa_model* m, const int* seq_ids, const int* tokens, const float* coins, int nseq,
+                                int* next_tokens);
+PA_API float* pa_model_params(pa_model* m);               /* device */
+PA_API float* pa_model_logits(pa_model* m, int* stride);  /* device, (nseq, stride) of the last step */
+
 /* ---- whole step with HOST buffers (the end-to-end entry: H2D, append, decode, D2H, sync) -- */
 /* qkv_host: (nseq, 3C) rows of the step's sequences [q | k | v]; out_host: (nseq, C).  Pinned
  * buffers (pa_host_alloc) are read and written by the kernel directly over PCIe (zero-copy);

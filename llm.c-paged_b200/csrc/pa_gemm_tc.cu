@@ -64,6 +64,9 @@ struct GemmTcParams {
     int n_dense;
     int C;
     int terms;               // 3: 3xTF32 (fp32-accurate), 1: plain TF32 (reduced precision)
+    const float* residual;   // optional: out = act(acc + bias) + residual[m][n] (may alias out)
+    int res_stride;
+    int act;                 // 0 none, 1 GELU (tanh form, paged_infer.c:243-251)
     unsigned long long* dbg; // optional timeline of CTA (0,0,0) (PA_GEMM_DEBUG=1), NULL normally
 };
 
@@ -158,6 +161,11 @@ __device__ __forceinline__ uint64_t smem_desc_k128(uint32_t addr) {
 }
 __host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ float gelu_tanh(float x) {           // gelu_forward, paged_infer.c:243-251
+    const float k = 0.7978845608028654f;                        // sqrtf(2/pi)
+    const float cube = 0.044715f * x * x * x;
+    return 0.5f * x * (1.0f + tanhf(k * (x + cube)));
 }
 // the part of an fp32 value the TF32 datapath drops
 __device__ __forceinline__ float tf32_lo(float a) {
@@ -422,13 +430,26 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 if (n < p.n_dense) dst = p.out + (size_t)m * p.out_stride + n;
                 else if (n - p.n_dense < p.C) dst = p.pool_k + slot_off + (n - p.n_dense);
                 else dst = p.pool_v + slot_off + (n - p.n_dense - p.C);
+                const float* res = p.residual ? p.residual + (size_t)m * p.res_stride + n : nullptr;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     if (n + i < p.N) {
-                        float4 o = make_float4(acc[c + i], acc[c + i + 1], acc[c + i + 2], acc[c + i + 3]);
+                        float o[4] = {acc[c + i], acc[c + i + 1], acc[c + i + 2], acc[c + i + 3]};
                         const float4 b = *reinterpret_cast<const float4*>(bias_s + c + i);
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                        *reinterpret_cast<float4*>(dst + i) = o;
+                        o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+                        if (p.act == 1) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) o[e] = gelu_tanh(o[e]);
+                        }
+                        if (n + i + 3 < p.N) {
+                            if (res) {
+                                const float4 rv = *reinterpret_cast<const float4*>(res + i);
+                                o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+                            }
+                            *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
+                        } else {                         // last, partial group of a row whose length is not a multiple of 4
+                            for (int e = 0; e < 4 && n + i + e < p.N; ++e) dst[i + e] = o[e] + (res ? res[i + e] : 0.0f);
+                        }
                     }
                 }
             }
@@ -538,11 +559,12 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
  * PA_ERR_UNSUPPORTED when the shape is outside the kernel's domain (caller falls back to SIMT). */
 extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
                              int M, int N, int K, int n_dense, float* pool_k, float* pool_v, const int* slots, int C,
-                             int terms, int n_split_override, void* stream) {
+                             int terms, int n_split_override, const float* residual, int res_stride, int act, void* stream) {
     if (M <= 0 || N <= 0) return PA_OK;
     if ((K & 3) || (x_stride & 3) || (out_stride & 3) || !aligned16(x) || !aligned16(w) || !aligned16(out) ||
-        (bias && !aligned16(bias)) || (N & 3))
+        (residual && ((res_stride & 3) || !aligned16(residual))))
         return PA_ERR_UNSUPPORTED;
+    if (pool_k && (N & 3)) return PA_ERR_UNSUPPORTED;
     // a 32-column group of the epilogue must not straddle the Q | K | V boundaries
     if (pool_k && ((n_dense & 31) || (C & 31))) return PA_ERR_UNSUPPORTED;
     const int BN = 64;
@@ -554,6 +576,7 @@ extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const
     p.bias = bias; p.out = out; p.pool_k = pool_k; p.pool_v = pool_v; p.slots = slots;
     p.M = M; p.N = N; p.K = K; p.out_stride = out_stride; p.n_dense = pool_k ? n_dense : N; p.C = C;
     p.terms = terms == 1 ? 1 : 3;
+    p.residual = residual; p.res_stride = res_stride; p.act = act;
     static unsigned long long* d_dbg = nullptr;
     p.dbg = nullptr;
     if (getenv("PA_GEMM_DEBUG")) { if (!d_dbg) cudaMalloc((void**)&d_dbg, 64); p.dbg = d_dbg; }

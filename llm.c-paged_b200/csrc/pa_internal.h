@@ -109,7 +109,10 @@ void pa_cu_prefill_tc_release(pa_handle* h);
 /* ---- implemented in pa_gemm_tc.cu: fp32-accurate (3xTF32) tensor-core GEMM ---------------- */
 int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
                   int M, int N, int K, int n_dense, float* pool_k, float* pool_v, const int* slots, int C,
-                  int terms, int n_split, void* stream);
+                  int terms, int n_split, const float* residual, int res_stride, int act, void* stream);
+/* out = act(x.w^T + bias) + residual: tensor cores when the shape allows, else the fp32 SIMT kernel (pa_qkv.cu) */
+int pa_cu_linear(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
+                 int M, int N, int K, const float* residual, int res_stride, int act, int path, void* stream);
 
 #ifdef __cplusplus
 }

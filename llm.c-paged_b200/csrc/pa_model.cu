@@ -1,0 +1,354 @@
+/*
+ * pa_model.cu -- the rest of the decode step around the paged-attention path:
+ * token + position embedding, layernorm, the dense projections (through pa_cu_linear: tensor-core
+ * 3xTF32 GEMM with bias / GELU / residual epilogues), final layernorm, LM head and the sampler,
+ * driven over ALL layers (the reference fork stops at `l < 1`, paged_infer.c:659) with one KV pool
+ * per layer behind one block table.
+ *
+ * Reference functions restated on the device (all paged_infer.c): encoder_forward :24-46,
+ * layernorm_forward :49-89, gelu_forward :243-251 (GEMM epilogue), residual_forward :253-257 (GEMM
+ * epilogue), softmax_forward :259-286 + sample_mult :838-848 (one fused kernel: the probabilities
+ * are never materialised), and the order of gpt2_forward :696-728.
+ *
+ * Parameters live in ONE device buffer in the checkpoint's tensor order (paged_infer.c:441-488):
+ * wte, wpe, ln1w, ln1b, qkvw, qkvb, attprojw, attprojb, ln2w, ln2b, fcw, fcb, fcprojw, fcprojb,
+ * lnfw, lnfb.
+ */
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "pa_internal.h"
+
+#define CU_CHECK(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            pa_set_error("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return PA_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+struct pa_model {
+    pa_handle* h;
+    pa_model_config cfg;
+    int C, V, L, maxT, Vp;                 // Vp: logits row stride (V rounded up to a multiple of 4)
+    float* params;                         // device, checkpoint order
+    size_t n_params;
+    const float *wte, *wpe, *ln1w, *ln1b, *qkvw, *qkvb, *attprojw, *attprojb, *ln2w, *ln2b, *fcw, *fcb, *fcprojw,
+        *fcprojb, *lnfw, *lnfb;
+    int max_batch;
+    float *x, *ln, *q, *atty, *fch, *logits;     // device activations for one step
+    int* d_io;                             // device: tokens[B] | positions[B] | next[B]
+    float* d_coins;
+    int* h_io;                             // pinned mirror
+    float* h_coins;
+};
+
+namespace {
+
+// ---- encoder_forward (paged_infer.c:24-46) for one new token per sequence ------------------------
+__global__ void pa_embed_kernel(float* __restrict__ x, const int* __restrict__ tokens, const int* __restrict__ positions,
+                                const float* __restrict__ wte, const float* __restrict__ wpe, int C) {
+    const int s = blockIdx.x;
+    const float* e = wte + (size_t)tokens[s] * C;
+    const float* ps = wpe + (size_t)positions[s] * C;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) x[(size_t)s * C + i] = e[i] + ps[i];
+}
+
+// ---- layernorm_forward (paged_infer.c:49-89): one warp per row, the row held in registers -------
+constexpr int kLnMaxPerLane = 64;          // C <= 2048
+__global__ void __launch_bounds__(128)
+pa_layernorm_kernel(float* __restrict__ out, const float* __restrict__ inp, const float* __restrict__ weight,
+                    const float* __restrict__ bias, int rows, int C) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* x = inp + (size_t)row * C;
+    float v[kLnMaxPerLane];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c < C ? x[c] : 0.0f;
+        sum += v[i];
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const float m = sum / C;
+    float var = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        const float dlt = v[i] - m;
+        if (c < C) var += dlt * dlt;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+    var = var / C;
+    const float s = 1.0f / sqrtf(var + 1e-5f);                   // eps, :56
+    float* o = out + (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) o[c] = (s * (v[i] - m)) * weight[c] + bias[c];
+    }
+}
+
+// ---- softmax_forward + sample_mult (paged_infer.c:259-286, :838-848) fused -------------------------
+// One CTA per row of logits.  maxval starts at -10000 as the reference's does; the probabilities
+// are exp(l - max) / sum; sample_mult returns the first index whose running sum exceeds the coin.
+// Here the comparison is made against coin * sum (no division per element) and the running sum is
+// a block-wide scan over contiguous chunks, so an index can differ from the sequential reference
+// only when the coin lies within rounding distance of a boundary of the distribution.
+// coin < 0 selects argmax (greedy).
+__global__ void __launch_bounds__(256)
+pa_sample_kernel(const float* __restrict__ logits, int stride, int V, const float* __restrict__ coins, int* __restrict__ next) {
+    __shared__ float red[256];
+    __shared__ int redi[256];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const float* l = logits + (size_t)row * stride;
+    const float coin = coins ? coins[row] : -1.0f;
+    const int chunk = (V + 255) / 256;
+    const int c0 = tid * chunk, c1 = min(V, c0 + chunk);
+    float mx = -10000.0f;                                           // :270
+    int arg = -1;
+    for (int i = c0; i < c1; ++i) if (l[i] > mx) { mx = l[i]; arg = i; }
+    red[tid] = mx; redi[tid] = arg;
+    __syncthreads();
+    for (int d = 128; d >= 1; d >>= 1) {
+        if (tid < d) {
+            // ties and order: the reference keeps the FIRST maximum (strict >); chunks are in index order
+            if (red[tid + d] > red[tid] || (red[tid + d] == red[tid] && redi[tid] < 0)) { red[tid] = red[tid + d]; redi[tid] = redi[tid + d]; }
+        }
+        __syncthreads();
+    }
+    const float maxval = red[0];
+    const int argmax = redi[0] < 0 ? 0 : redi[0];
+    __syncthreads();
+    if (coin < 0.0f) {
+        if (tid == 0) next[row] = argmax;
+        return;
+    }
+    float part = 0.0f;
+    for (int i = c0; i < c1; ++i) part += expf(l[i] - maxval);
+    red[tid] = part;
+    __syncthreads();
+    // inclusive scan of the chunk sums (Hillis-Steele over 256 entries)
+    for (int d = 1; d < 256; d <<= 1) {
+        const float t = tid >= d ? red[tid - d] : 0.0f;
+        __syncthreads();
+        red[tid] += t;
+        __syncthreads();
+    }
+    const float total = red[255];
+    const float target = coin * total;
+    const float before = tid > 0 ? red[tid - 1] : 0.0f;
+    if (tid == 0) redi[0] = V - 1;                                  // "in case of rounding errors", :847
+    __syncthreads();
+    if (target >= before && target < red[tid] && c0 < c1) {         // the crossing lies in this chunk (exactly one thread)
+        float cdf = before;
+        int pick = c1 - 1;
+        for (int i = c0; i < c1; ++i) {
+            cdf += expf(l[i] - maxval);
+            if (target < cdf) { pick = i; break; }
+        }
+        redi[0] = pick;
+    }
+    __syncthreads();
+    if (tid == 0) next[row] = redi[0];
+}
+
+size_t param_count(int V, int maxT, int L, int C) {
+    return (size_t)V * C + (size_t)maxT * C + (size_t)L * (2 * C + 3 * (size_t)C * C + 3 * C + (size_t)C * C + C + 2 * C +
+                                                            4 * (size_t)C * C + 4 * C + 4 * (size_t)C * C + C) + 2 * C;
+}
+
+// synthetic random-init weights on the device (no checkpoint is available offline): N(0, std) from a
+// counter-based hash; layernorm weights 1, biases 0 -- GPT-2's initialisation scheme
+__device__ __forceinline__ uint32_t hash32(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (uint32_t)x;
+}
+__global__ void pa_init_normal_kernel(float* p, size_t n, float stdv, float mean, uint64_t seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float u1 = (hash32(seed + 2 * i) >> 8) * (1.0f / 16777216.0f) + 1e-7f;
+        const float u2 = (hash32(seed + 2 * i + 1) >> 8) * (1.0f / 16777216.0f);
+        p[i] = mean + stdv * sqrtf(-2.0f * logf(u1)) * cosf(6.28318530718f * u2);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t pa_model_param_count(const pa_model_config* c) {
+    return c ? param_count(c->vocab_size, c->max_seq_len, c->n_layers, c->channels) : 0;
+}
+
+int pa_model_create(pa_handle* h, const pa_model_config* cfg, const float* params_host, unsigned long long seed,
+                    int max_batch, pa_model** out) {
+    if (!h || !cfg || !out) { pa_set_error("pa_model_create: NULL argument"); return PA_ERR_INVALID; }
+    *out = nullptr;
+    if (h->host_only || !h->pool_k) { pa_set_error("pa_model_create: handle has no device; there is no CPU fallback"); return PA_ERR_NO_DEVICE; }
+    if (cfg->channels != h->C || cfg->n_heads != h->cfg.n_heads || cfg->n_layers != h->cfg.n_layers) {
+        pa_set_error("pa_model_create: model (C=%d NH=%d L=%d) does not match the KV handle (C=%d NH=%d L=%d)", cfg->channels,
+                     cfg->n_heads, cfg->n_layers, h->C, h->cfg.n_heads, h->cfg.n_layers);
+        return PA_ERR_INVALID;
+    }
+    if (cfg->channels > 32 * kLnMaxPerLane || cfg->vocab_size < 1 || cfg->max_seq_len < 1 || max_batch < 1) {
+        pa_set_error("pa_model_create: unsupported geometry");
+        return PA_ERR_INVALID;
+    }
+    CU_CHECK(cudaSetDevice(h->cfg.device));
+    pa_model* m = (pa_model*)calloc(1, sizeof(pa_model));
+    if (!m) { pa_set_error("pa_model_create: out of host memory"); return PA_ERR_NOMEM; }
+    m->h = h; m->cfg = *cfg;
+    const int C = m->C = cfg->channels, V = m->V = cfg->vocab_size, L = m->L = cfg->n_layers, maxT = m->maxT = cfg->max_seq_len;
+    m->Vp = (V + 3) & ~3;
+    m->max_batch = max_batch;
+    m->n_params = param_count(V, maxT, L, C);
+    cudaError_t e = cudaMalloc((void**)&m->params, m->n_params * sizeof(float));
+    const size_t B = (size_t)max_batch;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->x, B * C * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->ln, B * C * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->q, B * C * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->atty, B * C * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->fch, B * 4 * C * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->logits, B * m->Vp * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_io, B * 3 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_coins, B * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&m->h_io, B * 3 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&m->h_coins, B * sizeof(float));
+    if (e != cudaSuccess) {
+        pa_set_error("pa_model_create: allocation failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        pa_model_destroy(m);
+        return PA_ERR_NOMEM;
+    }
+    float* p = m->params;
+    m->wte = p; p += (size_t)V * C;
+    m->wpe = p; p += (size_t)maxT * C;
+    m->ln1w = p; p += (size_t)L * C;
+    m->ln1b = p; p += (size_t)L * C;
+    m->qkvw = p; p += (size_t)L * 3 * C * C;
+    m->qkvb = p; p += (size_t)L * 3 * C;
+    m->attprojw = p; p += (size_t)L * C * C;
+    m->attprojb = p; p += (size_t)L * C;
+    m->ln2w = p; p += (size_t)L * C;
+    m->ln2b = p; p += (size_t)L * C;
+    m->fcw = p; p += (size_t)L * 4 * C * C;
+    m->fcb = p; p += (size_t)L * 4 * C;
+    m->fcprojw = p; p += (size_t)L * C * 4 * C;
+    m->fcprojb = p; p += (size_t)L * C;
+    m->lnfw = p; p += C;
+    m->lnfb = p; p += C;
+    cudaStream_t s = (cudaStream_t)h->stream;
+    if (params_host) {
+        CU_CHECK(cudaMemcpyAsync(m->params, params_host, m->n_params * sizeof(float), cudaMemcpyHostToDevice, s));
+    } else {
+        // GPT-2 style random init: weights N(0, 0.02), layernorm weights 1, every bias 0
+        struct { const float* ptr; size_t n; float stdv, mean; } parts[] = {
+            {m->wte, (size_t)V * C, 0.02f, 0.f}, {m->wpe, (size_t)maxT * C, 0.02f, 0.f},
+            {m->ln1w, (size_t)L * C, 0.f, 1.f}, {m->ln1b, (size_t)L * C, 0.f, 0.f},
+            {m->qkvw, (size_t)L * 3 * C * C, 0.02f, 0.f}, {m->qkvb, (size_t)L * 3 * C, 0.f, 0.f},
+            {m->attprojw, (size_t)L * C * C, 0.02f, 0.f}, {m->attprojb, (size_t)L * C, 0.f, 0.f},
+            {m->ln2w, (size_t)L * C, 0.f, 1.f}, {m->ln2b, (size_t)L * C, 0.f, 0.f},
+            {m->fcw, (size_t)L * 4 * C * C, 0.02f, 0.f}, {m->fcb, (size_t)L * 4 * C, 0.f, 0.f},
+            {m->fcprojw, (size_t)L * 4 * C * C, 0.02f, 0.f}, {m->fcprojb, (size_t)L * C, 0.f, 0.f},
+            {m->lnfw, (size_t)C, 0.f, 1.f}, {m->lnfb, (size_t)C, 0.f, 0.f}};
+        uint64_t sd = seed * 0x9e3779b97f4a7c15ull + 1;
+        for (auto& pt : parts) {
+            pa_init_normal_kernel<<<592, 256, 0, s>>>(const_cast<float*>(pt.ptr), pt.n, pt.stdv, pt.mean, sd);
+            sd += 2 * pt.n + 17;
+        }
+        CU_CHECK(cudaGetLastError());
+    }
+    CU_CHECK(cudaStreamSynchronize(s));
+    *out = m;
+    return PA_OK;
+}
+
+void pa_model_destroy(pa_model* m) {
+    if (!m) return;
+    cudaFree(m->params); cudaFree(m->x); cudaFree(m->ln); cudaFree(m->q); cudaFree(m->atty); cudaFree(m->fch);
+    cudaFree(m->logits); cudaFree(m->d_io); cudaFree(m->d_coins);
+    if (m->h_io) cudaFreeHost(m->h_io);
+    if (m->h_coins) cudaFreeHost(m->h_coins);
+    free(m);
+}
+
+float* pa_model_params(pa_model* m) { return m ? m->params : nullptr; }
+float* pa_model_logits(pa_model* m, int* stride) {
+    if (!m) return nullptr;
+    if (stride) *stride = m->Vp;
+    return m->logits;
+}
+
+/* One decode step for sequences seq_ids[0..nseq): each receives the token tokens[i] at its next
+ * position; next_tokens[i] is sampled from the logits with coins[i] in [0,1) (NULL: argmax).
+ * Runs: page choice + table mirror, embedding, then per layer ln1 -> QKV projection with fused KV
+ * append -> paged decode attention -> attproj (+residual) -> ln2 -> fc (+GELU) -> fcproj
+ * (+residual), then final layernorm, LM head, sampler; reads the tokens back. */
+int pa_model_decode_step(pa_model* m, const int* seq_ids, const int* tokens, const float* coins, int nseq, int* next_tokens) {
+    if (!m || !seq_ids || !tokens || !next_tokens || nseq < 1 || nseq > m->max_batch) {
+        pa_set_error("pa_model_decode_step: bad arguments (nseq=%d, max_batch=%d)", nseq, m ? m->max_batch : 0);
+        return PA_ERR_INVALID;
+    }
+    pa_handle* h = m->h;
+    const int C = m->C, L = m->L, V = m->V;
+    for (int i = 0; i < nseq; ++i) {
+        const int pos = pa_seq_len(h, seq_ids[i]);
+        if (tokens[i] < 0 || tokens[i] >= V) { pa_set_error("pa_model_decode_step: token %d out of range", tokens[i]); return PA_ERR_INVALID; }
+        if (pos < 0 || pos >= m->maxT) { pa_set_error("pa_model_decode_step: sequence %d is at position %d of %d", seq_ids[i], pos, m->maxT); return PA_ERR_INVALID; }
+        m->h_io[i] = tokens[i];
+        m->h_io[nseq + i] = pos;
+        if (coins) m->h_coins[i] = coins[i];
+    }
+    CU_CHECK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)h->stream;
+    std::vector<int> ones(nseq, 1);
+    int rc = pa_step_begin(h, seq_ids, ones.data(), nseq);
+    if (rc != PA_OK) return rc;
+    rc = pa_step_upload(h, s);
+    if (rc != PA_OK) return rc;
+    CU_CHECK(cudaMemcpyAsync(m->d_io, m->h_io, (size_t)nseq * 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (coins) CU_CHECK(cudaMemcpyAsync(m->d_coins, m->h_coins, (size_t)nseq * sizeof(float), cudaMemcpyHostToDevice, s));
+    pa_embed_kernel<<<nseq, 256, 0, s>>>(m->x, m->d_io, m->d_io + nseq, m->wte, m->wpe, C);
+    const int path = h->tune[PA_TUNE_GEMM_PATH];
+    const int ln_grid = (nseq + 3) / 4;
+    for (int l = 0; l < L; ++l) {
+        pa_layernorm_kernel<<<ln_grid, 128, 0, s>>>(m->ln, m->x, m->ln1w + (size_t)l * C, m->ln1b + (size_t)l * C, nseq, C);
+        rc = pa_qkv_append(h, l, m->ln, C, m->qkvw + (size_t)l * 3 * C * C, m->qkvb + (size_t)l * 3 * C, m->q, C, s);
+        if (rc != PA_OK) return rc;
+        rc = pa_decode(h, l, m->q, C, m->atty, C, s);
+        if (rc != PA_OK) return rc;
+        // x += atty . attprojw^T + attprojb      (matmul_forward + residual_forward, :716-717)
+        rc = pa_cu_linear(m->atty, C, m->attprojw + (size_t)l * C * C, m->attprojb + (size_t)l * C, m->x, C, nseq, C, C, m->x, C, 0, path, s);
+        if (rc != PA_OK) return rc;
+        pa_layernorm_kernel<<<ln_grid, 128, 0, s>>>(m->ln, m->x, m->ln2w + (size_t)l * C, m->ln2b + (size_t)l * C, nseq, C);
+        // fch = gelu(ln . fcw^T + fcb)           (:719-720)
+        rc = pa_cu_linear(m->ln, C, m->fcw + (size_t)l * 4 * C * C, m->fcb + (size_t)l * 4 * C, m->fch, 4 * C, nseq, 4 * C, C, nullptr, 0, 1, path, s);
+        if (rc != PA_OK) return rc;
+        // x += fch . fcprojw^T + fcprojb         (:721-722)
+        rc = pa_cu_linear(m->fch, 4 * C, m->fcprojw + (size_t)l * 4 * C * C, m->fcprojb + (size_t)l * C, m->x, C, nseq, C, 4 * C, m->x, C, 0, path, s);
+        if (rc != PA_OK) return rc;
+    }
+    pa_layernorm_kernel<<<ln_grid, 128, 0, s>>>(m->ln, m->x, m->lnfw, m->lnfb, nseq, C);
+    rc = pa_cu_linear(m->ln, C, m->wte, nullptr, m->logits, m->Vp, nseq, V, C, nullptr, 0, 0, path, s);       // logits = lnf . wte^T (:726)
+    if (rc != PA_OK) return rc;
+    pa_sample_kernel<<<nseq, 256, 0, s>>>(m->logits, m->Vp, V, coins ? m->d_coins : nullptr, m->d_io + 2 * nseq);
+    CU_CHECK(cudaGetLastError());
+    h->launches += 4 + 5 * (long)L;     // embed, lnf, head, sampler; per layer 2 layernorms + 3 projections (pa_qkv_append / pa_decode count themselves)
+    CU_CHECK(cudaMemcpyAsync(m->h_io + 2 * nseq, m->d_io + 2 * nseq, (size_t)nseq * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_CHECK(cudaStreamSynchronize(s));
+    memcpy(next_tokens, m->h_io + 2 * nseq, (size_t)nseq * sizeof(int));
+    return PA_OK;
+}
+
+}  // extern "C"

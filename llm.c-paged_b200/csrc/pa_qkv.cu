@@ -51,6 +51,9 @@ struct QkvParams {
     int x_stride, out_stride;
     int n_dense;             // columns [0, n_dense) are dense; then C columns of K, then C columns of V
     int C;
+    const float* residual;   // optional: out = act(acc + bias) + residual[m][n] (may alias out)
+    int res_stride;
+    int act;                 // 0 none, 1 GELU (tanh form, paged_infer.c:243-251)
 };
 
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -136,7 +139,12 @@ pa_qkv_kernel(const QkvParams p) {
         for (int j = 0; j < 4; ++j) {
             const int nn = n + j;
             if (nn >= p.N) continue;
-            const float v = acc[i][j] + (p.bias ? p.bias[nn] : 0.0f);
+            float v = acc[i][j] + (p.bias ? p.bias[nn] : 0.0f);
+            if (p.act == 1) {
+                const float cube = 0.044715f * v * v * v;
+                v = 0.5f * v * (1.0f + tanhf(0.7978845608028654f * (v + cube)));
+            }
+            if (p.residual) v += p.residual[(size_t)m * p.res_stride + nn];
             if (nn < p.n_dense) {
                 dense[nn] = v;
             } else {
@@ -181,12 +189,13 @@ int pa_qkv_append(pa_handle* h, int layer, const float* x, int x_stride, const f
     p.M = L.ntok; p.N = 3 * h->C; p.K = h->C;
     p.x_stride = x_stride; p.out_stride = q_stride;
     p.n_dense = h->C; p.C = h->C;
+    p.residual = nullptr; p.res_stride = 0; p.act = 0;
     cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)h->stream;
     const int path = h->tune[PA_TUNE_GEMM_PATH];
     int rc = PA_ERR_UNSUPPORTED;
     if (path != 1) {       // tensor cores: 3xTF32 keeps fp32 accuracy; plain TF32 only on request
         rc = pa_cu_gemm_tc(x, x_stride, w, bias, q_out, q_stride, p.M, p.N, p.K, p.n_dense, p.pool_k, p.pool_v, p.slots,
-                           p.C, path == 3 ? 1 : 3, h->tune[PA_TUNE_GEMM_SPLIT_K], (void*)s);
+                           p.C, path == 3 ? 1 : 3, h->tune[PA_TUNE_GEMM_SPLIT_K], nullptr, 0, 0, (void*)s);
         if (rc == PA_ERR_UNSUPPORTED && path >= 2) {
             pa_set_error("pa_qkv_append: tcgen05 GEMM needs C %% 32 == 0 and 16-byte aligned rows");
             return rc;
@@ -197,10 +206,16 @@ int pa_qkv_append(pa_handle* h, int layer, const float* x, int x_stride, const f
     return rc;
 }
 
-/* plain fp32 GEMM with bias on device pointers: out (M, N) = x (M, K) . w (N, K)^T + bias */
-int pa_matmul_bias(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
-                   int M, int N, int K, void* stream) {
-    if (!x || !w || !out || M < 0 || N < 0 || K < 1) { pa_set_error("pa_matmul_bias: bad arguments"); return PA_ERR_INVALID; }
+/* out = act(x.w^T + bias) + residual on device pointers; path as PA_TUNE_GEMM_PATH */
+int pa_cu_linear(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
+                 int M, int N, int K, const float* residual, int res_stride, int act, int path, void* stream) {
+    if (!x || !w || !out || M < 0 || N < 0 || K < 1) { pa_set_error("pa_cu_linear: bad arguments"); return PA_ERR_INVALID; }
+    int rc = PA_ERR_UNSUPPORTED;
+    if (path != 1) {
+        rc = pa_cu_gemm_tc(x, x_stride, w, bias, out, out_stride, M, N, K, N, nullptr, nullptr, nullptr, 0,
+                           path == 3 ? 1 : 3, 0, residual, res_stride, act, stream);
+        if (rc != PA_ERR_UNSUPPORTED) return rc;
+    }
     QkvParams p;
     p.x = x; p.in_rows = nullptr; p.w = w; p.bias = bias;
     p.out = out; p.out_rows = nullptr;
@@ -208,11 +223,15 @@ int pa_matmul_bias(const float* x, int x_stride, const float* w, const float* bi
     p.M = M; p.N = N; p.K = K;
     p.x_stride = x_stride; p.out_stride = out_stride;
     p.n_dense = N; p.C = 0;
-    int rc = pa_cu_gemm_tc(x, x_stride, w, bias, out, out_stride, M, N, K, N, nullptr, nullptr, nullptr, 0, 3, 0, stream);
-    if (rc != PA_ERR_UNSUPPORTED) return rc;
+    p.residual = residual; p.res_stride = res_stride; p.act = act;
     return launch(p, (cudaStream_t)stream);
 }
 
+/* plain fp32 GEMM with bias on device pointers: out (M, N) = x (M, K) . w (N, K)^T + bias */
+int pa_matmul_bias(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
+                   int M, int N, int K, void* stream) {
+    return pa_cu_linear(x, x_stride, w, bias, out, out_stride, M, N, K, nullptr, 0, 0, 0, stream);
+}
 
 /* ---- reference names (paged_infer.c:92-160), host or device pointers ------------------------ */
 namespace {
@@ -271,6 +290,7 @@ void matmul_cached(float* out, float* inp, float* weight, float* bias, int B, in
     p.out = o.d; p.out_rows = nullptr;
     p.pool_k = p.pool_v = nullptr; p.slots = nullptr;
     p.M = (int)rows; p.N = C; p.K = C; p.x_stride = C; p.out_stride = OC; p.n_dense = C; p.C = 0;
+    p.residual = nullptr; p.res_stride = 0; p.act = 0;
     int rc = launch(p, 0);                                   // Q for all rows
     if (rc == PA_OK) {
         p.in_rows = p.out_rows = d_last;

@@ -52,6 +52,11 @@ KV_p = C.POINTER(KVBlock)
 _lib = None
 
 
+class PaModelConfig(C.Structure):
+    _fields_ = [("max_seq_len", C.c_int), ("vocab_size", C.c_int), ("n_layers", C.c_int), ("n_heads", C.c_int),
+                ("channels", C.c_int)]
+
+
 class PagedAttnError(RuntimeError):
     pass
 
@@ -98,6 +103,12 @@ def load():
         "pa_prefill": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
         "pa_decode_append": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, vp]),
         "pa_decode_step_host": (C.c_int, [vp, C.c_int, vp, vp]),
+        "pa_model_param_count": (C.c_size_t, [C.POINTER(PaModelConfig)]),
+        "pa_model_create": (C.c_int, [vp, C.POINTER(PaModelConfig), vp, C.c_ulonglong, C.c_int, C.POINTER(vp)]),
+        "pa_model_destroy": (None, [vp]),
+        "pa_model_decode_step": (C.c_int, [vp, c_int_p, c_int_p, vp, C.c_int, c_int_p]),
+        "pa_model_params": (vp, [vp]),
+        "pa_model_logits": (vp, [vp, c_int_p]),
         "pa_qkv_append": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, vp]),
         "pa_matmul_bias": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "matmul_forward": (None, [vp, vp, vp, vp] + [C.c_int] * 4),
@@ -405,3 +416,46 @@ class ManagerAdapter:
     def block_info(self, idx):
         b = self.m.contents.blocks[idx]
         return b.filled, b.prompt_id, b.lru_counter
+
+
+class Model:
+    """pa_model_*: the whole decode step (embedding, L layers, LM head, sampler) on a PagedAttn handle."""
+
+    def __init__(self, eng, max_seq_len, vocab_size, params=None, seed=1337, max_batch=None):
+        self.eng = eng
+        self.lib = eng.lib
+        cfg = eng.cfg
+        self.cfg = PaModelConfig(max_seq_len, vocab_size, cfg.n_layers, cfg.n_heads, cfg.n_heads * cfg.head_dim)
+        self.V = vocab_size
+        self.n_params = self.lib.pa_model_param_count(C.byref(self.cfg))
+        ptr = None
+        if params is not None:
+            params = np.ascontiguousarray(params, dtype=np.float32)
+            assert params.size == self.n_params, (params.size, self.n_params)
+            ptr = params.ctypes.data
+        self.m = C.c_void_p()
+        check(self.lib.pa_model_create(eng.h, C.byref(self.cfg), ptr, seed, max_batch or cfg.max_seqs, C.byref(self.m)),
+              "pa_model_create")
+
+    def decode_step(self, seq_ids, tokens, coins=None):
+        seq = np.ascontiguousarray(seq_ids, dtype=np.int32)
+        tok = np.ascontiguousarray(tokens, dtype=np.int32)
+        nxt = np.zeros(len(seq), dtype=np.int32)
+        cptr = None
+        if coins is not None:
+            coins = np.ascontiguousarray(coins, dtype=np.float32)
+            cptr = coins.ctypes.data
+        check(self.lib.pa_model_decode_step(self.m, iptr(seq), iptr(tok), cptr, len(seq), iptr(nxt)), "pa_model_decode_step")
+        return nxt
+
+    def logits(self, nseq):
+        stride = C.c_int(0)
+        p = self.lib.pa_model_logits(self.m, C.byref(stride))
+        buf = np.zeros((nseq, stride.value), dtype=np.float32)
+        check(self.lib.pa_memcpy_d2h(buf.ctypes.data, p, buf.nbytes, None), "d2h")
+        return buf[:, :self.V]
+
+    def close(self):
+        if self.m:
+            self.lib.pa_model_destroy(self.m)
+            self.m = None

@@ -390,6 +390,121 @@ ORC_API void orc_matmul_cached(float* out, const float* inp, const float* weight
     }
 }
 
+/* ---- the rest of the decode layer ------------------------------------------------
+ * encoder_forward :24-46, layernorm_forward :49-89, gelu_forward :243-251, residual_forward
+ * :253-257, softmax_forward :259-286, sample_mult :838-848 (all paged_infer.c) */
+ORC_API void orc_encoder_forward(float* out, const int* inp, const float* wte, const float* wpe, int B, int T, int C) {
+    for (int b = 0; b < B; b++)
+        for (int t = 0; t < T; t++) {
+            const float* e = wte + (size_t)inp[b * T + t] * C;
+            const float* ps = wpe + (size_t)t * C;
+            float* o = out + ((size_t)b * T + t) * C;
+            for (int i = 0; i < C; i++) o[i] = e[i] + ps[i];
+        }
+}
+ORC_API void orc_layernorm_forward(float* out, float* mean, float* rstd, const float* inp, const float* weight,
+                                   const float* bias, int B, int T, int C) {
+    const float eps = 1e-5f;                                   /* :56 */
+    for (int r = 0; r < B * T; r++) {
+        const float* x = inp + (size_t)r * C;
+        float m = 0.0f;
+        for (int i = 0; i < C; i++) m += x[i];
+        m = m / C;
+        float v = 0.0f;
+        for (int i = 0; i < C; i++) { float d = x[i] - m; v += d * d; }
+        v = v / C;
+        float s = 1.0f / sqrtf(v + eps);
+        float* o = out + (size_t)r * C;
+        for (int i = 0; i < C; i++) o[i] = (s * (x[i] - m)) * weight[i] + bias[i];
+        if (mean) mean[r] = m;
+        if (rstd) rstd[r] = s;
+    }
+}
+ORC_API void orc_gelu_forward(float* out, const float* inp, int N) {
+    const float k = sqrtf(2.0f / M_PI);                        /* GELU_SCALING_FACTOR :243 */
+    for (int i = 0; i < N; i++) {
+        float x = inp[i];
+        float cube = 0.044715f * x * x * x;
+        out[i] = 0.5f * x * (1.0f + tanhf(k * (x + cube)));
+    }
+}
+ORC_API void orc_residual_forward(float* out, const float* a, const float* b, int N) {
+    for (int i = 0; i < N; i++) out[i] = a[i] + b[i];
+}
+ORC_API void orc_softmax_forward(float* probs, const float* logits, int B, int T, int V) {
+    #pragma omp parallel for
+    for (int r = 0; r < B * T; r++) {
+        const float* l = logits + (size_t)r * V;
+        float* p = probs + (size_t)r * V;
+        float maxval = -10000.0f;                              /* :270 */
+        for (int i = 0; i < V; i++) if (l[i] > maxval) maxval = l[i];
+        float sum = 0.0f;
+        for (int i = 0; i < V; i++) { p[i] = expf(l[i] - maxval); sum += p[i]; }
+        for (int i = 0; i < V; i++) p[i] /= sum;
+    }
+}
+ORC_API int orc_sample_mult(const float* probabilities, int n, float coin) {
+    float cdf = 0.0f;
+    for (int i = 0; i < n; i++) {
+        cdf += probabilities[i];
+        if (coin < cdf) return i;
+    }
+    return n - 1;
+}
+
+/* One decode step of the whole model for a batch of sequences, the reference's gpt2_forward
+ * (:646-728) with T = 1 rows, the layer loop run over all L layers (the fork stops at l < 1, :659)
+ * and one KV manager per layer.  params: the checkpoint's 16 tensors in file order (:441-488).
+ * Per layer: ln1 -> matmul (QKV) -> add_to_cache -> last-row attention -> attproj -> residual ->
+ * ln2 -> fc -> gelu -> fcproj -> residual; then lnf -> logits (wte^T) .  Returns logits (nseq, V). */
+ORC_API int orc_model_decode_step(orc_manager** layer_mgrs, int L, int NH, int C, int V, int maxT,
+                                  const float* params, const int* seq_ids, const int* tokens, const int* positions,
+                                  int nseq, float* logits) {
+    const float* wte = params;
+    const float* wpe = wte + (size_t)V * C;
+    const float* ln1w = wpe + (size_t)maxT * C;
+    const float* ln1b = ln1w + (size_t)L * C;
+    const float* qkvw = ln1b + (size_t)L * C;
+    const float* qkvb = qkvw + (size_t)L * 3 * C * C;
+    const float* attprojw = qkvb + (size_t)L * 3 * C;
+    const float* attprojb = attprojw + (size_t)L * C * C;
+    const float* ln2w = attprojb + (size_t)L * C;
+    const float* ln2b = ln2w + (size_t)L * C;
+    const float* fcw = ln2b + (size_t)L * C;
+    const float* fcb = fcw + (size_t)L * 4 * C * C;
+    const float* fcprojw = fcb + (size_t)L * 4 * C;
+    const float* fcprojb = fcprojw + (size_t)L * C * 4 * C;
+    const float* lnfw = fcprojb + (size_t)L * C;
+    const float* lnfb = lnfw + C;
+    float* x = (float*)malloc((size_t)nseq * C * sizeof(float));
+    float* ln = (float*)malloc((size_t)nseq * C * sizeof(float));
+    float* qkv = (float*)malloc((size_t)nseq * 3 * C * sizeof(float));
+    float* atty = (float*)malloc((size_t)nseq * C * sizeof(float));
+    float* proj = (float*)malloc((size_t)nseq * C * sizeof(float));
+    float* fch = (float*)malloc((size_t)nseq * 4 * C * sizeof(float));
+    if (!x || !ln || !qkv || !atty || !proj || !fch) return -1;
+    for (int s = 0; s < nseq; s++)                                  /* encoder_forward with the token's own position */
+        for (int i = 0; i < C; i++) x[(size_t)s * C + i] = wte[(size_t)tokens[s] * C + i] + wpe[(size_t)positions[s] * C + i];
+    for (int l = 0; l < L; l++) {
+        orc_layernorm_forward(ln, NULL, NULL, x, ln1w + (size_t)l * C, ln1b + (size_t)l * C, nseq, 1, C);
+        orc_matmul_forward(qkv, ln, qkvw + (size_t)l * 3 * C * C, qkvb + (size_t)l * 3 * C, nseq, 1, C, 3 * C);
+        for (int s = 0; s < nseq; s++)
+            if (orc_add_to_cache(layer_mgrs[l], seq_ids[s], qkv + (size_t)s * 3 * C, 1, 1, C, 1) < 0) return -2;
+        if (orc_decode_batch(layer_mgrs[l], seq_ids, NULL, nseq, NH, qkv, 3 * C, atty, C) != 0) return -3;
+        orc_matmul_forward(proj, atty, attprojw + (size_t)l * C * C, attprojb + (size_t)l * C, nseq, 1, C, C);
+        orc_residual_forward(x, x, proj, nseq * C);
+        orc_layernorm_forward(ln, NULL, NULL, x, ln2w + (size_t)l * C, ln2b + (size_t)l * C, nseq, 1, C);
+        orc_matmul_forward(fch, ln, fcw + (size_t)l * 4 * C * C, fcb + (size_t)l * 4 * C, nseq, 1, C, 4 * C);
+        orc_gelu_forward(fch, fch, nseq * 4 * C);
+        orc_matmul_forward(proj, fch, fcprojw + (size_t)l * C * 4 * C, fcprojb + (size_t)l * C, nseq, 1, 4 * C, C);
+        orc_residual_forward(x, x, proj, nseq * C);
+    }
+    orc_layernorm_forward(ln, NULL, NULL, x, lnfw, lnfb, nseq, 1, C);
+    orc_matmul_forward(logits, ln, wte, NULL, nseq, 1, C, V);
+    free(x); free(ln); free(qkv); free(atty); free(proj); free(fch);
+    return 0;
+}
+
 /* ---- deterministic inputs: the reference's xorshift64* (paged_infer.c:826-835)
  * with Box-Muller on top --------------------------------------------- */
 ORC_API unsigned int orc_random_u32(unsigned long long* state) {

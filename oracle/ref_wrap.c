@@ -157,5 +157,16 @@ REF_API void ref_matmul_cached(float* out, float* inp, float* w, float* bias, in
 }
 
 /* ---- the reference RNG (paged_infer.c:826-835) ------------------------------ */
+/* the rest of the decode layer: paged_infer.c:24-89, :243-286, :838-848 */
+REF_API void ref_encoder_forward(float* out, int* inp, float* wte, float* wpe, int B, int T, int C) {
+    encoder_forward(out, inp, wte, wpe, B, T, C);
+}
+REF_API void ref_layernorm_forward(float* out, float* mean, float* rstd, float* inp, float* w, float* b, int B, int T, int C) {
+    layernorm_forward(out, mean, rstd, inp, w, b, B, T, C);
+}
+REF_API void ref_gelu_forward(float* out, float* inp, int N) { gelu_forward(out, inp, N); }
+REF_API void ref_residual_forward(float* out, float* a, float* b, int N) { residual_forward(out, a, b, N); }
+REF_API void ref_softmax_forward(float* probs, float* logits, int B, int T, int V) { softmax_forward(probs, logits, B, T, V); }
+REF_API int ref_sample_mult(float* probs, int n, float coin) { return sample_mult(probs, n, coin); }
 REF_API unsigned int ref_random_u32(unsigned long long* s) { return random_u32(s); }
 REF_API float ref_random_f32(unsigned long long* s) { return random_f32(s); }

@@ -75,6 +75,13 @@ def load_ref(bs, mb, mp, flavor="strict"):
     lib.ref_time_attend_prompt.argtypes = [vp, C.c_int, c_float_p, c_float_p,
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.ref_time_attend_prompt.restype = C.c_double
+    lib.ref_encoder_forward.argtypes = [c_float_p, c_int_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int]
+    lib.ref_layernorm_forward.argtypes = [c_float_p] * 6 + [C.c_int] * 3
+    lib.ref_gelu_forward.argtypes = [c_float_p, c_float_p, C.c_int]
+    lib.ref_residual_forward.argtypes = [c_float_p, c_float_p, c_float_p, C.c_int]
+    lib.ref_softmax_forward.argtypes = [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int]
+    lib.ref_sample_mult.argtypes = [c_float_p, C.c_int, C.c_float]
+    lib.ref_sample_mult.restype = C.c_int
     for name in ("ref_matmul_forward", "ref_matmul_cached"):
         getattr(lib, name).argtypes = [c_float_p] * 4 + [C.c_int] * 4
     lib.ref_geometry.argtypes = [c_int_p, c_int_p, c_int_p]
@@ -245,6 +252,16 @@ def load_oracle(flavor="strict"):
                                     c_float_p, C.c_int, c_float_p, C.c_int]
     lib.orc_time_decode_batch.argtypes = [vp, c_int_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int, C.c_int]
     lib.orc_time_decode_batch.restype = C.c_double
+    lib.orc_encoder_forward.argtypes = [c_float_p, c_int_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int]
+    lib.orc_layernorm_forward.argtypes = [c_float_p] * 6 + [C.c_int] * 3
+    lib.orc_gelu_forward.argtypes = [c_float_p, c_float_p, C.c_int]
+    lib.orc_residual_forward.argtypes = [c_float_p, c_float_p, c_float_p, C.c_int]
+    lib.orc_softmax_forward.argtypes = [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int]
+    lib.orc_sample_mult.argtypes = [c_float_p, C.c_int, C.c_float]
+    lib.orc_sample_mult.restype = C.c_int
+    lib.orc_model_decode_step.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p,
+                                          c_int_p, c_int_p, c_int_p, C.c_int, c_float_p]
+    lib.orc_model_decode_step.restype = C.c_int
     for name in ("orc_matmul_forward", "orc_matmul_cached"):
         getattr(lib, name).argtypes = [c_float_p] * 4 + [C.c_int] * 4
     lib.orc_fill_normal.argtypes = [c_float_p, C.c_size_t, C.c_ulonglong]

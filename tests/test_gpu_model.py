@@ -1,0 +1,122 @@
+"""-m gpu parity tests of SURVEY 8f.2: the whole decode step of the model around the paged-attention
+path (embedding, L x {ln1, QKV + fused append, paged attention, attproj + residual, ln2, fc + GELU,
+fcproj + residual}, final layernorm, LM head, sampler) against the CPU oracle
+(orc_model_decode_step: the reference's gpt2_forward with the layer loop run over all layers)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_api as oa
+from gpu_common import pa
+
+pytestmark = pytest.mark.gpu
+
+# Logits after L layers of fp32 GEMMs / attention / layernorm: every stage is within ~1e-6 of the
+# oracle (see test_gpu_qkv / test_gpu_parity); the stated bar for the end of the chain is the path's
+# max|a-b| / max|ref| <= 1e-5 per layer of depth, i.e. L * 1e-5 (measured: see the printed worst case).
+LOGIT_TOL_PER_LAYER = 1e-5
+
+
+def make_params(V, maxT, L, Cc, seed):
+    """The checkpoint's 16 tensors in file order (paged_infer.c:441-488), GPT-2 style values."""
+    sizes = [V * Cc, maxT * Cc, L * Cc, L * Cc, L * 3 * Cc * Cc, L * 3 * Cc, L * Cc * Cc, L * Cc, L * Cc, L * Cc,
+             L * 4 * Cc * Cc, L * 4 * Cc, L * 4 * Cc * Cc, L * Cc, Cc, Cc]
+    kinds = ["w", "w", "g", "b", "w", "b", "w", "b", "g", "b", "w", "b", "w", "b", "g", "b"]
+    parts = []
+    for i, (n, k) in enumerate(zip(sizes, kinds)):
+        r = oa.normal((n,), seed=seed + i)
+        if k == "w":
+            parts.append(r * np.float32(0.08))
+        elif k == "g":
+            parts.append(np.float32(1.0) + r * np.float32(0.1))
+        else:
+            parts.append(r * np.float32(0.05))
+    return np.concatenate(parts).astype(np.float32)
+
+
+class OracleModel:
+    def __init__(self, L, NH, Cc, V, maxT, bs, max_blocks, max_seqs, params):
+        self.ol = oa.load_oracle()
+        self.mgrs = [oa.OrcManager(Cc, bs, max_blocks, max_seqs) for _ in range(L)]
+        self.arr = (C.c_void_p * L)(*[m.m for m in self.mgrs])
+        self.L, self.NH, self.C, self.V, self.maxT, self.params = L, NH, Cc, V, maxT, params
+
+    def step(self, seq_ids, tokens, positions):
+        seq = np.ascontiguousarray(seq_ids, dtype=np.int32)
+        tok = np.ascontiguousarray(tokens, dtype=np.int32)
+        pos = np.ascontiguousarray(positions, dtype=np.int32)
+        logits = np.zeros((len(seq), self.V), dtype=np.float32)
+        rc = self.ol.orc_model_decode_step(self.arr, self.L, self.NH, self.C, self.V, self.maxT, oa.fptr(self.params),
+                                           oa.iptr(seq), oa.iptr(tok), oa.iptr(pos), len(seq), oa.fptr(logits))
+        assert rc == 0, rc
+        return logits
+
+    def close(self):
+        for m in self.mgrs:
+            m.close()
+
+
+@pytest.mark.parametrize("L,NH,hs,V,bs,gemm_path", [
+    (3, 2, 64, 131, 16, 0),        # tensor-core projections (3xTF32), V not a multiple of 4
+    (2, 4, 64, 1000, 8, 0),
+    (2, 3, 20, 77, 4, 0),          # C = 60: SIMT projections, generic attention kernel
+    (2, 2, 64, 131, 16, 1),        # fp32 SIMT projections
+])
+def test_model_decode_steps_match_oracle(L, NH, hs, V, bs, gemm_path):
+    Cc, maxT, B = NH * hs, 96, 5
+    params = make_params(V, maxT, L, Cc, seed=300)
+    eng = pa.PagedAttn(bs, 64, B, NH, hs, n_layers=L, device=0, max_batch_tokens=B)
+    eng.tune(pa.PA_TUNE_GEMM_PATH, gemm_path)
+    model = pa.Model(eng, maxT, V, params=params, max_batch=B)
+    orc = OracleModel(L, NH, Cc, V, maxT, bs, 64, B, params)
+    ol = oa.load_oracle()
+    try:
+        rng = np.random.default_rng(5)
+        tokens = rng.integers(0, V, size=B).astype(np.int32)
+        pos = np.zeros(B, dtype=np.int32)
+        worst = 0.0
+        for step in range(20):                      # crosses page boundaries (bs 4/8/16)
+            active = [s for s in range(B) if (step + s) % 4 != 3] or [0]    # ragged: not every sequence every step
+            coins = rng.random(len(active)).astype(np.float32)
+            got_next = model.decode_step(active, tokens[active], coins)
+            got = model.logits(len(active))
+            want = orc.step(active, tokens[active], pos[active])
+            err = np.abs(got.astype(np.float64) - want).max() / np.abs(want).max()
+            worst = max(worst, err)
+            assert np.isfinite(got).all() and err <= LOGIT_TOL_PER_LAYER * L, f"step {step}: logits err {err:.3e}"
+            # sampler: softmax_forward + sample_mult of the reference on the ORACLE's logits
+            probs = np.zeros_like(want)
+            ol.orc_softmax_forward(oa.fptr(probs), oa.fptr(want), len(active), 1, V)
+            for i in range(len(active)):
+                row = np.ascontiguousarray(probs[i])
+                want_tok = ol.orc_sample_mult(oa.fptr(row), V, float(coins[i]))
+                if got_next[i] != want_tok:          # only legitimate when the coin sits on a boundary of the cdf
+                    cdf = np.cumsum(row.astype(np.float64))
+                    lo, hi = sorted((int(got_next[i]), int(want_tok)))
+                    assert abs(cdf[lo] - coins[i]) < 1e-5 and hi - lo <= 2, (step, i, got_next[i], want_tok, coins[i])
+            tokens[active] = got_next
+            pos[active] += 1
+            # block tables stay bit-exact with the oracle's allocator (one table drives all layers)
+            for s in active:
+                assert list(eng.table(s)) == list(orc.mgrs[0].table(s))
+        print(f"L={L} C={Cc} V={V} path={gemm_path}: worst logits err {worst:.2e}")
+    finally:
+        model.close(); eng.close(); orc.close()
+
+
+def test_model_greedy_and_random_init():
+    """coins=NULL -> argmax of the logits; params=NULL -> seeded synthetic weights on the device."""
+    L, NH, hs, V, maxT, B = 2, 2, 64, 257, 32, 4
+    eng = pa.PagedAttn(16, 32, B, NH, hs, n_layers=L, device=0, max_batch_tokens=B)
+    model = pa.Model(eng, maxT, V, params=None, seed=7, max_batch=B)
+    try:
+        tok = np.array([1, 2, 3, 4], dtype=np.int32)
+        for _ in range(5):
+            nxt = model.decode_step(list(range(B)), tok, None)
+            logits = model.logits(B)
+            assert np.isfinite(logits).all()
+            assert np.array_equal(nxt, logits.argmax(axis=1).astype(np.int32))
+            tok = nxt
+    finally:
+        model.close(); eng.close()

@@ -214,3 +214,53 @@ def test_matmul_cached_restatement():
         fn_r(oa.fptr(r), oa.fptr(x), oa.fptr(w), oa.fptr(bias), B, T, C, 3 * C)
         fn_o(oa.fptr(o), oa.fptr(x), oa.fptr(w), oa.fptr(bias), B, T, C, 3 * C)
         assert np.array_equal(r.view(np.uint32), o.view(np.uint32))
+
+
+def test_layer_ops_restatement():
+    """Next-row checkers: encoder / layernorm / gelu / residual / softmax / sample_mult
+    restated in oracle/paged_oracle.c == the compiled reference, bit for bit (strict flavour)."""
+    bs, mb, mp = 32, 100, 100
+    need_ref(bs, mb, mp)
+    rl = oa.load_ref(bs, mb, mp)
+    ol = oa.load_oracle()
+    B, T, C_, V = 2, 5, 48, 97
+    x = oa.normal((B, T, C_), seed=11)
+    w = oa.normal((C_,), seed=12)
+    b = oa.normal((C_,), seed=13)
+    # layernorm (+ mean, rstd)
+    outs = []
+    for lib, pre in ((rl, "ref_"), (ol, "orc_")):
+        o = np.zeros_like(x); m = np.zeros((B, T), np.float32); r = np.zeros((B, T), np.float32)
+        getattr(lib, pre + "layernorm_forward")(oa.fptr(o), oa.fptr(m), oa.fptr(r), oa.fptr(x), oa.fptr(w), oa.fptr(b), B, T, C_)
+        outs.append((o, m, r))
+    for a, c in zip(outs[0], outs[1]):
+        assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
+    # gelu, residual
+    y = oa.normal((B * T * C_,), seed=14) * np.float32(3.0)
+    for name, args in (("gelu_forward", (y,)), ("residual_forward", (y, y[::-1].copy()))):
+        res = []
+        for lib, pre in ((rl, "ref_"), (ol, "orc_")):
+            o = np.zeros_like(y)
+            getattr(lib, pre + name)(oa.fptr(o), *[oa.fptr(a) for a in args], y.size)
+            res.append(o)
+        assert np.array_equal(res[0].view(np.uint32), res[1].view(np.uint32)), name
+    # encoder
+    wte = oa.normal((V, C_), seed=15); wpe = oa.normal((T, C_), seed=16)
+    tok = (np.arange(B * T, dtype=np.int32) * 7 % V).astype(np.int32)
+    res = []
+    for lib, pre in ((rl, "ref_"), (ol, "orc_")):
+        o = np.zeros((B, T, C_), np.float32)
+        getattr(lib, pre + "encoder_forward")(oa.fptr(o), oa.iptr(tok), oa.fptr(wte), oa.fptr(wpe), B, T, C_)
+        res.append(o)
+    assert np.array_equal(res[0], res[1])
+    # softmax + sample_mult over a range of coins
+    logits = oa.normal((B, T, V), seed=17) * np.float32(4.0)
+    res = []
+    for lib, pre in ((rl, "ref_"), (ol, "orc_")):
+        pr = np.zeros_like(logits)
+        getattr(lib, pre + "softmax_forward")(oa.fptr(pr), oa.fptr(logits), B, T, V)
+        res.append(pr)
+    assert np.array_equal(res[0].view(np.uint32), res[1].view(np.uint32))
+    row = np.ascontiguousarray(res[0][0, 0])
+    for coin in (0.0, 1e-7, 0.25, 0.5, 0.75, 0.999999, 0.9999999):
+        assert rl.ref_sample_mult(oa.fptr(row), V, coin) == ol.orc_sample_mult(oa.fptr(row), V, coin)
