@@ -268,6 +268,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-model", action="store_true", help="skip the whole-model decode step section (SURVEY 8f.2)")
     ap.add_argument("--no-clock-hold", action="store_true", help="skip the untimed >=1.5 s continuation (ncu runs)")
     ap.add_argument("--hpg", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
@@ -477,6 +478,54 @@ def main():
                          "pulled over PCIe by the kernel's bulk copies, outputs stored to pinned host memory by the kernel, sync"),
                "wall_ms_per_step": wall * 1e3 / k_e2e}
 
+    # ---- whole-model decode step: embedding, L x {ln, QKV+append, paged attention,
+    # attproj, ln, MLP}, LM head, sampler through pa_model_decode_step (host tokens in, host tokens
+    # out); with N > 1 the sampled tokens of all ranks are gathered with one NCCL all_gather per step
+    model_info = None
+    if not args.no_model and hs == 64 and max(ctx) <= 4096:
+        try:
+            V, maxT = 50257, max(1024, max(ctx) + 8)
+            model = pa.Model(eng, maxT, V, params=None, seed=1337 + rank, max_batch=B)
+            toks = rng.integers(0, V, size=B).astype(np.int32)
+            coins = rng.random(B).astype(np.float32)
+            gathered = None
+            if dist is not None:
+                import torch
+                t_local = torch.zeros(B, dtype=torch.int32, device=f"cuda:{local_rank}")
+                gathered = torch.zeros(world * B, dtype=torch.int32, device=f"cuda:{local_rank}")
+
+            def model_step():
+                nxt = model.decode_step(seq_ids, toks, coins)
+                rollback()
+                if dist is not None:
+                    t_local.copy_(torch.from_numpy(nxt))
+                    dist.all_gather_into_tensor(gathered, t_local)
+                return nxt
+            for _ in range(3):
+                model_step()
+            barrier()
+            k_model = max(5, min(args.steps, 30))
+            hs_ = lib.pa_stream_of(eng.h)
+            l0 = eng.launches()
+            lib.pa_event_record(e0, hs_)
+            t0 = time.perf_counter()
+            for _ in range(k_model):
+                model_step()
+            lib.pa_event_record(e1, hs_)
+            barrier()
+            wall_ms = (time.perf_counter() - t0) * 1e3 / k_model
+            ms_model = allmax(max(lib.pa_event_elapsed_ms(e0, e1) / k_model, wall_ms))
+            model_info = {"tokens_per_s": world * B / (ms_model * 1e-3), "ms_per_step": ms_model, "steps": k_model,
+                          "vocab": V, "layers": L, "gpu_launches_per_step": (eng.launches() - l0) / k_model,
+                          "sampler": "softmax + multinomial (sample_mult) fused kernel, host coins",
+                          "projections": "tcgen05 3xTF32 (fp32-accurate) GEMMs with bias/GELU/residual epilogues",
+                          "weights": "random init on the device (no checkpoint offline)",
+                          "token_gather": ("NCCL all_gather of int32 next tokens, every step" if dist is not None else None),
+                          "entry": "pa_model_decode_step (host token ids in, host token ids out, sync per step)"}
+            model.close()
+        except Exception as ex:
+            model_info = {"error": repr(ex)}
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -521,7 +570,9 @@ def main():
                        "parallelism": f"sequences sharded over {world} GPU(s), no data-path collective"},
             "tokens_per_s": tokens_per_s, "frac_of_measured_peak": value / world / peak,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline}
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "model": model_info}
+    if model_info and "ms_per_step" in model_info:
+        model_info["attention_share_of_step"] = kms * L / model_info["ms_per_step"]
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()
