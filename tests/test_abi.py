@@ -74,5 +74,11 @@ def test_compute_fails_loudly_without_device():
         assert eng.decode(0, None, 128, None, 128) == pa.PA_ERR_NO_DEVICE
         assert eng.append(0, None, None, 128) == pa.PA_ERR_NO_DEVICE
         assert eng.decode_step_host(0, None, None) == pa.PA_ERR_NO_DEVICE
+        assert eng.prefill(0, None, 128, None, 128) == pa.PA_ERR_NO_DEVICE
+        assert eng.qkv_append(0, None, 128, None, None, None, 128) == pa.PA_ERR_NO_DEVICE
+        mcfg = pa.PaModelConfig(32, 100, 1, 2, 128)
+        m = C.c_void_p()
+        assert lib.pa_model_create(eng.h, C.byref(mcfg), None, 1, 2, C.byref(m)) == pa.PA_ERR_NO_DEVICE
+        assert "no CPU fallback" in pa.last_error()
     finally:
         eng.close()

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Whole-model decode step on one B200: GPT-2 shaped model with random-init weights,
+`pa_model_decode_step` (host token ids in, host token ids out).  Used for the ncu launch list of a step.
+
+  python tools/model_bench.py [--shape 124m|xl] [--B n] [--ctx n] [--layers n] [--steps n]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+SHAPES = {"124m": (12, 64, 12), "xl": (25, 64, 48)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="124m", choices=sorted(SHAPES))
+    ap.add_argument("--B", type=int, default=256)
+    ap.add_argument("--ctx", type=int, default=576)
+    ap.add_argument("--layers", type=int, default=0)
+    ap.add_argument("--bs", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--gemm-path", type=int, default=0)
+    args = ap.parse_args()
+    pa = ge.build(quiet=True)
+    lib = pa.load()
+    if lib.pa_device_count() < 1:
+        raise SystemExit("model_bench: no CUDA device; libpaged_attn has no CPU fallback")
+    NH, hs, L = SHAPES[args.shape]
+    if args.layers:
+        L = args.layers
+    B, bs, ctx = args.B, args.bs, args.ctx
+    pages = (ctx + bs - 1) // bs + 1
+    eng = pa.PagedAttn(bs, B * pages + 8, B, NH, hs, n_layers=L, device=0, max_batch_tokens=B)
+    eng.tune(pa.PA_TUNE_GEMM_PATH, args.gemm_path)
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(B * pages + 8)
+    for s in range(B):
+        assert eng.seq_adopt(s, perm[s * pages: s * pages + (ctx - 1 + bs - 1) // bs], ctx - 1) == 0, pa.last_error()
+    V = 50257
+    model = pa.Model(eng, max(1024, ctx + 8), V, params=None, seed=1, max_batch=B)
+    seq = np.arange(B, dtype=np.int32)
+    tok = rng.integers(0, V, size=B).astype(np.int32)
+    coins = rng.random(B).astype(np.float32)
+
+    def step():
+        nxt = model.decode_step(seq, tok, coins)
+        pa.check(eng.step_rollback(), "rollback")
+        return nxt
+    for _ in range(3):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    print(json.dumps({"tool": "model_bench", "shape": args.shape, "B": B, "ctx": ctx, "layers": L, "ms_per_step": dt * 1e3,
+                      "tokens_per_s": B / dt, "gemm_path": args.gemm_path}))
+    model.close(); eng.close()
+
+
+if __name__ == "__main__":
+    main()
