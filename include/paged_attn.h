@@ -207,6 +207,28 @@ PA_API int pa_model_decode_step(pa_model* m, const int* seq_ids, const int* toke
 PA_API float* pa_model_params(pa_model* m);               /* device */
 PA_API float* pa_model_logits(pa_model* m, int* stride);  /* device, (nseq, stride) of the last step */
 
+/* ---- the reference's on-disk formats (host only, no device needed) ---------------- */
+/* checkpoint gpt2_124M.bin (reader paged_infer.c:436-502): 256 x int32 header + 16 fp32 tensors */
+PA_API int pa_checkpoint_read_config(const char* path, pa_model_config* cfg);
+PA_API int pa_checkpoint_read_params(const char* path, float* params, size_t n_floats);
+PA_API int pa_checkpoint_write(const char* path, const pa_model_config* cfg, const float* params);
+PA_API int pa_model_create_from_checkpoint(pa_handle* h, const char* path, int max_batch, pa_model** out);
+/* token stream (dataloader_*, paged_infer.c:769-818): raw int32 ids, batches of B*T (+1 target) */
+typedef struct pa_dataloader pa_dataloader;
+PA_API int pa_dataloader_open(const char* path, int B, int T, pa_dataloader** out);
+PA_API void pa_dataloader_reset(pa_dataloader* d);
+PA_API int pa_dataloader_num_batches(const pa_dataloader* d);
+PA_API int pa_dataloader_next_batch(pa_dataloader* d, const int** inputs, const int** targets);
+PA_API void pa_dataloader_close(pa_dataloader* d);
+PA_API int pa_tokens_write(const char* path, const int* ids, size_t n);
+/* tokenizer gpt2_tokenizer.bin (tokenizer_init / tokenizer_decode, paged_infer.c:875-915) */
+typedef struct pa_tokenizer pa_tokenizer;
+PA_API int pa_tokenizer_open(const char* path, pa_tokenizer** out);
+PA_API unsigned pa_tokenizer_vocab_size(const pa_tokenizer* t);
+PA_API const char* pa_tokenizer_decode(const pa_tokenizer* t, unsigned token_id);
+PA_API void pa_tokenizer_close(pa_tokenizer* t);
+PA_API int pa_tokenizer_write(const char* path, const char* const* pieces, const unsigned char* lens, unsigned vocab_size);
+
 /* ---- whole step with HOST buffers (the end-to-end entry: H2D, append, decode, D2H, sync) -- */
 /* qkv_host: (nseq, 3C) rows of the step's sequences [q | k | v]; out_host: (nseq, C).  Pinned
  * buffers (pa_host_alloc) are read and written by the kernel directly over PCIe (zero-copy);

@@ -109,6 +109,21 @@ def load():
         "pa_model_decode_step": (C.c_int, [vp, c_int_p, c_int_p, vp, C.c_int, c_int_p]),
         "pa_model_params": (vp, [vp]),
         "pa_model_logits": (vp, [vp, c_int_p]),
+        "pa_checkpoint_read_config": (C.c_int, [C.c_char_p, C.POINTER(PaModelConfig)]),
+        "pa_checkpoint_read_params": (C.c_int, [C.c_char_p, vp, C.c_size_t]),
+        "pa_checkpoint_write": (C.c_int, [C.c_char_p, C.POINTER(PaModelConfig), vp]),
+        "pa_model_create_from_checkpoint": (C.c_int, [vp, C.c_char_p, C.c_int, C.POINTER(vp)]),
+        "pa_dataloader_open": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]),
+        "pa_dataloader_reset": (None, [vp]),
+        "pa_dataloader_num_batches": (C.c_int, [vp]),
+        "pa_dataloader_next_batch": (C.c_int, [vp, C.POINTER(c_int_p), C.POINTER(c_int_p)]),
+        "pa_dataloader_close": (None, [vp]),
+        "pa_tokens_write": (C.c_int, [C.c_char_p, c_int_p, C.c_size_t]),
+        "pa_tokenizer_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+        "pa_tokenizer_vocab_size": (C.c_uint, [vp]),
+        "pa_tokenizer_decode": (C.c_char_p, [vp, C.c_uint]),
+        "pa_tokenizer_close": (None, [vp]),
+        "pa_tokenizer_write": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_ubyte), C.c_uint]),
         "pa_qkv_append": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, vp]),
         "pa_matmul_bias": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "matmul_forward": (None, [vp, vp, vp, vp] + [C.c_int] * 4),

@@ -168,5 +168,36 @@ REF_API void ref_gelu_forward(float* out, float* inp, int N) { gelu_forward(out,
 REF_API void ref_residual_forward(float* out, float* a, float* b, int N) { residual_forward(out, a, b, N); }
 REF_API void ref_softmax_forward(float* probs, float* logits, int B, int T, int V) { softmax_forward(probs, logits, B, T, V); }
 REF_API int ref_sample_mult(float* probs, int n, float coin) { return sample_mult(probs, n, coin); }
+/* on-disk formats: the reference's own readers */
+REF_API long ref_checkpoint_load(const char* path, int* cfg5, float* params_out, long cap) {
+    GPT2 model;
+    gpt2_build_from_checkpoint(&model, path);                      /* prints the hyperparameters; exit(1) on a bad file */
+    cfg5[0] = model.config.max_seq_len; cfg5[1] = model.config.vocab_size; cfg5[2] = model.config.num_layers;
+    cfg5[3] = model.config.num_heads; cfg5[4] = model.config.channels;
+    long n = (long)model.num_parameters;
+    if (params_out && n <= cap) memcpy(params_out, model.params_memory, (size_t)n * sizeof(float));
+    free(model.params_memory);
+    return n;
+}
+REF_API void* ref_dataloader_open(const char* path, int B, int T) {
+    DataLoader* d = (DataLoader*)malloc(sizeof(DataLoader));
+    dataloader_init(d, path, B, T);
+    return d;
+}
+REF_API int ref_dataloader_num_batches(void* d) { return ((DataLoader*)d)->num_batches; }
+REF_API void ref_dataloader_next(void* dv, int* out) {
+    DataLoader* d = (DataLoader*)dv;
+    dataloader_next_batch(d);
+    memcpy(out, d->batch, ((size_t)d->B * d->T + 1) * sizeof(int));
+}
+REF_API void ref_dataloader_reset(void* d) { dataloader_reset((DataLoader*)d); }
+REF_API void ref_dataloader_free(void* d) { dataloader_free((DataLoader*)d); free(d); }
+REF_API void* ref_tokenizer_open(const char* path) {
+    Tokenizer* t = (Tokenizer*)malloc(sizeof(Tokenizer));
+    tokenizer_init(t, path);
+    return t;
+}
+REF_API int ref_tokenizer_vocab(void* t) { return ((Tokenizer*)t)->init_ok ? (int)((Tokenizer*)t)->vocab_size : -1; }
+REF_API const char* ref_tokenizer_decode(void* t, unsigned id) { return tokenizer_decode((Tokenizer*)t, id); }
 REF_API unsigned int ref_random_u32(unsigned long long* s) { return random_u32(s); }
 REF_API float ref_random_f32(unsigned long long* s) { return random_f32(s); }

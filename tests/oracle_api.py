@@ -75,6 +75,19 @@ def load_ref(bs, mb, mp, flavor="strict"):
     lib.ref_time_attend_prompt.argtypes = [vp, C.c_int, c_float_p, c_float_p,
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.ref_time_attend_prompt.restype = C.c_double
+    lib.ref_checkpoint_load.argtypes = [C.c_char_p, c_int_p, c_float_p, C.c_long]
+    lib.ref_checkpoint_load.restype = C.c_long
+    lib.ref_dataloader_open.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    lib.ref_dataloader_open.restype = vp
+    lib.ref_dataloader_num_batches.argtypes = [vp]
+    lib.ref_dataloader_next.argtypes = [vp, c_int_p]
+    lib.ref_dataloader_reset.argtypes = [vp]
+    lib.ref_dataloader_free.argtypes = [vp]
+    lib.ref_tokenizer_open.argtypes = [C.c_char_p]
+    lib.ref_tokenizer_open.restype = vp
+    lib.ref_tokenizer_vocab.argtypes = [vp]
+    lib.ref_tokenizer_decode.argtypes = [vp, C.c_uint]
+    lib.ref_tokenizer_decode.restype = C.c_char_p
     lib.ref_encoder_forward.argtypes = [c_float_p, c_int_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int]
     lib.ref_layernorm_forward.argtypes = [c_float_p] * 6 + [C.c_int] * 3
     lib.ref_gelu_forward.argtypes = [c_float_p, c_float_p, C.c_int]

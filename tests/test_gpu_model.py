@@ -120,3 +120,32 @@ def test_model_greedy_and_random_init():
             tok = nxt
     finally:
         model.close(); eng.close()
+
+
+def test_model_from_checkpoint_file(tmp_path):
+    """SURVEY 8f.3 meets 8f.2: a synthetic checkpoint in the reference's gpt2_124M.bin layout is
+    written, loaded with pa_model_create_from_checkpoint and gives the same logits as the same
+    parameters passed in memory."""
+    L, NH, hs, V, maxT, B = 2, 2, 64, 131, 48, 3
+    Cc = NH * hs
+    params = make_params(V, maxT, L, Cc, seed=500)
+    lib = pa.load()
+    cfg = pa.PaModelConfig(maxT, V, L, NH, Cc)
+    path = str(tmp_path / "gpt2_synth.bin").encode()
+    pa.check(lib.pa_checkpoint_write(path, C.byref(cfg), params.ctypes.data), "checkpoint write")
+    outs = []
+    for from_file in (False, True):
+        eng = pa.PagedAttn(16, 16, B, NH, hs, n_layers=L, device=0, max_batch_tokens=B)
+        if from_file:
+            model = pa.Model.__new__(pa.Model)
+            model.eng, model.lib, model.V = eng, lib, V
+            model.m = C.c_void_p()
+            pa.check(lib.pa_model_create_from_checkpoint(eng.h, path, B, C.byref(model.m)), "from checkpoint")
+        else:
+            model = pa.Model(eng, maxT, V, params=params, max_batch=B)
+        tok = np.array([5, 17, 99], dtype=np.int32)
+        for _ in range(3):
+            tok = model.decode_step([0, 1, 2], tok, None)
+        outs.append(model.logits(B).copy())
+        model.close(); eng.close()
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
