@@ -60,6 +60,9 @@ typedef struct BlockManager { /* block_manager.c:17-23 */
     int table_stride;             /* ints per block-table row */
     int* block_table;             /* flat [max_prompts][table_stride]; this is what is mirrored to HBM */
     pa_handle* pa;                /* owning handle (pool, streams); never NULL */
+    int* refcount;                /* [max_blocks] holders of a page: sequences (+1 if the prefix cache holds it); 0 = free.
+                                     Always 0/1 unless pa_seq_fork / pa_prefix_* are used */
+    void* prefix_cache;           /* opaque (pa_sharing.c), NULL until pa_prefix_insert */
 } BlockManager;
 
 typedef enum pa_status {
@@ -245,6 +248,22 @@ PA_API int pa_step_rollback(pa_handle* h);
 /* Install an externally built block table (e.g. a shuffled / fragmented layout for benchmarks):
  * the sequence must be empty and the pages free. */
 PA_API int pa_seq_adopt(pa_handle* h, int seq_id, const int* blocks, int n_blocks, int n_tokens);
+
+/* ---- allocator extensions (all OFF unless called: the reference trace is unchanged) ---- */
+/* Parallel sampling (the reference's unused `P`, paged_infer.c:958): dst (empty) becomes a copy of
+ * src.  Full pages are SHARED (reference-counted, read-only), the partial last page is copied on
+ * the device (all layers), so both sequences can append independently afterwards. */
+PA_API int pa_seq_fork(pa_handle* h, int src_seq, int dst_seq);
+/* Prefix sharing by hashing ("if you do hashing you need to change up this policy",
+ * block_manager.c:109-111): register the FULL pages of a prefilled sequence under the chained hash
+ * of their token ids; the cache keeps them alive after the sequence is freed (evicted LRU-first
+ * before any live sequence is). */
+PA_API int pa_prefix_insert(pa_handle* h, int seq_id, const int* tokens, int n_tokens);
+/* seq_id must be empty: adopts the longest cached page-aligned prefix of tokens (never the whole
+ * prompt: at least one token is left to compute) and returns the number of tokens matched. */
+PA_API int pa_prefix_match(pa_handle* h, int seq_id, const int* tokens, int n_tokens);
+PA_API int pa_prefix_cached_pages(pa_handle* h);
+PA_API int pa_page_refcount(pa_handle* h, int page);
 
 /* ---- pool access (tests, benchmarks, checkpointing) --------------------------------------- */
 PA_API float* pa_pool_k(pa_handle* h, int layer);                /* device, [max_blocks][bs][C] */

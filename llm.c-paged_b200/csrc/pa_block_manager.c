@@ -34,7 +34,8 @@ BlockManager* pa_bm_create(pa_handle* owner, int channels, int block_size, int m
     m->block_table = (int*)calloc((size_t)max_prompts * table_stride, sizeof(int));
     m->prompt_block_list = (int**)calloc((size_t)max_prompts, sizeof(int*));
     m->prompt_block_count = (int*)calloc((size_t)max_prompts, sizeof(int));
-    if (!m->blocks || !m->block_table || !m->prompt_block_list || !m->prompt_block_count) {
+    m->refcount = (int*)calloc((size_t)max_blocks, sizeof(int));
+    if (!m->blocks || !m->block_table || !m->prompt_block_list || !m->prompt_block_count || !m->refcount) {
         pa_bm_destroy(m);
         return NULL;
     }
@@ -45,6 +46,8 @@ BlockManager* pa_bm_create(pa_handle* owner, int channels, int block_size, int m
 
 void pa_bm_destroy(BlockManager* m) {
     if (!m) return;
+    pa_share_destroy(m);
+    free(m->refcount);
     free(m->blocks);
     free(m->block_table);
     free(m->prompt_block_list);
@@ -89,17 +92,27 @@ KVBlock* get_current_block(BlockManager* m, int prompt_id) {
     return &m->blocks[m->prompt_block_list[prompt_id][n - 1]];
 }
 
+/* Prompt p lets go of page idx.  Without sharing (refcount 1) this is the reference's free
+ * (block_manager.c:82-87); a shared page (pa_seq_fork / pa_prefix_*) stays with its other holders. */
+void pa_bm_release_page(BlockManager* m, int p, int idx) {
+    KVBlock* b = &m->blocks[idx];
+    if (m->refcount[idx] > 1) {
+        m->refcount[idx]--;
+        if (b->prompt_id == p) b->prompt_id = pa_share_other_holder(m, p, idx);   /* keep a valid owner for the LRU */
+        return;
+    }
+    m->refcount[idx] = 0;
+    b->keys = NULL;
+    b->values = NULL;
+    b->filled = 0;
+    b->prompt_id = -1;          /* lru_counter keeps its value, as in the reference */
+}
+
 void free_blocks_for_prompt(BlockManager* m, int prompt_id) {
     if (!m || !valid_prompt(m, prompt_id)) return;
     int n = m->prompt_block_count[prompt_id];
-    for (int i = 0; i < n; i++) {
-        KVBlock* b = &m->blocks[m->prompt_block_list[prompt_id][i]];
-        b->keys = NULL;
-        b->values = NULL;
-        b->filled = 0;
-        b->prompt_id = -1;      /* lru_counter keeps its value, as in the reference */
-    }
-    m->prompt_block_count[prompt_id] = 0;
+    m->prompt_block_count[prompt_id] = 0;      /* first: the holder search must not find this prompt */
+    for (int i = 0; i < n; i++) pa_bm_release_page(m, prompt_id, m->prompt_block_list[prompt_id][i]);
 }
 
 int find_least_recently_used_block(BlockManager* m) {
@@ -107,7 +120,7 @@ int find_least_recently_used_block(BlockManager* m) {
     int lowest = m->lru_epoch;
     for (int i = 0; i < m->max_blocks; i++) {
         const KVBlock* b = &m->blocks[i];
-        if (b->prompt_id != -1 && b->lru_counter < lowest) {
+        if (b->prompt_id >= 0 && b->lru_counter < lowest) {      /* (pages held only by the prefix cache are not a prompt's) */
             lowest = b->lru_counter;
             victim = i;
         }
@@ -136,9 +149,16 @@ KVBlock* request_block(BlockManager* m, int prompt_id) {
         return NULL;
     }
     int idx = lowest_free_page(m);
+    if (idx == -1 && pa_share_evict_one_cached(m)) idx = lowest_free_page(m);   /* extension: cached prefixes go first */
     if (idx == -1) {
-        page_out_lru_block(m);
-        idx = lowest_free_page(m);
+        /* the reference pages out ONE prompt (block_manager.c:130-133), which always frees a page;
+         * with shared pages (extension) a victim may free nothing, so keep going until one does */
+        for (int tries = 0; idx == -1 && tries < m->max_prompts; tries++) {
+            int victim = find_least_recently_used_block(m);
+            if (victim == -1) break;
+            free_blocks_for_prompt(m, m->blocks[victim].prompt_id);
+            idx = lowest_free_page(m);
+        }
         if (idx == -1) {
             fprintf(stderr, "No blocks available.\n");
             return NULL;
@@ -148,6 +168,7 @@ KVBlock* request_block(BlockManager* m, int prompt_id) {
     bind_page(m, idx);
     b->prompt_id = prompt_id;
     b->filled = 0;
+    m->refcount[idx] = 1;
     b->lru_counter = ++m->lru_epoch;
     /* note: if the eviction above hit prompt_id itself its count is 0 again here, exactly as
      * in the reference, which re-reads the count after paging out (block_manager.c:157) */

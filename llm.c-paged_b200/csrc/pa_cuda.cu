@@ -193,6 +193,20 @@ int pa_cu_ensure_stage(pa_handle* h, size_t floats) {
     return PA_OK;
 }
 
+int pa_cu_copy_page_rows(pa_handle* h, int src_page, int dst_page, int rows) {
+    if (h->host_only || !h->pool_k || rows <= 0) return PA_OK;
+    CU_CHECK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)h->stream;
+    const size_t page = (size_t)h->cfg.block_size * h->C, bytes = (size_t)rows * h->C * sizeof(float);
+    for (int l = 0; l < h->cfg.n_layers; l++) {
+        const size_t base = (size_t)l * h->layer_stride;
+        CU_CHECK(cudaMemcpyAsync(h->pool_k + base + dst_page * page, h->pool_k + base + src_page * page, bytes, cudaMemcpyDeviceToDevice, s));
+        CU_CHECK(cudaMemcpyAsync(h->pool_v + base + dst_page * page, h->pool_v + base + src_page * page, bytes, cudaMemcpyDeviceToDevice, s));
+    }
+    CU_CHECK(cudaStreamSynchronize(s));
+    return PA_OK;
+}
+
 int pa_cu_is_device_ptr(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }

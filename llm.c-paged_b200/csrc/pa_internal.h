@@ -79,6 +79,14 @@ void pa_bm_destroy(BlockManager* m);
 /* page choice of add_to_cache (paged_infer.c:518-529); returns page index or -1 */
 int pa_bm_choose_page(BlockManager* m, int prompt_id);
 int pa_bm_context_len(const BlockManager* m, int prompt_id);
+/* drop prompt p's hold on page idx: the page is freed when nobody else holds it (pa_sharing.c keeps holders valid) */
+void pa_bm_release_page(BlockManager* m, int p, int idx);
+
+/* ---- implemented in pa_sharing.c ------------------------------------------------ */
+#define PA_OWNER_CACHE (-2)      /* KVBlock.prompt_id of a page held only by the prefix cache */
+int pa_share_other_holder(BlockManager* m, int p, int idx);     /* another sequence holding idx, PA_OWNER_CACHE, or -1 */
+int pa_share_evict_one_cached(BlockManager* m);                 /* frees the LRU cache-only page; 1 if one was freed */
+void pa_share_destroy(BlockManager* m);
 
 /* ---- implemented in pa_step.c ------------------------------------------------------------- */
 int pa_create_compat(const pa_config* cfg, pa_handle** out);
@@ -97,6 +105,8 @@ int pa_cu_ensure_stage(pa_handle* h, size_t floats);
 int* pa_cu_step_host_buffer(pa_handle* h, size_t ints);
 int pa_cu_step_upload(pa_handle* h, void* stream);
 int pa_cu_is_device_ptr(const void* p);
+/* rows [0, rows) of page src -> page dst, K and V, every layer; stream-ordered on the handle's stream, then synchronised */
+int pa_cu_copy_page_rows(pa_handle* h, int src_page, int dst_page, int rows);
 
 /* ---- implemented in pa_prefill.cu / pa_prefill_tc.cu ------------------------------------- */
 /* PA_OK = launched; PA_ERR_UNSUPPORTED = shape outside the kernel's domain (use the generic rows kernel) */

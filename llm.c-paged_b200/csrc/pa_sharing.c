@@ -1,0 +1,200 @@
+/*
+ * pa_sharing.c -- allocator extensions the fork's comments point at, host side,
+ * plain C:
+ *   - parallel sampling (`int P = 5`, unused, paged_infer.c:958): pa_seq_fork shares a sequence's
+ *     full pages between copies, reference-counted;
+ *   - prefix sharing by hashing ("if you do hashing you need to change up this policy",
+ *     block_manager.c:109-111): pa_prefix_insert / pa_prefix_match.
+ * Everything here is OFF unless called: with every refcount at 0/1 and no prefix cache the block
+ * manager reproduces the reference trace bit for bit (tests/test_block_manager.py keeps checking
+ * that against the compiled reference).
+ *
+ * Invariants: refcount[i] = sequences whose table lists page i, + 1 if the prefix cache holds it;
+ * a shared page is FULL and read-only (appends only ever touch a sequence's private last page);
+ * KVBlock.prompt_id of a used page is always one of its holders (the LRU evicts whole prompts
+ * through it, block_manager.c:104-113) or PA_OWNER_CACHE.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pa_internal.h"
+
+typedef struct prefix_entry {
+    uint64_t key;            /* chained hash of all token ids up to and including this page */
+    int page;
+    int used;
+} prefix_entry;
+
+typedef struct prefix_cache {
+    prefix_entry* slots;     /* open addressing, capacity a power of two >= 2 * max_blocks */
+    int cap;
+    int n_pages;
+    int* page_tokens;        /* [max_blocks][block_size] token ids of a cached page (exact match on lookup) */
+    uint64_t* page_key;      /* [max_blocks] key under which the page is registered, 0 = not cached */
+} prefix_cache;
+
+static uint64_t mix(uint64_t h, uint64_t v) {
+    h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    h *= 0xff51afd7ed558ccdull;
+    return h ^ (h >> 33);
+}
+static uint64_t chain_key(uint64_t parent, const int* tokens, int n) {
+    uint64_t h = parent ^ 0x2545F4914F6CDD1Dull;
+    for (int i = 0; i < n; i++) h = mix(h, (uint64_t)(uint32_t)tokens[i]);
+    return h ? h : 1;
+}
+
+static prefix_cache* cache_get(BlockManager* m, int create) {
+    if (m->prefix_cache || !create) return (prefix_cache*)m->prefix_cache;
+    prefix_cache* c = (prefix_cache*)calloc(1, sizeof(*c));
+    if (!c) return NULL;
+    c->cap = 16;
+    while (c->cap < 2 * m->max_blocks) c->cap <<= 1;
+    c->slots = (prefix_entry*)calloc((size_t)c->cap, sizeof(prefix_entry));
+    c->page_tokens = (int*)calloc((size_t)m->max_blocks * m->block_size, sizeof(int));
+    c->page_key = (uint64_t*)calloc((size_t)m->max_blocks, sizeof(uint64_t));
+    if (!c->slots || !c->page_tokens || !c->page_key) { free(c->slots); free(c->page_tokens); free(c->page_key); free(c); return NULL; }
+    m->prefix_cache = c;
+    return c;
+}
+void pa_share_destroy(BlockManager* m) {
+    prefix_cache* c = (prefix_cache*)m->prefix_cache;
+    if (!c) return;
+    free(c->slots); free(c->page_tokens); free(c->page_key); free(c);
+    m->prefix_cache = NULL;
+}
+static prefix_entry* cache_find(prefix_cache* c, uint64_t key) {
+    for (int i = (int)(key & (uint64_t)(c->cap - 1)), n = 0; n < c->cap; i = (i + 1) & (c->cap - 1), n++) {
+        if (!c->slots[i].used) return NULL;
+        if (c->slots[i].used == 1 && c->slots[i].key == key) return &c->slots[i];
+    }
+    return NULL;
+}
+static void cache_put(prefix_cache* c, uint64_t key, int page) {
+    for (int i = (int)(key & (uint64_t)(c->cap - 1));; i = (i + 1) & (c->cap - 1)) {
+        if (c->slots[i].used != 1) { c->slots[i].key = key; c->slots[i].page = page; c->slots[i].used = 1; return; }
+    }
+}
+static void cache_remove(prefix_cache* c, uint64_t key) {
+    prefix_entry* e = cache_find(c, key);
+    if (e) e->used = 2;      /* tombstone */
+}
+
+int pa_share_other_holder(BlockManager* m, int p, int idx) {
+    for (int q = 0; q < m->max_prompts; q++) {
+        if (q == p) continue;
+        const int* row = m->prompt_block_list[q];
+        for (int i = 0; i < m->prompt_block_count[q]; i++)
+            if (row[i] == idx) return q;
+    }
+    prefix_cache* c = (prefix_cache*)m->prefix_cache;
+    if (c && c->page_key[idx]) return PA_OWNER_CACHE;
+    return -1;
+}
+
+/* the least recently used page that only the cache holds goes back to the free list */
+int pa_share_evict_one_cached(BlockManager* m) {
+    prefix_cache* c = (prefix_cache*)m->prefix_cache;
+    if (!c || c->n_pages == 0) return 0;
+    int victim = -1;
+    for (int i = 0; i < m->max_blocks; i++)
+        if (c->page_key[i] && m->refcount[i] == 1 && (victim < 0 || m->blocks[i].lru_counter < m->blocks[victim].lru_counter)) victim = i;
+    if (victim < 0) return 0;
+    cache_remove(c, c->page_key[victim]);
+    c->page_key[victim] = 0;
+    c->n_pages--;
+    m->refcount[victim] = 0;
+    m->blocks[victim].keys = m->blocks[victim].values = NULL;
+    m->blocks[victim].filled = 0;
+    m->blocks[victim].prompt_id = -1;
+    return 1;
+}
+
+static int bad_seq(pa_handle* h, int s) { return !h || s < 0 || s >= h->cfg.max_seqs; }
+
+int pa_seq_fork(pa_handle* h, int src, int dst) {
+    if (bad_seq(h, src) || bad_seq(h, dst) || src == dst) { pa_set_error("pa_seq_fork: bad sequence ids"); return PA_ERR_INVALID; }
+    BlockManager* m = h->mgr;
+    if (m->prompt_block_count[dst] != 0) { pa_set_error("pa_seq_fork: sequence %d is not empty", dst); return PA_ERR_INVALID; }
+    const int n = m->prompt_block_count[src];
+    if (n == 0) return PA_OK;
+    const int last = m->prompt_block_list[src][n - 1];
+    const int last_rows = m->blocks[last].filled;
+    const int shared = last_rows >= m->block_size ? n : n - 1;      /* a partial last page is copied, not shared */
+    for (int i = 0; i < shared; i++) {
+        const int idx = m->prompt_block_list[src][i];
+        m->prompt_block_list[dst][i] = idx;
+        m->refcount[idx]++;
+    }
+    m->prompt_block_count[dst] = shared;
+    if (shared < n) {
+        KVBlock* b = request_block(m, dst);       /* may evict (never src or dst pages that are shared: they have other holders) */
+        if (!b || m->prompt_block_count[src] != n || m->prompt_block_list[src][n - 1] != last) {
+            pa_set_error("pa_seq_fork: no page for the copy of the last page");
+            free_blocks_for_prompt(m, dst);
+            return PA_ERR_NO_BLOCKS;
+        }
+        b->filled = last_rows;
+        int rc = pa_cu_copy_page_rows(h, last, (int)(b - m->blocks), last_rows);
+        if (rc != PA_OK) { free_blocks_for_prompt(m, dst); return rc; }
+    }
+    return PA_OK;
+}
+
+int pa_prefix_insert(pa_handle* h, int seq, const int* tokens, int n_tokens) {
+    if (bad_seq(h, seq) || !tokens || n_tokens < 0) { pa_set_error("pa_prefix_insert: bad arguments"); return PA_ERR_INVALID; }
+    BlockManager* m = h->mgr;
+    const int bs = m->block_size;
+    if (n_tokens > pa_bm_context_len(m, seq)) { pa_set_error("pa_prefix_insert: %d tokens, %d cached", n_tokens, pa_bm_context_len(m, seq)); return PA_ERR_INVALID; }
+    prefix_cache* c = cache_get(m, 1);
+    if (!c) { pa_set_error("pa_prefix_insert: out of host memory"); return PA_ERR_NOMEM; }
+    uint64_t key = 0;
+    int added = 0;
+    for (int i = 0; (i + 1) * bs <= n_tokens; i++) {
+        key = chain_key(key, tokens + (size_t)i * bs, bs);
+        const int idx = m->prompt_block_list[seq][i];
+        prefix_entry* e = cache_find(c, key);
+        if (e) continue;                       /* this prefix is cached already (by this or another page) */
+        if (c->page_key[idx]) continue;        /* the page is registered under another prefix: leave it */
+        cache_put(c, key, idx);
+        c->page_key[idx] = key;
+        memcpy(c->page_tokens + (size_t)idx * bs, tokens + (size_t)i * bs, (size_t)bs * sizeof(int));
+        m->refcount[idx]++;                    /* the cache's own hold */
+        c->n_pages++;
+        added++;
+    }
+    return added;
+}
+
+int pa_prefix_match(pa_handle* h, int seq, const int* tokens, int n_tokens) {
+    if (bad_seq(h, seq) || !tokens || n_tokens < 0) { pa_set_error("pa_prefix_match: bad arguments"); return PA_ERR_INVALID; }
+    BlockManager* m = h->mgr;
+    if (m->prompt_block_count[seq] != 0) { pa_set_error("pa_prefix_match: sequence %d is not empty", seq); return PA_ERR_INVALID; }
+    prefix_cache* c = cache_get(m, 0);
+    if (!c) return 0;
+    const int bs = m->block_size;
+    uint64_t key = 0;
+    int n = 0;
+    for (int i = 0; (i + 1) * bs < n_tokens && i < m->table_stride; i++) {      /* '<': leave at least one token to compute */
+        key = chain_key(key, tokens + (size_t)i * bs, bs);
+        prefix_entry* e = cache_find(c, key);
+        if (!e || memcmp(c->page_tokens + (size_t)e->page * bs, tokens + (size_t)i * bs, (size_t)bs * sizeof(int)) != 0) break;
+        const int idx = e->page;
+        m->prompt_block_list[seq][n++] = idx;
+        m->refcount[idx]++;
+        if (m->blocks[idx].prompt_id < 0) m->blocks[idx].prompt_id = seq;        /* was held by the cache only */
+        m->blocks[idx].lru_counter = ++m->lru_epoch;                            /* a hit is a use */
+    }
+    m->prompt_block_count[seq] = n;
+    return n * bs;
+}
+
+int pa_prefix_cached_pages(pa_handle* h) {
+    prefix_cache* c = h ? (prefix_cache*)h->mgr->prefix_cache : NULL;
+    return c ? c->n_pages : 0;
+}
+int pa_page_refcount(pa_handle* h, int page) {
+    if (!h || page < 0 || page >= h->mgr->max_blocks) return PA_ERR_INVALID;
+    return h->mgr->refcount[page];
+}

@@ -353,13 +353,13 @@ int pa_seq_truncate(pa_handle* h, int seq_id, int new_len) {
     const int bs = m->block_size;
     int keep = (new_len + bs - 1) / bs;
     int n = m->prompt_block_count[seq_id];
-    for (int i = keep; i < n; i++) {
-        KVBlock* b = &m->blocks[m->prompt_block_list[seq_id][i]];
-        b->keys = b->values = NULL;
-        b->filled = 0;
-        b->prompt_id = -1;
+    if (keep > 0 && new_len - (keep - 1) * bs < bs && m->refcount[m->prompt_block_list[seq_id][keep - 1]] > 1) {
+        /* `filled` belongs to the page, and a shared page is full for all of its holders */
+        pa_set_error("pa_seq_truncate: position %d lies inside a page shared with another sequence", new_len);
+        return PA_ERR_UNSUPPORTED;
     }
     m->prompt_block_count[seq_id] = keep;
+    for (int i = keep; i < n; i++) pa_bm_release_page(m, seq_id, m->prompt_block_list[seq_id][i]);
     if (keep > 0) m->blocks[m->prompt_block_list[seq_id][keep - 1]].filled = new_len - (keep - 1) * bs;
     return PA_OK;
 }
@@ -402,6 +402,7 @@ int pa_seq_adopt(pa_handle* h, int seq_id, const int* blocks, int n_blocks, int 
         b->values = h->pool_v ? h->pool_v + off : NULL;
         b->filled = (i + 1 < n_blocks) ? bs : n_tokens - (n_blocks - 1) * bs;
         b->lru_counter = ++m->lru_epoch;
+        m->refcount[idx] = 1;
         m->prompt_block_list[seq_id][i] = idx;
     }
     m->prompt_block_count[seq_id] = n_blocks;

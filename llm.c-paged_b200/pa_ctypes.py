@@ -124,6 +124,11 @@ def load():
         "pa_tokenizer_decode": (C.c_char_p, [vp, C.c_uint]),
         "pa_tokenizer_close": (None, [vp]),
         "pa_tokenizer_write": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_ubyte), C.c_uint]),
+        "pa_seq_fork": (C.c_int, [vp, C.c_int, C.c_int]),
+        "pa_prefix_insert": (C.c_int, [vp, C.c_int, c_int_p, C.c_int]),
+        "pa_prefix_match": (C.c_int, [vp, C.c_int, c_int_p, C.c_int]),
+        "pa_prefix_cached_pages": (C.c_int, [vp]),
+        "pa_page_refcount": (C.c_int, [vp, C.c_int]),
         "pa_qkv_append": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, vp]),
         "pa_matmul_bias": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "matmul_forward": (None, [vp, vp, vp, vp] + [C.c_int] * 4),
@@ -286,6 +291,17 @@ class PagedAttn:
 
     def seq_free(self, s):
         return self.lib.pa_seq_free(self.h, s)
+
+    def seq_fork(self, src, dst):
+        return self.lib.pa_seq_fork(self.h, src, dst)
+
+    def prefix_insert(self, s, tokens):
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        return self.lib.pa_prefix_insert(self.h, s, iptr(t), len(t))
+
+    def prefix_match(self, s, tokens):
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        return self.lib.pa_prefix_match(self.h, s, iptr(t), len(t))
 
     def seq_adopt(self, s, blocks, n_tokens):
         b = np.ascontiguousarray(blocks, dtype=np.int32)
