@@ -619,7 +619,9 @@ extern "C" int pa_cu_prefill_tc(pa_handle* h, int layer, const float* q, int q_s
     const pa_step_layout& L = h->step;
     const int hs = h->cfg.head_dim, bs = h->cfg.block_size;
     if (!(hs == 64 || hs == 128)) return PA_ERR_UNSUPPORTED;
-    const int BN = (hs == 64 && h->tune[PA_TUNE_TC_KEY_TILE] != 64) ? 128 : 64;     // keys per tile
+    // keys per tile: head_dim 64 runs best with 64-key tiles, two 96 KB CTAs per SM (measured,
+    // profiles/r01_prefill.md); 128-key tiles on request
+    const int BN = (hs == 64 && h->tune[PA_TUNE_TC_KEY_TILE] == 128) ? 128 : 64;
     // a page must be whole 8-row swizzle groups and divide the key tile
     if (bs < 8 || (bs & (bs - 1)) || bs > BN) return PA_ERR_UNSUPPORTED;
     if ((h->C % 4) || (q_stride % 4) || (out_stride % 4) || !aligned16(q) || !aligned16(out)) return PA_ERR_UNSUPPORTED;
