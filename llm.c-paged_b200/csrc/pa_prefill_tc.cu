@@ -217,26 +217,28 @@ __device__ __forceinline__ void find_tile(const TcParams& p, int tile_lin, int& 
     }
 }
 
-template <int HS, int BN, int NWG, int NST>
+template <int HS, int BN, int NWG, int NST, int SBUF>
 struct TcCfg {
     static constexpr int kThreads = NWG * 128 + 64;
     // two CTAs per SM when their tiles fit (one-warpgroup CTAs overlap through co-residency)
-    static constexpr int kMinBlocks = (NWG == 1 && 2 * (1024 + 2 * NST * BN * HS * 4 + 512) <= 227 * 1024 && 2 * (HS + BN + HS) <= 512) ? 2 : 1;
+    static constexpr int kMinBlocks = (NWG == 1 && 2 * (1024 + 2 * NST * BN * HS * 4 + 512) <= 227 * 1024 && 2 * (HS + SBUF * BN + HS) <= 512) ? 2 : 1;
     static constexpr int kQBytes = kBM * HS * 4;
     static constexpr int kKVBytes = BN * HS * 4;
     static constexpr int kTileBytes = 2 * NST * kKVBytes;      // NST-deep rings of K and V tiles
-    static constexpr int kBarBytes = (3 * NWG + 4 * NST) * 8 + 32;
+    static constexpr int kBarBytes = ((2 * SBUF + 1) * NWG + 4 * NST) * 8 + 32;
     static constexpr size_t kSmem = 1024 + kTileBytes + kBarBytes;     // 1024: manual alignment slack
-    static constexpr int kCols = HS + NWG * (BN + HS);      // Q | S[NWG] | O[NWG]
+    static constexpr int kCols = HS + NWG * (SBUF * BN + HS);      // Q | S[NWG][SBUF] | O[NWG]
+    static constexpr int kLag = NWG * SBUF - 1;              // Q.K^T runs this many key tiles ahead of P.V
+    static_assert(NST > kLag, "the K ring must hold the tiles whose Q.K^T has been issued ahead");
     static constexpr int kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
-    static_assert(HS + NWG * BN + NWG * HS <= 512, "TMEM columns");
+    static_assert(HS + NWG * SBUF * BN + NWG * HS <= 512, "TMEM columns");
     static_assert((NWG - 1) * kBM * (HS + 2) * 4 <= 2 * NST * kKVBytes, "merge scratch must fit the K/V buffers");
 };
 
-template <int HS, int BN, int NWG, int NST>
-__global__ void __launch_bounds__(NWG * 128 + 64, (TcCfg<HS, BN, NWG, NST>::kMinBlocks))
+template <int HS, int BN, int NWG, int NST, int SBUF>
+__global__ void __launch_bounds__(NWG * 128 + 64, (TcCfg<HS, BN, NWG, NST, SBUF>::kMinBlocks))
 pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const TcParams p) {
-    using Cfg = TcCfg<HS, BN, NWG, NST>;
+    using Cfg = TcCfg<HS, BN, NWG, NST, SBUF>;
     constexpr int DB = HS / 32;                         // 32-column blocks per row
     constexpr uint32_t kIdescQK = instr_desc(kBM, BN, 0, 0);
     constexpr uint32_t kIdescPV = instr_desc(kBM, HS, 0, 1);
@@ -250,10 +252,10 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
     uint64_t* v_full = bars + NST;           // [NST]
     uint64_t* k_empty = bars + 2 * NST;      // [NST] the Q.K^T that read the K tile has completed
     uint64_t* v_empty = bars + 3 * NST;      // [NST] the P.V that read the V tile has completed
-    uint64_t* s_full = bars + 4 * NST;       // [NWG] Q.K^T committed: S readable
-    uint64_t* p_ready = s_full + NWG;        // [NWG] the warpgroup wrote P over S
-    uint64_t* o_full = s_full + 2 * NWG;     // [NWG] P.V committed: O holds this tile too
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3 * NWG);
+    uint64_t* s_full = bars + 4 * NST;       // [NWG][SBUF] Q.K^T committed: S readable
+    uint64_t* p_ready = s_full + NWG * SBUF; // [NWG][SBUF] the warpgroup wrote P over S
+    uint64_t* o_full = p_ready + NWG * SBUF; // [NWG] P.V committed: O holds this tile too
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NWG);
     int* s_unit = reinterpret_cast<int*>(tmem_slot + 1);
 
     const int tid = threadIdx.x;
@@ -274,11 +276,11 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
             mbar_init(smem_u32(&k_empty[b]), 1);
             mbar_init(smem_u32(&v_empty[b]), 1);
         }
-        for (int b = 0; b < NWG; ++b) {
+        for (int b = 0; b < NWG * SBUF; ++b) {
             mbar_init(smem_u32(&s_full[b]), 1);
             mbar_init(smem_u32(&p_ready[b]), 128);
-            mbar_init(smem_u32(&o_full[b]), 1);
         }
+        for (int b = 0; b < NWG; ++b) mbar_init(smem_u32(&o_full[b]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kProducerWarp) {
@@ -374,12 +376,13 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
             const bool leader = elect_one();
             auto issue_pv = [&](int it) {
                 const int b = it % NWG, j = it / NWG, st = it % NST;
+                const int sb = b * SBUF + (j % SBUF);              // S/P buffer of this tile
                 mbar_wait(smem_u32(&v_full[st]), (it / NST) & 1);
-                mbar_wait(smem_u32(&p_ready[b]), j & 1);
+                mbar_wait(smem_u32(&p_ready[sb]), (j / SBUF) & 1);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(Vs + st * Cfg::kKVBytes);
-                const uint32_t p_tmem = tmem_base + HS + b * BN;
-                const uint32_t o_tmem = tmem_base + HS + NWG * BN + b * HS;
+                const uint32_t p_tmem = tmem_base + HS + sb * BN;
+                const uint32_t o_tmem = tmem_base + HS + NWG * SBUF * BN + b * HS;
                 if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < BN / 8; ++ks)          // 8 keys per instruction = two 4-row swizzle groups
@@ -392,23 +395,26 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
             };
             for (int it = 0; it < n_kt; ++it) {
                 const int b = it % NWG, st = it % NST;
+                const int sb = b * SBUF + ((it / NWG) % SBUF);
                 mbar_wait(smem_u32(&k_full[st]), (it / NST) & 1);
                 tc_fence_after();
                 const uint32_t k_addr = smem_u32(Ks + st * Cfg::kKVBytes);
-                const uint32_t s_tmem = tmem_base + HS + b * BN;
+                // the P.V that read this S/P buffer last was issued SBUF tiles of this warpgroup ago, before
+                // this instruction in program order: the tensor pipe executes them in order
+                const uint32_t s_tmem = tmem_base + HS + sb * BN;
                 if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < HS / 8; ++ks) {        // 8 floats (32 B) of the head dimension per instruction
                         const uint32_t koff = (ks >> 2) * (BN * 128) + (ks & 3) * 32;
                         mma_tf32_ts(s_tmem, tmem_base + ks * 8, smem_desc(k_addr + koff, 16, 1024), kIdescQK, ks > 0);
                     }
-                    tc_commit(smem_u32(&s_full[b]));
+                    tc_commit(smem_u32(&s_full[sb]));
                     tc_commit(smem_u32(&k_empty[st]));
                 }
                 __syncwarp();
-                if (it >= NWG - 1) issue_pv(it - (NWG - 1));
+                if (it >= Cfg::kLag) issue_pv(it - Cfg::kLag);
             }
-            for (int it = max(0, n_kt - (NWG - 1)); it < n_kt; ++it) issue_pv(it);
+            for (int it = max(0, n_kt - Cfg::kLag); it < n_kt; ++it) issue_pv(it);
         }
     } else {
         // ============================== softmax warpgroups ====================================
@@ -418,8 +424,8 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
         const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
         const int lim = kv_end - (nq - 1 - (j0 + r));    // this row sees keys [kv_start, lim)
         const int lim_first = kv_end - (nq - 1 - j0);
-        const uint32_t s_tmem = tmem_base + lane_off + HS + g * BN;
-        const uint32_t o_tmem = tmem_base + lane_off + HS + NWG * BN + g * HS;
+        const uint32_t s_tmem0 = tmem_base + lane_off + HS + g * SBUF * BN;
+        const uint32_t o_tmem = tmem_base + lane_off + HS + NWG * SBUF * BN + g * HS;
         // exp2-domain online softmax.  The O accumulator stays in TMEM across this warpgroup's key
         // tiles; it is rescaled only when the row maximum has grown by more than 2^8 since the
         // maximum in use (probabilities stay <= 256, far inside fp32/tf32 range), so the common
@@ -434,7 +440,9 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
             constexpr bool MASK = decltype(mask_tag)::value;
             const int j = it / NWG;
             const int g0 = k_begin + it * BN;
-            mbar_wait(smem_u32(&s_full[g]), j & 1);
+            const int sb = g * SBUF + (j % SBUF);
+            const uint32_t s_tmem = s_tmem0 + (j % SBUF) * BN;
+            mbar_wait(smem_u32(&s_full[sb]), (j / SBUF) & 1);
             tc_fence_after();
             float sv[BN];
 #pragma unroll
@@ -484,7 +492,7 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
             m_run = m_use;
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(smem_u32(&p_ready[g]));
+            mbar_arrive(smem_u32(&p_ready[sb]));
         };
         for (int it = g; it < n_kt; it += NWG, ++n_mine) {
             const int g0 = k_begin + it * BN;
@@ -590,10 +598,10 @@ int make_pool_map(CUtensorMap* map, float* pool, const pa_handle* h, CUtensorMap
     return PA_OK;
 }
 
-template <int HS, int BN, int NWG, int NST>
+template <int HS, int BN, int NWG, int NST, int SBUF>
 int launch_tc(const TcState* st, const TcParams& p, cudaStream_t s) {
-    using Cfg = TcCfg<HS, BN, NWG, NST>;
-    auto fn = pa_prefill_tc_kernel<HS, BN, NWG, NST>;
+    using Cfg = TcCfg<HS, BN, NWG, NST, SBUF>;
+    auto fn = pa_prefill_tc_kernel<HS, BN, NWG, NST, SBUF>;
     static bool attr_done = false;
     if (!attr_done) {
         CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
@@ -657,16 +665,18 @@ extern "C" int pa_cu_prefill_tc(pa_handle* h, int layer, const float* q, int q_s
     if (n_tiles * p.NH > 0x7fffffffLL) return PA_ERR_UNSUPPORTED;
     p.n_tiles = (int)n_tiles;
     cudaStream_t s = (cudaStream_t)stream;
-    // measured (profiles/r01_prefill.md): head_dim 64 runs best as two 1-warpgroup CTAs per SM,
-    // head_dim 128 (one CTA per SM) with two warpgroups
+    // measured (profiles/r01_prefill.md): one softmax warpgroup with two S/P buffers beats two
+    // warpgroups with one buffer each for both head sizes (head_dim 64: two such CTAs per SM)
     const int want_wg = h->tune[PA_TUNE_TC_WARPGROUPS];
-    const int nwg = want_wg == 1 || want_wg == 2 ? want_wg : (hs == 64 ? 1 : 2);
+    const int nwg = want_wg == 2 ? 2 : 1;
     int rc;
     // K/V rings are 3 tiles deep (the load of tile i+3 starts when the MMAs of tile i have completed:
     // with 2 the tensor pipe waited a full L2 round trip every other tile)
-    if (hs == 64 && BN == 128) rc = nwg == 1 ? launch_tc<64, 128, 1, 3>(st, p, s) : launch_tc<64, 128, 2, 3>(st, p, s);
-    else if (hs == 64) rc = nwg == 1 ? launch_tc<64, 64, 1, 3>(st, p, s) : launch_tc<64, 64, 2, 3>(st, p, s);
-    else rc = nwg == 1 ? launch_tc<128, 64, 1, 3>(st, p, s) : launch_tc<128, 64, 2, 3>(st, p, s);
+    // One-warpgroup CTAs keep two S/P buffers, so Q.K^T of the next tile runs while the softmax of the
+    // current one does; two-warpgroup CTAs alternate warpgroups instead (TMEM has no room for both).
+    if (hs == 64 && BN == 128) rc = nwg == 1 ? launch_tc<64, 128, 1, 3, 2>(st, p, s) : launch_tc<64, 128, 2, 3, 1>(st, p, s);
+    else if (hs == 64) rc = nwg == 1 ? launch_tc<64, 64, 1, 3, 2>(st, p, s) : launch_tc<64, 64, 2, 3, 1>(st, p, s);
+    else rc = nwg == 1 ? launch_tc<128, 64, 1, 3, 2>(st, p, s) : launch_tc<128, 64, 2, 3, 1>(st, p, s);
     if (rc == PA_OK) h->launches++;
     return rc;
 }
