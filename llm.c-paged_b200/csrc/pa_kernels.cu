@@ -1079,7 +1079,17 @@ int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out
     return launch_rows(h, layer, q, q_stride, out, out_stride, true, s);
 }
 
+static int decode_step_host_impl(pa_handle* h, int layer, const float* qkv_host, float* out_host, bool sync);
 int pa_decode_step_host(pa_handle* h, int layer, const float* qkv_host, float* out_host) {
+    return decode_step_host_impl(h, layer, qkv_host, out_host, true);
+}
+/* Same, stream-ordered on the handle's stream without the final synchronisation: PINNED buffers only
+ * (pa_host_alloc); the caller synchronises (pa_stream_sync(pa_stream_of(h))) before reading out_host
+ * or reusing qkv_host.  Lets a host queue several layers / steps behind each other. */
+int pa_decode_step_host_async(pa_handle* h, int layer, const float* qkv_host, float* out_host) {
+    return decode_step_host_impl(h, layer, qkv_host, out_host, false);
+}
+static int decode_step_host_impl(pa_handle* h, int layer, const float* qkv_host, float* out_host, bool sync) {
     if (!h || h->host_only) { pa_set_error("pa_decode_step_host: no device; there is no CPU fallback"); return PA_ERR_NO_DEVICE; }
     if (!qkv_host || !out_host) { pa_set_error("pa_decode_step_host: NULL buffer"); return PA_ERR_INVALID; }
     const pa_step_layout& L = h->step;
@@ -1101,7 +1111,22 @@ int pa_decode_step_host(pa_handle* h, int layer, const float* qkv_host, float* o
          * output rows are stored straight to host memory -- no staging copies, one launch. */
         rc = pa_decode_append(h, layer, in_alias, in_alias + C, in_alias + 2 * C, (int)(3 * C), out_alias, (int)C, s);
         if (rc != PA_OK) return rc;
-        CU_CHECK(cudaStreamSynchronize(s));
+        if (sync) CU_CHECK(cudaStreamSynchronize(s));
+        return PA_OK;
+    }
+    if (!sync && (!in_pinned || !out_pinned)) {
+        pa_set_error("pa_decode_step_host_async: pageable host buffers need the synchronous entry (they are staged through one pinned buffer)");
+        return PA_ERR_INVALID;
+    }
+    if (!sync) {      /* pinned, but zero-copy switched off: stage through per-layer regions so queued layers do not collide */
+        rc = pa_cu_ensure_stage(h, (size_t)h->cfg.n_layers * n * 4 * C);
+        if (rc != PA_OK) return rc;
+        float* d_qkv_l = h->d_stage + (size_t)layer * n * 4 * C;
+        float* d_out_l = d_qkv_l + n * 3 * C;
+        CU_CHECK(cudaMemcpyAsync(d_qkv_l, qkv_host, n * 3 * C * sizeof(float), cudaMemcpyHostToDevice, s));
+        rc = pa_decode_append(h, layer, d_qkv_l, d_qkv_l + C, d_qkv_l + 2 * C, (int)(3 * C), d_out_l, (int)C, s);
+        if (rc != PA_OK) return rc;
+        CU_CHECK(cudaMemcpyAsync(out_host, d_out_l, n * C * sizeof(float), cudaMemcpyDeviceToHost, s));
         return PA_OK;
     }
     rc = pa_cu_ensure_stage(h, n * 4 * C);

@@ -103,6 +103,7 @@ def load():
         "pa_prefill": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
         "pa_decode_append": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_int, vp]),
         "pa_decode_step_host": (C.c_int, [vp, C.c_int, vp, vp]),
+        "pa_decode_step_host_async": (C.c_int, [vp, C.c_int, vp, vp]),
         "pa_model_param_count": (C.c_size_t, [C.POINTER(PaModelConfig)]),
         "pa_model_create": (C.c_int, [vp, C.POINTER(PaModelConfig), vp, C.c_ulonglong, C.c_int, C.POINTER(vp)]),
         "pa_model_destroy": (None, [vp]),
@@ -329,6 +330,9 @@ class PagedAttn:
 
     def qkv_append(self, layer, x_ptr, x_stride, w_ptr, bias_ptr, q_ptr, q_stride, stream=None):
         return self.lib.pa_qkv_append(self.h, layer, x_ptr, x_stride, w_ptr, bias_ptr, q_ptr, q_stride, stream)
+
+    def decode_step_host_async(self, layer, qkv_ptr, out_ptr):
+        return self.lib.pa_decode_step_host_async(self.h, layer, qkv_ptr, out_ptr)
 
     def decode_step_host(self, layer, qkv_ptr, out_ptr):
         return self.lib.pa_decode_step_host(self.h, layer, qkv_ptr, out_ptr)

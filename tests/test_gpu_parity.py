@@ -309,6 +309,44 @@ def test_decode_step_device_and_host_entry():
         sc.close()
 
 
+def test_decode_step_host_async_matches_sync():
+    """pa_decode_step_host_async: layers queued on the handle's stream, one sync; same results as the
+    synchronous entry (zero-copy and staged), pageable buffers are refused."""
+    import ctypes as Ct
+    NH, hs, bs, B, L = 4, 64, 16, 6, 3
+    Cc = NH * hs
+    sc = Scenario(NH, hs, bs, [33, 1, 16, 70, 5, 48], n_layers=L, layer=0, seed=77, extra_blocks=16)
+    lib = sc.eng.lib
+    hin = [lib.pa_host_alloc(B * 3 * Cc * 4) for _ in range(L)]
+    hout = [lib.pa_host_alloc(B * Cc * 4) for _ in range(2 * L)]
+    try:
+        eng = sc.eng
+        for l in range(L):
+            arr = np.ctypeslib.as_array(Ct.cast(hin[l], Ct.POINTER(Ct.c_float)), (B, 3 * Cc))
+            arr[:] = oa.normal((B, 3 * Cc), seed=80 + l)
+        results = {}
+        for mode in ("sync", "async", "async-staged"):
+            eng.tune(pa.PA_TUNE_NO_ZEROCOPY, 1 if mode == "async-staged" else 0)
+            assert eng.step_begin(sc.seq_ids, [1] * B) == 0, pa.last_error()
+            outs = hout[:L] if mode == "sync" else hout[L:]
+            for l in range(L):
+                fn = eng.decode_step_host if mode == "sync" else eng.decode_step_host_async
+                pa.check(fn(l, hin[l], outs[l]), mode)
+            pa.check(lib.pa_stream_sync(lib.pa_stream_of(eng.h)), "sync")
+            results[mode] = [np.ctypeslib.as_array(Ct.cast(o, Ct.POINTER(Ct.c_float)), (B, Cc)).copy() for o in outs]
+            pa.check(eng.step_rollback(), "rollback")
+        for l in range(L):
+            assert np.array_equal(results["sync"][l], results["async"][l])
+            assert np.array_equal(results["sync"][l], results["async-staged"][l])
+        pageable = np.zeros((B, 3 * Cc), dtype=np.float32)
+        assert eng.step_begin(sc.seq_ids, [1] * B) == 0
+        assert eng.decode_step_host_async(0, pageable.ctypes.data, hout[0]) == pa.PA_ERR_INVALID
+    finally:
+        for p in hin + hout:
+            lib.pa_host_free(p)
+        sc.close()
+
+
 # --------------------------------------------------------------------------------- prefill rows
 def _run_prefill(NH, hs, bs, before, n_new, path, seed=61, kv_start=None, dist="normal", shuffle=False, nwg=0, bn=0):
     """Append + causal rows for a mixed batch; returns (got, want32, scenario-free copies)."""
