@@ -71,6 +71,8 @@ DECODE_CASES = [
     pytest.param(4, 128, 32, [5, 64, 700], False, id="hs128-bs32"),
     pytest.param(8, 128, 8, [9, 130], True, id="hs128-bs8"),
     pytest.param(12, 64, 16, [0, 5, 0, 40], False, id="empty-sequences"),
+    pytest.param(2, 64, 16, [1 + (i * 7) % 40 for i in range(1100)], True, id="batch-1100-beyond-smem-prefix-table"),
+    pytest.param(4, 128, 16, [32768, 5], True, id="cfg5-32k-context"),
 ]
 
 
