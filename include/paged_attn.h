@@ -199,7 +199,8 @@ typedef struct pa_model_config {
     int channels;      /* C  (== n_heads * head_dim of the handle) */
 } pa_model_config;
 PA_API size_t pa_model_param_count(const pa_model_config* cfg);
-/* params_host: pa_model_param_count floats, or NULL for synthetic random-init weights (seeded). */
+/* params_host: pa_model_param_count floats, or NULL for synthetic random-init weights (seeded).
+ * max_batch: the most tokens (and sequences) one step may carry. */
 PA_API int pa_model_create(pa_handle* h, const pa_model_config* cfg, const float* params_host, unsigned long long seed,
                            int max_batch, pa_model** out);
 PA_API void pa_model_destroy(pa_model* m);
@@ -207,6 +208,11 @@ PA_API void pa_model_destroy(pa_model* m);
  * logits with coins[i] in [0,1) as sample_mult does (paged_infer.c:838-848), or argmax if coins is NULL. */
 PA_API int pa_model_decode_step(pa_model* m, const int* seq_ids, const int* tokens, const float* coins, int nseq,
                                 int* next_tokens);
+/* General step (prompt prefill, chunked prefill, decode, or a mix): sequence seq_ids[i] receives n_new[i] >= 1
+ * tokens, packed in step order in `tokens`; next_tokens[i] comes from the logits of its last new position.
+ * max_batch of pa_model_create bounds the tokens of one step. */
+PA_API int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins,
+                            int nseq, int* next_tokens);
 PA_API float* pa_model_params(pa_model* m);               /* device */
 PA_API float* pa_model_logits(pa_model* m, int* stride);  /* device, (nseq, stride) of the last step */
 

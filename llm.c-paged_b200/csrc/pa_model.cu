@@ -42,9 +42,9 @@ struct pa_model {
     size_t n_params;
     const float *wte, *wpe, *ln1w, *ln1b, *qkvw, *qkvb, *attprojw, *attprojb, *ln2w, *ln2b, *fcw, *fcb, *fcprojw,
         *fcprojb, *lnfw, *lnfb;
-    int max_batch;
+    int max_batch;                         // most tokens (and sequences) in one step
     float *x, *ln, *q, *atty, *fch, *logits;     // device activations for one step
-    int* d_io;                             // device: tokens[B] | positions[B] | next[B]
+    int* d_io;                             // device: tokens[ntok] | positions[ntok] | last_row[nseq] | next[nseq]
     float* d_coins;
     int* h_io;                             // pinned mirror
     float* h_coins;
@@ -92,6 +92,44 @@ pa_layernorm_kernel(float* __restrict__ out, const float* __restrict__ inp, cons
     for (int d = 16; d >= 1; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
     var = var / C;
     const float s = 1.0f / sqrtf(var + 1e-5f);                   // eps, :56
+    float* o = out + (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) o[c] = (s * (v[i] - m)) * weight[c] + bias[c];
+    }
+}
+
+// the same over gathered input rows (final layernorm of each sequence's last position), compact output
+__global__ void __launch_bounds__(128)
+pa_layernorm_rows_kernel(float* __restrict__ out, const float* __restrict__ inp, const int* __restrict__ rows_in,
+                         const float* __restrict__ weight, const float* __restrict__ bias, int rows, int C) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* x = inp + (size_t)rows_in[row] * C;
+    float v[kLnMaxPerLane];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c < C ? x[c] : 0.0f;
+        sum += v[i];
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const float m = sum / C;
+    float var = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        const float dlt = v[i] - m;
+        if (c < C) var += dlt * dlt;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+    var = var / C;
+    const float s = 1.0f / sqrtf(var + 1e-5f);
     float* o = out + (size_t)row * C;
 #pragma unroll
     for (int i = 0; i < kLnMaxPerLane; ++i) {
@@ -221,9 +259,9 @@ int pa_model_create(pa_handle* h, const pa_model_config* cfg, const float* param
     if (e == cudaSuccess) e = cudaMalloc((void**)&m->atty, B * C * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&m->fch, B * 4 * C * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&m->logits, B * m->Vp * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_io, B * 3 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_io, B * 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_coins, B * sizeof(float));
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&m->h_io, B * 3 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&m->h_io, B * 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&m->h_coins, B * sizeof(float));
     if (e != cudaSuccess) {
         pa_set_error("pa_model_create: allocation failed: %s", cudaGetErrorString(e));
@@ -290,65 +328,98 @@ float* pa_model_logits(pa_model* m, int* stride) {
     return m->logits;
 }
 
-/* One decode step for sequences seq_ids[0..nseq): each receives the token tokens[i] at its next
- * position; next_tokens[i] is sampled from the logits with coins[i] in [0,1) (NULL: argmax).
- * Runs: page choice + table mirror, embedding, then per layer ln1 -> QKV projection with fused KV
- * append -> paged decode attention -> attproj (+residual) -> ln2 -> fc (+GELU) -> fcproj
- * (+residual), then final layernorm, LM head, sampler; reads the tokens back. */
-int pa_model_decode_step(pa_model* m, const int* seq_ids, const int* tokens, const float* coins, int nseq, int* next_tokens) {
-    if (!m || !seq_ids || !tokens || !next_tokens || nseq < 1 || nseq > m->max_batch) {
-        pa_set_error("pa_model_decode_step: bad arguments (nseq=%d, max_batch=%d)", nseq, m ? m->max_batch : 0);
+/* The forward pass for a step of the batch: sequence seq_ids[i] receives n_new[i] >= 1 tokens
+ * (its prompt, a chunk of it, or one decode token; packed in step order in `tokens`) at its next
+ * positions; next_tokens[i] is sampled from the logits of its LAST new position with coins[i] in
+ * [0,1) (NULL: argmax).  Runs: page choice + table mirror, embedding, then per layer ln1 -> QKV
+ * projection with fused KV append -> paged attention (decode kernel when every sequence has one
+ * new token, else the causal prefill kernel) -> attproj (+residual) -> ln2 -> fc (+GELU) -> fcproj
+ * (+residual); final layernorm, LM head and sampler on the last rows only. */
+int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins, int nseq,
+                     int* next_tokens) {
+    if (!m || !seq_ids || !n_new || !tokens || !next_tokens || nseq < 1) {
+        pa_set_error("pa_model_forward: bad arguments");
         return PA_ERR_INVALID;
     }
     pa_handle* h = m->h;
     const int C = m->C, L = m->L, V = m->V;
+    long long ntok_ll = 0;
+    int max_q = 0;
     for (int i = 0; i < nseq; ++i) {
-        const int pos = pa_seq_len(h, seq_ids[i]);
-        if (tokens[i] < 0 || tokens[i] >= V) { pa_set_error("pa_model_decode_step: token %d out of range", tokens[i]); return PA_ERR_INVALID; }
-        if (pos < 0 || pos >= m->maxT) { pa_set_error("pa_model_decode_step: sequence %d is at position %d of %d", seq_ids[i], pos, m->maxT); return PA_ERR_INVALID; }
-        m->h_io[i] = tokens[i];
-        m->h_io[nseq + i] = pos;
+        if (n_new[i] < 1) { pa_set_error("pa_model_forward: n_new[%d] = %d (every sequence of the step needs a token)", i, n_new[i]); return PA_ERR_INVALID; }
+        ntok_ll += n_new[i];
+        if (n_new[i] > max_q) max_q = n_new[i];
+    }
+    if (ntok_ll > m->max_batch || nseq > m->max_batch) {
+        pa_set_error("pa_model_forward: %lld tokens in the step, the model was created for %d", ntok_ll, m->max_batch);
+        return PA_ERR_INVALID;
+    }
+    const int ntok = (int)ntok_ll;
+    // host io layout: tokens[ntok] | positions[ntok] | last_row[nseq] | next[nseq]
+    int* h_tok = m->h_io, *h_pos = m->h_io + ntok, *h_last = m->h_io + 2 * ntok, *h_next = m->h_io + 2 * ntok + nseq;
+    for (int i = 0, row = 0; i < nseq; ++i) {
+        const int pos0 = pa_seq_len(h, seq_ids[i]);
+        if (pos0 < 0 || pos0 + n_new[i] > m->maxT) {
+            pa_set_error("pa_model_forward: sequence %d would reach position %d of %d", seq_ids[i], pos0 + n_new[i], m->maxT);
+            return PA_ERR_INVALID;
+        }
+        for (int j = 0; j < n_new[i]; ++j, ++row) {
+            if (tokens[row] < 0 || tokens[row] >= V) { pa_set_error("pa_model_forward: token %d out of range", tokens[row]); return PA_ERR_INVALID; }
+            h_tok[row] = tokens[row];
+            h_pos[row] = pos0 + j;
+        }
+        h_last[i] = row - 1;
         if (coins) m->h_coins[i] = coins[i];
     }
     CU_CHECK(cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)h->stream;
-    std::vector<int> ones(nseq, 1);
-    int rc = pa_step_begin(h, seq_ids, ones.data(), nseq);
+    int rc = pa_step_begin(h, seq_ids, n_new, nseq);
     if (rc != PA_OK) return rc;
     rc = pa_step_upload(h, s);
     if (rc != PA_OK) return rc;
-    CU_CHECK(cudaMemcpyAsync(m->d_io, m->h_io, (size_t)nseq * 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+    int* d_tok = m->d_io, *d_pos = m->d_io + ntok, *d_last = m->d_io + 2 * ntok, *d_next = m->d_io + 2 * ntok + nseq;
+    CU_CHECK(cudaMemcpyAsync(m->d_io, m->h_io, (size_t)(2 * ntok + nseq) * sizeof(int), cudaMemcpyHostToDevice, s));
     if (coins) CU_CHECK(cudaMemcpyAsync(m->d_coins, m->h_coins, (size_t)nseq * sizeof(float), cudaMemcpyHostToDevice, s));
-    pa_embed_kernel<<<nseq, 256, 0, s>>>(m->x, m->d_io, m->d_io + nseq, m->wte, m->wpe, C);
+    pa_embed_kernel<<<ntok, 256, 0, s>>>(m->x, d_tok, d_pos, m->wte, m->wpe, C);
     const int path = h->tune[PA_TUNE_GEMM_PATH];
-    const int ln_grid = (nseq + 3) / 4;
+    const int ln_grid = (ntok + 3) / 4;
+    long launches = 1;
     for (int l = 0; l < L; ++l) {
-        pa_layernorm_kernel<<<ln_grid, 128, 0, s>>>(m->ln, m->x, m->ln1w + (size_t)l * C, m->ln1b + (size_t)l * C, nseq, C);
+        pa_layernorm_kernel<<<ln_grid, 128, 0, s>>>(m->ln, m->x, m->ln1w + (size_t)l * C, m->ln1b + (size_t)l * C, ntok, C);
         rc = pa_qkv_append(h, l, m->ln, C, m->qkvw + (size_t)l * 3 * C * C, m->qkvb + (size_t)l * 3 * C, m->q, C, s);
         if (rc != PA_OK) return rc;
-        rc = pa_decode(h, l, m->q, C, m->atty, C, s);
+        rc = max_q == 1 ? pa_decode(h, l, m->q, C, m->atty, C, s) : pa_prefill(h, l, m->q, C, m->atty, C, s);
         if (rc != PA_OK) return rc;
         // x += atty . attprojw^T + attprojb      (matmul_forward + residual_forward, :716-717)
-        rc = pa_cu_linear(m->atty, C, m->attprojw + (size_t)l * C * C, m->attprojb + (size_t)l * C, m->x, C, nseq, C, C, m->x, C, 0, path, s);
+        rc = pa_cu_linear(m->atty, C, m->attprojw + (size_t)l * C * C, m->attprojb + (size_t)l * C, m->x, C, ntok, C, C, m->x, C, 0, path, s);
         if (rc != PA_OK) return rc;
-        pa_layernorm_kernel<<<ln_grid, 128, 0, s>>>(m->ln, m->x, m->ln2w + (size_t)l * C, m->ln2b + (size_t)l * C, nseq, C);
+        pa_layernorm_kernel<<<ln_grid, 128, 0, s>>>(m->ln, m->x, m->ln2w + (size_t)l * C, m->ln2b + (size_t)l * C, ntok, C);
         // fch = gelu(ln . fcw^T + fcb)           (:719-720)
-        rc = pa_cu_linear(m->ln, C, m->fcw + (size_t)l * 4 * C * C, m->fcb + (size_t)l * 4 * C, m->fch, 4 * C, nseq, 4 * C, C, nullptr, 0, 1, path, s);
+        rc = pa_cu_linear(m->ln, C, m->fcw + (size_t)l * 4 * C * C, m->fcb + (size_t)l * 4 * C, m->fch, 4 * C, ntok, 4 * C, C, nullptr, 0, 1, path, s);
         if (rc != PA_OK) return rc;
         // x += fch . fcprojw^T + fcprojb         (:721-722)
-        rc = pa_cu_linear(m->fch, 4 * C, m->fcprojw + (size_t)l * 4 * C * C, m->fcprojb + (size_t)l * C, m->x, C, nseq, C, 4 * C, m->x, C, 0, path, s);
+        rc = pa_cu_linear(m->fch, 4 * C, m->fcprojw + (size_t)l * 4 * C * C, m->fcprojb + (size_t)l * C, m->x, C, ntok, C, 4 * C, m->x, C, 0, path, s);
         if (rc != PA_OK) return rc;
+        launches += 5;
     }
-    pa_layernorm_kernel<<<ln_grid, 128, 0, s>>>(m->ln, m->x, m->lnfw, m->lnfb, nseq, C);
+    // only each sequence's last new position feeds the LM head: final layernorm over the gathered rows
+    pa_layernorm_rows_kernel<<<(nseq + 3) / 4, 128, 0, s>>>(m->ln, m->x, d_last, m->lnfw, m->lnfb, nseq, C);
     rc = pa_cu_linear(m->ln, C, m->wte, nullptr, m->logits, m->Vp, nseq, V, C, nullptr, 0, 0, path, s);       // logits = lnf . wte^T (:726)
     if (rc != PA_OK) return rc;
-    pa_sample_kernel<<<nseq, 256, 0, s>>>(m->logits, m->Vp, V, coins ? m->d_coins : nullptr, m->d_io + 2 * nseq);
+    pa_sample_kernel<<<nseq, 256, 0, s>>>(m->logits, m->Vp, V, coins ? m->d_coins : nullptr, d_next);
     CU_CHECK(cudaGetLastError());
-    h->launches += 4 + 5 * (long)L;     // embed, lnf, head, sampler; per layer 2 layernorms + 3 projections (pa_qkv_append / pa_decode count themselves)
-    CU_CHECK(cudaMemcpyAsync(m->h_io + 2 * nseq, m->d_io + 2 * nseq, (size_t)nseq * sizeof(int), cudaMemcpyDeviceToHost, s));
+    h->launches += launches + 3;        // (pa_qkv_append / pa_decode / pa_prefill count themselves)
+    CU_CHECK(cudaMemcpyAsync(h_next, d_next, (size_t)nseq * sizeof(int), cudaMemcpyDeviceToHost, s));
     CU_CHECK(cudaStreamSynchronize(s));
-    memcpy(next_tokens, m->h_io + 2 * nseq, (size_t)nseq * sizeof(int));
+    memcpy(next_tokens, h_next, (size_t)nseq * sizeof(int));
     return PA_OK;
+}
+
+/* One decode step: one new token per sequence (pa_model_forward with n_new = 1). */
+int pa_model_decode_step(pa_model* m, const int* seq_ids, const int* tokens, const float* coins, int nseq, int* next_tokens) {
+    if (!m || nseq < 1 || nseq > m->max_batch) { pa_set_error("pa_model_decode_step: bad arguments (nseq=%d, max_batch=%d)", nseq, m ? m->max_batch : 0); return PA_ERR_INVALID; }
+    std::vector<int> ones(nseq, 1);
+    return pa_model_forward(m, seq_ids, ones.data(), tokens, coins, nseq, next_tokens);
 }
 
 }  // extern "C"

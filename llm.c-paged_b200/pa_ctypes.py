@@ -108,6 +108,7 @@ def load():
         "pa_model_create": (C.c_int, [vp, C.POINTER(PaModelConfig), vp, C.c_ulonglong, C.c_int, C.POINTER(vp)]),
         "pa_model_destroy": (None, [vp]),
         "pa_model_decode_step": (C.c_int, [vp, c_int_p, c_int_p, vp, C.c_int, c_int_p]),
+        "pa_model_forward": (C.c_int, [vp, c_int_p, c_int_p, c_int_p, vp, C.c_int, c_int_p]),
         "pa_model_params": (vp, [vp]),
         "pa_model_logits": (vp, [vp, c_int_p]),
         "pa_checkpoint_read_config": (C.c_int, [C.c_char_p, C.POINTER(PaModelConfig)]),
@@ -481,6 +482,18 @@ class Model:
             coins = np.ascontiguousarray(coins, dtype=np.float32)
             cptr = coins.ctypes.data
         check(self.lib.pa_model_decode_step(self.m, iptr(seq), iptr(tok), cptr, len(seq), iptr(nxt)), "pa_model_decode_step")
+        return nxt
+
+    def forward(self, seq_ids, n_new, tokens, coins=None):
+        seq = np.ascontiguousarray(seq_ids, dtype=np.int32)
+        nn = np.ascontiguousarray(n_new, dtype=np.int32)
+        tok = np.ascontiguousarray(tokens, dtype=np.int32)
+        nxt = np.zeros(len(seq), dtype=np.int32)
+        cptr = None
+        if coins is not None:
+            coins = np.ascontiguousarray(coins, dtype=np.float32)
+            cptr = coins.ctypes.data
+        check(self.lib.pa_model_forward(self.m, iptr(seq), iptr(nn), iptr(tok), cptr, len(seq), iptr(nxt)), "pa_model_forward")
         return nxt
 
     def logits(self, nseq):

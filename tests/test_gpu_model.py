@@ -149,3 +149,59 @@ def test_model_from_checkpoint_file(tmp_path):
         outs.append(model.logits(B).copy())
         model.close(); eng.close()
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("prefill_path", [0, 3], ids=["fp32-prefill", "tcgen05-tf32-prefill"])
+def test_model_prefill_then_decode_matches_token_by_token_oracle(prefill_path):
+    """pa_model_forward with whole prompts (and a prompt chunk on top of cached tokens, and a decode
+    token, mixed in one step) gives the logits the oracle gets feeding the same tokens one at a time."""
+    L, NH, hs, V, maxT, bs = 2, 2, 64, 211, 160, 16
+    Cc = NH * hs
+    params = make_params(V, maxT, L, Cc, seed=700)
+    B = 3
+    eng = pa.PagedAttn(bs, 64, B, NH, hs, n_layers=L, device=0, max_batch_tokens=256)
+    eng.tune(pa.PA_TUNE_PREFILL_PATH, prefill_path)
+    model = pa.Model(eng, maxT, V, params=params, max_batch=256)
+    orc = OracleModel(L, NH, Cc, V, maxT, bs, 64, B, params)
+    tol = LOGIT_TOL_PER_LAYER * L if prefill_path == 0 else 5e-3       # TF32 attention: its own stated tolerance (gpu_common.TC_REL_TOL)
+    try:
+        rng = np.random.default_rng(9)
+        prompts = [rng.integers(0, V, size=n).astype(np.int32) for n in (70, 33, 5)]
+        pos = [0, 0, 0]
+
+        def oracle_feed(seq, toks):
+            last = None
+            for t in toks:
+                last = orc.step([seq], [int(t)], [pos[seq]])
+                pos[seq] += 1
+            return last[0]
+
+        # step 1: prompts of sequences 0 and 1 entirely, the first 3 tokens of sequence 2
+        n_new = [70, 33, 3]
+        toks = np.concatenate([prompts[0], prompts[1], prompts[2][:3]])
+        nxt = model.forward([0, 1, 2], n_new, toks, None)
+        got = model.logits(3)
+        want = np.stack([oracle_feed(0, prompts[0]), oracle_feed(1, prompts[1]), oracle_feed(2, prompts[2][:3])])
+        err = np.abs(got.astype(np.float64) - want).max() / np.abs(want).max()
+        assert err <= tol, f"prefill logits err {err:.3e}"
+        if prefill_path == 0:
+            assert np.array_equal(nxt, want.argmax(axis=1).astype(np.int32))
+        # step 2: sequence 2 gets the rest of its prompt (chunked prefill) while 0 and 1 decode one token
+        n_new = [1, 1, 2]
+        toks = np.concatenate([[nxt[0]], [nxt[1]], prompts[2][3:]]).astype(np.int32)
+        nxt2 = model.forward([0, 1, 2], n_new, toks, None)
+        got = model.logits(3)
+        want = np.stack([oracle_feed(0, [nxt[0]]), oracle_feed(1, [nxt[1]]), oracle_feed(2, prompts[2][3:])])
+        err2 = np.abs(got.astype(np.float64) - want).max() / np.abs(want).max()
+        assert err2 <= tol, f"mixed step logits err {err2:.3e}"
+        # step 3: plain decode for all
+        nxt3 = model.decode_step([0, 1, 2], nxt2, None)
+        got = model.logits(3)
+        want = np.stack([oracle_feed(s, [nxt2[s]]) for s in range(3)])
+        err3 = np.abs(got.astype(np.float64) - want).max() / np.abs(want).max()
+        assert err3 <= tol, f"decode logits err {err3:.3e}"
+        for s in range(3):
+            assert list(eng.table(s)) == list(orc.mgrs[0].table(s)) and eng.seq_len(s) == pos[s]
+        print(f"prefill path {prefill_path}: logits err {err:.2e} / {err2:.2e} / {err3:.2e}")
+    finally:
+        model.close(); eng.close(); orc.close()
