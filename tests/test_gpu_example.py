@@ -58,3 +58,66 @@ def test_plain_c_host_example():
     assert abs(float(m2.group(6)) - want) <= 1e-5 * max(1.0, abs(want)) + 1e-3
     for o in orcs:
         o.close()
+
+
+def test_plain_c_generate_example_matches_oracle_generation():
+    """examples/generate.c (gcc only): synthetic checkpoint + token file in the reference's formats,
+    whole prompts prefilled in one step, then sampling with the reference's RNG and sample_mult.
+    The CPU oracle fed token by token with the same coins must generate the same token ids."""
+    import ctypes as C
+    exe = os.path.join(ge.ROOT, "examples", "generate")
+    assert os.path.exists(exe), "build() should have produced the example"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stderr + r.stdout
+    got = {}
+    for line in r.stdout.splitlines():
+        m = re.match(r"sequence (\d+):((?: \d+)+)", line)
+        if m:
+            got[int(m.group(1))] = [int(t) for t in m.group(2).split()]
+    assert sorted(got) == [0, 1, 2, 3] and all(len(v) == 18 for v in got.values()), r.stdout
+
+    pa = ge.load_binding()
+    lib = pa.load()
+    ol = oa.load_oracle()
+    cfg = pa.PaModelConfig()
+    pa.check(lib.pa_checkpoint_read_config(b"/tmp/pa_synth_gpt2.bin", C.byref(cfg)), "config")
+    n = lib.pa_model_param_count(C.byref(cfg))
+    params = np.zeros(n, dtype=np.float32)
+    pa.check(lib.pa_checkpoint_read_params(b"/tmp/pa_synth_gpt2.bin", params.ctypes.data, n), "params")
+    ids = np.fromfile("/tmp/pa_synth_tokens.bin", dtype=np.int32)
+    B, P, total = 4, 32, 50
+    L, NH, Cc, V, maxT = cfg.n_layers, cfg.n_heads, cfg.channels, cfg.vocab_size, cfg.max_seq_len
+    mgrs = [oa.OrcManager(Cc, 16, 64, B) for _ in range(L)]
+    arr = (C.c_void_p * L)(*[m.m for m in mgrs])
+
+    def step(seqs, toks, pos):
+        seq = np.ascontiguousarray(seqs, dtype=np.int32); tok = np.ascontiguousarray(toks, dtype=np.int32)
+        ps = np.ascontiguousarray(pos, dtype=np.int32)
+        logits = np.zeros((len(seq), V), dtype=np.float32)
+        assert ol.orc_model_decode_step(arr, L, NH, Cc, V, maxT, oa.fptr(params), oa.iptr(seq), oa.iptr(tok), oa.iptr(ps),
+                                        len(seq), oa.fptr(logits)) == 0
+        return logits
+
+    def sample(logits, coins):
+        probs = np.zeros_like(logits)
+        ol.orc_softmax_forward(oa.fptr(probs), oa.fptr(logits), len(logits), 1, V)
+        return [ol.orc_sample_mult(oa.fptr(np.ascontiguousarray(probs[i])), V, float(coins[i])) for i in range(len(logits))]
+
+    state = C.c_ulonglong(1337)
+    draw = lambda: [ol.orc_random_f32(C.byref(state)) for _ in range(B)]      # noqa: E731
+    try:
+        coins = draw()
+        for t in range(P):
+            logits = step(list(range(B)), [ids[b * P + t] for b in range(B)], [t] * B)
+        nxt = sample(logits, coins)
+        want = {b: [] for b in range(B)}
+        for t in range(P, total):
+            for b in range(B):
+                want[b].append(nxt[b])
+            coins = draw()
+            if t + 1 < total:
+                nxt = sample(step(list(range(B)), nxt, [t] * B), coins)
+        assert got == want
+    finally:
+        for m in mgrs:
+            m.close()
