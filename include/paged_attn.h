@@ -300,7 +300,7 @@ typedef enum pa_tune_key {
     PA_TUNE_PREFILL_PATH = 13, /* 0 auto (tiled fp32 SIMT), 1 tiled fp32 SIMT, 2 generic rows kernel, 3 tcgen05 TF32 (own tolerance) */
     PA_TUNE_TC_WARPGROUPS = 14,/* tcgen05 prefill: softmax warpgroups per CTA, 0 auto, 1 or 2 */
     PA_TUNE_TC_KEY_TILE = 15,  /* tcgen05 prefill, head_dim 64: keys per tile, 0 auto (64), 64 or 128 */
-    PA_TUNE_GEMM_PATH = 16,    /* projections: 0 auto (tcgen05 3xTF32, fp32-accurate), 1 fp32 SIMT, 2 tcgen05 3xTF32, 3 tcgen05 plain TF32 (reduced precision, own tolerance) */
+    PA_TUNE_GEMM_PATH = 16,    /* projections: 0 auto (<= 4 rows: weight-streaming GEMV, else tcgen05 3xTF32, fp32-accurate), 1 fp32 SIMT, 2 tcgen05 3xTF32, 3 tcgen05 plain TF32 (reduced precision, own tolerance), 4 GEMV */
     PA_TUNE_GEMM_SPLIT_K = 17, /* tensor-core projections: CTAs per cluster splitting K, 0 auto, 1, 2 or 4 */
     PA_TUNE_MAX
 } pa_tune_key;

@@ -156,6 +156,102 @@ pa_qkv_kernel(const QkvParams p) {
     }
 }
 
+// ---- small-M path (decode with a handful of sequences): a weight-streaming GEMV --------------------
+// With M <= 4 rows the projection is a pure read of the weight matrix (3C*C*4 bytes for QKV): one
+// warp per group of 4 output features streams their weight rows with 16-byte loads (24+ loads in
+// flight per lane), the M input rows sit in shared memory, fp32 FMA, warp-shuffle reduction, same
+// epilogue as the tiled kernels.  Roofline: HBM (weights are read exactly once).
+constexpr int kGemvMaxM = 4;
+constexpr int kGemvFeat = 4;         // output features per warp pass
+__global__ void __launch_bounds__(256)
+pa_gemv_kernel(const QkvParams p) {
+    extern __shared__ __align__(16) float xs[];          // [M][K]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int K4 = p.K >> 2;
+    for (int i = tid; i < p.M * K4; i += blockDim.x) {
+        const int m = i / K4, c = i - m * K4;
+        const float* row = p.x + (size_t)(p.in_rows ? p.in_rows[m] : m) * p.x_stride;
+        reinterpret_cast<float4*>(xs)[i] = __ldg(reinterpret_cast<const float4*>(row) + c);
+    }
+    __syncthreads();
+    const int warp_global = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    for (int n0 = warp_global * kGemvFeat; n0 < p.N; n0 += n_warps * kGemvFeat) {
+        float acc[kGemvFeat][kGemvMaxM];
+#pragma unroll
+        for (int f = 0; f < kGemvFeat; ++f)
+#pragma unroll
+            for (int m = 0; m < kGemvMaxM; ++m) acc[f][m] = 0.0f;
+        for (int c = lane; c < K4; c += 32) {
+            float4 wv[kGemvFeat];
+#pragma unroll
+            for (int f = 0; f < kGemvFeat; ++f) {
+                const int n = min(n0 + f, p.N - 1);
+                wv[f] = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * p.K) + c);
+            }
+#pragma unroll
+            for (int m = 0; m < kGemvMaxM; ++m) {
+                if (m < p.M) {
+                    const float4 xv = reinterpret_cast<const float4*>(xs)[m * K4 + c];
+#pragma unroll
+                    for (int f = 0; f < kGemvFeat; ++f)
+                        acc[f][m] = fmaf(wv[f].w, xv.w, fmaf(wv[f].z, xv.z, fmaf(wv[f].y, xv.y, fmaf(wv[f].x, xv.x, acc[f][m]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < kGemvFeat; ++f)
+#pragma unroll
+            for (int m = 0; m < kGemvMaxM; ++m)
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) acc[f][m] += __shfl_xor_sync(0xffffffffu, acc[f][m], d);
+        // lane (f, m) finishes output (m, n0 + f)
+        const int f = lane >> 2, m = lane & 3;
+        if (f < kGemvFeat && m < p.M && n0 + f < p.N) {
+            float v = 0.0f;
+#pragma unroll
+            for (int ff = 0; ff < kGemvFeat; ++ff)
+#pragma unroll
+                for (int mm = 0; mm < kGemvMaxM; ++mm)
+                    if (ff == f && mm == m) v = acc[ff][mm];
+            const int nn = n0 + f;
+            v += p.bias ? p.bias[nn] : 0.0f;
+            if (p.act == 1) {
+                const float cube = 0.044715f * v * v * v;
+                v = 0.5f * v * (1.0f + tanhf(0.7978845608028654f * (v + cube)));
+            }
+            if (p.residual) v += p.residual[(size_t)m * p.res_stride + nn];
+            if (nn < p.n_dense) {
+                p.out[(size_t)(p.out_rows ? p.out_rows[m] : m) * p.out_stride + nn] = v;
+            } else {
+                const size_t slot_off = (size_t)p.slots[m] * p.C;
+                const int c = nn - p.n_dense;
+                if (c < p.C) p.pool_k[slot_off + c] = v;
+                else p.pool_v[slot_off + (c - p.C)] = v;
+            }
+        }
+    }
+}
+
+bool gemv_ok(const QkvParams& p) {
+    return p.M >= 1 && p.M <= kGemvMaxM && (p.K & 3) == 0 && (p.x_stride & 3) == 0 &&
+           ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w)) & 15) == 0 &&
+           (size_t)p.M * p.K * sizeof(float) <= 96 * 1024;
+}
+int launch_gemv(const QkvParams& p, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        CU_CHECK(cudaFuncSetAttribute(pa_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done = true;
+    }
+    const int groups = (p.N + kGemvFeat - 1) / kGemvFeat;            // warp passes needed
+    int blocks = (groups + 7) / 8;
+    if (blocks > 592) blocks = 592;                                   // 4 CTAs per SM: the rest loops
+    pa_gemv_kernel<<<blocks, 256, (size_t)p.M * p.K * sizeof(float), s>>>(p);
+    CU_CHECK(cudaGetLastError());
+    return PA_OK;
+}
+
 int launch(const QkvParams& p, cudaStream_t s) {
     if (p.M <= 0 || p.N <= 0) return PA_OK;
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
@@ -193,6 +289,12 @@ int pa_qkv_append(pa_handle* h, int layer, const float* x, int x_stride, const f
     cudaStream_t s = stream ? (cudaStream_t)stream : (cudaStream_t)h->stream;
     const int path = h->tune[PA_TUNE_GEMM_PATH];
     int rc = PA_ERR_UNSUPPORTED;
+    if ((path == 0 || path == 4) && gemv_ok(p)) {       // a handful of rows: stream the weights once
+        rc = launch_gemv(p, s);
+        if (rc == PA_OK) h->launches++;
+        return rc;
+    }
+    if (path == 4) { pa_set_error("pa_qkv_append: the GEMV path takes at most %d rows", kGemvMaxM); return PA_ERR_UNSUPPORTED; }
     if (path != 1) {       // tensor cores: 3xTF32 keeps fp32 accuracy; plain TF32 only on request
         rc = pa_cu_gemm_tc(x, x_stride, w, bias, q_out, q_stride, p.M, p.N, p.K, p.n_dense, p.pool_k, p.pool_v, p.slots,
                            p.C, path == 3 ? 1 : 3, h->tune[PA_TUNE_GEMM_SPLIT_K], nullptr, 0, 0, (void*)s);
@@ -211,6 +313,15 @@ int pa_cu_linear(const float* x, int x_stride, const float* w, const float* bias
                  int M, int N, int K, const float* residual, int res_stride, int act, int path, void* stream) {
     if (!x || !w || !out || M < 0 || N < 0 || K < 1) { pa_set_error("pa_cu_linear: bad arguments"); return PA_ERR_INVALID; }
     int rc = PA_ERR_UNSUPPORTED;
+    if (path == 0 || path == 4) {
+        QkvParams g;
+        g.x = x; g.in_rows = nullptr; g.w = w; g.bias = bias; g.out = out; g.out_rows = nullptr;
+        g.pool_k = g.pool_v = nullptr; g.slots = nullptr;
+        g.M = M; g.N = N; g.K = K; g.x_stride = x_stride; g.out_stride = out_stride; g.n_dense = N; g.C = 0;
+        g.residual = residual; g.res_stride = res_stride; g.act = act;
+        if (gemv_ok(g)) return launch_gemv(g, (cudaStream_t)stream);
+        if (path == 4) { pa_set_error("pa_cu_linear: the GEMV path takes at most %d rows", kGemvMaxM); return PA_ERR_UNSUPPORTED; }
+    }
     if (path != 1) {
         rc = pa_cu_gemm_tc(x, x_stride, w, bias, out, out_stride, M, N, K, N, nullptr, nullptr, nullptr, 0,
                            path == 3 ? 1 : 3, 0, residual, res_stride, act, stream);

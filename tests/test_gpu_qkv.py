@@ -113,6 +113,32 @@ def test_qkv_append_split_k_clusters(B, NH, hs, split):
         sc.close()
 
 
+@pytest.mark.parametrize("B,NH,hs", [(1, 12, 64), (4, 25, 64), (3, 3, 20), (2, 8, 128)])
+def test_qkv_append_small_batch_gemv(B, NH, hs):
+    """<= 4 new tokens: the weight-streaming GEMV kernel (auto-selected), with the KV scatter epilogue."""
+    bs = 16
+    Cc = NH * hs
+    sc = Scenario(NH, hs, bs, [7] * B, seed=195, extra_blocks=B + 8)
+    try:
+        eng = sc.eng
+        x = oa.normal((B, Cc), seed=196)
+        w = (oa.normal((3 * Cc, Cc), seed=197) * np.float32(1.0 / np.sqrt(Cc))).astype(np.float32)
+        bias = oa.normal((3 * Cc,), seed=198)
+        want = _oracle_matmul(x, w, bias)
+        for path in (0, 4):
+            eng.tune(pa.PA_TUNE_GEMM_PATH, path)
+            assert eng.step_begin(sc.seq_ids, [1] * B) == 0, pa.last_error()
+            pa.check(eng.upload(), "upload")
+            dx, dw, db, dq = pa.DevBuf.from_numpy(x), pa.DevBuf.from_numpy(w), pa.DevBuf.from_numpy(bias), pa.DevBuf(B * Cc * 4)
+            pa.check(eng.qkv_append(0, dx.ptr, Cc, dw.ptr, db.ptr, dq.ptr, Cc), "qkv_append")
+            eng.sync()
+            k, v = eng.read_pool_rows(0, eng.slot_mapping())
+            assert_close_gemm(np.concatenate([dq.download((B, Cc)), k, v], axis=1), want, f"gemv path {path}")
+            pa.check(eng.step_rollback(), "rollback")
+    finally:
+        sc.close()
+
+
 def test_qkv_append_plain_tf32_has_its_own_tolerance():
     """PA_TUNE_GEMM_PATH=3: one TF32 MMA per k-step (reduced precision, opt-in): ~1e-3 of max|ref|."""
     NH, hs, bs, B = 12, 64, 16, 70
