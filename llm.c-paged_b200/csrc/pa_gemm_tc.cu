@@ -34,6 +34,7 @@
 #include <mutex>
 
 #include "pa_internal.h"
+#include "pa_pdl.cuh"
 
 #define CU_CHECK(call)                                                                         \
     do {                                                                                       \
@@ -229,6 +230,7 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
     auto stamp = [&](int i) { if (dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[i] = t; } };
     stamp(0);
+    pdl_launch_dependents();      // the next kernel of the step may start its own prologue
     const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
     const int n_split = gridDim.z;
     const int krank = n_split > 1 ? (int)cluster_rank() : 0;
@@ -258,6 +260,9 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     stamp(1);
     // page slot of this thread's row (fused KV append), fetched long before the epilogue needs it
     const int my_slot = (p.slots && warp < 4 && m0 + tid < p.M) ? __ldg(p.slots + m0 + tid) : 0;
+    // everything above touched only weights, the step tables (mirrored before the chain started) and
+    // on-chip state; x (and the buffers written below) belong to the previous kernel until it has completed
+    pdl_wait();
 
     if (warp == 4) {
         // ================================ TMA producer ========================================
@@ -533,20 +538,7 @@ int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams
         CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
         attr_done = true;
     }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, n_split);
-    cfg.blockDim = dim3(192);
-    cfg.dynamicSmemBytes = Cfg::kSmem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;     // the K splits of a tile form one cluster
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = n_split;
-    cfg.attrs = attr;
-    cfg.numAttrs = n_split > 1 ? 1 : 0;
-    CU_CHECK(cudaLaunchKernelEx(&cfg, fn, tx, tw, p));
+    CU_CHECK(pa_launch_pdl(fn, dim3((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, n_split), dim3(192), Cfg::kSmem, s, n_split, tx, tw, p));
     return PA_OK;
 }
 

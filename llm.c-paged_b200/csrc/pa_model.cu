@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "pa_internal.h"
+#include "pa_pdl.cuh"
 
 #define CU_CHECK(call)                                                                         \
     do {                                                                                       \
@@ -55,6 +56,8 @@ namespace {
 // ---- encoder_forward (paged_infer.c:24-46) for one new token per sequence ------------------------
 __global__ void pa_embed_kernel(float* __restrict__ x, const int* __restrict__ tokens, const int* __restrict__ positions,
                                 const float* __restrict__ wte, const float* __restrict__ wpe, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int s = blockIdx.x;
     const float* e = wte + (size_t)tokens[s] * C;
     const float* ps = wpe + (size_t)positions[s] * C;
@@ -66,6 +69,8 @@ constexpr int kLnMaxPerLane = 64;          // C <= 2048
 __global__ void __launch_bounds__(128)
 pa_layernorm_kernel(float* __restrict__ out, const float* __restrict__ inp, const float* __restrict__ weight,
                     const float* __restrict__ bias, int rows, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -104,6 +109,8 @@ pa_layernorm_kernel(float* __restrict__ out, const float* __restrict__ inp, cons
 __global__ void __launch_bounds__(128)
 pa_layernorm_rows_kernel(float* __restrict__ out, const float* __restrict__ inp, const int* __restrict__ rows_in,
                          const float* __restrict__ weight, const float* __restrict__ bias, int rows, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -149,6 +156,8 @@ __global__ void __launch_bounds__(256)
 pa_sample_kernel(const float* __restrict__ logits, int stride, int V, const float* __restrict__ coins, int* __restrict__ next) {
     __shared__ float red[256];
     __shared__ int redi[256];
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x, tid = threadIdx.x;
     const float* l = logits + (size_t)row * stride;
     const float coin = coins ? coins[row] : -1.0f;
@@ -380,12 +389,12 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
     int* d_tok = m->d_io, *d_pos = m->d_io + ntok, *d_last = m->d_io + 2 * ntok, *d_next = m->d_io + 2 * ntok + nseq;
     CU_CHECK(cudaMemcpyAsync(m->d_io, m->h_io, (size_t)(2 * ntok + nseq) * sizeof(int), cudaMemcpyHostToDevice, s));
     if (coins) CU_CHECK(cudaMemcpyAsync(m->d_coins, m->h_coins, (size_t)nseq * sizeof(float), cudaMemcpyHostToDevice, s));
-    pa_embed_kernel<<<ntok, 256, 0, s>>>(m->x, d_tok, d_pos, m->wte, m->wpe, C);
+    CU_CHECK(pa_launch_pdl(pa_embed_kernel, dim3(ntok), dim3(256), 0, s, 1, m->x, (const int*)d_tok, (const int*)d_pos, m->wte, m->wpe, C));
     const int path = h->tune[PA_TUNE_GEMM_PATH];
     const int ln_grid = (ntok + 3) / 4;
     long launches = 1;
     for (int l = 0; l < L; ++l) {
-        pa_layernorm_kernel<<<ln_grid, 128, 0, s>>>(m->ln, m->x, m->ln1w + (size_t)l * C, m->ln1b + (size_t)l * C, ntok, C);
+        CU_CHECK(pa_launch_pdl(pa_layernorm_kernel, dim3(ln_grid), dim3(128), 0, s, 1, m->ln, (const float*)m->x, m->ln1w + (size_t)l * C, m->ln1b + (size_t)l * C, ntok, C));
         rc = pa_qkv_append(h, l, m->ln, C, m->qkvw + (size_t)l * 3 * C * C, m->qkvb + (size_t)l * 3 * C, m->q, C, s);
         if (rc != PA_OK) return rc;
         rc = max_q == 1 ? pa_decode(h, l, m->q, C, m->atty, C, s) : pa_prefill(h, l, m->q, C, m->atty, C, s);
@@ -393,7 +402,7 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
         // x += atty . attprojw^T + attprojb      (matmul_forward + residual_forward, :716-717)
         rc = pa_cu_linear(m->atty, C, m->attprojw + (size_t)l * C * C, m->attprojb + (size_t)l * C, m->x, C, ntok, C, C, m->x, C, 0, path, s);
         if (rc != PA_OK) return rc;
-        pa_layernorm_kernel<<<ln_grid, 128, 0, s>>>(m->ln, m->x, m->ln2w + (size_t)l * C, m->ln2b + (size_t)l * C, ntok, C);
+        CU_CHECK(pa_launch_pdl(pa_layernorm_kernel, dim3(ln_grid), dim3(128), 0, s, 1, m->ln, (const float*)m->x, m->ln2w + (size_t)l * C, m->ln2b + (size_t)l * C, ntok, C));
         // fch = gelu(ln . fcw^T + fcb)           (:719-720)
         rc = pa_cu_linear(m->ln, C, m->fcw + (size_t)l * 4 * C * C, m->fcb + (size_t)l * 4 * C, m->fch, 4 * C, ntok, 4 * C, C, nullptr, 0, 1, path, s);
         if (rc != PA_OK) return rc;
@@ -403,11 +412,10 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
         launches += 5;
     }
     // only each sequence's last new position feeds the LM head: final layernorm over the gathered rows
-    pa_layernorm_rows_kernel<<<(nseq + 3) / 4, 128, 0, s>>>(m->ln, m->x, d_last, m->lnfw, m->lnfb, nseq, C);
+    CU_CHECK(pa_launch_pdl(pa_layernorm_rows_kernel, dim3((nseq + 3) / 4), dim3(128), 0, s, 1, m->ln, (const float*)m->x, (const int*)d_last, m->lnfw, m->lnfb, nseq, C));
     rc = pa_cu_linear(m->ln, C, m->wte, nullptr, m->logits, m->Vp, nseq, V, C, nullptr, 0, 0, path, s);       // logits = lnf . wte^T (:726)
     if (rc != PA_OK) return rc;
-    pa_sample_kernel<<<nseq, 256, 0, s>>>(m->logits, m->Vp, V, coins ? m->d_coins : nullptr, d_next);
-    CU_CHECK(cudaGetLastError());
+    CU_CHECK(pa_launch_pdl(pa_sample_kernel, dim3(nseq), dim3(256), 0, s, 1, (const float*)m->logits, m->Vp, V, (const float*)(coins ? m->d_coins : nullptr), d_next));
     h->launches += launches + 3;        // (pa_qkv_append / pa_decode / pa_prefill count themselves)
     CU_CHECK(cudaMemcpyAsync(h_next, d_next, (size_t)nseq * sizeof(int), cudaMemcpyDeviceToHost, s));
     CU_CHECK(cudaStreamSynchronize(s));

@@ -1,0 +1,42 @@
+/*
+ * pa_pdl.cuh -- programmatic dependent launch for the chain of small kernels of a decode step.
+ * A kernel launched through pa_launch_pdl may start (be scheduled, run its prologue) while its
+ * predecessor in the stream is still running; it MUST execute pdl_wait() before it reads anything
+ * an earlier kernel wrote or writes anything an earlier kernel may read -- the wait returns once
+ * the predecessor grid has completed and its memory is visible (transitively the whole chain).
+ * pdl_launch_dependents() at the top lets the successor's launch overlap this kernel.
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+extern "C" int pa_pdl_enabled;     /* 1 by default; PA_TUNE_NO_PDL switches it off (pa_step.c) */
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pa_launch_pdl(void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                        int cluster_z, Args... args) {
+    cudaLaunchConfig_t cfg;
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (pa_pdl_enabled) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_z > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = 1;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = (unsigned)cluster_z;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, fn, KArgs(args)...);
+}

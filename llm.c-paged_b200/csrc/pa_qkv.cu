@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "pa_internal.h"
+#include "pa_pdl.cuh"
 
 #define CU_CHECK(call)                                                                         \
     do {                                                                                       \
@@ -63,6 +64,8 @@ __global__ void __launch_bounds__(kThreads)
 pa_qkv_kernel(const QkvParams p) {
     __shared__ __align__(16) float As[2][BK][BM + 4];     // x tile, transposed: [k][m]
     __shared__ __align__(16) float Bs[2][BK][BN + 4];     // w tile, transposed: [k][n]
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -166,6 +169,8 @@ constexpr int kGemvFeat = 4;         // output features per warp pass
 __global__ void __launch_bounds__(256)
 pa_gemv_kernel(const QkvParams p) {
     extern __shared__ __align__(16) float xs[];          // [M][K]
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31;
     const int K4 = p.K >> 2;
     for (int i = tid; i < p.M * K4; i += blockDim.x) {
@@ -247,16 +252,14 @@ int launch_gemv(const QkvParams& p, cudaStream_t s) {
     const int groups = (p.N + kGemvFeat - 1) / kGemvFeat;            // warp passes needed
     int blocks = (groups + 7) / 8;
     if (blocks > 592) blocks = 592;                                   // 4 CTAs per SM: the rest loops
-    pa_gemv_kernel<<<blocks, 256, (size_t)p.M * p.K * sizeof(float), s>>>(p);
-    CU_CHECK(cudaGetLastError());
+    CU_CHECK(pa_launch_pdl(pa_gemv_kernel, dim3(blocks), dim3(256), (size_t)p.M * p.K * sizeof(float), s, 1, p));
     return PA_OK;
 }
 
 int launch(const QkvParams& p, cudaStream_t s) {
     if (p.M <= 0 || p.N <= 0) return PA_OK;
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
-    pa_qkv_kernel<<<grid, kThreads, 0, s>>>(p);
-    CU_CHECK(cudaGetLastError());
+    CU_CHECK(pa_launch_pdl(pa_qkv_kernel, grid, dim3(kThreads), 0, s, 1, p));
     return PA_OK;
 }
 

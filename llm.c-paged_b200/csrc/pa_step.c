@@ -15,6 +15,7 @@
 #include "pa_internal.h"
 
 static __thread char g_err[512] = "";
+int pa_pdl_enabled = 1;      /* programmatic dependent launch for the step's kernel chain (pa_pdl.cuh) */
 
 void pa_set_error(const char* fmt, ...) {
     va_list ap;
@@ -96,6 +97,7 @@ int pa_tune_set(pa_handle* h, int key, int value) {
     if (!h || key < 0 || key >= PA_TUNE_MAX || key == PA_TUNE_COUNT_LAUNCHES ||
         (key >= PA_TUNE_LAST_HPG && key <= PA_TUNE_LAST_GRID)) return PA_ERR_INVALID;
     h->tune[key] = value;
+    if (key == PA_TUNE_NO_PDL) pa_pdl_enabled = value ? 0 : 1;
     return PA_OK;
 }
 int pa_tune_get(pa_handle* h, int key) {
