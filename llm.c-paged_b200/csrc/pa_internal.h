@@ -72,6 +72,7 @@ struct pa_handle {
 
 void pa_set_error(const char* fmt, ...);
 extern int pa_pdl_enabled;
+extern int pa_pdl_gate;
 
 /* ---- implemented in pa_block_manager.c (plain C, integer only) ------------------------- */
 BlockManager* pa_bm_create(pa_handle* owner, int channels, int block_size, int max_blocks,

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 extern "C" int pa_pdl_enabled;     /* 1 by default; PA_TUNE_NO_PDL switches it off (pa_step.c) */
+extern "C" int pa_pdl_gate;        /* per-step gate set by the caller of the chain (pa_model_forward) */
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -24,7 +25,7 @@ static inline cudaError_t pa_launch_pdl(void (*fn)(KArgs...), dim3 grid, dim3 bl
     cfg.stream = s;
     cudaLaunchAttribute attr[2];
     int n = 0;
-    if (pa_pdl_enabled) {
+    if (pa_pdl_enabled && pa_pdl_gate) {
         attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;
