@@ -272,6 +272,13 @@ PA_API int pa_prefix_insert(pa_handle* h, int seq_id, const int* tokens, int n_t
  * prompt: at least one token is left to compute) and returns the number of tokens matched. */
 PA_API int pa_prefix_match(pa_handle* h, int seq_id, const int* tokens, int n_tokens);
 PA_API int pa_prefix_cached_pages(pa_handle* h);
+/* Swap-out instead of drop-on-evict: with swapping on, a sequence evicted by the allocator (LRU, whole
+ * prompt, as block_manager.c:104-113) keeps a host copy of its pages (all layers) and is brought back
+ * -- into whatever pages are free then -- the next time pa_step_begin* names it. */
+PA_API int pa_set_evict_swap(pa_handle* h, int enable);
+PA_API int pa_seq_swap_out(pa_handle* h, int seq_id);       /* explicit */
+PA_API int pa_seq_swap_in(pa_handle* h, int seq_id);
+PA_API int pa_seq_swapped_tokens(pa_handle* h, int seq_id);  /* tokens held in the host copy, 0 if resident or unknown */
 PA_API int pa_page_refcount(pa_handle* h, int page);
 
 /* ---- pool access (tests, benchmarks, checkpointing) --------------------------------------- */

@@ -156,6 +156,7 @@ KVBlock* request_block(BlockManager* m, int prompt_id) {
         for (int tries = 0; idx == -1 && tries < m->max_prompts; tries++) {
             int victim = find_least_recently_used_block(m);
             if (victim == -1) break;
+            if (m->pa && m->pa->swap_enabled) pa_swap_on_evict(m->pa, m->blocks[victim].prompt_id);   /* extension */
             free_blocks_for_prompt(m, m->blocks[victim].prompt_id);
             idx = lowest_free_page(m);
         }

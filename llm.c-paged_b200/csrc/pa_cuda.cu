@@ -207,6 +207,25 @@ int pa_cu_copy_page_rows(pa_handle* h, int src_page, int dst_page, int rows) {
     return PA_OK;
 }
 
+int pa_cu_swap_page(pa_handle* h, int page, float* host_k, float* host_v, int to_host) {
+    if (h->host_only || !h->pool_k) return PA_OK;
+    CU_CHECK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)h->stream;
+    const size_t page_bytes = (size_t)h->cfg.block_size * h->C * sizeof(float);
+    const size_t lpitch = h->layer_stride * sizeof(float);
+    float* dk = h->pool_k + (size_t)page * h->cfg.block_size * h->C;
+    float* dv = h->pool_v + (size_t)page * h->cfg.block_size * h->C;
+    if (to_host) {
+        CU_CHECK(cudaMemcpy2DAsync(host_k, page_bytes, dk, lpitch, page_bytes, h->cfg.n_layers, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(cudaMemcpy2DAsync(host_v, page_bytes, dv, lpitch, page_bytes, h->cfg.n_layers, cudaMemcpyDeviceToHost, s));
+    } else {
+        CU_CHECK(cudaMemcpy2DAsync(dk, lpitch, host_k, page_bytes, page_bytes, h->cfg.n_layers, cudaMemcpyHostToDevice, s));
+        CU_CHECK(cudaMemcpy2DAsync(dv, lpitch, host_v, page_bytes, page_bytes, h->cfg.n_layers, cudaMemcpyHostToDevice, s));
+    }
+    CU_CHECK(cudaStreamSynchronize(s));
+    return PA_OK;
+}
+
 int pa_cu_is_device_ptr(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -68,6 +68,8 @@ struct pa_handle {
     void* decode_attr_fn;         /* kernel whose dynamic-smem attribute has been raised */
     int max_heads;                /* heads the split workspace was sized for */
     void* tc_state;               /* TMA tensor maps of the pool (pa_prefill_tc.cu), lazily built */
+    int swap_enabled;             /* extension: evicted sequences are swapped out to host memory instead of dropped */
+    void* swap_state;             /* pa_sharing.c */
 };
 
 void pa_set_error(const char* fmt, ...);
@@ -89,6 +91,10 @@ void pa_bm_release_page(BlockManager* m, int p, int idx);
 int pa_share_other_holder(BlockManager* m, int p, int idx);     /* another sequence holding idx, PA_OWNER_CACHE, or -1 */
 int pa_share_evict_one_cached(BlockManager* m);                 /* frees the LRU cache-only page; 1 if one was freed */
 void pa_share_destroy(BlockManager* m);
+/* called by the allocator just before it evicts prompt p (block_manager.c:104-113): keeps a host copy when swapping is on */
+void pa_swap_on_evict(pa_handle* h, int p);
+void pa_swap_destroy(pa_handle* h);
+int pa_swap_in_if_needed(pa_handle* h, int seq);
 
 /* ---- implemented in pa_step.c ------------------------------------------------------------- */
 int pa_create_compat(const pa_config* cfg, pa_handle** out);
@@ -109,6 +115,8 @@ int pa_cu_step_upload(pa_handle* h, void* stream);
 int pa_cu_is_device_ptr(const void* p);
 /* rows [0, rows) of page src -> page dst, K and V, every layer; stream-ordered on the handle's stream, then synchronised */
 int pa_cu_copy_page_rows(pa_handle* h, int src_page, int dst_page, int rows);
+/* one page <-> host, K and V, every layer; host layout [layer][block_size*C] for K then the same for V */
+int pa_cu_swap_page(pa_handle* h, int page, float* host_k, float* host_v, int to_host);
 
 /* ---- implemented in pa_prefill.cu / pa_prefill_tc.cu ------------------------------------- */
 /* PA_OK = launched; PA_ERR_UNSUPPORTED = shape outside the kernel's domain (use the generic rows kernel) */

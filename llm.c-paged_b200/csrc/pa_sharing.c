@@ -198,3 +198,115 @@ int pa_page_refcount(pa_handle* h, int page) {
     if (!h || page < 0 || page >= h->mgr->max_blocks) return PA_ERR_INVALID;
     return h->mgr->refcount[page];
 }
+
+/* ---- swap-out instead of drop-on-evict ---------------------------------------------------------
+ * The reference drops the victim prompt's KV when the pool is exhausted (page_out_lru_block,
+ * block_manager.c:104-113) and the prompt has to be prefilled again.  With swapping on, the
+ * allocator's eviction first copies the victim's pages (every layer) to host memory; the sequence
+ * is brought back -- into whatever pages are free then -- the next time a step names it. */
+typedef struct swap_slot {
+    float* buf;          /* [pages][2 (K,V)][n_layers][block_size*C] */
+    int n_tokens;
+    int n_pages;
+} swap_slot;
+
+static swap_slot* swap_slots(pa_handle* h, int create) {
+    if (!h->swap_state && create) h->swap_state = calloc((size_t)h->cfg.max_seqs, sizeof(swap_slot));
+    return (swap_slot*)h->swap_state;
+}
+static size_t swap_page_floats(const pa_handle* h) { return (size_t)2 * h->cfg.n_layers * h->cfg.block_size * h->C; }
+
+int pa_set_evict_swap(pa_handle* h, int enable) {
+    if (!h) return PA_ERR_INVALID;
+    if (enable && !swap_slots(h, 1)) { pa_set_error("pa_set_evict_swap: out of host memory"); return PA_ERR_NOMEM; }
+    h->swap_enabled = enable ? 1 : 0;
+    return PA_OK;
+}
+int pa_seq_swapped_tokens(pa_handle* h, int seq) {
+    if (bad_seq(h, seq)) return PA_ERR_INVALID;
+    swap_slot* sl = swap_slots(h, 0);
+    return sl && sl[seq].buf ? sl[seq].n_tokens : 0;
+}
+void pa_swap_destroy(pa_handle* h) {
+    swap_slot* sl = swap_slots(h, 0);
+    if (!sl) return;
+    for (int i = 0; i < h->cfg.max_seqs; i++) free(sl[i].buf);
+    free(sl);
+    h->swap_state = NULL;
+}
+
+int pa_seq_swap_out(pa_handle* h, int seq) {
+    if (bad_seq(h, seq)) { pa_set_error("pa_seq_swap_out: bad sequence id"); return PA_ERR_INVALID; }
+    BlockManager* m = h->mgr;
+    const int n = m->prompt_block_count[seq];
+    if (n == 0) return PA_OK;
+    swap_slot* sl = swap_slots(h, 1);
+    if (!sl) { pa_set_error("pa_seq_swap_out: out of host memory"); return PA_ERR_NOMEM; }
+    const size_t pf = swap_page_floats(h);
+    free(sl[seq].buf);
+    sl[seq].buf = (float*)malloc((size_t)n * pf * sizeof(float));
+    if (!sl[seq].buf) { pa_set_error("pa_seq_swap_out: out of host memory (%d pages)", n); return PA_ERR_NOMEM; }
+    sl[seq].n_tokens = pa_bm_context_len(m, seq);
+    sl[seq].n_pages = n;
+    for (int i = 0; i < n; i++) {
+        float* k = sl[seq].buf + (size_t)i * pf;
+        int rc = pa_cu_swap_page(h, m->prompt_block_list[seq][i], k, k + pf / 2, 1);
+        if (rc != PA_OK) { free(sl[seq].buf); sl[seq].buf = NULL; return rc; }
+    }
+    free_blocks_for_prompt(m, seq);
+    return PA_OK;
+}
+
+/* allocator hook: the victim is about to lose its pages; keep a host copy (errors degrade to the
+ * reference's behaviour: the sequence is simply dropped) */
+void pa_swap_on_evict(pa_handle* h, int p) {
+    if (bad_seq(h, p)) return;
+    BlockManager* m = h->mgr;
+    const int n = m->prompt_block_count[p];
+    if (n == 0) return;
+    swap_slot* sl = swap_slots(h, 1);
+    if (!sl) return;
+    const size_t pf = swap_page_floats(h);
+    free(sl[p].buf);
+    sl[p].buf = (float*)malloc((size_t)n * pf * sizeof(float));
+    if (!sl[p].buf) return;
+    sl[p].n_tokens = pa_bm_context_len(m, p);
+    sl[p].n_pages = n;
+    for (int i = 0; i < n; i++) {
+        float* k = sl[p].buf + (size_t)i * pf;
+        if (pa_cu_swap_page(h, m->prompt_block_list[p][i], k, k + pf / 2, 1) != PA_OK) { free(sl[p].buf); sl[p].buf = NULL; return; }
+    }
+}
+
+int pa_seq_swap_in(pa_handle* h, int seq) {
+    if (bad_seq(h, seq)) { pa_set_error("pa_seq_swap_in: bad sequence id"); return PA_ERR_INVALID; }
+    swap_slot* sl = swap_slots(h, 0);
+    if (!sl || !sl[seq].buf) return PA_OK;
+    BlockManager* m = h->mgr;
+    if (m->prompt_block_count[seq] != 0) { pa_set_error("pa_seq_swap_in: sequence %d holds pages and a swap copy", seq); return PA_ERR_INVALID; }
+    float* buf = sl[seq].buf;          /* detach first: the allocations below may evict (and swap out) other sequences */
+    const int n = sl[seq].n_pages, n_tokens = sl[seq].n_tokens;
+    sl[seq].buf = NULL;
+    const size_t pf = swap_page_floats(h);
+    int rc = PA_OK;
+    for (int i = 0; i < n && rc == PA_OK; i++) {
+        KVBlock* b = request_block(m, seq);
+        if (!b || m->prompt_block_count[seq] != i + 1) { pa_set_error("pa_seq_swap_in: No blocks available (sequence %d)", seq); rc = PA_ERR_NO_BLOCKS; break; }
+        b->filled = (i + 1 < n) ? m->block_size : n_tokens - (n - 1) * m->block_size;
+        float* k = buf + (size_t)i * pf;
+        rc = pa_cu_swap_page(h, (int)(b - m->blocks), k, k + pf / 2, 0);
+    }
+    if (rc != PA_OK) {                 /* put the copy back so nothing is lost */
+        free_blocks_for_prompt(m, seq);
+        free(sl[seq].buf);
+        sl[seq].buf = buf; sl[seq].n_pages = n; sl[seq].n_tokens = n_tokens;
+        return rc;
+    }
+    free(buf);
+    return PA_OK;
+}
+int pa_swap_in_if_needed(pa_handle* h, int seq) {
+    swap_slot* sl = swap_slots(h, 0);
+    if (!sl || bad_seq(h, seq) || !sl[seq].buf) return PA_OK;
+    return pa_seq_swap_in(h, seq);
+}

@@ -78,6 +78,7 @@ static int create_impl(const pa_config* cfg, pa_handle** out, int compat) {
 
 void pa_destroy(pa_handle* h) {
     if (!h) return;
+    pa_swap_destroy(h);
     pa_cu_release(h);
     pa_bm_destroy(h->mgr);
     free(h->step_seq_ids);
@@ -206,6 +207,10 @@ int pa_step_begin(pa_handle* h, const int* seq_ids, const int* n_new, int nseq) 
         int p = seq_ids[i];
         h->step_seq_ids[i] = p;
         h->step_n_new[i] = n_new[i];
+        if (h->swap_enabled) {                       /* extension: a swapped-out sequence comes back before it grows */
+            int rcs = pa_swap_in_if_needed(h, p);
+            if (rcs != PA_OK) { h->step.nseq = 0; return rcs; }
+        }
         int left = n_new[i];
         while (left > 0) {
             int idx = pa_bm_choose_page(m, p);
@@ -285,7 +290,14 @@ int pa_step_begin_raw(pa_handle* h, int nseq, const int* const* tables, const in
 int pa_step_begin_readonly(pa_handle* h, const int* seq_ids, int nseq) {
     int rc = check_batch(h, seq_ids, nseq, "pa_step_begin_readonly");
     if (rc != PA_OK) return rc;
-    for (int i = 0; i < nseq; i++) { h->step_seq_ids[i] = seq_ids[i]; h->step_n_new[i] = 0; }
+    for (int i = 0; i < nseq; i++) {
+        h->step_seq_ids[i] = seq_ids[i];
+        h->step_n_new[i] = 0;
+        if (h->swap_enabled) {
+            int rcs = pa_swap_in_if_needed(h, seq_ids[i]);
+            if (rcs != PA_OK) return rcs;
+        }
+    }
     return build_tables(h, nseq, 0, NULL);
 }
 

@@ -127,6 +127,10 @@ def load():
         "pa_tokenizer_close": (None, [vp]),
         "pa_tokenizer_write": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_ubyte), C.c_uint]),
         "pa_seq_fork": (C.c_int, [vp, C.c_int, C.c_int]),
+        "pa_set_evict_swap": (C.c_int, [vp, C.c_int]),
+        "pa_seq_swap_out": (C.c_int, [vp, C.c_int]),
+        "pa_seq_swap_in": (C.c_int, [vp, C.c_int]),
+        "pa_seq_swapped_tokens": (C.c_int, [vp, C.c_int]),
         "pa_prefix_insert": (C.c_int, [vp, C.c_int, c_int_p, C.c_int]),
         "pa_prefix_match": (C.c_int, [vp, C.c_int, c_int_p, C.c_int]),
         "pa_prefix_cached_pages": (C.c_int, [vp]),

@@ -97,3 +97,48 @@ def test_prefix_cache_hit_gives_the_same_attention_as_a_full_prefill():
         assert np.array_equal(ka, kb)
     finally:
         sc.close()
+
+
+def test_swapped_out_sequence_attends_identically_after_swap_in():
+    """Eviction with swapping on: the victim's K/V (both layers) go to host memory and come back into
+    different pages; decode over it equals the never-evicted oracle."""
+    NH, hs, bs, L = 2, 64, 16, 2
+    Cc = NH * hs
+    ctx = [40, 33, 48]
+    eng = pa.PagedAttn(bs, 9, 3, NH, hs, n_layers=L, device=0, max_batch_tokens=64)      # 9 pages: exactly full
+    orcs = [oa.OrcManager(Cc, bs, 64, 3) for _ in range(L)]
+    lib = eng.lib
+    try:
+        assert lib.pa_set_evict_swap(eng.h, 1) == 0
+        for s, n in enumerate(ctx):
+            assert eng.step_begin([s], [n]) == 0, pa.last_error()
+            slots = eng.slot_mapping().copy()
+            for l in range(L):
+                kv = oa.normal((n, 2, Cc), seed=900 + 10 * s + l)
+                eng.write_pool_rows(l, slots, kv[:, 0], kv[:, 1])
+                for t in range(n):
+                    row = np.concatenate([np.zeros(Cc, np.float32), kv[t, 0], kv[t, 1]])
+                    orcs[l].add_to_cache(row[None, None, :], 1, 1, 1, prompt=s)
+        # sequence 1 grows into a new page: the pool is full, the LRU prompt (0) is swapped out
+        assert eng.step_begin([1], [16]) == 0, pa.last_error()
+        assert eng.seq_len(0) == 0 and lib.pa_seq_swapped_tokens(eng.h, 0) == 40
+        old_table = None
+        # decode over sequence 0 again: it is swapped back in (into other pages); the next victim of the
+        # reference's page-LRU is swapped out in turn
+        q = oa.normal((1, Cc), seed=950)
+        for l in range(L):
+            assert eng.step_begin_readonly([0]) == 0, pa.last_error()
+            if old_table is None:
+                old_table = list(eng.table(0))
+                assert eng.seq_len(0) == 40 and lib.pa_seq_swapped_tokens(eng.h, 0) == 0
+                assert lib.pa_seq_swapped_tokens(eng.h, 1) + lib.pa_seq_swapped_tokens(eng.h, 2) > 0
+            pa.check(eng.upload(), "upload")
+            dq, do = pa.DevBuf.from_numpy(q), pa.DevBuf(Cc * 4)
+            pa.check(eng.decode(l, dq.ptr, Cc, do.ptr, Cc), "decode")
+            eng.sync()
+            want = orcs[l].decode_batch([0], NH, q)
+            assert_close(do.download((1, Cc)), want, f"layer {l} after swap-in")
+    finally:
+        eng.close()
+        for o in orcs:
+            o.close()

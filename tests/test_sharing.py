@@ -123,3 +123,44 @@ def test_extensions_off_leave_refcounts_binary():
             assert used == sum(len(eng.table(p)) for p in range(3))
     finally:
         eng.close()
+
+
+def test_swap_out_on_eviction_and_swap_in_on_next_use():
+    """With pa_set_evict_swap the allocator's LRU eviction keeps a host copy; the sequence returns with
+    its length intact the next time a step names it (integer logic; the copies are device-side)."""
+    eng = make(bs=4, blocks=6, seqs=4)
+    lib = eng.lib
+    try:
+        assert lib.pa_set_evict_swap(eng.h, 1) == 0
+        assert eng.step_begin([0], [8]) == 0        # pages 0,1
+        assert eng.step_begin([1], [8]) == 0        # pages 2,3
+        assert eng.step_begin([2], [8]) == 0        # pages 4,5: full
+        assert eng.step_begin([1], [1]) == 0        # needs a page: the LRU prompt (0) is swapped out, not lost
+        assert eng.seq_len(0) == 0 and lib.pa_seq_swapped_tokens(eng.h, 0) == 8
+        assert eng.seq_len(1) == 9
+        # naming sequence 0 again brings it back; whoever the reference's page-LRU picks as the next victim
+        # (the prompt owning the oldest page: 1, whose first pages are older than 2's) is swapped out, not lost
+        assert eng.step_begin([0], [1]) == 0
+        assert eng.seq_len(0) == 9 and lib.pa_seq_swapped_tokens(eng.h, 0) == 0
+        want = {0: 9, 1: 9, 2: 8}
+        for s_, n in want.items():                    # nothing is ever lost: resident + swapped = everything appended
+            assert eng.seq_len(s_) + lib.pa_seq_swapped_tokens(eng.h, s_) == n
+            assert eng.seq_len(s_) == 0 or lib.pa_seq_swapped_tokens(eng.h, s_) == 0
+        assert lib.pa_seq_swapped_tokens(eng.h, 1) == 9
+        # explicit swap in / out
+        assert lib.pa_seq_swap_in(eng.h, 1) == 0
+        assert eng.seq_len(1) == 9
+        for s_, n in want.items():
+            assert eng.seq_len(s_) + lib.pa_seq_swapped_tokens(eng.h, s_) == n
+        resident = [s_ for s_ in want if eng.seq_len(s_)]
+        assert lib.pa_seq_swap_out(eng.h, resident[0]) == 0
+        assert eng.seq_len(resident[0]) == 0 and lib.pa_seq_swapped_tokens(eng.h, resident[0]) == want[resident[0]]
+        assert lib.pa_seq_swap_in(eng.h, resident[0]) == 0
+        # switched off: the reference's behaviour (the victim is dropped)
+        assert lib.pa_set_evict_swap(eng.h, 0) == 0
+        before = {s_: lib.pa_seq_swapped_tokens(eng.h, s_) for s_ in want}
+        assert eng.step_begin([3], [8]) == 0
+        assert {s_: lib.pa_seq_swapped_tokens(eng.h, s_) for s_ in want} == before      # no new host copies
+        assert sum(eng.seq_len(s_) + before[s_] for s_ in want) < sum(want.values())     # somebody was dropped
+    finally:
+        eng.close()
