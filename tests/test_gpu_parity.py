@@ -257,6 +257,51 @@ def test_decode_constant_values_property():
         sc.close()
 
 
+# --------------------------------------------------------------------------------- BASELINE full sizes
+def _ctx_cfg3():
+    rng = np.random.default_rng(42)
+    return [int(x) for x in rng.integers(128, 1025, size=256)]
+
+
+@pytest.mark.parametrize("name,NH,hs,ctx", [
+    ("cfg2: 64 sequences x 1024 ctx, GPT-2 small", 12, 64, [1024] * 64),
+    ("cfg3: batch 256, mixed ctx 128..1024", 12, 64, _ctx_cfg3()),
+    ("cfg4: GPT-2 XL shape, one GPU's 64 sequences x 1024", 25, 64, [1024] * 64),
+], ids=["cfg2", "cfg3", "cfg4-xl"])
+def test_baseline_full_size_decode_parity_and_properties(name, NH, hs, ctx):
+    """BASELINE.json configurations at their full single-GPU sizes, fragmented block tables: direct
+    parity with the oracle (the last-row restatement is cheap enough), plus the size-independent
+    properties of the domain: constant values come back unchanged (weights sum to 1), the output is
+    linear in V, and the result does not depend on how the page stream is split over CTAs."""
+    sc = Scenario(NH, hs, 16, ctx, shuffle=True, seed=2024)
+    try:
+        q = oa.normal((sc.B, sc.C), seed=8)
+        want = sc.oracle_decode(q)
+        got = sc.decode(q, path=1)
+        assert_close(got, want, name)
+        # split invariance: another tile shape / grid gives the same numbers up to summation order
+        other = sc.decode(q, path=1, hpg=1 if NH % 2 else 2, grid=37)
+        assert np.abs(other - got).max() <= 2e-6 * np.abs(got).max() + 1e-6
+        lib = sc.eng.lib
+        v1 = sc.pool_v
+        # linearity in V: attention(V1 + V2) = attention(V1) + attention(V2)
+        v2 = oa.normal(v1.shape, seed=77)
+        pa.check(lib.pa_memcpy_h2d(sc.eng.pool_v(0), v2.ctypes.data, v2.nbytes, None), "h2d")
+        got2 = sc.decode(q, path=1)
+        vs = (v1 + v2).astype(np.float32)
+        pa.check(lib.pa_memcpy_h2d(sc.eng.pool_v(0), vs.ctypes.data, vs.nbytes, None), "h2d")
+        got12 = sc.decode(q, path=1)
+        assert np.abs(got12 - (got + got2)).max() <= 1e-5 * np.abs(got12).max()
+        # constant V rows -> the constant
+        c = oa.normal((sc.C,), seed=99)
+        vs[:] = c
+        pa.check(lib.pa_memcpy_h2d(sc.eng.pool_v(0), vs.ctypes.data, vs.nbytes, None), "h2d")
+        gc = sc.decode(q, path=1)
+        assert np.abs(gc - c[None, :]).max() <= 2e-6 * np.abs(c).max() + 1e-6
+    finally:
+        sc.close()
+
+
 # --------------------------------------------------------------------------------- full step
 def test_decode_step_device_and_host_entry():
     """append + decode of a real step (GPT-2 124M shape, 2 layers), device-resident and through
