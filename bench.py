@@ -456,7 +456,7 @@ def main():
             pa.check(eng.step_begin(seq_ids, ones), "step_begin")
             for layer in range(L):      # the layers of a step are queued behind each other, one sync per step
                 pa.check(eng.decode_step_host_async(layer, qkv_host, out_host), "decode_step_host_async")
-            pa.check(lib.pa_stream_sync(hstream), "sync")
+            pa.check(lib.pa_decode_step_host_sync(eng.h), "sync")
             rollback()
             return float(out_np[0, 0])      # the step's result is read on the host
         k_e2e = max(5, min(args.steps, 50))

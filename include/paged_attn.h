@@ -243,9 +243,12 @@ PA_API int pa_tokenizer_write(const char* path, const char* const* pieces, const
  * buffers (pa_host_alloc) are read and written by the kernel directly over PCIe (zero-copy);
  * pageable buffers are staged through pinned memory with cudaMemcpyAsync. */
 PA_API int pa_decode_step_host(pa_handle* h, int layer, const float* qkv_host, float* out_host);
-/* The same without the final synchronisation (PINNED buffers only): stream-ordered on pa_stream_of(h), so a
- * host can queue the layers of a step, or several steps, and synchronise once. */
+/* The same without the final synchronisation (PINNED buffers only), so a host can queue the layers of a
+ * step, or several steps, and call pa_decode_step_host_sync once before it reads out_host or reuses
+ * qkv_host.  Zero-copy (default) or, with PA_TUNE_NO_ZEROCOPY, staged copies on their own streams that
+ * overlap the neighbouring layers' kernels. */
 PA_API int pa_decode_step_host_async(pa_handle* h, int layer, const float* qkv_host, float* out_host);
+PA_API int pa_decode_step_host_sync(pa_handle* h);
 
 /* ---- sequence bookkeeping ----------------------------------------------------------------- */
 PA_API int pa_seq_len(pa_handle* h, int seq_id);                 /* cached tokens */

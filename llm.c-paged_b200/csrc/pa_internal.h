@@ -68,6 +68,7 @@ struct pa_handle {
     void* decode_attr_fn;         /* kernel whose dynamic-smem attribute has been raised */
     int max_heads;                /* heads the split workspace was sized for */
     void* tc_state;               /* TMA tensor maps of the pool (pa_prefill_tc.cu), lazily built */
+    void* host_pipe;              /* copy streams + events of pa_decode_step_host_async (pa_kernels.cu) */
     int swap_enabled;             /* extension: evicted sequences are swapped out to host memory instead of dropped */
     void* swap_state;             /* pa_sharing.c */
 };
@@ -113,6 +114,7 @@ int pa_cu_ensure_stage(pa_handle* h, size_t floats);
 int* pa_cu_step_host_buffer(pa_handle* h, size_t ints);
 int pa_cu_step_upload(pa_handle* h, void* stream);
 int pa_cu_is_device_ptr(const void* p);
+void pa_cu_host_pipe_release(pa_handle* h);
 /* rows [0, rows) of page src -> page dst, K and V, every layer; stream-ordered on the handle's stream, then synchronised */
 int pa_cu_copy_page_rows(pa_handle* h, int src_page, int dst_page, int rows);
 /* one page <-> host, K and V, every layer; host layout [layer][block_size*C] for K then the same for V */

@@ -25,6 +25,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "pa_internal.h"
 
@@ -1079,13 +1080,37 @@ int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out
     return launch_rows(h, layer, q, q_stride, out, out_stride, true, s);
 }
 
+struct HostPipe {            // streams and events of the staged host-buffer pipeline (pa_decode_step_host_async)
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    std::vector<cudaEvent_t> ev;      // per layer: input landed, kernel done, output copied
+    std::vector<bool> used;
+    int n_layers = 0;
+};
+void pa_cu_host_pipe_release(pa_handle* h) {
+    HostPipe* hp = (HostPipe*)h->host_pipe;
+    if (!hp) return;
+    for (auto e : hp->ev) if (e) cudaEventDestroy(e);
+    if (hp->h2d) cudaStreamDestroy(hp->h2d);
+    if (hp->d2h) cudaStreamDestroy(hp->d2h);
+    delete hp;
+    h->host_pipe = nullptr;
+}
+/* everything queued by pa_decode_step_host_async (kernels and both copy directions) has completed */
+int pa_decode_step_host_sync(pa_handle* h) {
+    if (!h || h->host_only) { pa_set_error("pa_decode_step_host_sync: no device"); return PA_ERR_NO_DEVICE; }
+    CU_CHECK(cudaSetDevice(h->cfg.device));
+    CU_CHECK(cudaStreamSynchronize((cudaStream_t)h->stream));
+    HostPipe* hp = (HostPipe*)h->host_pipe;
+    if (hp) { CU_CHECK(cudaStreamSynchronize(hp->h2d)); CU_CHECK(cudaStreamSynchronize(hp->d2h)); }
+    return PA_OK;
+}
 static int decode_step_host_impl(pa_handle* h, int layer, const float* qkv_host, float* out_host, bool sync);
 int pa_decode_step_host(pa_handle* h, int layer, const float* qkv_host, float* out_host) {
     return decode_step_host_impl(h, layer, qkv_host, out_host, true);
 }
 /* Same, stream-ordered on the handle's stream without the final synchronisation: PINNED buffers only
- * (pa_host_alloc); the caller synchronises (pa_stream_sync(pa_stream_of(h))) before reading out_host
- * or reusing qkv_host.  Lets a host queue several layers / steps behind each other. */
+ * (pa_host_alloc); the caller calls pa_decode_step_host_sync(h) before reading out_host or reusing
+ * qkv_host.  Lets a host queue several layers / steps behind each other. */
 int pa_decode_step_host_async(pa_handle* h, int layer, const float* qkv_host, float* out_host) {
     return decode_step_host_impl(h, layer, qkv_host, out_host, false);
 }
@@ -1118,15 +1143,40 @@ static int decode_step_host_impl(pa_handle* h, int layer, const float* qkv_host,
         pa_set_error("pa_decode_step_host_async: pageable host buffers need the synchronous entry (they are staged through one pinned buffer)");
         return PA_ERR_INVALID;
     }
-    if (!sync) {      /* pinned, but zero-copy switched off: stage through per-layer regions so queued layers do not collide */
+    if (!sync) {
+        /* pinned, zero-copy switched off: a three-stream pipeline.  The H2D copy of layer l+1 runs on its
+         * own stream while the kernel of layer l computes, and the D2H copy of layer l's output overlaps the
+         * kernel of layer l+1; per-layer staging regions and events keep the queued layers apart. */
         rc = pa_cu_ensure_stage(h, (size_t)h->cfg.n_layers * n * 4 * C);
         if (rc != PA_OK) return rc;
+        HostPipe* hp = (HostPipe*)h->host_pipe;
+        if (!hp) {
+            hp = new HostPipe();
+            hp->n_layers = h->cfg.n_layers;
+            CU_CHECK(cudaStreamCreateWithFlags(&hp->h2d, cudaStreamNonBlocking));
+            CU_CHECK(cudaStreamCreateWithFlags(&hp->d2h, cudaStreamNonBlocking));
+            hp->ev.resize((size_t)3 * hp->n_layers);
+            for (auto& e : hp->ev) CU_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            hp->used.assign(hp->n_layers, false);
+            h->host_pipe = hp;
+        }
+        cudaEvent_t ev_in = hp->ev[3 * layer], ev_k = hp->ev[3 * layer + 1], ev_out = hp->ev[3 * layer + 2];
         float* d_qkv_l = h->d_stage + (size_t)layer * n * 4 * C;
         float* d_out_l = d_qkv_l + n * 3 * C;
-        CU_CHECK(cudaMemcpyAsync(d_qkv_l, qkv_host, n * 3 * C * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (hp->used[layer]) {                       // the previous step's kernel / D2H of this layer's regions
+            CU_CHECK(cudaStreamWaitEvent(hp->h2d, ev_k, 0));
+            CU_CHECK(cudaStreamWaitEvent(s, ev_out, 0));
+        }
+        CU_CHECK(cudaMemcpyAsync(d_qkv_l, qkv_host, n * 3 * C * sizeof(float), cudaMemcpyHostToDevice, hp->h2d));
+        CU_CHECK(cudaEventRecord(ev_in, hp->h2d));
+        CU_CHECK(cudaStreamWaitEvent(s, ev_in, 0));
         rc = pa_decode_append(h, layer, d_qkv_l, d_qkv_l + C, d_qkv_l + 2 * C, (int)(3 * C), d_out_l, (int)C, s);
         if (rc != PA_OK) return rc;
-        CU_CHECK(cudaMemcpyAsync(out_host, d_out_l, n * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CU_CHECK(cudaEventRecord(ev_k, s));
+        CU_CHECK(cudaStreamWaitEvent(hp->d2h, ev_k, 0));
+        CU_CHECK(cudaMemcpyAsync(out_host, d_out_l, n * C * sizeof(float), cudaMemcpyDeviceToHost, hp->d2h));
+        CU_CHECK(cudaEventRecord(ev_out, hp->d2h));
+        hp->used[layer] = true;
         return PA_OK;
     }
     rc = pa_cu_ensure_stage(h, n * 4 * C);

@@ -379,7 +379,7 @@ def test_decode_step_host_async_matches_sync():
             for l in range(L):
                 fn = eng.decode_step_host if mode == "sync" else eng.decode_step_host_async
                 pa.check(fn(l, hin[l], outs[l]), mode)
-            pa.check(lib.pa_stream_sync(lib.pa_stream_of(eng.h)), "sync")
+            pa.check(lib.pa_decode_step_host_sync(eng.h), "sync")
             results[mode] = [np.ctypeslib.as_array(Ct.cast(o, Ct.POINTER(Ct.c_float)), (B, Cc)).copy() for o in outs]
             pa.check(eng.step_rollback(), "rollback")
         for l in range(L):
