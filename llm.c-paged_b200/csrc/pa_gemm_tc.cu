@@ -35,6 +35,7 @@
 
 #include "pa_internal.h"
 #include "pa_pdl.cuh"
+#include "pa_ptx.cuh"
 
 #define CU_CHECK(call)                                                                         \
     do {                                                                                       \
@@ -46,6 +47,9 @@
     } while (0)
 
 namespace {
+
+// K-major SWIZZLE_128B operand: rows of 128 bytes, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t smem_desc_k(uint32_t addr) { return smem_desc(addr, 16, 1024, 2); }
 
 constexpr int kBM = 128;          // rows per CTA = TMEM lanes
 constexpr int kBK = 32;           // floats per k-slab = one 128-byte swizzle row
@@ -71,98 +75,6 @@ struct GemmTcParams {
     unsigned long long* dbg; // optional timeline of CTA (0,0,0) (PA_GEMM_DEBUG=1), NULL normally
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "GT_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra GT_DONE;\n"
-        "bra GT_WAIT;\n"
-        "GT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_box_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-// one lane of a CONVERGED warp: tcgen05.mma / TMA issued under an elect.sync predicate are emitted
-// straight; under a plain `lane == 0` test the compiler serialises each one (~100 cycles, tools/mma_bench.cu)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t smem_desc_k128(uint32_t addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr & 0x3ffff) >> 4);
-    d |= (uint64_t)1 << 16;                    // LBO (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;          // SBO
-    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-    return d;
-}
-__host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 __device__ __forceinline__ float gelu_tanh(float x) {           // gelu_forward, paged_infer.c:243-251
     const float k = 0.7978845608028654f;                        // sqrtf(2/pi)
     const float cube = 0.044715f * x * x * x;
@@ -189,31 +101,13 @@ struct GemmCfg {
     static_assert((kMaxSplit - 1) * kBM * BN * 4 <= kStages * kStageBytes, "reduction scratch");
 };
 
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// address of the same shared-memory location in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, const float4& v) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 
 // grid (N tiles, M tiles, n_split); the n_split CTAs of a cluster share an output tile and split K.
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const GemmTcParams p) {
     using Cfg = GemmCfg<BN>;
-    constexpr uint32_t kIdesc = instr_desc_tf32(kBM, BN);
+    constexpr uint32_t kIdesc = instr_desc(kBM, BN, 0, 0);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + kStages * Cfg::kStageBytes);
@@ -246,12 +140,11 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
         mbar_init(smem_u32(done), 1);
         for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&chunk_done[b]), 1); mbar_init(smem_u32(&chunk_free[b]), 128); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     if (tid < BN) bias_s[tid] = (p.bias && n0 + tid < p.N) ? __ldg(p.bias + n0 + tid) : 0.0f;
     if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
@@ -299,10 +192,10 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             if (leader) {
 #pragma unroll
                 for (int ks = 0; ks < kBK / 8; ++ks) {
-                    mma_tf32_ts(d_main, a_raw + ks * 8, smem_desc_k128(w_addr + ks * 32), kIdesc, (chunk_start && ks == 0) ? 0u : 1u);
+                    mma_tf32_ts(d_main, a_raw + ks * 8, smem_desc_k(w_addr + ks * 32), kIdesc, (chunk_start && ks == 0) ? 0u : 1u);
                     if (p.terms == 3) {
-                        mma_tf32_ts(d_small, a_lo + ks * 8, smem_desc_k128(w_addr + ks * 32), kIdesc, (s > 0 || ks > 0) ? 1u : 0u);
-                        mma_tf32_ts(d_small, a_raw + ks * 8, smem_desc_k128(wlo_addr + ks * 32), kIdesc, 1u);
+                        mma_tf32_ts(d_small, a_lo + ks * 8, smem_desc_k(w_addr + ks * 32), kIdesc, (s > 0 || ks > 0) ? 1u : 0u);
+                        mma_tf32_ts(d_small, a_raw + ks * 8, smem_desc_k(wlo_addr + ks * 32), kIdesc, 1u);
                     }
                 }
                 tc_commit(smem_u32(&empty[st]));
@@ -372,7 +265,7 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     const float4 v = ws[tid + i * 128];
                     wl[tid + i * 128] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+                fence_proxy_async_smem();      // generic-proxy stores -> visible to the MMA
             }
             tmem_wait_st();
             tc_fence_before();
@@ -465,31 +358,14 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-encode_tiled_fn get_encode() {
-    static encode_tiled_fn fn = nullptr;
-    if (!fn) {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
-            qres != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        fn = reinterpret_cast<encode_tiled_fn>(sym);
-    }
-    return fn;
-}
 // (rows, K) fp32 matrix with a row stride; box = 32 columns x box_rows rows, 128-byte swizzle, zero fill outside
 int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int row_stride, int box_rows) {
-    encode_tiled_fn enc = get_encode();
+    pa_encode_tiled_fn enc = pa_get_encode_tiled();
     if (!enc) { pa_set_error("cuTensorMapEncodeTiled not available from the driver"); return PA_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)row_stride * 4};

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "pa_internal.h"
+#include "pa_ptx.cuh"
 
 #define CU_CHECK(call)                                                                         \
     do {                                                                                       \
@@ -74,54 +75,6 @@ pa_append_kernel(const float* __restrict__ k_src, const float* __restrict__ v_sr
     }
 }
 
-// =============================================================================================
-// mbarrier / TMA bulk-copy primitives (inline PTX; SASS: SYNCS.*, UBLKCP)
-// =============================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "PA_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra PA_DONE;\n"
-        "bra PA_WAIT;\n"
-        "PA_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-// global -> shared bulk copy executed by the TMA engine; completion is signalled on `bar` as
-// `bytes` transaction bytes.  bytes % 16 == 0, both addresses 16-byte aligned.
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-// One lane of a CONVERGED warp.  Bulk-copy (UBLKCP) operands live in uniform registers: issued
-// under a per-lane test the compiler wraps every copy in a lane-serialisation loop (~100 cycles
-// each, tools/mma_bench.cu); under an elect.sync predicate they are emitted straight.
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // =============================================================================================
 // decode: flat page-stream kernel

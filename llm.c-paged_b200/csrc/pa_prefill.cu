@@ -21,6 +21,7 @@
 #include <cstdint>
 
 #include "pa_internal.h"
+#include "pa_ptx.cuh"
 
 #define CU_CHECK(call)                                                                         \
     do {                                                                                       \
@@ -48,17 +49,6 @@ struct PrefillParams {
     int n_tiles;            // sum over sequences of ceil(nq / BM)
     float scale;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-// 16-byte async copy global -> shared; src_bytes = 0 writes zeros (rows outside the sequence)
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // tile_lin -> (sequence, q tile inside it): warp-parallel scan over ceil(nq/BM)
 template <int BM>

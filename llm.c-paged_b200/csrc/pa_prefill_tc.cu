@@ -36,6 +36,7 @@
 #include <type_traits>
 
 #include "pa_internal.h"
+#include "pa_ptx.cuh"
 
 #define CU_CHECK(call)                                                                         \
     do {                                                                                       \
@@ -64,130 +65,7 @@ struct TcParams {
     float sl2;              // scale * log2(e): scores are handled in the exp2 domain
 };
 
-// ---- PTX wrappers ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "TC_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra TC_DONE;\n"
-        "bra TC_WAIT;\n"
-        "TC_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// TMA: 3-D tensor-map box (columns, rows, layer) -> shared memory, completes on an mbarrier
-__device__ __forceinline__ void tma_box_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-        : "memory");
-}
-// One lane of a CONVERGED warp.  tcgen05.mma / TMA instructions take their operands from uniform
-// registers: issued under a plain `lane == 0` test the compiler wraps each one in a per-lane
-// serialisation loop (~100 cycles per instruction, measured with tools/mma_bench.cu); under an
-// elect.sync predicate they are emitted straight and issue at the hardware rate.
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]
-__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// 32 consecutive columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float ex2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
-// Shared-memory matrix descriptor (sm_100 format): 128-byte swizzle, 8-row groups 1024 B apart.
-//   K-major  operand: rows = M or N index, 32 floats (128 B) of K per row; LBO unused
-//   MN-major operand: rows = K index, 32 floats (128 B) of M/N per row; LBO = bytes between
-//                     consecutive 32-column blocks
-// Layout types: 2 = SWIZZLE_128B (16-byte chunks XOR row%8; K-major operands), 1 = SWIZZLE_128B with
-// 32-byte chunks XOR row%4 -- the only layout tcgen05 accepts for an MN-major 32-bit operand
-// (rows = K index in groups of 4, SBO = bytes between groups).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr & 0x3ffff) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-    d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
-    d |= (uint64_t)layout_type << 61;
-    return d;
-}
-// Instruction descriptor: tf32 x tf32 -> f32, M x N, operand majors (0 = K-major, 1 = MN-major)
-__host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // tile_lin -> (sequence, q tile): warp-parallel scan over ceil(nq/128)
 __device__ __forceinline__ void find_tile(const TcParams& p, int tile_lin, int& seq, int& qt, int& n_qt) {
@@ -281,11 +159,10 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
             mbar_init(smem_u32(&p_ready[b]), 128);
         }
         for (int b = 0; b < NWG; ++b) mbar_init(smem_u32(&o_full[b]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     if (warp == kProducerWarp) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
@@ -466,13 +343,13 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
             float psum = 0.0f;
 #pragma unroll
             for (int i = 0; i < BN; ++i) {
-                const float e = ex2(fmaf(sv[i], p.sl2, neg_m));
+                const float e = ex2_approx(fmaf(sv[i], p.sl2, neg_m));
                 sv[i] = e;
                 psum += e;
             }
 #pragma unroll
             for (int c = 0; c < BN; c += 32) tmem_st32(s_tmem + c, sv + c);
-            const float alpha = grow ? ex2(m_run - m_new) : 1.0f;
+            const float alpha = grow ? ex2_approx(m_run - m_new) : 1.0f;
             if (j > 0 && __any_sync(0xffffffffu, grow)) {
                 // rescale this warpgroup's O: its previous P.V must have completed, and the next one
                 // cannot start before p_ready below
@@ -533,7 +410,7 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
                     const float* src = scratch + ((og - 1) * kBM + r) * (HS + 2);
                     const float m1 = src[HS], l1 = src[HS + 1];
                     const float m = fmaxf(m_run, m1);
-                    const float w0 = ex2(m_run - m), w1 = ex2(m1 - m);
+                    const float w0 = ex2_approx(m_run - m), w1 = ex2_approx(m1 - m);
                     l_run = l_run * w0 + l1 * w1;
 #pragma unroll
                     for (int i = 0; i < HS; ++i) o[i] = o[i] * w0 + src[i] * w1;
@@ -554,38 +431,19 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
     __syncthreads();
     if (warp == kProducerWarp) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 struct TcState {
     CUtensorMap tm_k, tm_v;
     bool ready;
 };
 
-encode_tiled_fn get_encode() {
-    static encode_tiled_fn fn = nullptr;
-    if (!fn) {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
-            qres != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        fn = reinterpret_cast<encode_tiled_fn>(sym);
-    }
-    return fn;
-}
-
 // pool viewed as (layer, row = page*bs + slot, column) fp32; box = one page x 32 columns, 128-byte swizzle
 int make_pool_map(CUtensorMap* map, float* pool, const pa_handle* h, CUtensorMapSwizzle swizzle) {
-    encode_tiled_fn enc = get_encode();
+    pa_encode_tiled_fn enc = pa_get_encode_tiled();
     if (!enc) { pa_set_error("cuTensorMapEncodeTiled not available from the driver"); return PA_ERR_CUDA; }
     const cuuint64_t rows = (cuuint64_t)h->cfg.max_blocks * h->cfg.block_size;
     cuuint64_t dims[3] = {(cuuint64_t)h->C, rows, (cuuint64_t)h->cfg.n_layers};
