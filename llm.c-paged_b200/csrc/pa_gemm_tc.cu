@@ -73,6 +73,13 @@ struct GemmTcParams {
     int res_stride;
     int act;                 // 0 none, 1 GELU (tanh form, paged_infer.c:243-251)
     unsigned long long* dbg; // optional timeline of CTA (0,0,0) (PA_GEMM_DEBUG=1), NULL normally
+    // split-K through an L2-resident workspace (gridDim.z CTAs per tile, no cluster): partial tiles
+    // [tile][split][float4 column][row], and one arrival counter per tile.  Two counter sets alternate
+    // between launches: a launch counts in ws_cnt and zeroes ws_cnt_next for its successor (which
+    // cannot touch it before this grid has completed), so nobody has to wait for a reset.
+    float4* ws;
+    unsigned* ws_cnt;
+    unsigned* ws_cnt_next;
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {           // gelu_forward, paged_infer.c:243-251
@@ -127,7 +134,7 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     pdl_launch_dependents();      // the next kernel of the step may start its own prologue
     const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
     const int n_split = gridDim.z;
-    const int krank = n_split > 1 ? (int)cluster_rank() : 0;
+    const int krank = blockIdx.z;                 // = the CTA's rank in its cluster when K is split over a cluster
     const int total_slabs = (p.K + kBK - 1) / kBK;
     const int slab0 = (int)((long long)krank * total_slabs / n_split);
     const int n_slabs = (int)((long long)(krank + 1) * total_slabs / n_split) - slab0;     // >= 1: the host keeps n_split <= total_slabs
@@ -153,9 +160,27 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     stamp(1);
     // page slot of this thread's row (fused KV append), fetched long before the epilogue needs it
     const int my_slot = (p.slots && warp < 4 && m0 + tid < p.M) ? __ldg(p.slots + m0 + tid) : 0;
+    // The weights are never written inside a chain of dependent launches, so the producer requests the
+    // w boxes of the first ring pass BEFORE waiting for the previous kernel: they stream in from HBM
+    // while that kernel drains.  (`full` expects x + w bytes; the x box follows after the wait.)
+    const int n_pre = n_slabs < kStages ? n_slabs : kStages;
+    if (warp == 4) {
+        if (elect_one()) {
+            for (int s = 0; s < n_pre; ++s) {
+                const uint32_t bar = smem_u32(&full[s]);
+                mbar_arrive_expect_tx(bar, Cfg::kXBytes + Cfg::kWBytes);
+                tma_box_2d(smem_u32(base + s * Cfg::kStageBytes + Cfg::kXBytes), &tm_w, (slab0 + s) * kBK, n0, bar);
+            }
+        }
+        __syncwarp();
+    }
     // everything above touched only weights, the step tables (mirrored before the chain started) and
     // on-chip state; x (and the buffers written below) belong to the previous kernel until it has completed
     pdl_wait();
+    if (p.ws && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid < 128) {
+        p.ws_cnt_next[tid] = 0;
+        p.ws_cnt_next[tid + 128] = 0;
+    }
 
     if (warp == 4) {
         // ================================ TMA producer ========================================
@@ -166,9 +191,11 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             unsigned char* stage = base + st * Cfg::kStageBytes;
             const uint32_t bar = smem_u32(&full[st]);
             if (leader) {
-                mbar_arrive_expect_tx(bar, Cfg::kXBytes + Cfg::kWBytes);
+                if (s >= n_pre) {
+                    mbar_arrive_expect_tx(bar, Cfg::kXBytes + Cfg::kWBytes);
+                    tma_box_2d(smem_u32(stage + Cfg::kXBytes), &tm_w, (slab0 + s) * kBK, n0, bar);
+                }
                 tma_box_2d(smem_u32(stage), &tm_x, (slab0 + s) * kBK, m0, bar);          // rows/columns past the matrix read as zero
-                tma_box_2d(smem_u32(stage + Cfg::kXBytes), &tm_w, (slab0 + s) * kBK, n0, bar);
             }
             __syncwarp();
         }
@@ -289,67 +316,136 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         tc_fence_before();
     }
 
-    // ---- split-K: the peers hand their partial rows to the leader through distributed shared
-    // memory; the leader adds them in rank order (deterministic) ---------------------------------
-    __syncwarp();
-    if (n_split > 1) {
-        cluster_sync_all();                              // the leader's stage buffers are idle from here on
-        if (warp < 4 && krank > 0) {
-            const uint32_t dst = mapa(smem_u32(base + (size_t)(krank - 1) * kBM * BN * 4), 0);
+    // ---- epilogue for 4 columns of row r: bias, activation, residual, then the dense row or the
+    // token's page slot (a float4 lies entirely in one destination: the Q | K | V boundaries are
+    // multiples of 32 whenever this kernel is chosen) ----------------------------------------------
+    const int m = m0 + r;
+    const size_t slot_off = (size_t)my_slot * p.C;
+    // rv: the residual values of a full group, fetched by the caller (ahead of time where it can)
+    auto emit4 = [&](int c4, float4 a, float4 rv) {
+        const int n = n0 + 4 * c4;
+        if (n >= p.N) return;
+        float o[4] = {a.x, a.y, a.z, a.w};
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + 4 * c4);
+        o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+        if (p.act == 1) {
 #pragma unroll
-            for (int c4 = 0; c4 < BN / 4; ++c4)
-                st_cluster_v4(dst + (uint32_t)(c4 * kBM + r) * 16u, make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]));
+            for (int e = 0; e < 4; ++e) o[e] = gelu_tanh(o[e]);
         }
-        cluster_sync_all();
-        if (warp < 4 && krank == 0) {
-            for (int pr = 0; pr < n_split - 1; ++pr) {
-                const float4* src = reinterpret_cast<const float4*>(base + (size_t)pr * kBM * BN * 4);
+        float* dst;
+        if (n < p.n_dense) dst = p.out + (size_t)m * p.out_stride + n;
+        else if (n - p.n_dense < p.C) dst = p.pool_k + slot_off + (n - p.n_dense);
+        else dst = p.pool_v + slot_off + (n - p.n_dense - p.C);
+        if (n + 3 < p.N) {
+            if (p.residual) { o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w; }
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {                                         // last, partial group of a row whose length is not a multiple of 4
+            const float* res = p.residual ? p.residual + (size_t)m * p.res_stride + n : nullptr;
+            for (int e = 0; e < 4 && n + e < p.N; ++e) dst[e] = o[e] + (res ? res[e] : 0.0f);
+        }
+    };
+
+    __syncwarp();
+    if (n_split > 1 && p.ws) {
+        // ---- split-K through the L2 workspace: every CTA of the tile publishes its partial rows,
+        // waits until all n_split partials are there (the grid is co-resident: the host keeps
+        // tiles * n_split <= SMs), then reduces and stores ITS share of the tile's float4 columns --
+        // the sum runs in split order, so the result does not depend on arrival order -------------
+        if (warp < 4) {
+            const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+            const int rows = (p.M - m0) < kBM ? (p.M - m0) : kBM;             // valid rows of this tile
+            float4* part = p.ws + ((size_t)tile * n_split + krank) * (BN / 4) * kBM;
+            if (r < rows) {
 #pragma unroll
-                for (int c4 = 0; c4 < BN / 4; ++c4) {
-                    const float4 v = src[c4 * kBM + r];
-                    acc[4 * c4] += v.x; acc[4 * c4 + 1] += v.y; acc[4 * c4 + 2] += v.z; acc[4 * c4 + 3] += v.w;
+                for (int c4 = 0; c4 < BN / 4; ++c4)
+                    __stcg(part + c4 * kBM + r, make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]));
+            }
+            // this CTA's share of the tile's float4 columns, and the residual values it will need
+            const int c4b = krank * (BN / 4) / n_split, nsh = (krank + 1) * (BN / 4) / n_split - c4b;      // 1..8 columns
+            float4 resv[BN / 8];
+            if (p.residual && r < rows) {
+#pragma unroll
+                for (int i = 0; i < BN / 8; ++i) {
+                    const int n = n0 + 4 * (c4b + i);
+                    if (i < nsh && n + 3 < p.N) resv[i] = __ldcg(reinterpret_cast<const float4*>(p.residual + (size_t)m * p.res_stride + n));
+                }
+            }
+            // publish: the barrier orders the warpgroup's stores before thread 0's release
+            named_bar_sync(1, 128);
+            unsigned* cnt = p.ws_cnt + tile;
+            if (tid == 0) {
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+                unsigned seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+                } while (seen < (unsigned)n_split);
+            }
+            named_bar_sync(1, 128);
+            stamp(5);
+            // all n_split partials of the share -> shared memory (the stage ring is idle now) in ONE
+            // round trip: 16-byte async copies (L2 only), [split][column][row]
+            float4* stage4 = reinterpret_cast<float4*>(base);
+            const int per_split = nsh * kBM;
+            if (r < rows) {                                                   // thread r moves row r of every (split, column)
+                for (int sp = 0; sp < n_split; ++sp) {
+                    const float4* src = p.ws + (((size_t)tile * n_split + sp) * (BN / 4) + c4b) * kBM + r;
+                    for (int i = 0; i < nsh; ++i) cp_async16(smem_u32(stage4 + sp * per_split + i * kBM + r), src + i * kBM, 16);
+                }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            named_bar_sync(1, 128);
+            if (r < rows) {
+                for (int i = 0; i < nsh; ++i) {
+                    float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    for (int sp = 0; sp < n_split; ++sp) {                        // split order: deterministic
+                        const float4 v = stage4[sp * per_split + i * kBM + r];
+                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                    }
+                    float4 rv = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                    for (int u = 0; u < BN / 8; ++u) if (u == i) rv = resv[u];
+                    emit4(c4b + i, sum, rv);
                 }
             }
         }
-    }
-
-    stamp(5);
-    // ---- epilogue: bias, then the dense row or the token's page slot ------------------------------
-    if (warp < 4 && krank == 0) {
-        const int m = m0 + r;
-        if (m < p.M) {
-            const size_t slot_off = (size_t)my_slot * p.C;
+    } else {
+        // ---- split-K over a cluster: the peers hand their partial rows to the leader through
+        // distributed shared memory; the leader adds them in rank order (deterministic) -----------
+        if (n_split > 1) {
+            cluster_sync_all();                          // the leader's stage buffers are idle from here on
+            if (warp < 4 && krank > 0) {
+                const uint32_t dst = mapa(smem_u32(base + (size_t)(krank - 1) * kBM * BN * 4), 0);
 #pragma unroll
-            for (int c = 0; c < BN; c += 32) {
-                const int n = n0 + c;
-                // a 32-column group lies entirely in one destination (the Q | K | V boundaries are multiples
-                // of 32 whenever this kernel is chosen)
-                float* dst;
-                if (n < p.n_dense) dst = p.out + (size_t)m * p.out_stride + n;
-                else if (n - p.n_dense < p.C) dst = p.pool_k + slot_off + (n - p.n_dense);
-                else dst = p.pool_v + slot_off + (n - p.n_dense - p.C);
-                const float* res = p.residual ? p.residual + (size_t)m * p.res_stride + n : nullptr;
+                for (int c4 = 0; c4 < BN / 4; ++c4)
+                    st_cluster_v4(dst + (uint32_t)(c4 * kBM + r) * 16u, make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]));
+            }
+            cluster_sync_all();
+            if (warp < 4 && krank == 0) {
+                for (int pr = 0; pr < n_split - 1; ++pr) {
+                    const float4* src = reinterpret_cast<const float4*>(base + (size_t)pr * kBM * BN * 4);
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    if (n + i < p.N) {
-                        float o[4] = {acc[c + i], acc[c + i + 1], acc[c + i + 2], acc[c + i + 3]};
-                        const float4 b = *reinterpret_cast<const float4*>(bias_s + c + i);
-                        o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
-                        if (p.act == 1) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) o[e] = gelu_tanh(o[e]);
-                        }
-                        if (n + i + 3 < p.N) {
-                            if (res) {
-                                const float4 rv = *reinterpret_cast<const float4*>(res + i);
-                                o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
-                            }
-                            *reinterpret_cast<float4*>(dst + i) = make_float4(o[0], o[1], o[2], o[3]);
-                        } else {                         // last, partial group of a row whose length is not a multiple of 4
-                            for (int e = 0; e < 4 && n + i + e < p.N; ++e) dst[i + e] = o[e] + (res ? res[i + e] : 0.0f);
-                        }
+                    for (int c4 = 0; c4 < BN / 4; ++c4) {
+                        const float4 v = src[c4 * kBM + r];
+                        acc[4 * c4] += v.x; acc[4 * c4 + 1] += v.y; acc[4 * c4 + 2] += v.z; acc[4 * c4 + 3] += v.w;
                     }
                 }
+            }
+        }
+        stamp(5);
+        if (warp < 4 && krank == 0 && m < p.M) {
+#pragma unroll
+            for (int g = 0; g < BN / 4; g += 8) {        // 8 residual loads in flight, then 8 stores
+                float4 rv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int n = n0 + 4 * (g + i);
+                    rv[i] = (p.residual && n + 3 < p.N) ? __ldcg(reinterpret_cast<const float4*>(p.residual + (size_t)m * p.res_stride + n))
+                                                        : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    emit4(g + i, make_float4(acc[4 * (g + i)], acc[4 * (g + i) + 1], acc[4 * (g + i) + 2], acc[4 * (g + i) + 3]), rv[i]);
             }
         }
     }
@@ -405,8 +501,49 @@ int get_map(CUtensorMap* out, const float* ptr, int rows, int K, int row_stride,
     return PA_OK;
 }
 
+// ---- split-K workspace: one per (device, stream) -- launches on a stream are serialised (also under
+// programmatic dependent launch: the reduction runs after griddepcontrol.wait), so they can share it.
+constexpr int kWsMaxSplit = 16;       // = BN / 4 float4 columns of a tile: every CTA of a tile reduces at least one
+constexpr int kWsMaxCtas = 256;       // partial tiles in the workspace (>= SMs of the device)
+struct SplitWs { int dev; cudaStream_t stream; float4* ws; unsigned* cnt; int parity; };
+static_assert(kWsMaxCtas == 256, "the kernel zeroes the next counter set with 128 threads x 2");
+struct SplitWsCache {
+    static constexpr int N = 16;
+    SplitWs e[N];
+    int used = 0;
+    std::mutex mu;
+};
+SplitWsCache g_ws;
+// false when the cache is full or the allocation fails (the caller then splits over a cluster instead);
+// hands out the counter set of this launch and flips to the other one for the next
+bool get_split_ws(int dev, cudaStream_t s, int BN, GemmTcParams* p) {
+    std::lock_guard<std::mutex> lock(g_ws.mu);
+    SplitWs* w = nullptr;
+    for (int i = 0; i < g_ws.used && !w; ++i)
+        if (g_ws.e[i].dev == dev && g_ws.e[i].stream == s) w = &g_ws.e[i];
+    if (!w) {
+        if (g_ws.used == SplitWsCache::N) return false;
+        SplitWs n{dev, s, nullptr, nullptr, 0};
+        const size_t bytes = (size_t)kWsMaxCtas * kBM * BN * sizeof(float);
+        if (cudaMalloc((void**)&n.ws, bytes) != cudaSuccess || cudaMalloc((void**)&n.cnt, 2 * kWsMaxCtas * sizeof(unsigned)) != cudaSuccess ||
+            cudaMemsetAsync(n.cnt, 0, 2 * kWsMaxCtas * sizeof(unsigned), s) != cudaSuccess) {
+            cudaGetLastError();
+            if (n.ws) cudaFree(n.ws);
+            if (n.cnt) cudaFree(n.cnt);
+            return false;
+        }
+        g_ws.e[g_ws.used] = n;
+        w = &g_ws.e[g_ws.used++];
+    }
+    p->ws = w->ws;
+    p->ws_cnt = w->cnt + w->parity * kWsMaxCtas;
+    p->ws_cnt_next = w->cnt + (1 - w->parity) * kWsMaxCtas;
+    w->parity ^= 1;
+    return true;
+}
+
 template <int BN>
-int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams& p, int n_split, cudaStream_t s) {
+int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams& p, int n_split, bool cluster, cudaStream_t s) {
     using Cfg = GemmCfg<BN>;
     auto fn = pa_gemm3x_kernel<BN>;
     static bool attr_done = false;
@@ -414,7 +551,7 @@ int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams
         CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
         attr_done = true;
     }
-    CU_CHECK(pa_launch_pdl(fn, dim3((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, n_split), dim3(192), Cfg::kSmem, s, n_split, tx, tw, p));
+    CU_CHECK(pa_launch_pdl(fn, dim3((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, n_split), dim3(192), Cfg::kSmem, s, cluster ? n_split : 1, tx, tw, p));
     return PA_OK;
 }
 
@@ -448,24 +585,42 @@ extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const
     static unsigned long long* d_dbg = nullptr;
     p.dbg = nullptr;
     if (getenv("PA_GEMM_DEBUG")) { if (!d_dbg) cudaMalloc((void**)&d_dbg, 64); p.dbg = d_dbg; }
-    // Small M (decode): a handful of CTAs each walking all of K is latency-bound (one HBM round trip
-    // per ring refill), so K is split over a cluster until the grid covers the machine.
+    // Small M (decode): a handful of CTAs each walking all of K is latency-bound (a CTA turns a
+    // k-slab around in ~0.4 us, bounded by its shared-memory traffic), so K is split until the grid
+    // covers the machine: n_split CTAs per tile, each with at least two k-slabs, all co-resident
+    // (tiles * n_split <= SMs: they wait for each other), partials reduced through the L2 workspace.
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms > kWsMaxCtas) sms = kWsMaxCtas;
     const long long tiles = (long long)((N + BN - 1) / BN) * ((M + kBM - 1) / kBM);
     const int total_slabs = (K + kBK - 1) / kBK;
+    const int ws_cap = tiles <= sms ? (int)(sms / tiles) : 1;          // co-residency bound
     int n_split = 1;
-    // clusters of 4 one-CTA-per-SM blocks fit 4 to a GPC (measured: 36 of them run in two waves), so
-    // 4-way splits only up to 32 tiles; 2-way while the grid still fits the machine in one wave
-    if (tiles * 4 <= (sms / 37) * 32 && total_slabs >= 16) n_split = 4;
-    else if (tiles * 2 <= sms && total_slabs >= 8) n_split = 2;
-    if (n_split_override > 0) {
-        n_split = n_split_override > kMaxSplit ? kMaxSplit : n_split_override;
-        if (n_split == 3) n_split = 2;
+    bool cluster = false;
+    if (n_split_override == 0) {
+        n_split = ws_cap < kWsMaxSplit ? ws_cap : kWsMaxSplit;
+        if (n_split > total_slabs / 2) n_split = total_slabs / 2;
+        if (n_split < 1) n_split = 1;
+    } else if (n_split_override > 0) {                                  // forced split count (clamped to what can run)
+        n_split = n_split_override < kWsMaxSplit ? n_split_override : kWsMaxSplit;
+        if (n_split > ws_cap) n_split = ws_cap;
+        if (n_split > total_slabs) n_split = total_slabs;
+    } else {                                                            // negative: K split over a cluster of 2 or 4 CTAs
+        cluster = true;
+        n_split = -n_split_override >= kMaxSplit ? kMaxSplit : 2;
         while (n_split > 1 && total_slabs < n_split) n_split /= 2;
     }
-    rc = launch_gemm<64>(tx, tw, p, n_split, (cudaStream_t)stream);
+    p.ws = nullptr; p.ws_cnt = nullptr; p.ws_cnt_next = nullptr;
+    if (n_split > 1 && !cluster) {
+        if (!get_split_ws(dev, (cudaStream_t)stream, BN, &p)) {                                                        // no workspace: clusters of 2 or 4
+            cluster = true;
+            n_split = (n_split >= 4 && tiles * 4 <= (sms / 37) * 32) ? 4 : 2;
+            while (n_split > 1 && (total_slabs < n_split || tiles * n_split > sms)) n_split /= 2;
+        }
+    }
+    if (n_split == 1) cluster = false;
+    rc = launch_gemm<64>(tx, tw, p, n_split, cluster, (cudaStream_t)stream);
     if (p.dbg) {      // ns since kernel entry: TMEM ready, first slab landed, splitter done, MMAs done, reduction done, stores issued
         unsigned long long hst[8];
         cudaDeviceSynchronize();

@@ -152,63 +152,82 @@ pa_layernorm_rows_kernel(float* __restrict__ out, const float* __restrict__ inp,
 // a block-wide scan over contiguous chunks, so an index can differ from the sequential reference
 // only when the coin lies within rounding distance of a boundary of the distribution.
 // coin < 0 selects argmax (greedy).
-__global__ void __launch_bounds__(256)
+constexpr int kSampleThreads = 512;
+__global__ void __launch_bounds__(kSampleThreads)
 pa_sample_kernel(const float* __restrict__ logits, int stride, int V, const float* __restrict__ coins, int* __restrict__ next) {
-    __shared__ float red[256];
-    __shared__ int redi[256];
+    constexpr int NW = kSampleThreads / 32;
+    __shared__ float red[NW];
+    __shared__ int redi[NW];
+    __shared__ float wsum[NW];
+    __shared__ int pick_s;
     pdl_launch_dependents();
     pdl_wait();
-    const int row = blockIdx.x, tid = threadIdx.x;
+    const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* l = logits + (size_t)row * stride;
     const float coin = coins ? coins[row] : -1.0f;
-    const int chunk = (V + 255) / 256;
-    const int c0 = tid * chunk, c1 = min(V, c0 + chunk);
+    // a warp owns a contiguous range of the vocabulary (ranges in index order), its lanes interleave: coalesced reads
+    const int chunk = ((V + NW - 1) / NW + 31) & ~31;
+    const int c0 = min(V, warp * chunk), c1 = min(V, c0 + chunk);
+    constexpr int kNone = 0x7fffffff;
     float mx = -10000.0f;                                           // :270
-    int arg = -1;
-    for (int i = c0; i < c1; ++i) if (l[i] > mx) { mx = l[i]; arg = i; }
-    red[tid] = mx; redi[tid] = arg;
-    __syncthreads();
-    for (int d = 128; d >= 1; d >>= 1) {
-        if (tid < d) {
-            // ties and order: the reference keeps the FIRST maximum (strict >); chunks are in index order
-            if (red[tid + d] > red[tid] || (red[tid + d] == red[tid] && redi[tid] < 0)) { red[tid] = red[tid + d]; redi[tid] = redi[tid + d]; }
-        }
-        __syncthreads();
+    int arg = kNone;
+    for (int i = c0 + lane; i < c1; i += 32) { const float v = l[i]; if (v > mx) { mx = v; arg = i; } }
+    // ties and order: the reference keeps the FIRST maximum (strict >), i.e. the smallest index of the largest value
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, d);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
     }
-    const float maxval = red[0];
-    const int argmax = redi[0] < 0 ? 0 : redi[0];
+    if (lane == 0) { red[warp] = mx; redi[warp] = arg; }
+    if (tid == 0) pick_s = -1;
     __syncthreads();
+    float maxval = red[0];
+    int argmax = redi[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w)
+        if (red[w] > maxval || (red[w] == maxval && redi[w] < argmax)) { maxval = red[w]; argmax = redi[w]; }
+    if (argmax == kNone) argmax = 0;
     if (coin < 0.0f) {
         if (tid == 0) next[row] = argmax;
         return;
     }
     float part = 0.0f;
-    for (int i = c0; i < c1; ++i) part += expf(l[i] - maxval);
-    red[tid] = part;
+    for (int i = c0 + lane; i < c1; i += 32) part += expf(l[i] - maxval);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == 0) wsum[warp] = part;
     __syncthreads();
-    // inclusive scan of the chunk sums (Hillis-Steele over 256 entries)
-    for (int d = 1; d < 256; d <<= 1) {
-        const float t = tid >= d ? red[tid - d] : 0.0f;
-        __syncthreads();
-        red[tid] += t;
-        __syncthreads();
+    // running sums over the warp ranges, formed identically by every thread
+    float before = 0.0f, upto = 0.0f, total = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        if (w == warp) before = total;
+        total += wsum[w];
+        if (w == warp) upto = total;
     }
-    const float total = red[255];
     const float target = coin * total;
-    const float before = tid > 0 ? red[tid - 1] : 0.0f;
-    if (tid == 0) redi[0] = V - 1;                                  // "in case of rounding errors", :847
-    __syncthreads();
-    if (target >= before && target < red[tid] && c0 < c1) {         // the crossing lies in this chunk (exactly one thread)
+    if (target >= before && target < upto && c0 < c1) {             // the crossing lies in this warp's range (exactly one warp)
         float cdf = before;
-        int pick = c1 - 1;
-        for (int i = c0; i < c1; ++i) {
-            cdf += expf(l[i] - maxval);
-            if (target < cdf) { pick = i; break; }
+        int pick = -1;
+        for (int b = c0; b < c1 && pick < 0; b += 32) {
+            const int i = b + lane;
+            float sc = i < c1 ? expf(l[i] - maxval) : 0.0f;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {                      // inclusive scan over the 32 entries
+                const float t = __shfl_up_sync(0xffffffffu, sc, d);
+                if (lane >= d) sc += t;
+            }
+            const float incl = cdf + sc;
+            const unsigned hit = __ballot_sync(0xffffffffu, i < c1 && target < incl);
+            if (hit) pick = b + __ffs(hit) - 1;
+            cdf = __shfl_sync(0xffffffffu, incl, 31);
         }
-        redi[0] = pick;
+        if (pick < 0) pick = c1 - 1;                                // the range sum and the scan round differently
+        if (lane == 0) pick_s = pick;
     }
     __syncthreads();
-    if (tid == 0) next[row] = redi[0];
+    if (tid == 0) next[row] = pick_s >= 0 ? pick_s : V - 1;         // "in case of rounding errors", :847
 }
 
 size_t param_count(int V, int maxT, int L, int C) {
@@ -384,7 +403,8 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
     cudaStream_t s = (cudaStream_t)h->stream;
     // Overlapping launches pay off while the step is a chain of latency-bound kernels (measured: +8 % at 64
     // tokens, -3 % at 256, where early-resident successors get in the way of the cluster launches)
-    pa_pdl_gate = ntok <= 128;
+    static const int pdl_max_tokens = getenv("PA_PDL_MAX_TOKENS") ? atoi(getenv("PA_PDL_MAX_TOKENS")) : 128;
+    pa_pdl_gate = ntok <= pdl_max_tokens;
     int rc = pa_step_begin(h, seq_ids, n_new, nseq);
     if (rc != PA_OK) return rc;
     rc = pa_step_upload(h, s);
@@ -418,7 +438,7 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
     CU_CHECK(pa_launch_pdl(pa_layernorm_rows_kernel, dim3((nseq + 3) / 4), dim3(128), 0, s, 1, m->ln, (const float*)m->x, (const int*)d_last, m->lnfw, m->lnfb, nseq, C));
     rc = pa_cu_linear(m->ln, C, m->wte, nullptr, m->logits, m->Vp, nseq, V, C, nullptr, 0, 0, path, s);       // logits = lnf . wte^T (:726)
     if (rc != PA_OK) return rc;
-    CU_CHECK(pa_launch_pdl(pa_sample_kernel, dim3(nseq), dim3(256), 0, s, 1, (const float*)m->logits, m->Vp, V, (const float*)(coins ? m->d_coins : nullptr), d_next));
+    CU_CHECK(pa_launch_pdl(pa_sample_kernel, dim3(nseq), dim3(kSampleThreads), 0, s, 1, (const float*)m->logits, m->Vp, V, (const float*)(coins ? m->d_coins : nullptr), d_next));
     h->launches += launches + 3;        // (pa_qkv_append / pa_decode / pa_prefill count themselves)
     CU_CHECK(cudaMemcpyAsync(h_next, d_next, (size_t)nseq * sizeof(int), cudaMemcpyDeviceToHost, s));
     CU_CHECK(cudaStreamSynchronize(s));

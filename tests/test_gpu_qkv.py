@@ -80,12 +80,14 @@ def test_qkv_append_then_decode_matches_oracle(NH, hs, bs, ctx, path):
         sc.close()
 
 
-@pytest.mark.parametrize("split", [1, 2, 4])
-@pytest.mark.parametrize("B,NH,hs", [(70, 12, 64), (130, 25, 64), (3, 2, 64)])
-def test_qkv_append_split_k_clusters(B, NH, hs, split):
-    """Tensor-core GEMM with K split over a cluster of 1/2/4 CTAs (partial rows reduced through
-    distributed shared memory in rank order): same result within the path tolerance, and
-    bit-identical between two runs (deterministic reduction)."""
+@pytest.mark.parametrize("split", [0, 1, 2, 3, 4, 8, 16, -2, -4])
+@pytest.mark.parametrize("B,NH,hs", [(70, 12, 64), (130, 25, 64), (3, 2, 64), (20, 4, 64)])
+def test_qkv_append_split_k(B, NH, hs, split):
+    """Tensor-core GEMM with K split over several CTAs per tile -- split > 0: partial tiles through
+    the L2 workspace, every CTA of a tile reducing its share of the columns in split order (0 = the
+    automatic choice); split < 0: a cluster of 2/4 CTAs reducing through distributed shared memory in
+    rank order.  Same result within the path tolerance, and bit-identical between two runs
+    (deterministic reduction)."""
     bs = 16
     Cc = NH * hs
     sc = Scenario(NH, hs, bs, [3] * B, seed=95, extra_blocks=B + 8)
@@ -215,3 +217,35 @@ def test_compat_matmul_forward_and_cached(B, T, Cc, device_buffers):
         untouched = want == sentinel
         assert np.array_equal(got[untouched], want[untouched]), f"{name}: wrote outside its columns"
         assert_close_gemm(got, want, name)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 768, 3072), (200, 768, 768), (7, 128, 2048), (64, 100, 1024), (130, 1600, 1600),
+                                   (64, 3072, 768), (33, 64, 4096)])
+def test_matmul_bias_auto_split_k(M, N, K):
+    """pa_matmul_bias on device pointers at decode-step shapes: the tensor-core GEMM picks up to 16
+    K-splits per tile by itself (workspace reduction).  Within the path tolerance of the oracle's
+    matmul_forward, bit-identical across runs, and the workspace counters are back at rest (a third
+    launch with another shape on the same stream still gives the right answer)."""
+    lib = pa.load()
+    x = oa.normal((M, K), seed=301)
+    w = (oa.normal((N, K), seed=302) * np.float32(1.0 / np.sqrt(K))).astype(np.float32)
+    bias = oa.normal((N,), seed=303)
+    want = _oracle_matmul(x, w, bias)
+    dx, dw, db, do = pa.DevBuf.from_numpy(x), pa.DevBuf.from_numpy(w), pa.DevBuf.from_numpy(bias), pa.DevBuf(M * N * 4)
+    runs = []
+    for _ in range(3):
+        pa.check(lib.pa_memset(do.ptr, 0xff, M * N * 4, None), "memset")
+        pa.check(lib.pa_matmul_bias(dx.ptr, K, dw.ptr, db.ptr, do.ptr, N, M, N, K, None), "pa_matmul_bias")
+        pa.check(lib.pa_device_sync(), "sync")
+        runs.append(do.download((M, N)))
+    assert_close_gemm(runs[0], want, f"auto split-K {M}x{N}x{K}")
+    assert np.array_equal(runs[0].view(np.uint32), runs[1].view(np.uint32))
+    assert np.array_equal(runs[0].view(np.uint32), runs[2].view(np.uint32))
+    # another shape on the same stream right after: the tile counters were reset
+    x2 = oa.normal((M, 768), seed=304)
+    w2 = (oa.normal((768, 768), seed=305) * np.float32(1.0 / np.sqrt(768))).astype(np.float32)
+    want2 = _oracle_matmul(x2, w2, None)
+    dx2, dw2, do2 = pa.DevBuf.from_numpy(x2), pa.DevBuf.from_numpy(w2), pa.DevBuf(M * 768 * 4)
+    pa.check(lib.pa_matmul_bias(dx2.ptr, 768, dw2.ptr, None, do2.ptr, 768, M, 768, 768, None), "pa_matmul_bias")
+    pa.check(lib.pa_device_sync(), "sync")
+    assert_close_gemm(do2.download((M, 768)), want2, "second shape")
