@@ -53,8 +53,6 @@ __device__ __forceinline__ uint64_t smem_desc_k(uint32_t addr) { return smem_des
 
 constexpr int kBM = 128;          // rows per CTA = TMEM lanes
 constexpr int kBK = 32;           // floats per k-slab = one 128-byte swizzle row
-constexpr int kStages = 6;        // shared-memory ring (32 KB per stage at BN = 64)
-constexpr int kAStages = 4;       // TMEM ring of A slabs
 constexpr int kMaxSplit = 4;      // CTAs of a cluster splitting K
 constexpr int kChunk = 8;          // k-slabs per main-accumulator chunk (256 floats of K)
 
@@ -94,6 +92,8 @@ __device__ __forceinline__ float tf32_lo(float a) {
 
 template <int BN>
 struct GemmCfg {
+    static constexpr int kStages = BN == 64 ? 6 : 4;     // shared-memory ring: 32 KB (BN 64) / 48 KB (BN 128) per stage, 192 KB in all
+    static constexpr int kAStages = BN == 64 ? 4 : 2;    // TMEM ring of A slabs (what is left of the 512 columns)
     static constexpr int kXBytes = kBM * 128;            // one k-slab of x: 128 rows x 128 B
     static constexpr int kWBytes = BN * 128;
     static constexpr int kStageBytes = kXBytes + 2 * kWBytes;     // x | w | w_lo
@@ -105,7 +105,7 @@ struct GemmCfg {
     static constexpr int kTmemCols = kCols <= 256 ? 256 : 512;
     static_assert(kCols <= 512, "TMEM columns");
     // split-K reduction scratch in the leader's (idle) stage buffers: [peer][float4 column][row]
-    static_assert((kMaxSplit - 1) * kBM * BN * 4 <= kStages * kStageBytes, "reduction scratch");
+    // (cluster splits are only launched with BN = 64: three peers' tiles fit the leader's ring)
 };
 
 
@@ -114,6 +114,7 @@ template <int BN>
 __global__ void __launch_bounds__(192, 1)
 pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const GemmTcParams p) {
     using Cfg = GemmCfg<BN>;
+    constexpr int kStages = Cfg::kStages, kAStages = Cfg::kAStages;
     constexpr uint32_t kIdesc = instr_desc(kBM, BN, 0, 0);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -503,7 +504,7 @@ int get_map(CUtensorMap* out, const float* ptr, int rows, int K, int row_stride,
 
 // ---- split-K workspace: one per (device, stream) -- launches on a stream are serialised (also under
 // programmatic dependent launch: the reduction runs after griddepcontrol.wait), so they can share it.
-constexpr int kWsMaxSplit = 16;       // = BN / 4 float4 columns of a tile: every CTA of a tile reduces at least one
+constexpr int kWsMaxSplit = 16;       // <= BN / 4 float4 columns of a tile: every CTA of a tile reduces at least one
 constexpr int kWsMaxCtas = 256;       // partial tiles in the workspace (>= SMs of the device)
 struct SplitWs { int dev; cudaStream_t stream; float4* ws; unsigned* cnt; int parity; };
 static_assert(kWsMaxCtas == 256, "the kernel zeroes the next counter set with 128 threads x 2");
@@ -516,7 +517,8 @@ struct SplitWsCache {
 SplitWsCache g_ws;
 // false when the cache is full or the allocation fails (the caller then splits over a cluster instead);
 // hands out the counter set of this launch and flips to the other one for the next
-bool get_split_ws(int dev, cudaStream_t s, int BN, GemmTcParams* p) {
+bool get_split_ws(int dev, cudaStream_t s, GemmTcParams* p) {
+    constexpr int BN = 128;        // sized for the widest tile
     std::lock_guard<std::mutex> lock(g_ws.mu);
     SplitWs* w = nullptr;
     for (int i = 0; i < g_ws.used && !w; ++i)
@@ -572,11 +574,6 @@ extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const
     if (pool_k && (N & 3)) return PA_ERR_UNSUPPORTED;
     // a 32-column group of the epilogue must not straddle the Q | K | V boundaries
     if (pool_k && ((n_dense & 31) || (C & 31))) return PA_ERR_UNSUPPORTED;
-    const int BN = 64;
-    CUtensorMap tx, tw;
-    int rc = get_map(&tx, x, M, K, x_stride, kBM);
-    if (rc == PA_OK) rc = get_map(&tw, w, N, K, K, BN);
-    if (rc != PA_OK) return rc;
     GemmTcParams p;
     p.bias = bias; p.out = out; p.pool_k = pool_k; p.pool_v = pool_v; p.slots = slots;
     p.M = M; p.N = N; p.K = K; p.out_stride = out_stride; p.n_dense = pool_k ? n_dense : N; p.C = C;
@@ -586,15 +583,26 @@ extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const
     p.dbg = nullptr;
     if (getenv("PA_GEMM_DEBUG")) { if (!d_dbg) cudaMalloc((void**)&d_dbg, 64); p.dbg = d_dbg; }
     // Small M (decode): a handful of CTAs each walking all of K is latency-bound (a CTA turns a
-    // k-slab around in ~0.4 us, bounded by its shared-memory traffic), so K is split until the grid
-    // covers the machine: n_split CTAs per tile, each with at least two k-slabs, all co-resident
-    // (tiles * n_split <= SMs: they wait for each other), partials reduced through the L2 workspace.
+    // k-slab around in ~0.4 us at BN = 64 / ~0.5 us at BN = 128, bounded by its shared-memory
+    // traffic), so K is split until the grid covers the machine: n_split CTAs per tile, each with at
+    // least two k-slabs, all co-resident (tiles * n_split <= SMs: they wait for each other), partials
+    // reduced through the L2 workspace.  Tiles are 64 columns wide while that leaves room to split;
+    // when 64-wide tiles alone (nearly) fill the machine, 128-wide tiles halve their number -- less
+    // shared-memory traffic per flop, and K can be split again.
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms > kWsMaxCtas) sms = kWsMaxCtas;
-    const long long tiles = (long long)((N + BN - 1) / BN) * ((M + kBM - 1) / kBM);
     const int total_slabs = (K + kBK - 1) / kBK;
+    const long long m_tiles = (M + kBM - 1) / kBM;
+    static const int bn_env = getenv("PA_GEMM_BN") ? atoi(getenv("PA_GEMM_BN")) : 0;      // experiments: force 64 or 128
+    int BN = 64;
+    if (n_split_override >= 0 && N >= 128) {
+        const long long tiles64 = (long long)((N + 63) / 64) * m_tiles;
+        if (tiles64 * 2 > sms) BN = 128;
+        if (bn_env == 64 || bn_env == 128) BN = bn_env;
+    }
+    const long long tiles = (long long)((N + BN - 1) / BN) * m_tiles;
     const int ws_cap = tiles <= sms ? (int)(sms / tiles) : 1;          // co-residency bound
     int n_split = 1;
     bool cluster = false;
@@ -606,21 +614,29 @@ extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const
         n_split = n_split_override < kWsMaxSplit ? n_split_override : kWsMaxSplit;
         if (n_split > ws_cap) n_split = ws_cap;
         if (n_split > total_slabs) n_split = total_slabs;
-    } else {                                                            // negative: K split over a cluster of 2 or 4 CTAs
+    } else {                                                            // negative: K split over a cluster of 2 or 4 CTAs (BN = 64)
         cluster = true;
         n_split = -n_split_override >= kMaxSplit ? kMaxSplit : 2;
         while (n_split > 1 && total_slabs < n_split) n_split /= 2;
     }
     p.ws = nullptr; p.ws_cnt = nullptr; p.ws_cnt_next = nullptr;
     if (n_split > 1 && !cluster) {
-        if (!get_split_ws(dev, (cudaStream_t)stream, BN, &p)) {                                                        // no workspace: clusters of 2 or 4
-            cluster = true;
-            n_split = (n_split >= 4 && tiles * 4 <= (sms / 37) * 32) ? 4 : 2;
-            while (n_split > 1 && (total_slabs < n_split || tiles * n_split > sms)) n_split /= 2;
+        if (!get_split_ws(dev, (cudaStream_t)stream, &p)) {             // no workspace: clusters of 2 or 4
+            if (BN == 128) n_split = 1;
+            else {
+                cluster = true;
+                n_split = (n_split >= 4 && tiles * 4 <= (sms / 37) * 32) ? 4 : 2;
+                while (n_split > 1 && (total_slabs < n_split || tiles * n_split > sms)) n_split /= 2;
+            }
         }
     }
     if (n_split == 1) cluster = false;
-    rc = launch_gemm<64>(tx, tw, p, n_split, cluster, (cudaStream_t)stream);
+    CUtensorMap tx, tw;
+    int rc = get_map(&tx, x, M, K, x_stride, kBM);
+    if (rc == PA_OK) rc = get_map(&tw, w, N, K, K, BN);
+    if (rc != PA_OK) return rc;
+    rc = BN == 128 ? launch_gemm<128>(tx, tw, p, n_split, false, (cudaStream_t)stream)
+                   : launch_gemm<64>(tx, tw, p, n_split, cluster, (cudaStream_t)stream);
     if (p.dbg) {      // ns since kernel entry: TMEM ready, first slab landed, splitter done, MMAs done, reduction done, stores issued
         unsigned long long hst[8];
         cudaDeviceSynchronize();
