@@ -25,6 +25,7 @@
 
 #include "pa_internal.h"
 #include "pa_pdl.cuh"
+#include "pa_model_dev.cuh"
 
 #define CU_CHECK(call)                                                                         \
     do {                                                                                       \
@@ -49,6 +50,9 @@ struct pa_model {
     float* d_coins;
     int* h_io;                             // pinned mirror
     float* h_coins;
+    float* mega_part;                      // attention split workspace of the persistent small-batch kernel
+    size_t mega_part_floats;
+    unsigned* mega_bar;                    // its grid-barrier counter
 };
 
 namespace {
@@ -65,44 +69,14 @@ __global__ void pa_embed_kernel(float* __restrict__ x, const int* __restrict__ t
 }
 
 // ---- layernorm_forward (paged_infer.c:49-89): one warp per row, the row held in registers -------
-constexpr int kLnMaxPerLane = 64;          // C <= 2048
 __global__ void __launch_bounds__(128)
 pa_layernorm_kernel(float* __restrict__ out, const float* __restrict__ inp, const float* __restrict__ weight,
                     const float* __restrict__ bias, int rows, int C) {
     pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const float* x = inp + (size_t)row * C;
-    float v[kLnMaxPerLane];
-    float sum = 0.0f;
-#pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        const int c = lane + 32 * i;
-        v[i] = c < C ? x[c] : 0.0f;
-        sum += v[i];
-    }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    const float m = sum / C;
-    float var = 0.0f;
-#pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        const int c = lane + 32 * i;
-        const float dlt = v[i] - m;
-        if (c < C) var += dlt * dlt;
-    }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
-    var = var / C;
-    const float s = 1.0f / sqrtf(var + 1e-5f);                   // eps, :56
-    float* o = out + (size_t)row * C;
-#pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        const int c = lane + 32 * i;
-        if (c < C) o[c] = (s * (v[i] - m)) * weight[c] + bias[c];
-    }
+    pa_layernorm_row<false>(out + (size_t)row * C, inp + (size_t)row * C, weight, bias, C, threadIdx.x & 31);
 }
 
 // the same over gathered input rows (final layernorm of each sequence's last position), compact output
@@ -112,122 +86,20 @@ pa_layernorm_rows_kernel(float* __restrict__ out, const float* __restrict__ inp,
     pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const float* x = inp + (size_t)rows_in[row] * C;
-    float v[kLnMaxPerLane];
-    float sum = 0.0f;
-#pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        const int c = lane + 32 * i;
-        v[i] = c < C ? x[c] : 0.0f;
-        sum += v[i];
-    }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    const float m = sum / C;
-    float var = 0.0f;
-#pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        const int c = lane + 32 * i;
-        const float dlt = v[i] - m;
-        if (c < C) var += dlt * dlt;
-    }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
-    var = var / C;
-    const float s = 1.0f / sqrtf(var + 1e-5f);
-    float* o = out + (size_t)row * C;
-#pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        const int c = lane + 32 * i;
-        if (c < C) o[c] = (s * (v[i] - m)) * weight[c] + bias[c];
-    }
+    pa_layernorm_row<false>(out + (size_t)row * C, inp + (size_t)rows_in[row] * C, weight, bias, C, threadIdx.x & 31);
 }
 
-// ---- softmax_forward + sample_mult (paged_infer.c:259-286, :838-848) fused -------------------------
-// One CTA per row of logits.  maxval starts at -10000 as the reference's does; the probabilities
-// are exp(l - max) / sum; sample_mult returns the first index whose running sum exceeds the coin.
-// Here the comparison is made against coin * sum (no division per element) and the running sum is
-// a block-wide scan over contiguous chunks, so an index can differ from the sequential reference
-// only when the coin lies within rounding distance of a boundary of the distribution.
-// coin < 0 selects argmax (greedy).
+// ---- softmax_forward + sample_mult (paged_infer.c:259-286, :838-848) fused: one CTA per row of logits
+// (pa_sample_row in pa_model_dev.cuh)
 constexpr int kSampleThreads = 512;
 __global__ void __launch_bounds__(kSampleThreads)
 pa_sample_kernel(const float* __restrict__ logits, int stride, int V, const float* __restrict__ coins, int* __restrict__ next) {
-    constexpr int NW = kSampleThreads / 32;
-    __shared__ float red[NW];
-    __shared__ int redi[NW];
-    __shared__ float wsum[NW];
-    __shared__ int pick_s;
+    __shared__ PaSampleSmem<kSampleThreads> sm;
     pdl_launch_dependents();
     pdl_wait();
-    const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float* l = logits + (size_t)row * stride;
-    const float coin = coins ? coins[row] : -1.0f;
-    // a warp owns a contiguous range of the vocabulary (ranges in index order), its lanes interleave: coalesced reads
-    const int chunk = ((V + NW - 1) / NW + 31) & ~31;
-    const int c0 = min(V, warp * chunk), c1 = min(V, c0 + chunk);
-    constexpr int kNone = 0x7fffffff;
-    float mx = -10000.0f;                                           // :270
-    int arg = kNone;
-    for (int i = c0 + lane; i < c1; i += 32) { const float v = l[i]; if (v > mx) { mx = v; arg = i; } }
-    // ties and order: the reference keeps the FIRST maximum (strict >), i.e. the smallest index of the largest value
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        const float om = __shfl_xor_sync(0xffffffffu, mx, d);
-        const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
-        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
-    }
-    if (lane == 0) { red[warp] = mx; redi[warp] = arg; }
-    if (tid == 0) pick_s = -1;
-    __syncthreads();
-    float maxval = red[0];
-    int argmax = redi[0];
-#pragma unroll
-    for (int w = 1; w < NW; ++w)
-        if (red[w] > maxval || (red[w] == maxval && redi[w] < argmax)) { maxval = red[w]; argmax = redi[w]; }
-    if (argmax == kNone) argmax = 0;
-    if (coin < 0.0f) {
-        if (tid == 0) next[row] = argmax;
-        return;
-    }
-    float part = 0.0f;
-    for (int i = c0 + lane; i < c1; i += 32) part += expf(l[i] - maxval);
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-    if (lane == 0) wsum[warp] = part;
-    __syncthreads();
-    // running sums over the warp ranges, formed identically by every thread
-    float before = 0.0f, upto = 0.0f, total = 0.0f;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        if (w == warp) before = total;
-        total += wsum[w];
-        if (w == warp) upto = total;
-    }
-    const float target = coin * total;
-    if (target >= before && target < upto && c0 < c1) {             // the crossing lies in this warp's range (exactly one warp)
-        float cdf = before;
-        int pick = -1;
-        for (int b = c0; b < c1 && pick < 0; b += 32) {
-            const int i = b + lane;
-            float sc = i < c1 ? expf(l[i] - maxval) : 0.0f;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {                      // inclusive scan over the 32 entries
-                const float t = __shfl_up_sync(0xffffffffu, sc, d);
-                if (lane >= d) sc += t;
-            }
-            const float incl = cdf + sc;
-            const unsigned hit = __ballot_sync(0xffffffffu, i < c1 && target < incl);
-            if (hit) pick = b + __ffs(hit) - 1;
-            cdf = __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (pick < 0) pick = c1 - 1;                                // the range sum and the scan round differently
-        if (lane == 0) pick_s = pick;
-    }
-    __syncthreads();
-    if (tid == 0) next[row] = pick_s >= 0 ? pick_s : V - 1;         // "in case of rounding errors", :847
+    const int row = blockIdx.x;
+    pa_sample_row<kSampleThreads>(logits + (size_t)row * stride, V, coins ? coins[row] : -1.0f, next + row, sm);
 }
 
 size_t param_count(int V, int maxT, int L, int C) {
@@ -247,6 +119,51 @@ __global__ void pa_init_normal_kernel(float* p, size_t n, float stdv, float mean
         const float u2 = (hash32(seed + 2 * i + 1) >> 8) * (1.0f / 16777216.0f);
         p[i] = mean + stdv * sqrtf(-2.0f * logf(u1)) * cosf(6.28318530718f * u2);
     }
+}
+
+// the decode step of <= 8 sequences through the persistent kernel; the step tables are already on the device
+int mega_step(pa_model* m, int nseq, const int* d_tok, const int* d_pos, const float* d_coins, int* d_next, cudaStream_t s) {
+    pa_handle* h = m->h;
+    const pa_step_layout& L = h->step;
+    pa_mega_args a;
+    a.wte = m->wte; a.wpe = m->wpe; a.ln1w = m->ln1w; a.ln1b = m->ln1b; a.qkvw = m->qkvw; a.qkvb = m->qkvb;
+    a.attprojw = m->attprojw; a.attprojb = m->attprojb; a.ln2w = m->ln2w; a.ln2b = m->ln2b; a.fcw = m->fcw; a.fcb = m->fcb;
+    a.fcprojw = m->fcprojw; a.fcprojb = m->fcprojb; a.lnfw = m->lnfw; a.lnfb = m->lnfb;
+    a.C = m->C; a.NH = h->cfg.n_heads; a.hs = h->cfg.head_dim; a.L = m->L; a.V = m->V; a.Vp = m->Vp;
+    a.M = nseq; a.tokens = d_tok; a.positions = d_pos; a.coins = d_coins; a.next = d_next;
+    a.x = m->x; a.q = m->q; a.atty = m->atty; a.fch = m->fch; a.logits = m->logits;
+    a.pool_k = h->pool_k; a.pool_v = h->pool_v; a.layer_stride = h->layer_stride;
+    a.kv_end = h->d_step + L.off_kv_end; a.kv_start = h->d_step + L.off_kv_start;
+    a.slots = h->d_step + L.off_slot; a.table = h->d_step + L.off_table;
+    a.tstride = L.tstride; a.bs = h->cfg.block_size;
+    a.scale = (float)(1.0 / sqrtf((float)h->cfg.head_dim));            // :174
+    a.sm_count = h->sm_count;
+    // attention split: about one (sequence, head, chunk) unit per warp of the grid, chunks of >= 16 tokens
+    long long tokens = 0;
+    int max_len = 1;
+    for (int i = 0; i < nseq; ++i) {
+        const int len = h->h_step[L.off_kv_end + i] - h->h_step[L.off_kv_start + i];
+        tokens += len;
+        if (len > max_len) max_len = len;
+    }
+    const long long warps = (long long)h->sm_count * 8;
+    long long chunk = (tokens * a.NH + warps - 1) / warps;
+    chunk = ((chunk + 15) / 16) * 16;
+    if (chunk < 16) chunk = 16;
+    a.chunk_tokens = (int)chunk;
+    a.max_chunks = (max_len + a.chunk_tokens - 1) / a.chunk_tokens;
+    const int tpi = 32 / (a.hs / 4);
+    const size_t need = (size_t)nseq * a.NH * a.max_chunks * tpi * (a.hs + 4);
+    if (need > m->mega_part_floats) {
+        CU_CHECK(cudaStreamSynchronize(s));
+        cudaFree(m->mega_part);
+        m->mega_part = nullptr; m->mega_part_floats = 0;
+        CU_CHECK(cudaMalloc((void**)&m->mega_part, need * 2 * sizeof(float)));
+        m->mega_part_floats = need * 2;
+    }
+    if (!m->mega_bar) CU_CHECK(cudaMalloc((void**)&m->mega_bar, sizeof(unsigned)));
+    a.part = m->mega_part; a.bar = m->mega_bar;
+    return pa_cu_model_mega_step(&a, s);
 }
 
 }  // namespace
@@ -343,7 +260,7 @@ int pa_model_create(pa_handle* h, const pa_model_config* cfg, const float* param
 void pa_model_destroy(pa_model* m) {
     if (!m) return;
     cudaFree(m->params); cudaFree(m->x); cudaFree(m->ln); cudaFree(m->q); cudaFree(m->atty); cudaFree(m->fch);
-    cudaFree(m->logits); cudaFree(m->d_io); cudaFree(m->d_coins);
+    cudaFree(m->logits); cudaFree(m->d_io); cudaFree(m->d_coins); cudaFree(m->mega_part); cudaFree(m->mega_bar);
     if (m->h_io) cudaFreeHost(m->h_io);
     if (m->h_coins) cudaFreeHost(m->h_coins);
     free(m);
@@ -401,6 +318,17 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
     }
     CU_CHECK(cudaSetDevice(h->cfg.device));
     cudaStream_t s = (cudaStream_t)h->stream;
+    // A handful of sequences with one new token each: the whole step is ONE persistent kernel (pa_model_mega.cu)
+    const int model_path = h->tune[PA_TUNE_MODEL_PATH];
+    bool use_mega = false;
+    if (model_path != 1) {
+        const size_t mega_smem = (max_q == 1 && nseq <= PA_MEGA_MAX_SEQS) ? pa_cu_model_mega_smem(nseq, C, h->cfg.head_dim) : 0;
+        use_mega = mega_smem && (size_t)h->smem_optin >= mega_smem + 1024;
+        if (!use_mega && model_path == 2) {
+            pa_set_error("pa_model_forward: the persistent step kernel takes at most %d sequences of one new token each (head_dim 64 or 128)", PA_MEGA_MAX_SEQS);
+            return PA_ERR_UNSUPPORTED;
+        }
+    }
     // Overlapping launches pay off while the step is a chain of latency-bound kernels (measured: +8 % at 64
     // tokens, -3 % at 256, where early-resident successors get in the way of the cluster launches)
     static const int pdl_max_tokens = getenv("PA_PDL_MAX_TOKENS") ? atoi(getenv("PA_PDL_MAX_TOKENS")) : 128;
@@ -412,6 +340,16 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
     int* d_tok = m->d_io, *d_pos = m->d_io + ntok, *d_last = m->d_io + 2 * ntok, *d_next = m->d_io + 2 * ntok + nseq;
     CU_CHECK(cudaMemcpyAsync(m->d_io, m->h_io, (size_t)(2 * ntok + nseq) * sizeof(int), cudaMemcpyHostToDevice, s));
     if (coins) CU_CHECK(cudaMemcpyAsync(m->d_coins, m->h_coins, (size_t)nseq * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (use_mega) {
+        rc = mega_step(m, nseq, d_tok, d_pos, coins ? m->d_coins : nullptr, d_next, s);
+        if (rc != PA_OK) return rc;
+        h->launches += 1;
+        CU_CHECK(cudaMemcpyAsync(h_next, d_next, (size_t)nseq * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU_CHECK(cudaStreamSynchronize(s));
+        pa_pdl_gate = 1;
+        memcpy(next_tokens, h_next, (size_t)nseq * sizeof(int));
+        return PA_OK;
+    }
     CU_CHECK(pa_launch_pdl(pa_embed_kernel, dim3(ntok), dim3(256), 0, s, 1, m->x, (const int*)d_tok, (const int*)d_pos, m->wte, m->wpe, C));
     const int path = h->tune[PA_TUNE_GEMM_PATH];
     const int ln_grid = (ntok + 3) / 4;

@@ -27,6 +27,7 @@ PA_TUNE_TC_WARPGROUPS = 14
 PA_TUNE_TC_KEY_TILE = 15
 PA_TUNE_GEMM_PATH = 16
 PA_TUNE_GEMM_SPLIT_K = 17
+PA_TUNE_MODEL_PATH = 18
 
 
 class KVBlock(C.Structure):

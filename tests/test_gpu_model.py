@@ -63,11 +63,15 @@ class OracleModel:
     (2, 3, 20, 77, 4, 0),          # C = 60: SIMT projections, generic attention kernel
     (2, 2, 64, 131, 16, 1),        # fp32 SIMT projections
 ])
-def test_model_decode_steps_match_oracle(L, NH, hs, V, bs, gemm_path):
+@pytest.mark.parametrize("model_path", [1, 0], ids=["per-op-chain", "auto"])
+def test_model_decode_steps_match_oracle(L, NH, hs, V, bs, gemm_path, model_path):
+    """model_path auto: these 5-sequence steps run as ONE persistent kernel (pa_model_mega.cu) when
+    head_dim is 64/128, else (and with model_path 1) as the chain of per-op kernels."""
     Cc, maxT, B = NH * hs, 96, 5
     params = make_params(V, maxT, L, Cc, seed=300)
     eng = pa.PagedAttn(bs, 64, B, NH, hs, n_layers=L, device=0, max_batch_tokens=B)
     eng.tune(pa.PA_TUNE_GEMM_PATH, gemm_path)
+    eng.tune(pa.PA_TUNE_MODEL_PATH, model_path)
     model = pa.Model(eng, maxT, V, params=params, max_batch=B)
     orc = OracleModel(L, NH, Cc, V, maxT, bs, 64, B, params)
     ol = oa.load_oracle()
@@ -79,7 +83,10 @@ def test_model_decode_steps_match_oracle(L, NH, hs, V, bs, gemm_path):
         for step in range(20):                      # crosses page boundaries (bs 4/8/16)
             active = [s for s in range(B) if (step + s) % 4 != 3] or [0]    # ragged: not every sequence every step
             coins = rng.random(len(active)).astype(np.float32)
+            l0 = eng.launches()
             got_next = model.decode_step(active, tokens[active], coins)
+            if model_path == 0 and hs in (64, 128):
+                assert eng.launches() - l0 == 1, "the small-batch step did not run as one persistent kernel"
             got = model.logits(len(active))
             want = orc.step(active, tokens[active], pos[active])
             err = np.abs(got.astype(np.float64) - want).max() / np.abs(want).max()
@@ -205,3 +212,70 @@ def test_model_prefill_then_decode_matches_token_by_token_oracle(prefill_path):
         print(f"prefill path {prefill_path}: logits err {err:.2e} / {err2:.2e} / {err3:.2e}")
     finally:
         model.close(); eng.close(); orc.close()
+
+
+@pytest.mark.parametrize("NH,hs,bs,B,ctx0", [(12, 64, 16, 1, 250), (4, 128, 16, 8, 70), (6, 64, 32, 8, 130), (2, 64, 4, 3, 1)])
+def test_model_persistent_step_kernel(NH, hs, bs, B, ctx0):
+    """The persistent small-batch kernel on its own terms: batch 1 at a few hundred tokens of context
+    (BASELINE configs[0] shape), 8 sequences, head_dim 128, ragged lengths crossing page boundaries
+    -- contexts are built by decoding ctx0 (+ a per-sequence offset) tokens through the oracle and the
+    device model alike; every step's logits within the chain tolerance of the oracle, greedy tokens
+    equal, tables bit-exact."""
+    L, V = 2, 211
+    Cc = NH * hs
+    maxT = ctx0 + B + 40
+    pages = (maxT + bs - 1) // bs + 1
+    params = make_params(V, maxT, L, Cc, seed=410)
+    eng = pa.PagedAttn(bs, B * pages, B, NH, hs, n_layers=L, device=0, max_batch_tokens=B)
+    eng.tune(pa.PA_TUNE_MODEL_PATH, 2)
+    model = pa.Model(eng, maxT, V, params=params, max_batch=B)
+    orc = OracleModel(L, NH, Cc, V, maxT, bs, B * pages, B, params)
+    try:
+        rng = np.random.default_rng(11)
+        tokens = rng.integers(0, V, size=B).astype(np.int32)
+        pos = np.zeros(B, dtype=np.int32)
+        worst = 0.0
+        for step in range(ctx0 + B + 6):
+            # sequence s joins at step s: ragged context lengths
+            active = [s for s in range(B) if step >= s]
+            l0 = eng.launches()
+            got_next = model.decode_step(active, tokens[active], None)
+            assert eng.launches() - l0 == 1
+            want = orc.step(active, tokens[active], pos[active])
+            if step % 16 == 0 or step >= ctx0:
+                got = model.logits(len(active))
+                err = np.abs(got.astype(np.float64) - want).max() / np.abs(want).max()
+                worst = max(worst, err)
+                assert np.isfinite(got).all() and err <= LOGIT_TOL_PER_LAYER * L, f"step {step}: logits err {err:.3e}"
+            # keep the two models on the same token stream: follow the oracle's greedy choice
+            want_next = want.argmax(axis=1).astype(np.int32)
+            top2 = np.sort(want, axis=1)[:, -2:]
+            clear = (top2[:, 1] - top2[:, 0]) > 1e-4 * np.abs(top2[:, 1])
+            assert np.array_equal(got_next[clear], want_next[clear]), f"step {step}: greedy tokens differ"
+            tokens[active] = want_next
+            pos[active] += 1
+            for s in active:
+                assert list(eng.table(s)) == list(orc.mgrs[0].table(s))
+        print(f"persistent step kernel NH={NH} hs={hs} B={B}: worst logits err {worst:.2e}")
+    finally:
+        model.close(); eng.close(); orc.close()
+
+
+def test_model_persistent_step_kernel_domain():
+    """Forced (model_path 2) outside its domain the persistent kernel fails loudly; auto falls back to the chain."""
+    L, NH, hs, V, maxT, B = 1, 2, 64, 50, 16, 9
+    eng = pa.PagedAttn(16, 32, B, NH, hs, n_layers=L, device=0, max_batch_tokens=B)
+    model = pa.Model(eng, maxT, V, params=None, seed=3, max_batch=B)
+    try:
+        tok = np.arange(B, dtype=np.int32)
+        eng.tune(pa.PA_TUNE_MODEL_PATH, 2)
+        with pytest.raises(Exception):
+            model.decode_step(list(range(B)), tok, None)          # 9 sequences
+        eng.tune(pa.PA_TUNE_MODEL_PATH, 0)
+        for s in range(B):
+            eng.seq_free(s)
+        l0 = eng.launches()
+        nxt = model.decode_step(list(range(B)), tok, None)
+        assert eng.launches() - l0 > 1 and len(nxt) == B
+    finally:
+        model.close(); eng.close()

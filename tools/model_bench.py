@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--gemm-path", type=int, default=0)
     ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--model-path", type=int, default=0, help="0 auto, 1 chain of per-op kernels, 2 persistent step kernel")
     args = ap.parse_args()
     pa = ge.build(quiet=True)
     lib = pa.load()
@@ -42,6 +43,7 @@ def main():
     eng = pa.PagedAttn(bs, B * pages + 8, B, NH, hs, n_layers=L, device=0, max_batch_tokens=B)
     eng.tune(pa.PA_TUNE_GEMM_PATH, args.gemm_path)
     eng.tune(pa.PA_TUNE_NO_PDL, 1 if args.no_pdl else 0)
+    eng.tune(pa.PA_TUNE_MODEL_PATH, args.model_path)
     rng = np.random.default_rng(3)
     perm = rng.permutation(B * pages + 8)
     for s in range(B):
@@ -63,7 +65,8 @@ def main():
         step()
     dt = (time.perf_counter() - t0) / args.steps
     print(json.dumps({"tool": "model_bench", "shape": args.shape, "B": B, "ctx": ctx, "layers": L, "ms_per_step": dt * 1e3,
-                      "tokens_per_s": B / dt, "gemm_path": args.gemm_path, "pdl": not args.no_pdl}))
+                      "tokens_per_s": B / dt, "gemm_path": args.gemm_path, "pdl": not args.no_pdl,
+                      "model_path": args.model_path}))
     model.close(); eng.close()
 
 
