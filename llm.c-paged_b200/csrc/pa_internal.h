@@ -139,6 +139,7 @@ int pa_cu_linear(const float* x, int x_stride, const float* w, const float* bias
 /* ---- implemented in pa_model_mega.cu: the whole decode step of a handful of sequences as ONE
  * persistent cooperative kernel (every op of gpt2_forward for one new token per sequence) ------- */
 #define PA_MEGA_MAX_SEQS 8
+#define PA_MEGA_AUTO_SEQS 4      /* chosen by itself up to this many sequences (measured against the chain of per-op kernels) */
 typedef struct pa_mega_args {
     /* parameters, checkpoint order (paged_infer.c:441-488) */
     const float *wte, *wpe, *ln1w, *ln1b, *qkvw, *qkvb, *attprojw, *attprojb, *ln2w, *ln2b, *fcw, *fcb, *fcprojw,
@@ -146,25 +147,27 @@ typedef struct pa_mega_args {
     int C, NH, hs, L, V, Vp;
     /* the step: M sequences, one new token each */
     int M;
-    const int *tokens, *positions;      /* device [M] */
-    const float* coins;                 /* device [M] or NULL (argmax) */
-    int* next;                          /* device [M] */
+    int tokens[PA_MEGA_MAX_SEQS], positions[PA_MEGA_MAX_SEQS];     /* by value: no copy to wait for */
+    float coins[PA_MEGA_MAX_SEQS];
+    int use_coins;                      /* 0: argmax */
+    int* next;                          /* [M] sampled tokens: device-visible (mapped pinned host memory is fine) */
     float *x, *q, *atty, *fch, *logits; /* device activations: (M,C) (M,C) (M,C) (M,4C) (M,Vp) */
     /* paged KV cache and the mirrored step tables */
     float *pool_k, *pool_v;
     size_t layer_stride;
     const int *kv_end, *kv_start, *slots, *table;
-    int tstride, bs;
+    int tstride, bs, bs_shift;          /* block size (a power of two) and its log2 */
     float scale;
     /* attention split: tokens per chunk, chunks per sequence at most, partial (o[hs], m, l) workspace */
     int chunk_tokens, max_chunks;
     float* part;
-    unsigned* bar;                      /* grid barrier counter, zero at launch */
+    unsigned* bar;                      /* grid barrier counter: monotonic, bar_base at launch */
+    unsigned bar_base;
     int sm_count;
     unsigned long long* dbg;            /* optional timeline of CTA 0 (PA_MEGA_DEBUG=1), NULL normally */
 } pa_mega_args;
 /* bytes of dynamic shared memory the kernel needs for this geometry, or 0 when it is outside its domain */
-size_t pa_cu_model_mega_smem(int M, int C, int hs);
+size_t pa_cu_model_mega_smem(int M, int C, int hs, int block_size);
 int pa_cu_model_mega_step(const pa_mega_args* a, void* stream);
 
 #ifdef __cplusplus

@@ -52,7 +52,8 @@ struct pa_model {
     float* h_coins;
     float* mega_part;                      // attention split workspace of the persistent small-batch kernel
     size_t mega_part_floats;
-    unsigned* mega_bar;                    // its grid-barrier counter
+    unsigned* mega_bar;                    // its grid-barrier counter (monotonic over launches) ...
+    unsigned mega_bar_base;                // ... and its value when the next launch starts
 };
 
 namespace {
@@ -122,7 +123,7 @@ __global__ void pa_init_normal_kernel(float* p, size_t n, float stdv, float mean
 }
 
 // the decode step of <= 8 sequences through the persistent kernel; the step tables are already on the device
-int mega_step(pa_model* m, int nseq, const int* d_tok, const int* d_pos, const float* d_coins, int* d_next, cudaStream_t s) {
+int mega_step(pa_model* m, int nseq, const int* tok, const int* pos, const float* coins, int* next_mapped, cudaStream_t s) {
     pa_handle* h = m->h;
     const pa_step_layout& L = h->step;
     pa_mega_args a;
@@ -130,12 +131,15 @@ int mega_step(pa_model* m, int nseq, const int* d_tok, const int* d_pos, const f
     a.attprojw = m->attprojw; a.attprojb = m->attprojb; a.ln2w = m->ln2w; a.ln2b = m->ln2b; a.fcw = m->fcw; a.fcb = m->fcb;
     a.fcprojw = m->fcprojw; a.fcprojb = m->fcprojb; a.lnfw = m->lnfw; a.lnfb = m->lnfb;
     a.C = m->C; a.NH = h->cfg.n_heads; a.hs = h->cfg.head_dim; a.L = m->L; a.V = m->V; a.Vp = m->Vp;
-    a.M = nseq; a.tokens = d_tok; a.positions = d_pos; a.coins = d_coins; a.next = d_next;
+    a.M = nseq; a.use_coins = coins != nullptr; a.next = next_mapped;
+    for (int i = 0; i < nseq; ++i) { a.tokens[i] = tok[i]; a.positions[i] = pos[i]; a.coins[i] = coins ? coins[i] : -1.0f; }
     a.x = m->x; a.q = m->q; a.atty = m->atty; a.fch = m->fch; a.logits = m->logits;
     a.pool_k = h->pool_k; a.pool_v = h->pool_v; a.layer_stride = h->layer_stride;
     a.kv_end = h->d_step + L.off_kv_end; a.kv_start = h->d_step + L.off_kv_start;
     a.slots = h->d_step + L.off_slot; a.table = h->d_step + L.off_table;
     a.tstride = L.tstride; a.bs = h->cfg.block_size;
+    a.bs_shift = 0;
+    while ((1 << a.bs_shift) < a.bs) ++a.bs_shift;
     a.scale = (float)(1.0 / sqrtf((float)h->cfg.head_dim));            // :174
     a.sm_count = h->sm_count;
     // attention split: about one (sequence, head, chunk) unit per warp of the grid, chunks of >= 16 tokens
@@ -161,8 +165,14 @@ int mega_step(pa_model* m, int nseq, const int* d_tok, const int* d_pos, const f
         CU_CHECK(cudaMalloc((void**)&m->mega_part, need * 2 * sizeof(float)));
         m->mega_part_floats = need * 2;
     }
-    if (!m->mega_bar) CU_CHECK(cudaMalloc((void**)&m->mega_bar, sizeof(unsigned)));
-    a.part = m->mega_part; a.bar = m->mega_bar;
+    if (!m->mega_bar) {
+        CU_CHECK(cudaMalloc((void**)&m->mega_bar, sizeof(unsigned)));
+        CU_CHECK(cudaMemsetAsync(m->mega_bar, 0, sizeof(unsigned), s));
+        m->mega_bar_base = 0;
+    }
+    // the barrier counter only ever grows: this launch counts from where the last one stopped
+    a.part = m->mega_part; a.bar = m->mega_bar; a.bar_base = m->mega_bar_base;
+    m->mega_bar_base += (unsigned)(2 + 6 * m->L) * (unsigned)h->sm_count;
     return pa_cu_model_mega_step(&a, s);
 }
 
@@ -322,7 +332,7 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
     const int model_path = h->tune[PA_TUNE_MODEL_PATH];
     bool use_mega = false;
     if (model_path != 1) {
-        const size_t mega_smem = (max_q == 1 && nseq <= PA_MEGA_MAX_SEQS) ? pa_cu_model_mega_smem(nseq, C, h->cfg.head_dim) : 0;
+        const size_t mega_smem = (max_q == 1 && nseq <= (model_path == 2 ? PA_MEGA_MAX_SEQS : PA_MEGA_AUTO_SEQS)) ? pa_cu_model_mega_smem(nseq, C, h->cfg.head_dim, h->cfg.block_size) : 0;
         use_mega = mega_smem && (size_t)h->smem_optin >= mega_smem + 1024;
         if (!use_mega && model_path == 2) {
             pa_set_error("pa_model_forward: the persistent step kernel takes at most %d sequences of one new token each (head_dim 64 or 128)", PA_MEGA_MAX_SEQS);
@@ -337,19 +347,20 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
     if (rc != PA_OK) return rc;
     rc = pa_step_upload(h, s);
     if (rc != PA_OK) return rc;
-    int* d_tok = m->d_io, *d_pos = m->d_io + ntok, *d_last = m->d_io + 2 * ntok, *d_next = m->d_io + 2 * ntok + nseq;
-    CU_CHECK(cudaMemcpyAsync(m->d_io, m->h_io, (size_t)(2 * ntok + nseq) * sizeof(int), cudaMemcpyHostToDevice, s));
-    if (coins) CU_CHECK(cudaMemcpyAsync(m->d_coins, m->h_coins, (size_t)nseq * sizeof(float), cudaMemcpyHostToDevice, s));
     if (use_mega) {
-        rc = mega_step(m, nseq, d_tok, d_pos, coins ? m->d_coins : nullptr, d_next, s);
+        // token ids, positions and coins travel as kernel arguments, the sampled tokens come back through
+        // mapped pinned memory: the step is ONE table copy, ONE launch and ONE synchronisation
+        rc = mega_step(m, nseq, h_tok, h_pos, coins ? m->h_coins : nullptr, h_next, s);
         if (rc != PA_OK) return rc;
         h->launches += 1;
-        CU_CHECK(cudaMemcpyAsync(h_next, d_next, (size_t)nseq * sizeof(int), cudaMemcpyDeviceToHost, s));
         CU_CHECK(cudaStreamSynchronize(s));
         pa_pdl_gate = 1;
         memcpy(next_tokens, h_next, (size_t)nseq * sizeof(int));
         return PA_OK;
     }
+    int* d_tok = m->d_io, *d_pos = m->d_io + ntok, *d_last = m->d_io + 2 * ntok, *d_next = m->d_io + 2 * ntok + nseq;
+    CU_CHECK(cudaMemcpyAsync(m->d_io, m->h_io, (size_t)(2 * ntok + nseq) * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (coins) CU_CHECK(cudaMemcpyAsync(m->d_coins, m->h_coins, (size_t)nseq * sizeof(float), cudaMemcpyHostToDevice, s));
     CU_CHECK(pa_launch_pdl(pa_embed_kernel, dim3(ntok), dim3(256), 0, s, 1, m->x, (const int*)d_tok, (const int*)d_pos, m->wte, m->wpe, C));
     const int path = h->tune[PA_TUNE_GEMM_PATH];
     const int ln_grid = (ntok + 3) / 4;

@@ -16,14 +16,14 @@ template <bool kCg>
 static __device__ __forceinline__ float pa_ld(const float* p) { return kCg ? __ldcg(p) : *p; }
 
 // layernorm_forward (paged_infer.c:49-89) for ONE row on one warp: mean, variance around the mean,
-// rstd = 1/sqrtf(var + 1e-5f), o = (rstd * (x - mean)) * weight + bias.  `o` may be shared memory.
-template <bool kCg>
-static __device__ __forceinline__ void pa_layernorm_row(float* o, const float* x, const float* __restrict__ weight,
-                                                        const float* __restrict__ bias, int C, int lane) {
-    float v[kLnMaxPerLane];
+// rstd = 1/sqrtf(var + 1e-5f), o = (rstd * (x - mean)) * weight + bias.  `o`, `weight` and `bias` may be shared memory.
+// kPerLane * 32 >= C bounds the registers (the loops are fully unrolled and predicated).
+template <bool kCg, int kPerLane = kLnMaxPerLane>
+static __device__ __forceinline__ void pa_layernorm_row(float* o, const float* x, const float* weight, const float* bias, int C, int lane) {
+    float v[kPerLane];
     float sum = 0.0f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
+    for (int i = 0; i < kPerLane; ++i) {
         const int c = lane + 32 * i;
         v[i] = c < C ? pa_ld<kCg>(x + c) : 0.0f;
         sum += v[i];
@@ -33,7 +33,7 @@ static __device__ __forceinline__ void pa_layernorm_row(float* o, const float* x
     const float m = sum / C;
     float var = 0.0f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
+    for (int i = 0; i < kPerLane; ++i) {
         const int c = lane + 32 * i;
         const float dlt = v[i] - m;
         if (c < C) var += dlt * dlt;
@@ -43,7 +43,7 @@ static __device__ __forceinline__ void pa_layernorm_row(float* o, const float* x
     var = var / C;
     const float s = 1.0f / sqrtf(var + 1e-5f);                   // eps, :56
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
+    for (int i = 0; i < kPerLane; ++i) {
         const int c = lane + 32 * i;
         if (c < C) o[c] = (s * (v[i] - m)) * weight[c] + bias[c];
     }

@@ -31,6 +31,7 @@
 
 #include "pa_internal.h"
 #include "pa_model_dev.cuh"
+#include "pa_ptx.cuh"
 
 #define CU_CHECK(call)                                                                         \
     do {                                                                                       \
@@ -51,201 +52,205 @@ constexpr float kMaxInit = -10000.0f;      // paged_infer.c:187
 
 // All CTAs of the (cooperative, hence co-resident) grid meet: the barrier orders the CTA's stores
 // before thread 0's release-add; the acquire-poll plus the second barrier orders everybody's later
-// loads after the other CTAs' stores.  The counter only grows: barrier i completes at (i+1)*gridDim.
-__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& passed) {
+// loads after the other CTAs' stores.  The counter only grows (over launches too, so nothing resets
+// it): barrier i of this launch completes at base + (i+1)*gridDim, compared modulo 2^32.
+// The barrier is split: between arriving and waiting a CTA requests whatever the next phase needs
+// that does not depend on other CTAs (weights, biases, layernorm parameters, old K/V), so those
+// loads are issued and travel while the grid meets.
+__device__ __forceinline__ void grid_arrive(unsigned* bar) {
     __syncthreads();
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+}
+__device__ __forceinline__ void grid_wait(unsigned* bar, unsigned base, unsigned& passed) {
     if (threadIdx.x == 0) {
-        const unsigned target = (passed + 1) * gridDim.x;
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        const unsigned target = base + (passed + 1) * gridDim.x;
         unsigned seen;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
-        } while (seen < target);
+        } while ((int)(seen - target) < 0);
     }
     __syncthreads();
     ++passed;
 }
 
-// M rows of K floats, global (written by other CTAs before the last barrier) -> shared memory
-__device__ __forceinline__ void stage_rows(float* xs, const float* src, int M, int K) {
-    const int K4 = K >> 2;
-    for (int i = threadIdx.x; i < M * K4; i += kThreads)
-        reinterpret_cast<float4*>(xs)[i] = __ldcg(reinterpret_cast<const float4*>(src) + i);
-    __syncthreads();
-}
-// layernorm of the M rows of x into shared memory: warp m takes row m (M <= 8 warps)
-__device__ __forceinline__ void ln_rows(float* xs, const float* x, const float* w, const float* b, int M, int C) {
-    const int warp = threadIdx.x >> 5;
-    if (warp < M) pa_layernorm_row<true>(xs + (size_t)warp * C, x + (size_t)warp * C, w, b, C, threadIdx.x & 31);
-    __syncthreads();
-}
+// The kernel body is deliberately COMPACT: every phase runs its code once per layer with eight warps
+// per SM, so the instruction stream itself has to be fetched every time -- a first version with one
+// inlined GEMV per call site and feature count (47 k instructions, 755 KB) spent ~10 us per phase on
+// instruction fetch alone.  Hence ONE loop over the projection phases with one copy of each routine,
+// run-time feature counts, and the batch bound as a template parameter.
 
-// out(m, n) for the M rows in shared memory and every feature n of w (N, K): FEAT features per warp
-// pass, lanes interleave the 16-byte chunks of a row.  epi(m, n, dot) finishes one output.
-template <int FEAT, typename Epi>
-__device__ __forceinline__ void gemv_rows(const float* __restrict__ w, int N, int K, int M, const float* xs, Epi epi) {
-    constexpr int UN = kLoads / FEAT;
-    const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * kWarps + (threadIdx.x >> 5), nw = gridDim.x * kWarps;
-    const int K4 = K >> 2;
-    const float4* xs4 = reinterpret_cast<const float4*>(xs);
-    for (int n0 = gw * FEAT; n0 < N; n0 += nw * FEAT) {
-        float acc[FEAT][kMaxM];
+// ---- projections: out(m, n) for the M rows in shared memory and every feature n of w (N, K) -------
+// A warp pass covers `feat` (1, 2 or 4: the fewest that cover N in one pass of the grid's warps)
+// output features; its lanes interleave the 16-byte chunks of those weight rows and keep kLoads
+// loads in flight.  Load j of a batch belongs to feature j % feat and chunk j / feat; it always
+// accumulates into slot j % 4, and the slots of a feature are folded at the end.
+__device__ __forceinline__ int pick_feat_shift(int N) {
+    const int nw = gridDim.x * kWarps;
+    return N <= nw ? 0 : (N <= 2 * nw ? 1 : 2);
+}
+// The weight loads of a warp's FIRST batch are issued BEFORE the grid barrier in front of the phase:
+// weights never depend on another CTA, so they stream in from HBM while the grid meets.
+__device__ __forceinline__ void gemv_issue(float4 (&wv)[kLoads], const float* __restrict__ w, int N, int K, int sh, int n0, int cb) {
+    const int K4 = K >> 2, fmask = (1 << sh) - 1;
 #pragma unroll
-        for (int f = 0; f < FEAT; ++f)
-#pragma unroll
-            for (int m = 0; m < kMaxM; ++m) acc[f][m] = 0.0f;
-        const float4* wr[FEAT];
-#pragma unroll
-        for (int f = 0; f < FEAT; ++f) wr[f] = reinterpret_cast<const float4*>(w + (size_t)min(n0 + f, N - 1) * K);
-        for (int cb = lane; cb < K4; cb += 32 * UN) {
-            float4 wv[UN][FEAT];
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                const int c = cb + 32 * u;
-#pragma unroll
-                for (int f = 0; f < FEAT; ++f) wv[u][f] = c < K4 ? __ldg(wr[f] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                const int c = cb + 32 * u;
-                if (c < K4) {
-#pragma unroll
-                    for (int m = 0; m < kMaxM; ++m) {
-                        if (m < M) {
-                            const float4 xv = xs4[m * K4 + c];
-#pragma unroll
-                            for (int f = 0; f < FEAT; ++f)
-                                acc[f][m] = fmaf(wv[u][f].w, xv.w, fmaf(wv[u][f].z, xv.z, fmaf(wv[u][f].y, xv.y, fmaf(wv[u][f].x, xv.x, acc[f][m]))));
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < kMaxM; ++m) {
-            if (m < M) {
-#pragma unroll
-                for (int f = 0; f < FEAT; ++f)
-#pragma unroll
-                    for (int d = 16; d >= 1; d >>= 1) acc[f][m] += __shfl_xor_sync(0xffffffffu, acc[f][m], d);
-            }
-        }
-        // lane (f, m) finishes output (m, n0 + f)
-        const int f = lane >> 3, m = lane & 7;
-        if (f < FEAT && m < M && n0 + f < N) {
-            float v = 0.0f;
-#pragma unroll
-            for (int ff = 0; ff < FEAT; ++ff)
-#pragma unroll
-                for (int mm = 0; mm < kMaxM; ++mm)
-                    if (ff == f && mm == m) v = acc[ff][mm];
-            epi(m, n0 + f, v);
-        }
+    for (int j = 0; j < kLoads; ++j) {
+        const int c = cb + 32 * (j >> sh);
+        wv[j] = (c < K4 && n0 < N) ? __ldg(reinterpret_cast<const float4*>(w + (size_t)min(n0 + (j & fmask), N - 1) * K) + c)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
-// features per warp pass: the fewest that still cover N in one pass of the grid's warps
-template <typename Epi>
-__device__ __forceinline__ void gemv_auto(const float* __restrict__ w, int N, int K, int M, const float* xs, Epi epi) {
-    const int nw = gridDim.x * kWarps;
-    if (N <= nw) gemv_rows<1>(w, N, K, M, xs, epi);
-    else if (N <= 2 * nw) gemv_rows<2>(w, N, K, M, xs, epi);
-    else gemv_rows<4>(w, N, K, M, xs, epi);
-}
+
+struct StepSmem { int kv_start[kMaxM], kv_end[kMaxM], slot[kMaxM]; };
 
 // ---- attention, phase 1: a warp per (sequence, head, chunk); LPT = hs/4 lanes per token ---------
 template <int LPT>
-__device__ __forceinline__ void attn_partials(const pa_mega_args& a, const float* pool_k, const float* pool_v) {
-    constexpr int TPI = 32 / LPT;          // tokens per warp iteration (sub-groups of the warp)
-    constexpr int UN = 8;                  // iterations in flight
+struct KvBatch {                           // one batch of a warp's unit: UN iterations x TPI tokens, this lane's 16 bytes of each
+    static constexpr int TPI = 32 / LPT, UN = 8;
+    float4 k[UN], v[UN];
+};
+// Requests K/V of the tokens [tb, tb + TPI*UN) of the unit.  only_new = false: every token except the
+// step's new one (position last-1, still being written by the QKV phase) -- issued BEFORE the barrier;
+// only_new = true: just that one, after the barrier.
+template <int LPT>
+__device__ __forceinline__ void attn_issue(KvBatch<LPT>& kb, const pa_mega_args& a, const float* pool_k, const float* pool_v,
+                                           const int* tbl, int h, int tb, int t1, int last, bool only_new) {
+    constexpr int TPI = KvBatch<LPT>::TPI, UN = KvBatch<LPT>::UN;
+    const int lane = threadIdx.x & 31, sub = lane / LPT, li = lane % LPT;
+#pragma unroll
+    for (int i = 0; i < UN; ++i) {
+        const int t = tb + i * TPI + sub;
+        const bool is_new = t == last - 1;
+        if (t < t1 && is_new == only_new) {
+            const size_t off = ((size_t)((tbl[t >> a.bs_shift] << a.bs_shift) + (t & (a.bs - 1)))) * a.C + h * a.hs;
+            kb.k[i] = __ldcg(reinterpret_cast<const float4*>(pool_k + off) + li);
+            kb.v[i] = __ldcg(reinterpret_cast<const float4*>(pool_v + off) + li);
+        } else if (!only_new) {
+            kb.k[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            kb.v[i] = kb.k[i];
+        }
+    }
+}
+// unit u -> (sequence*NH + head, chunk, token range); false when the chunk lies beyond the sequence
+__device__ __forceinline__ bool attn_unit(const pa_mega_args& a, const StepSmem& st, int u, int& sh, int& c, int& t0, int& t1, int& last) {
+    c = u % a.max_chunks; sh = u / a.max_chunks;
+    const int s = sh / a.NH;
+    last = st.kv_end[s];
+    t0 = st.kv_start[s] + c * a.chunk_tokens;
+    t1 = min(last, t0 + a.chunk_tokens);
+    return t0 < last;
+}
+template <int LPT>
+__device__ __forceinline__ void attn_partials(KvBatch<LPT>& kb, const pa_mega_args& a, const StepSmem& st, const float* pool_k, const float* pool_v) {
+    constexpr int TPI = KvBatch<LPT>::TPI, UN = KvBatch<LPT>::UN;
     const int lane = threadIdx.x & 31, sub = lane / LPT, li = lane % LPT;
     const int gw = blockIdx.x * kWarps + (threadIdx.x >> 5), nw = gridDim.x * kWarps;
     const int hs = a.hs, C = a.C;
     const int n_units = a.M * a.NH * a.max_chunks;
+    bool have = true;                                               // kb holds the first batch of unit gw (all but the new token)
     for (int u = gw; u < n_units; u += nw) {
-        const int c = u % a.max_chunks, sh = u / a.max_chunks, h = sh % a.NH, s = sh / a.NH;
-        const int first = a.kv_start[s], last = a.kv_end[s];
-        const int t0 = first + c * a.chunk_tokens;
-        if (t0 >= last) continue;                                   // warp-uniform
-        const int t1 = min(last, t0 + a.chunk_tokens);
+        int sh, c, t0, t1, last;
+        if (!attn_unit(a, st, u, sh, c, t0, t1, last)) { have = false; continue; }      // warp-uniform
+        const int h = sh % a.NH, s = sh / a.NH;
         const int* tbl = a.table + (size_t)s * a.tstride;
         const float4 q4 = __ldcg(reinterpret_cast<const float4*>(a.q + (size_t)s * C + h * hs) + li);
         float m_run = kMaxInit, l_run = 0.0f;
         float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int tb = t0; tb < t1; tb += TPI * UN) {
-            float4 k4[UN], v4[UN];
+            if (!have) attn_issue<LPT>(kb, a, pool_k, pool_v, tbl, h, tb, t1, last, false);
+            have = false;
+            attn_issue<LPT>(kb, a, pool_k, pool_v, tbl, h, tb, t1, last, true);
+            // the batch's scores, then ONE rescale of the running state for all of them
+            float sc[UN];
+            float m_new = m_run;
 #pragma unroll
             for (int i = 0; i < UN; ++i) {
-                const int t = tb + i * TPI + sub;
-                if (t < t1) {
-                    const size_t off = ((size_t)tbl[t / a.bs] * a.bs + (t % a.bs)) * C + h * hs;
-                    k4[i] = __ldcg(reinterpret_cast<const float4*>(pool_k + off) + li);
-                    v4[i] = __ldcg(reinterpret_cast<const float4*>(pool_v + off) + li);
-                } else {
-                    k4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    v4[i] = k4[i];
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < UN; ++i) {
-                const int t = tb + i * TPI + sub;
-                float dot = fmaf(q4.w, k4[i].w, fmaf(q4.z, k4[i].z, fmaf(q4.y, k4[i].y, q4.x * k4[i].x)));
+                float dot = fmaf(q4.w, kb.k[i].w, fmaf(q4.z, kb.k[i].z, fmaf(q4.y, kb.k[i].y, q4.x * kb.k[i].x)));
 #pragma unroll
                 for (int d = LPT / 2; d >= 1; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
-                if (t < t1) {                                       // uniform over the token's LPT lanes
-                    const float sc = dot * a.scale;
-                    const float m_new = fmaxf(m_run, sc);
-                    const float alpha = expf(m_run - m_new), e = expf(sc - m_new);
-                    l_run = l_run * alpha + e;
-                    o4.x = fmaf(e, v4[i].x, o4.x * alpha); o4.y = fmaf(e, v4[i].y, o4.y * alpha);
-                    o4.z = fmaf(e, v4[i].z, o4.z * alpha); o4.w = fmaf(e, v4[i].w, o4.w * alpha);
-                    m_run = m_new;
-                }
+                sc[i] = (tb + i * TPI + sub < t1) ? dot * a.scale : -INFINITY;      // uniform over the token's LPT lanes
+                m_new = fmaxf(m_new, sc[i]);
+            }
+            const float alpha = expf(m_run - m_new);
+            l_run *= alpha; o4.x *= alpha; o4.y *= alpha; o4.z *= alpha; o4.w *= alpha;
+            m_run = m_new;
+#pragma unroll 1
+            for (int i = 0; i < UN; ++i) {                          // (not unrolled: one expf body; sc/kb indexed through a switch-free select)
+                float s_i = sc[0];
+                float4 v_i = kb.v[0];
+#pragma unroll
+                for (int jx = 1; jx < UN; ++jx) if (jx == i) { s_i = sc[jx]; v_i = kb.v[jx]; }
+                const float e = expf(s_i - m_new);                  // exp(-inf) = 0 for the padding
+                l_run += e;
+                o4.x = fmaf(e, v_i.x, o4.x); o4.y = fmaf(e, v_i.y, o4.y); o4.z = fmaf(e, v_i.z, o4.z); o4.w = fmaf(e, v_i.w, o4.w);
             }
         }
-        float* pr = a.part + ((size_t)(sh * a.max_chunks + c) * TPI + sub) * (hs + 4);
-        reinterpret_cast<float4*>(pr)[li] = o4;
-        if (li == 0) { pr[hs] = m_run; pr[hs + 1] = l_run; }
+        if (TPI == 2) {                                             // the two token sub-groups of the warp -> one partial
+            const float m_o = __shfl_xor_sync(0xffffffffu, m_run, LPT), l_o = __shfl_xor_sync(0xffffffffu, l_run, LPT);
+            float4 o_o;
+            o_o.x = __shfl_xor_sync(0xffffffffu, o4.x, LPT); o_o.y = __shfl_xor_sync(0xffffffffu, o4.y, LPT);
+            o_o.z = __shfl_xor_sync(0xffffffffu, o4.z, LPT); o_o.w = __shfl_xor_sync(0xffffffffu, o4.w, LPT);
+            const float m_t = fmaxf(m_run, m_o);
+            const float wa = expf(m_run - m_t), wb = expf(m_o - m_t);
+            l_run = fmaf(l_run, wa, l_o * wb);
+            o4.x = fmaf(o4.x, wa, o_o.x * wb); o4.y = fmaf(o4.y, wa, o_o.y * wb);
+            o4.z = fmaf(o4.z, wa, o_o.z * wb); o4.w = fmaf(o4.w, wa, o_o.w * wb);
+            m_run = m_t;
+        }
+        if (sub == 0) {
+            float* pr = a.part + (size_t)(sh * a.max_chunks + c) * (hs + 4);
+            reinterpret_cast<float4*>(pr)[li] = o4;
+            if (li == 0) { pr[hs] = m_run; pr[hs + 1] = l_run; }
+        }
     }
 }
 
-// ---- attention, phase 2: a warp per (sequence, head) merges its chunks' partials in order --------
-template <int LPT>
-__device__ __forceinline__ void attn_merge(const pa_mega_args& a) {
-    constexpr int TPI = 32 / LPT;
-    constexpr int UN = 8;
+// ---- attention, phase 2: a warp per (sequence, head) merges its chunks' partials in chunk order ----
+// lane i weighs partial i (one expf per lane), the weights travel by shuffle; every lane owns the
+// head dims lane, lane + 32, ...
+__device__ __forceinline__ void attn_merge(const pa_mega_args& a, const StepSmem& st) {
+    constexpr int UN = 16;
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * kWarps + (threadIdx.x >> 5), nw = gridDim.x * kWarps;
     const int hs = a.hs;
     for (int sh = gw; sh < a.M * a.NH; sh += nw) {
         const int s = sh / a.NH, h = sh % a.NH;
-        const int len = a.kv_end[s] - a.kv_start[s];
-        const int n_part = ((len + a.chunk_tokens - 1) / a.chunk_tokens) * TPI;
-        const float* pr = a.part + (size_t)sh * a.max_chunks * TPI * (hs + 4);
+        const int len = st.kv_end[s] - st.kv_start[s];
+        const int n_part = (len + a.chunk_tokens - 1) / a.chunk_tokens;
+        const float* pr = a.part + (size_t)sh * a.max_chunks * (hs + 4);
         float m_tot = kMaxInit;
-        for (int i = lane; i < n_part; i += 32) m_tot = fmaxf(m_tot, __ldcg(pr + (size_t)i * (hs + 4) + hs));
+        if (n_part > UN) {                                          // several batches: the maxima first
+            for (int i = lane; i < n_part; i += 32) m_tot = fmaxf(m_tot, __ldcg(pr + (size_t)i * (hs + 4) + hs));
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) m_tot = fmaxf(m_tot, __shfl_xor_sync(0xffffffffu, m_tot, d));
-        // lane owns dims lane, lane + 32, ... of the head
+            for (int d = 16; d >= 1; d >>= 1) m_tot = fmaxf(m_tot, __shfl_xor_sync(0xffffffffu, m_tot, d));
+        }
         float o[4] = {0.f, 0.f, 0.f, 0.f};
         float l_tot = 0.0f;
         for (int ib = 0; ib < n_part; ib += UN) {
-            float pm[UN], pl[UN], po[UN][4];
+            float po[UN][4];
 #pragma unroll
-            for (int i = 0; i < UN; ++i) {
+            for (int i = 0; i < UN; ++i) {                          // the batch's o values in flight at once
                 const float* pp = pr + (size_t)min(ib + i, n_part - 1) * (hs + 4);
-                pm[i] = __ldcg(pp + hs); pl[i] = __ldcg(pp + hs + 1);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) po[i][j] = (lane + 32 * j < hs) ? __ldcg(pp + lane + 32 * j) : 0.0f;
             }
+            const int mine = ib + (lane & (UN - 1));                // lanes 0..15 (and their mirrors) weigh partial ib + lane
+            const float* pp = pr + (size_t)min(mine, n_part - 1) * (hs + 4);
+            const float pm = mine < n_part ? __ldcg(pp + hs) : kMaxInit;
+            const float pl = mine < n_part ? __ldcg(pp + hs + 1) : 0.0f;
+            if (n_part <= UN) {                                     // one batch: its maxima arrive with everything else
+                m_tot = pm;
 #pragma unroll
-            for (int i = 0; i < UN; ++i) {
-                if (ib + i < n_part) {
-                    const float wgt = expf(pm[i] - m_tot);
-                    l_tot = fmaf(pl[i], wgt, l_tot);
+                for (int d = 16; d >= 1; d >>= 1) m_tot = fmaxf(m_tot, __shfl_xor_sync(0xffffffffu, m_tot, d));
+                m_tot = fmaxf(m_tot, kMaxInit);
+            }
+            const float wgt = mine < n_part ? expf(pm - m_tot) : 0.0f;
+            const float lw = pl * wgt;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = fmaf(po[i][j], wgt, o[j]);
-                }
+            for (int i = 0; i < UN; ++i) {                          // chunk order
+                const float w_i = __shfl_sync(0xffffffffu, wgt, i);
+                l_tot += __shfl_sync(0xffffffffu, lw, i);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = fmaf(po[i][j], w_i, o[j]);
             }
         }
         const float inv = (l_tot == 0.0f) ? 0.0f : 1.0f / l_tot;        // :213
@@ -255,12 +260,43 @@ __device__ __forceinline__ void attn_merge(const pa_mega_args& a) {
     }
 }
 
-template <int LPT>
+enum { PH_QKV = 0, PH_ATTPROJ = 1, PH_FC = 2, PH_FCPROJ = 3, PH_LM = 4 };
+struct PhaseDesc { const float *w, *bias; int N, K; };
+__device__ __forceinline__ PhaseDesc phase_desc(const pa_mega_args& a, int ph) {
+    const int C = a.C, l = ph >> 2;
+    PhaseDesc d;
+    if (ph >= 4 * a.L) { d.w = a.wte; d.bias = nullptr; d.N = a.V; d.K = C; return d; }
+    switch (ph & 3) {
+        case PH_QKV: d.w = a.qkvw + (size_t)l * 3 * C * C; d.bias = a.qkvb + (size_t)l * 3 * C; d.N = 3 * C; d.K = C; break;
+        case PH_ATTPROJ: d.w = a.attprojw + (size_t)l * C * C; d.bias = a.attprojb + (size_t)l * C; d.N = C; d.K = C; break;
+        case PH_FC: d.w = a.fcw + (size_t)l * 4 * C * C; d.bias = a.fcb + (size_t)l * 4 * C; d.N = 4 * C; d.K = C; break;
+        default: d.w = a.fcprojw + (size_t)l * 4 * C * C; d.bias = a.fcprojb + (size_t)l * C; d.N = C; d.K = 4 * C; break;
+    }
+    return d;
+}
+
+// LPT: lanes per token (head_dim / 4); MAXM: bound of the batch (unrolling of the row loops);
+// LNREGS: registers per lane of a layernorm row (32 * LNREGS >= C)
+template <int LPT, int MAXM, int LNREGS>
 __global__ void __launch_bounds__(kThreads, 1)
 pa_decode_step_mega_kernel(const pa_mega_args a) {
-    extern __shared__ __align__(16) float xs[];          // [M][4C] staged / normalised input rows
+    extern __shared__ __align__(16) float xs[];          // [M][4C] staged / normalised input rows | layernorm weight [C] | bias [C]
     __shared__ PaSampleSmem<kThreads> samp;
+    __shared__ StepSmem st;
     const int M = a.M, C = a.C;
+    float* ln_ws = xs + (size_t)M * 4 * C;
+    float* ln_bs = ln_ws + C;
+    // the next layernorm's weight and bias -> shared memory with fire-and-forget 16-byte copies, issued before a
+    // barrier and waited for after it (they are parameters: nothing to wait for but HBM)
+    auto ln_params_issue = [&](const float* lw, const float* lb) {
+        for (int i = threadIdx.x; i < (C >> 2); i += kThreads) {
+            cp_async16(smem_u32(ln_ws + 4 * i), lw + 4 * i, 16);
+            cp_async16(smem_u32(ln_bs + 4 * i), lb + 4 * i, 16);
+        }
+        cp_async_commit();
+    };
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * kWarps + warp, nw = gridDim.x * kWarps;
     unsigned passed = 0;
     int n_stamp = 0;
     auto stamp = [&]() {            // PA_MEGA_DEBUG: CTA 0 records when it reaches each barrier and when it leaves it
@@ -270,96 +306,211 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
             a.dbg[n_stamp++] = t;
         }
     };
-#define GRID_SYNC() do { stamp(); grid_sync(a.bar, passed); stamp(); } while (0)
+#define GRID_ARRIVE() do { stamp(); grid_arrive(a.bar); } while (0)
+#define GRID_WAIT() do { grid_wait(a.bar, a.bar_base, passed); stamp(); } while (0)
+    int n_sub = 0;
+    auto substamp = [&](int ph) {   // finer timeline of layer 1's four projection phases
+        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && (ph >> 2) == 1) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            a.dbg[2048 + n_sub++] = t;
+        }
+    };
+    float4 wv[kLoads];               // a warp's first batch of weight loads for the NEXT projection, in flight across barriers
+    // ... and the bias of the output this lane will finish in that first pass (lane (f, m) -> feature n0 + f)
+    auto bias_issue = [&](const PhaseDesc& pd, int shift) {
+        const int n = (gw << shift) + (lane >> 3);
+        return (pd.bias && (lane >> 3) < (1 << shift) && n < pd.N) ? __ldg(pd.bias + n) : 0.0f;
+    };
+    KvBatch<LPT> kb;                 // likewise the first batch of K/V for the attention phase
 
+    if (threadIdx.x < M) {
+        st.kv_start[threadIdx.x] = a.kv_start[threadIdx.x];
+        st.kv_end[threadIdx.x] = a.kv_end[threadIdx.x];
+        st.slot[threadIdx.x] = a.slots[threadIdx.x];
+    }
     // encoder_forward (:24-46): CTA m writes row m of the residual stream
     if ((int)blockIdx.x < M) {
         const float* e = a.wte + (size_t)a.tokens[blockIdx.x] * C;
         const float* ps = a.wpe + (size_t)a.positions[blockIdx.x] * C;
         for (int i = threadIdx.x; i < C; i += kThreads) a.x[(size_t)blockIdx.x * C + i] = e[i] + ps[i];
     }
-    GRID_SYNC();
+    GRID_ARRIVE();
+    PhaseDesc d = phase_desc(a, 0);
+    int sh = pick_feat_shift(d.N);
+    gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane);
+    float bias_first = bias_issue(d, sh);
+    ln_params_issue(a.ln1w, a.ln1b);
+    GRID_WAIT();
 
-    for (int l = 0; l < a.L; ++l) {
+    const int n_phases = 4 * a.L + 1;
+    for (int ph = 0; ph < n_phases; ++ph) {
+        const int l = ph >> 2, kind = ph == n_phases - 1 ? PH_LM : (ph & 3);
         float* pool_k = a.pool_k + (size_t)l * a.layer_stride;
         float* pool_v = a.pool_v + (size_t)l * a.layer_stride;
-        // ln1 -> QKV projection; Q to the dense buffer, K and V straight to the token's page slot (:703-710)
-        ln_rows(xs, a.x, a.ln1w + (size_t)l * C, a.ln1b + (size_t)l * C, M, C);
+        const int N = d.N, K = d.K, K4 = K >> 2, feat = 1 << sh;
+        substamp(ph);
+
+        // ---- the phase's input rows -> shared memory: layernorm of the residual stream (ln1 :703, ln2 :718,
+        // lnf :724), or the previous op's output as it is (atty, fch)
+        if (kind == PH_ATTPROJ || kind == PH_FCPROJ) {
+            const float4* src = reinterpret_cast<const float4*>(kind == PH_ATTPROJ ? a.atty : a.fch);
+            for (int i = threadIdx.x; i < M * K4; i += kThreads) reinterpret_cast<float4*>(xs)[i] = __ldcg(src + i);
+        } else {
+            cp_async_wait<0>();
+            __syncthreads();                                  // everybody's copies of the layernorm parameters have landed
+            if (warp < M) pa_layernorm_row<true, LNREGS>(xs + (size_t)warp * C, a.x + (size_t)warp * C, ln_ws, ln_bs, C, lane);
+        }
+        __syncthreads();
+        substamp(ph);
+
+        // ---- the projection (matmul_forward :92-114 on M rows): weight-streaming GEMV ------------------
         {
-            const float* bias = a.qkvb + (size_t)l * 3 * C;
-            gemv_auto(a.qkvw + (size_t)l * 3 * C * C, 3 * C, C, M, xs, [&](int m, int n, float v) {
-                v += bias[n];
-                if (n < C) a.q[(size_t)m * C + n] = v;
-                else {
-                    const size_t slot_off = (size_t)a.slots[m] * C;
-                    if (n < 2 * C) pool_k[slot_off + (n - C)] = v;
-                    else pool_v[slot_off + (n - 2 * C)] = v;
+            const float4* xs4 = reinterpret_cast<const float4*>(xs);
+            const float* res = (kind == PH_ATTPROJ || kind == PH_FCPROJ) ? a.x : nullptr;     // residual_forward :253-257
+            bool have = true;                                // wv holds (n0 = gw * feat, cb = lane)
+            for (int n0 = gw << sh; n0 < N; n0 += nw << sh) {
+                // lane (f, m) finishes output (m, n0 + f): its bias and residual are requested now, used after the reduction
+                const int f = lane >> 3, m = lane & 7;
+                const bool mine = f < feat && m < M && n0 + f < N;
+                const float bv = have ? bias_first : ((mine && d.bias) ? __ldg(d.bias + n0 + f) : 0.0f);
+                const float rv = (mine && res) ? __ldcg(res + (size_t)m * C + n0 + f) : 0.0f;
+                if (n0 + (nw << sh) < N) {                   // the rows of the warp's next pass -> L2 while this pass computes
+                    const int lines = K >> 5;                // 128-byte lines per row
+                    for (int i = lane; i < feat * lines; i += 32) {
+                        const int pf = i / lines, pl = i - pf * lines;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(d.w + (size_t)min(n0 + (nw << sh) + pf, N - 1) * K + pl * 32));
+                    }
                 }
-            });
+                float acc[MAXM][4];
+#pragma unroll
+                for (int mm = 0; mm < MAXM; ++mm)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[mm][q] = 0.0f;
+                for (int cb = lane; cb < K4; cb += 32 * (kLoads >> sh)) {
+                    if (!have) gemv_issue(wv, d.w, N, K, sh, n0, cb);
+                    have = false;
+#pragma unroll
+                    for (int j = 0; j < kLoads; ++j) {
+                        const int c = cb + 32 * (j >> sh);
+                        if (c < K4) {
+#pragma unroll
+                            for (int mm = 0; mm < MAXM; ++mm) {
+                                if (mm < M) {
+                                    const float4 xv = xs4[mm * K4 + c];
+                                    acc[mm][j & 3] = fmaf(wv[j].w, xv.w, fmaf(wv[j].z, xv.z, fmaf(wv[j].y, xv.y, fmaf(wv[j].x, xv.x, acc[mm][j & 3]))));
+                                }
+                            }
+                        }
+                    }
+                }
+                substamp(ph);
+                float v = 0.0f;
+#pragma unroll
+                for (int mm = 0; mm < MAXM; ++mm) {
+                    if (mm < M) {
+                        // fold the slots of a feature, then the lanes
+                        if (feat <= 2) { acc[mm][0] += acc[mm][2]; acc[mm][1] += acc[mm][3]; }
+                        if (feat == 1) acc[mm][0] += acc[mm][1];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (q < feat) {
+#pragma unroll
+                                for (int dd = 16; dd >= 1; dd >>= 1) acc[mm][q] += __shfl_xor_sync(0xffffffffu, acc[mm][q], dd);
+                                if (q == f && mm == m) v = acc[mm][q];
+                            }
+                        }
+                    }
+                }
+                substamp(ph);
+                if (mine) {
+                    const int n = n0 + f;
+                    v += bv;
+                    if (kind == PH_QKV) {                    // Q to the dense buffer, K and V straight to the token's page slot (:706-710)
+                        if (n < C) a.q[(size_t)m * C + n] = v;
+                        else {
+                            const size_t slot_off = (size_t)st.slot[m] * C;
+                            if (n < 2 * C) pool_k[slot_off + (n - C)] = v;
+                            else pool_v[slot_off + (n - 2 * C)] = v;
+                        }
+                    } else if (kind == PH_FC) a.fch[(size_t)m * 4 * C + n] = pa_gelu(v);      // :719-720
+                    else if (kind == PH_LM) a.logits[(size_t)m * a.Vp + n] = v;                // :726
+                    else a.x[(size_t)m * C + n] = v + rv;                                      // :716-717, :721-722
+                }
+            }
         }
-        GRID_SYNC();
-        attn_partials<LPT>(a, pool_k, pool_v);
-        GRID_SYNC();
-        attn_merge<LPT>(a);
-        GRID_SYNC();
-        // x += atty . attprojw^T + attprojb (:716-717)
-        stage_rows(xs, a.atty, M, C);
-        {
-            const float* bias = a.attprojb + (size_t)l * C;
-            gemv_auto(a.attprojw + (size_t)l * C * C, C, C, M, xs, [&](int m, int n, float v) {
-                float* xp = a.x + (size_t)m * C + n;
-                *xp = v + bias[n] + __ldcg(xp);
-            });
+
+        substamp(ph);
+        // ---- paged attention between the QKV projection and attproj (:713-715) -------------------------
+        if (kind == PH_QKV) {
+            GRID_ARRIVE();
+            int ush, uc, t0, t1, last;
+            if (gw < M * a.NH * a.max_chunks && attn_unit(a, st, gw, ush, uc, t0, t1, last))
+                attn_issue<LPT>(kb, a, pool_k, pool_v, a.table + (size_t)(ush / a.NH) * a.tstride, ush % a.NH, t0, t1, last, false);
+            GRID_WAIT();
+            attn_partials<LPT>(kb, a, st, pool_k, pool_v);
+            GRID_ARRIVE();
+            GRID_WAIT();
+            attn_merge(a, st);
         }
-        GRID_SYNC();
-        // fch = gelu(ln2(x) . fcw^T + fcb) (:718-720)
-        ln_rows(xs, a.x, a.ln2w + (size_t)l * C, a.ln2b + (size_t)l * C, M, C);
-        {
-            const float* bias = a.fcb + (size_t)l * 4 * C;
-            gemv_auto(a.fcw + (size_t)l * 4 * C * C, 4 * C, C, M, xs, [&](int m, int n, float v) {
-                a.fch[(size_t)m * 4 * C + n] = pa_gelu(v + bias[n]);
-            });
+        GRID_ARRIVE();
+        if (ph + 1 < n_phases) {
+            d = phase_desc(a, ph + 1);
+            sh = ph + 1 == n_phases - 1 ? 2 : pick_feat_shift(d.N);
+            gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane);
+            bias_first = bias_issue(d, sh);
+            // (this phase read ln_ws/ln_bs before its __syncthreads at the latest; nobody reads them again before the barrier)
+            if (kind == PH_ATTPROJ) ln_params_issue(a.ln2w + (size_t)l * C, a.ln2b + (size_t)l * C);
+            else if (kind == PH_FCPROJ) {
+                if (ph + 2 < n_phases) ln_params_issue(a.ln1w + (size_t)(l + 1) * C, a.ln1b + (size_t)(l + 1) * C);
+                else ln_params_issue(a.lnfw, a.lnfb);
+            }
         }
-        GRID_SYNC();
-        // x += fch . fcprojw^T + fcprojb (:721-722)
-        stage_rows(xs, a.fch, M, 4 * C);
-        {
-            const float* bias = a.fcprojb + (size_t)l * C;
-            gemv_auto(a.fcprojw + (size_t)l * 4 * C * C, C, 4 * C, M, xs, [&](int m, int n, float v) {
-                float* xp = a.x + (size_t)m * C + n;
-                *xp = v + bias[n] + __ldcg(xp);
-            });
-        }
-        GRID_SYNC();
+        GRID_WAIT();
     }
-    // final layernorm, logits = lnf . wte^T (:724-726), then softmax + sample_mult per row
-    ln_rows(xs, a.x, a.lnfw, a.lnfb, M, C);
-    gemv_rows<4>(a.wte, a.V, C, M, xs, [&](int m, int n, float v) { a.logits[(size_t)m * a.Vp + n] = v; });
-    GRID_SYNC();
+    // softmax_forward + sample_mult on each row of logits
     if ((int)blockIdx.x < M)
-        pa_sample_row<kThreads>(a.logits + (size_t)blockIdx.x * a.Vp, a.V, a.coins ? a.coins[blockIdx.x] : -1.0f, a.next + blockIdx.x, samp);
+        pa_sample_row<kThreads>(a.logits + (size_t)blockIdx.x * a.Vp, a.V, a.use_coins ? a.coins[blockIdx.x] : -1.0f, a.next + blockIdx.x, samp);
+}
+
+typedef void (*MegaKernel)(const pa_mega_args);
+template <int LPT, int LNREGS>
+MegaKernel pick_kernel_m(int M) {
+    if (M <= 1) return pa_decode_step_mega_kernel<LPT, 1, LNREGS>;
+    if (M <= 2) return pa_decode_step_mega_kernel<LPT, 2, LNREGS>;
+    if (M <= 4) return pa_decode_step_mega_kernel<LPT, 4, LNREGS>;
+    return pa_decode_step_mega_kernel<LPT, 8, LNREGS>;
+}
+MegaKernel pick_kernel(int M, int C, int hs) {
+    if (hs == 64) return C <= 1024 ? pick_kernel_m<16, 32>(M) : pick_kernel_m<16, kLnMaxPerLane>(M);
+    return C <= 1024 ? pick_kernel_m<32, 32>(M) : pick_kernel_m<32, kLnMaxPerLane>(M);
 }
 
 }  // namespace
 
-extern "C" size_t pa_cu_model_mega_smem(int M, int C, int hs) {
+extern "C" size_t pa_cu_model_mega_smem(int M, int C, int hs, int block_size) {
     if (M < 1 || M > kMaxM || (C & 3) || C > 32 * kLnMaxPerLane || (hs != 64 && hs != 128)) return 0;
-    const size_t bytes = (size_t)M * 4 * C * sizeof(float);
+    if (block_size < 1 || (block_size & (block_size - 1))) return 0;          // pages are addressed with shifts
+    const size_t bytes = ((size_t)M * 4 * C + 2 * (size_t)C) * sizeof(float);        // input rows + layernorm weight and bias
     return bytes <= 200 * 1024 ? bytes : 0;
 }
 
 extern "C" int pa_cu_model_mega_step(const pa_mega_args* a, void* stream) {
-    const size_t smem = pa_cu_model_mega_smem(a->M, a->C, a->hs);
+    const size_t smem = pa_cu_model_mega_smem(a->M, a->C, a->hs, a->bs);
     if (!smem) return PA_ERR_UNSUPPORTED;
-    auto fn = a->hs == 64 ? pa_decode_step_mega_kernel<16> : pa_decode_step_mega_kernel<32>;
-    static size_t attr_smem[2] = {0, 0};
-    size_t& cur = attr_smem[a->hs == 64 ? 0 : 1];
-    if (smem > cur) {
+    MegaKernel fn = pick_kernel(a->M, a->C, a->hs);
+    // (each instantiation needs its own opt-in for more than 48 KB of dynamic shared memory)
+    static MegaKernel attr_fn[32];
+    static size_t attr_smem[32];
+    static int attr_n = 0;
+    int ai = 0;
+    while (ai < attr_n && attr_fn[ai] != fn) ++ai;
+    if (ai == attr_n || attr_smem[ai] < smem) {
         CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cur = smem;
+        if (ai == attr_n && attr_n < 32) ++attr_n;
+        if (ai < 32) { attr_fn[ai] = fn; attr_smem[ai] = smem; }
     }
     cudaStream_t s = (cudaStream_t)stream;
-    CU_CHECK(cudaMemsetAsync(a->bar, 0, sizeof(unsigned), s));
     pa_mega_args args = *a;
     void* kargs[] = {&args};
     // cooperative: the launch fails instead of deadlocking the grid barrier if the grid could not be co-resident
@@ -381,6 +532,12 @@ extern "C" int pa_cu_model_mega_step(const pa_mega_args* a, void* stream) {
                 work[p] += (double)(hst[2 * b] - hst[2 * b - 1]);
                 wait[p] += (double)(hst[2 * b + 1] - hst[2 * b]);
             }
+        fprintf(stderr, "mega sub (layer 1: phase start, input ready, fma done, reduced, stored):");
+        for (int p = 0; p < 4; ++p) {
+            fprintf(stderr, " |");
+            for (int i = 1; i < 5; ++i) fprintf(stderr, " %lld", (long long)(hst[2048 + 5 * p + i] - hst[2048 + 5 * p]));
+        }
+        fprintf(stderr, "\n");
         fprintf(stderr, "mega dbg: embed barrier %lld ns;", (long long)(hst[1] - hst[0]));
         for (int p = 0; p < per_layer; ++p) fprintf(stderr, " %s %.0f+%.0f", names[p], work[p] / a->L, wait[p] / a->L);
         fprintf(stderr, "; lm head %lld+%lld; total %lld ns\n", (long long)(hst[2 * (n - 1)] - hst[2 * (n - 1) - 1]),
