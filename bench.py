@@ -518,10 +518,16 @@ def main():
             barrier()
             wall_ms = (time.perf_counter() - t0) * 1e3 / k_model
             ms_model = allmax(max(lib.pa_event_elapsed_ms(e0, e1) / k_model, wall_ms))
+            per_step = (eng.launches() - l0) / k_model
+            persistent = per_step <= 1.0
             model_info = {"tokens_per_s": world * B / (ms_model * 1e-3), "ms_per_step": ms_model, "steps": k_model,
-                          "vocab": V, "layers": L, "gpu_launches_per_step": (eng.launches() - l0) / k_model,
-                          "sampler": "softmax + multinomial (sample_mult) fused kernel, host coins",
-                          "projections": "tcgen05 3xTF32 (fp32-accurate) GEMMs with bias/GELU/residual epilogues",
+                          "vocab": V, "layers": L, "gpu_launches_per_step": per_step,
+                          "path": ("ONE persistent cooperative kernel for the whole step (pa_model_mega.cu: weight-streaming "
+                                   "fp32 GEMV phases, chunked paged attention, grid barriers)" if persistent else
+                                   "chain of per-op kernels (layernorm, tcgen05 3xTF32 projections, paged decode attention, sampler)"),
+                          "sampler": "softmax + multinomial (sample_mult) fused, host coins",
+                          "projections": ("fp32 FMA weight-streaming GEMV with bias/GELU/residual epilogues" if persistent else
+                                          "tcgen05 3xTF32 (fp32-accurate) GEMMs with bias/GELU/residual epilogues"),
                           "weights": "random init on the device (no checkpoint offline)",
                           "token_gather": ("NCCL all_gather of int32 next tokens, every step" if dist is not None else None),
                           "entry": "pa_model_decode_step (host token ids in, host token ids out, sync per step)"}
@@ -574,7 +580,7 @@ def main():
             "tokens_per_s": tokens_per_s, "frac_of_measured_peak": value / world / peak,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "model": model_info}
-    if model_info and "ms_per_step" in model_info:
+    if model_info and "ms_per_step" in model_info and model_info["gpu_launches_per_step"] > 1:
         model_info["attention_share_of_step"] = kms * L / model_info["ms_per_step"]
     print(json.dumps(line))
     if dist is not None:

@@ -283,6 +283,7 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
     extern __shared__ __align__(16) float xs[];          // [M][4C] staged / normalised input rows | layernorm weight [C] | bias [C]
     __shared__ PaSampleSmem<kThreads> samp;
     __shared__ StepSmem st;
+    __shared__ float ln_red[2 * kWarps];
     const int M = a.M, C = a.C;
     float* ln_ws = xs + (size_t)M * 4 * C;
     float* ln_bs = ln_ws + C;
@@ -357,9 +358,48 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
             const float4* src = reinterpret_cast<const float4*>(kind == PH_ATTPROJ ? a.atty : a.fch);
             for (int i = threadIdx.x; i < M * K4; i += kThreads) reinterpret_cast<float4*>(xs)[i] = __ldcg(src + i);
         } else {
+            // layernorm_forward (:49-89), 8 / MAXM warps per row (a single warp would leave every latency exposed)
+            constexpr int W = kWarps / MAXM, PER = (LNREGS + W - 1) / W;
+            const int row = warp / W, wr = warp % W;
+            const bool act = row < M;
+            const float* xr = a.x + (size_t)row * C;
+            float v[PER];
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int c = wr * 32 + lane + 32 * W * i;
+                v[i] = (act && c < C) ? __ldcg(xr + c) : 0.0f;
+                sum += v[i];
+            }
+#pragma unroll
+            for (int dd = 16; dd >= 1; dd >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dd);
+            if (lane == 0) ln_red[warp] = sum;
             cp_async_wait<0>();
-            __syncthreads();                                  // everybody's copies of the layernorm parameters have landed
-            if (warp < M) pa_layernorm_row<true, LNREGS>(xs + (size_t)warp * C, a.x + (size_t)warp * C, ln_ws, ln_bs, C, lane);
+            __syncthreads();                                  // the partial sums, and everybody's copies of the layernorm parameters
+            float tot = 0.0f;
+#pragma unroll
+            for (int k = 0; k < W; ++k) tot += ln_red[row * W + k];
+            const float mean = tot / C;
+            float var = 0.0f;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int c = wr * 32 + lane + 32 * W * i;
+                const float dlt = v[i] - mean;
+                if (c < C) var += dlt * dlt;
+            }
+#pragma unroll
+            for (int dd = 16; dd >= 1; dd >>= 1) var += __shfl_xor_sync(0xffffffffu, var, dd);
+            if (lane == 0) ln_red[kWarps + warp] = var;
+            __syncthreads();
+            float totv = 0.0f;
+#pragma unroll
+            for (int k = 0; k < W; ++k) totv += ln_red[kWarps + row * W + k];
+            const float rstd = 1.0f / sqrtf(totv / C + 1e-5f);           // eps, :56
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int c = wr * 32 + lane + 32 * W * i;
+                if (act && c < C) xs[(size_t)row * C + c] = (rstd * (v[i] - mean)) * ln_ws[c] + ln_bs[c];
+            }
         }
         __syncthreads();
         substamp(ph);
@@ -375,11 +415,16 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
                 const bool mine = f < feat && m < M && n0 + f < N;
                 const float bv = have ? bias_first : ((mine && d.bias) ? __ldg(d.bias + n0 + f) : 0.0f);
                 const float rv = (mine && res) ? __ldcg(res + (size_t)m * C + n0 + f) : 0.0f;
-                if (n0 + (nw << sh) < N) {                   // the rows of the warp's next pass -> L2 while this pass computes
-                    const int lines = K >> 5;                // 128-byte lines per row
-                    for (int i = lane; i < feat * lines; i += 32) {
-                        const int pf = i / lines, pl = i - pf * lines;
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(d.w + (size_t)min(n0 + (nw << sh) + pf, N - 1) * K + pl * 32));
+                // the rows of the warp's passes after this one -> L2 while this pass computes (two passes ahead;
+                // the first pass also requests the one right after it)
+                for (int ahead = have ? 1 : 2; ahead <= 2; ++ahead) {
+                    const int np = n0 + ahead * (nw << sh);
+                    if (np < N) {
+                        const int lines = K >> 5;            // 128-byte lines per row
+                        for (int i = lane; i < feat * lines; i += 32) {
+                            const int pf = i / lines, pl = i - pf * lines;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(d.w + (size_t)min(np + pf, N - 1) * K + pl * 32));
+                        }
                     }
                 }
                 float acc[MAXM][4];
