@@ -64,10 +64,13 @@ __device__ __forceinline__ void grid_arrive(unsigned* bar) {
 __device__ __forceinline__ void grid_wait(unsigned* bar, unsigned base, unsigned& passed) {
     if (threadIdx.x == 0) {
         const unsigned target = base + (passed + 1) * gridDim.x;
+        // relaxed polls and ONE acquire fence at the end: an acquire load invalidates the SM's whole L1
+        // every time it executes, under the feet of the loads the CTA has in flight
         unsigned seen;
         do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
         } while ((int)(seen - target) < 0);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
     ++passed;
@@ -90,13 +93,59 @@ __device__ __forceinline__ int pick_feat_shift(int N) {
 }
 // The weight loads of a warp's FIRST batch are issued BEFORE the grid barrier in front of the phase:
 // weights never depend on another CTA, so they stream in from HBM while the grid meets.
-__device__ __forceinline__ void gemv_issue(float4 (&wv)[kLoads], const float* __restrict__ w, int N, int K, int sh, int n0, int cb) {
-    const int K4 = K >> 2, fmask = (1 << sh) - 1;
+// read-only, read-once: straight from L2, no L1 line to allocate
+__device__ __forceinline__ float4 ld_weight(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+// One specialisation per feature count (SH = log2): with everything about the batch's shape known at
+// compile time a load is an add and an LDG, and an FMA group an LDS and four FFMAs -- with run-time
+// shapes the same loop was ~900 instructions of address arithmetic and branches per pass, and at
+// two warps per scheduler those are paid at full latency.  Load u*FEAT + f = chunk u of feature f.
+template <int SH>
+__device__ __forceinline__ void gemv_issue_t(float4 (&wv)[kLoads], const float* __restrict__ w, int N, int K, int n0, int cb) {
+    constexpr int FEAT = 1 << SH, UN = kLoads >> SH;
+    const int K4 = K >> 2;
 #pragma unroll
-    for (int j = 0; j < kLoads; ++j) {
-        const int c = cb + 32 * (j >> sh);
-        wv[j] = (c < K4 && n0 < N) ? __ldg(reinterpret_cast<const float4*>(w + (size_t)min(n0 + (j & fmask), N - 1) * K) + c)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int f = 0; f < FEAT; ++f) {
+        const float4* row = reinterpret_cast<const float4*>(w + (size_t)min(n0 + f, N - 1) * K) + cb;
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+            wv[u * FEAT + f] = (cb + 32 * u < K4 && n0 < N) ? ld_weight(row + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+__device__ __forceinline__ void gemv_issue(float4 (&wv)[kLoads], const float* __restrict__ w, int N, int K, int sh, int n0, int cb, int noload = 0) {
+    if (noload) {
+#pragma unroll
+        for (int j = 0; j < kLoads; ++j) wv[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+        return;
+    }
+    if (sh == 0) gemv_issue_t<0>(wv, w, N, K, n0, cb);
+    else if (sh == 1) gemv_issue_t<1>(wv, w, N, K, n0, cb);
+    else gemv_issue_t<2>(wv, w, N, K, n0, cb);
+}
+// acc[m][slot] += w . x for one batch; a feature's chunks spread over 4 / FEAT slots (independent FMA
+// chains), folded by the caller.  Chunks past the row carry zero weights: their x index is clamped.
+template <int SH, int MAXM>
+__device__ __forceinline__ void gemv_fma_t(const float4 (&wv)[kLoads], const float4* xs4, int cb, int K4, int M, float (&acc)[MAXM][4]) {
+    constexpr int FEAT = 1 << SH, UN = kLoads >> SH;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+        const int c = min(cb + 32 * u, K4 - 1);
+#pragma unroll
+        for (int mm = 0; mm < MAXM; ++mm) {
+            if (mm < M) {
+                const float4 xv = xs4[mm * K4 + c];
+#pragma unroll
+                for (int f = 0; f < FEAT; ++f) {
+                    constexpr int kSpread = 4 / FEAT;
+                    const int slot = f + FEAT * (u % kSpread);
+                    const float4 wq = wv[u * FEAT + f];
+                    acc[mm][slot] = fmaf(wq.w, xv.w, fmaf(wq.z, xv.z, fmaf(wq.y, xv.y, fmaf(wq.x, xv.x, acc[mm][slot]))));
+                }
+            }
+        }
     }
 }
 
@@ -339,7 +388,7 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
     GRID_ARRIVE();
     PhaseDesc d = phase_desc(a, 0);
     int sh = pick_feat_shift(d.N);
-    gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane);
+    gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane, a.exp_flags & 1);
     float bias_first = bias_issue(d, sh);
     ln_params_issue(a.ln1w, a.ln1b);
     GRID_WAIT();
@@ -432,22 +481,13 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
                 for (int mm = 0; mm < MAXM; ++mm)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[mm][q] = 0.0f;
+                substamp(ph);
                 for (int cb = lane; cb < K4; cb += 32 * (kLoads >> sh)) {
                     if (!have) gemv_issue(wv, d.w, N, K, sh, n0, cb);
                     have = false;
-#pragma unroll
-                    for (int j = 0; j < kLoads; ++j) {
-                        const int c = cb + 32 * (j >> sh);
-                        if (c < K4) {
-#pragma unroll
-                            for (int mm = 0; mm < MAXM; ++mm) {
-                                if (mm < M) {
-                                    const float4 xv = xs4[mm * K4 + c];
-                                    acc[mm][j & 3] = fmaf(wv[j].w, xv.w, fmaf(wv[j].z, xv.z, fmaf(wv[j].y, xv.y, fmaf(wv[j].x, xv.x, acc[mm][j & 3]))));
-                                }
-                            }
-                        }
-                    }
+                    if (sh == 0) gemv_fma_t<0, MAXM>(wv, xs4, cb, K4, M, acc);
+                    else if (sh == 1) gemv_fma_t<1, MAXM>(wv, xs4, cb, K4, M, acc);
+                    else gemv_fma_t<2, MAXM>(wv, xs4, cb, K4, M, acc);
                 }
                 substamp(ph);
                 float v = 0.0f;
@@ -502,7 +542,7 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
         if (ph + 1 < n_phases) {
             d = phase_desc(a, ph + 1);
             sh = ph + 1 == n_phases - 1 ? 2 : pick_feat_shift(d.N);
-            gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane);
+            gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane, a.exp_flags & 1);
             bias_first = bias_issue(d, sh);
             // (this phase read ln_ws/ln_bs before its __syncthreads at the latest; nobody reads them again before the barrier)
             if (kind == PH_ATTPROJ) ln_params_issue(a.ln2w + (size_t)l * C, a.ln2b + (size_t)l * C);
@@ -563,6 +603,7 @@ extern "C" int pa_cu_model_mega_step(const pa_mega_args* a, void* stream) {
     const bool dbg = getenv("PA_MEGA_DEBUG") != nullptr;
     if (dbg && !d_dbg) CU_CHECK(cudaMalloc((void**)&d_dbg, 4096 * sizeof(unsigned long long)));
     args.dbg = dbg ? d_dbg : nullptr;
+    args.exp_flags = getenv("PA_MEGA_EXP") ? atoi(getenv("PA_MEGA_EXP")) : 0;      // timing experiments only (wrong results)
     CU_CHECK(cudaLaunchCooperativeKernel((const void*)fn, dim3(a->sm_count), dim3(kThreads), kargs, smem, s));
     if (dbg) {        // per phase (averaged over the layers): ns of work before the barrier, ns inside the barrier
         static unsigned long long hst[4096];
@@ -577,10 +618,10 @@ extern "C" int pa_cu_model_mega_step(const pa_mega_args* a, void* stream) {
                 work[p] += (double)(hst[2 * b] - hst[2 * b - 1]);
                 wait[p] += (double)(hst[2 * b + 1] - hst[2 * b]);
             }
-        fprintf(stderr, "mega sub (layer 1: phase start, input ready, fma done, reduced, stored):");
+        fprintf(stderr, "mega sub (layer 1: phase start, input ready, loop entered, fma done, reduced, stored):");
         for (int p = 0; p < 4; ++p) {
             fprintf(stderr, " |");
-            for (int i = 1; i < 5; ++i) fprintf(stderr, " %lld", (long long)(hst[2048 + 5 * p + i] - hst[2048 + 5 * p]));
+            for (int i = 1; i < 6; ++i) fprintf(stderr, " %lld", (long long)(hst[2048 + 6 * p + i] - hst[2048 + 6 * p]));
         }
         fprintf(stderr, "\n");
         fprintf(stderr, "mega dbg: embed barrier %lld ns;", (long long)(hst[1] - hst[0]));
