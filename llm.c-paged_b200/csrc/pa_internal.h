@@ -139,7 +139,8 @@ int pa_cu_linear(const float* x, int x_stride, const float* w, const float* bias
 /* ---- implemented in pa_model_mega.cu: the whole decode step of a handful of sequences as ONE
  * persistent cooperative kernel (every op of gpt2_forward for one new token per sequence) ------- */
 #define PA_MEGA_MAX_SEQS 8
-#define PA_MEGA_AUTO_SEQS 4      /* chosen by itself up to this many sequences (measured against the chain of per-op kernels) */
+#define PA_MEGA_WARPS_PER_SM 16
+#define PA_MEGA_AUTO_SEQS 8      /* chosen by itself up to this many sequences (measured against the chain of per-op kernels: ahead up to 8 at short contexts, level at 8 x 1024) */
 typedef struct pa_mega_args {
     /* parameters, checkpoint order (paged_infer.c:441-488) */
     const float *wte, *wpe, *ln1w, *ln1b, *qkvw, *qkvb, *attprojw, *attprojb, *ln2w, *ln2b, *fcw, *fcb, *fcprojw,
@@ -160,6 +161,7 @@ typedef struct pa_mega_args {
     float scale;
     /* attention split: tokens per chunk, chunks per sequence at most, partial (o[hs], m, l) workspace */
     int chunk_tokens, max_chunks;
+    int local_attn;                     /* 1: the warps of one CTA share a (sequence, head) and merge in shared memory (max_chunks = warps per CTA) */
     float* part;
     unsigned* bar;                      /* grid barrier counter: monotonic, bar_base at launch */
     unsigned bar_base;

@@ -44,10 +44,10 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
+constexpr int kWarps = PA_MEGA_WARPS_PER_SM;       // 16: at 8 (two per scheduler) every dependent instruction was paid at full latency
+constexpr int kThreads = kWarps * 32;
 constexpr int kMaxM = PA_MEGA_MAX_SEQS;
-constexpr int kLoads = 24;                 // 16-byte weight loads in flight per lane
+constexpr int kLoads = 12;                 // 16-byte weight loads in flight per lane (registers: 512 threads leave 128 each)
 constexpr float kMaxInit = -10000.0f;      // paged_infer.c:187
 
 // All CTAs of the (cooperative, hence co-resident) grid meet: the barrier orders the CTA's stores
@@ -87,9 +87,12 @@ __device__ __forceinline__ void grid_wait(unsigned* bar, unsigned base, unsigned
 // output features; its lanes interleave the 16-byte chunks of those weight rows and keep kLoads
 // loads in flight.  Load j of a batch belongs to feature j % feat and chunk j / feat; it always
 // accumulates into slot j % 4, and the slots of a feature are folded at the end.
-__device__ __forceinline__ int pick_feat_shift(int N) {
+__device__ __forceinline__ int pick_feat_shift(int N, int K) {
     const int nw = gridDim.x * kWarps;
-    return N <= nw ? 0 : (N <= 2 * nw ? 1 : 2);
+    int sh = N <= nw ? 0 : (N <= 2 * nw ? 1 : 2);
+    // ... but a warp's first batch should cover its whole rows when it can (the rest is not prefetched)
+    while (sh > 0 && (kLoads >> sh) * 128 < K) --sh;
+    return sh;
 }
 // The weight loads of a warp's FIRST batch are issued BEFORE the grid barrier in front of the phase:
 // weights never depend on another CTA, so they stream in from HBM while the grid meets.
@@ -154,7 +157,7 @@ struct StepSmem { int kv_start[kMaxM], kv_end[kMaxM], slot[kMaxM]; };
 // ---- attention, phase 1: a warp per (sequence, head, chunk); LPT = hs/4 lanes per token ---------
 template <int LPT>
 struct KvBatch {                           // one batch of a warp's unit: UN iterations x TPI tokens, this lane's 16 bytes of each
-    static constexpr int TPI = 32 / LPT, UN = 8;
+    static constexpr int TPI = 32 / LPT, UN = 4;
     float4 k[UN], v[UN];
 };
 // Requests K/V of the tokens [tb, tb + TPI*UN) of the unit.  only_new = false: every token except the
@@ -180,31 +183,40 @@ __device__ __forceinline__ void attn_issue(KvBatch<LPT>& kb, const pa_mega_args&
     }
 }
 // unit u -> (sequence*NH + head, chunk, token range); false when the chunk lies beyond the sequence
+// Two shapes of the split: GLOBAL -- chunks of a.chunk_tokens spread over the whole grid, partials to the
+// workspace, merged after a grid barrier (long contexts); LOCAL (a.local_attn) -- the warps of ONE CTA
+// share a (sequence, head), kWarps chunks of ceil(len / kWarps) tokens, merged through shared memory
+// right away: no partial traffic, no merge phase, one grid barrier less per layer.
 __device__ __forceinline__ bool attn_unit(const pa_mega_args& a, const StepSmem& st, int u, int& sh, int& c, int& t0, int& t1, int& last) {
     c = u % a.max_chunks; sh = u / a.max_chunks;
+    if (sh >= a.M * a.NH) { t0 = t1 = last = 0; return false; }
     const int s = sh / a.NH;
     last = st.kv_end[s];
-    t0 = st.kv_start[s] + c * a.chunk_tokens;
-    t1 = min(last, t0 + a.chunk_tokens);
+    const int chunk = a.local_attn ? (last - st.kv_start[s] + kWarps - 1) / kWarps : a.chunk_tokens;
+    t0 = st.kv_start[s] + c * chunk;
+    t1 = min(last, t0 + chunk);
     return t0 < last;
 }
 template <int LPT>
-__device__ __forceinline__ void attn_partials(KvBatch<LPT>& kb, const pa_mega_args& a, const StepSmem& st, const float* pool_k, const float* pool_v) {
+__device__ __forceinline__ void attn_partials(KvBatch<LPT>& kb, const pa_mega_args& a, const StepSmem& st, const float* pool_k, const float* pool_v,
+                                              float (*ps)[132]) {
     constexpr int TPI = KvBatch<LPT>::TPI, UN = KvBatch<LPT>::UN;
     const int lane = threadIdx.x & 31, sub = lane / LPT, li = lane % LPT;
     const int gw = blockIdx.x * kWarps + (threadIdx.x >> 5), nw = gridDim.x * kWarps;
     const int hs = a.hs, C = a.C;
     const int n_units = a.M * a.NH * a.max_chunks;
     bool have = true;                                               // kb holds the first batch of unit gw (all but the new token)
-    for (int u = gw; u < n_units; u += nw) {
+    for (int u = gw; u < n_units; u += nw) {              // (LOCAL: the CTA's warps run this loop in lockstep, one (sequence, head) at a time)
         int sh, c, t0, t1, last;
-        if (!attn_unit(a, st, u, sh, c, t0, t1, last)) { have = false; continue; }      // warp-uniform
+        const bool valid = attn_unit(a, st, u, sh, c, t0, t1, last);                  // warp-uniform
+        if (!valid) have = false;
+        if (!valid && !a.local_attn) continue;
         const int h = sh % a.NH, s = sh / a.NH;
         const int* tbl = a.table + (size_t)s * a.tstride;
-        const float4 q4 = __ldcg(reinterpret_cast<const float4*>(a.q + (size_t)s * C + h * hs) + li);
+        const float4 q4 = valid ? __ldcg(reinterpret_cast<const float4*>(a.q + (size_t)s * C + h * hs) + li) : make_float4(0.f, 0.f, 0.f, 0.f);
         float m_run = kMaxInit, l_run = 0.0f;
         float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int tb = t0; tb < t1; tb += TPI * UN) {
+        for (int tb = t0; tb < t1; tb += TPI * UN) {              // (no iteration for an empty chunk)
             if (!have) attn_issue<LPT>(kb, a, pool_k, pool_v, tbl, h, tb, t1, last, false);
             have = false;
             attn_issue<LPT>(kb, a, pool_k, pool_v, tbl, h, tb, t1, last, true);
@@ -245,10 +257,34 @@ __device__ __forceinline__ void attn_partials(KvBatch<LPT>& kb, const pa_mega_ar
             o4.z = fmaf(o4.z, wa, o_o.z * wb); o4.w = fmaf(o4.w, wa, o_o.w * wb);
             m_run = m_t;
         }
-        if (sub == 0) {
-            float* pr = a.part + (size_t)(sh * a.max_chunks + c) * (hs + 4);
-            reinterpret_cast<float4*>(pr)[li] = o4;
-            if (li == 0) { pr[hs] = m_run; pr[hs + 1] = l_run; }
+        if (!a.local_attn) {
+            if (sub == 0) {
+                float* pr = a.part + (size_t)(sh * a.max_chunks + c) * (hs + 4);
+                reinterpret_cast<float4*>(pr)[li] = o4;
+                if (li == 0) { pr[hs] = m_run; pr[hs + 1] = l_run; }
+            }
+        } else {
+            // the CTA's kWarps partials (an empty chunk leaves the neutral state) -> shared memory, merged in chunk order
+            if (sub == 0) {
+                reinterpret_cast<float4*>(ps[c])[li] = o4;
+                if (li == 0) { ps[c][hs] = m_run; ps[c][hs + 1] = l_run; }
+            }
+            __syncthreads();
+            if ((int)threadIdx.x < hs && sh < a.M * a.NH) {
+                const int dd = threadIdx.x;
+                float m_tot = kMaxInit;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) m_tot = fmaxf(m_tot, ps[w][hs]);
+                float l_tot = 0.0f, o = 0.0f;
+#pragma unroll 4
+                for (int w = 0; w < kWarps; ++w) {
+                    const float wgt = expf(ps[w][hs] - m_tot);
+                    l_tot = fmaf(ps[w][hs + 1], wgt, l_tot);
+                    o = fmaf(ps[w][dd], wgt, o);
+                }
+                a.atty[(size_t)s * C + h * hs + dd] = o * ((l_tot == 0.0f) ? 0.0f : 1.0f / l_tot);      // :213
+            }
+            __syncthreads();
         }
     }
 }
@@ -256,8 +292,9 @@ __device__ __forceinline__ void attn_partials(KvBatch<LPT>& kb, const pa_mega_ar
 // ---- attention, phase 2: a warp per (sequence, head) merges its chunks' partials in chunk order ----
 // lane i weighs partial i (one expf per lane), the weights travel by shuffle; every lane owns the
 // head dims lane, lane + 32, ...
+template <int LPT>
 __device__ __forceinline__ void attn_merge(const pa_mega_args& a, const StepSmem& st) {
-    constexpr int UN = 16;
+    constexpr int UN = 8, NJ = LPT / 8;            // partials per batch; head dims per lane (head_dim / 32)
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * kWarps + (threadIdx.x >> 5), nw = gridDim.x * kWarps;
     const int hs = a.hs;
@@ -272,15 +309,17 @@ __device__ __forceinline__ void attn_merge(const pa_mega_args& a, const StepSmem
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) m_tot = fmaxf(m_tot, __shfl_xor_sync(0xffffffffu, m_tot, d));
         }
-        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        float o[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) o[j] = 0.0f;
         float l_tot = 0.0f;
         for (int ib = 0; ib < n_part; ib += UN) {
-            float po[UN][4];
+            float po[UN][NJ];
 #pragma unroll
             for (int i = 0; i < UN; ++i) {                          // the batch's o values in flight at once
                 const float* pp = pr + (size_t)min(ib + i, n_part - 1) * (hs + 4);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) po[i][j] = (lane + 32 * j < hs) ? __ldcg(pp + lane + 32 * j) : 0.0f;
+                for (int j = 0; j < NJ; ++j) po[i][j] = __ldcg(pp + lane + 32 * j);
             }
             const int mine = ib + (lane & (UN - 1));                // lanes 0..15 (and their mirrors) weigh partial ib + lane
             const float* pp = pr + (size_t)min(mine, n_part - 1) * (hs + 4);
@@ -299,13 +338,13 @@ __device__ __forceinline__ void attn_merge(const pa_mega_args& a, const StepSmem
                 const float w_i = __shfl_sync(0xffffffffu, wgt, i);
                 l_tot += __shfl_sync(0xffffffffu, lw, i);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = fmaf(po[i][j], w_i, o[j]);
+                for (int j = 0; j < NJ; ++j) o[j] = fmaf(po[i][j], w_i, o[j]);
             }
         }
         const float inv = (l_tot == 0.0f) ? 0.0f : 1.0f / l_tot;        // :213
         float* out = a.atty + (size_t)s * a.C + h * hs;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (lane + 32 * j < hs) out[lane + 32 * j] = o[j] * inv;
+        for (int j = 0; j < NJ; ++j) out[lane + 32 * j] = o[j] * inv;
     }
 }
 
@@ -333,6 +372,7 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
     __shared__ PaSampleSmem<kThreads> samp;
     __shared__ StepSmem st;
     __shared__ float ln_red[2 * kWarps];
+    __shared__ __align__(16) float attn_ps[kWarps][132];     // LOCAL attention: the CTA's partials (o[hs], m, l)
     const int M = a.M, C = a.C;
     float* ln_ws = xs + (size_t)M * 4 * C;
     float* ln_bs = ln_ws + C;
@@ -387,7 +427,7 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
     }
     GRID_ARRIVE();
     PhaseDesc d = phase_desc(a, 0);
-    int sh = pick_feat_shift(d.N);
+    int sh = pick_feat_shift(d.N, d.K);
     gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane, a.exp_flags & 1);
     float bias_first = bias_issue(d, sh);
     ln_params_issue(a.ln1w, a.ln1b);
@@ -485,9 +525,14 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
                 for (int cb = lane; cb < K4; cb += 32 * (kLoads >> sh)) {
                     if (!have) gemv_issue(wv, d.w, N, K, sh, n0, cb);
                     have = false;
-                    if (sh == 0) gemv_fma_t<0, MAXM>(wv, xs4, cb, K4, M, acc);
-                    else if (sh == 1) gemv_fma_t<1, MAXM>(wv, xs4, cb, K4, M, acc);
-                    else gemv_fma_t<2, MAXM>(wv, xs4, cb, K4, M, acc);
+                    const int reps = (a.exp_flags & 2) ? 3 : 1;          // experiment: the same code again (instruction cache warm)
+#pragma unroll 1
+                    for (int rep = 0; rep < reps; ++rep) {
+                        if (sh == 0) gemv_fma_t<0, MAXM>(wv, xs4, cb, K4, M, acc);
+                        else if (sh == 1) gemv_fma_t<1, MAXM>(wv, xs4, cb, K4, M, acc);
+                        else gemv_fma_t<2, MAXM>(wv, xs4, cb, K4, M, acc);
+                        if (reps > 1) substamp(ph);
+                    }
                 }
                 substamp(ph);
                 float v = 0.0f;
@@ -530,18 +575,20 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
         if (kind == PH_QKV) {
             GRID_ARRIVE();
             int ush, uc, t0, t1, last;
-            if (gw < M * a.NH * a.max_chunks && attn_unit(a, st, gw, ush, uc, t0, t1, last))
+            if (attn_unit(a, st, gw, ush, uc, t0, t1, last))
                 attn_issue<LPT>(kb, a, pool_k, pool_v, a.table + (size_t)(ush / a.NH) * a.tstride, ush % a.NH, t0, t1, last, false);
             GRID_WAIT();
-            attn_partials<LPT>(kb, a, st, pool_k, pool_v);
-            GRID_ARRIVE();
-            GRID_WAIT();
-            attn_merge(a, st);
+            attn_partials<LPT>(kb, a, st, pool_k, pool_v, attn_ps);
+            if (!a.local_attn) {
+                GRID_ARRIVE();
+                GRID_WAIT();
+                attn_merge<LPT>(a, st);
+            }
         }
         GRID_ARRIVE();
         if (ph + 1 < n_phases) {
             d = phase_desc(a, ph + 1);
-            sh = ph + 1 == n_phases - 1 ? 2 : pick_feat_shift(d.N);
+            sh = pick_feat_shift(d.N, d.K);
             gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane, a.exp_flags & 1);
             bias_first = bias_issue(d, sh);
             // (this phase read ln_ws/ln_bs before its __syncthreads at the latest; nobody reads them again before the barrier)
@@ -609,15 +656,22 @@ extern "C" int pa_cu_model_mega_step(const pa_mega_args* a, void* stream) {
         static unsigned long long hst[4096];
         CU_CHECK(cudaStreamSynchronize(s));
         CU_CHECK(cudaMemcpy(hst, d_dbg, sizeof(hst), cudaMemcpyDeviceToHost));
-        const int per_layer = 6, n = 1 + per_layer * a->L + 1;       // barriers
-        const char* names[per_layer] = {"qkv", "attn", "merge", "attproj", "fc", "fcproj"};
-        double work[per_layer] = {0}, wait[per_layer] = {0};
+        const int per_layer = a->local_attn ? 5 : 6, n = 1 + per_layer * a->L + 1;       // barriers
+        const char* names6[6] = {"qkv", "attn", "merge", "attproj", "fc", "fcproj"};
+        const char* names5[5] = {"qkv", "attn+merge", "attproj", "fc", "fcproj"};
+        const char* const* names = a->local_attn ? names5 : names6;
+        double work[6] = {0}, wait[6] = {0};
         for (int l = 0; l < a->L; ++l)
             for (int p = 0; p < per_layer; ++p) {
                 const int b = 1 + l * per_layer + p;                   // barrier index: stamps 2b (arrive), 2b+1 (leave)
                 work[p] += (double)(hst[2 * b] - hst[2 * b - 1]);
                 wait[p] += (double)(hst[2 * b + 1] - hst[2 * b]);
             }
+        if (args.exp_flags & 2) {
+            fprintf(stderr, "mega sub raw:");
+            for (int i = 1; i < 40; ++i) fprintf(stderr, " %lld", (long long)(hst[2048 + i] - hst[2048 + i - 1]));
+            fprintf(stderr, "\n");
+        }
         fprintf(stderr, "mega sub (layer 1: phase start, input ready, loop entered, fma done, reduced, stored):");
         for (int p = 0; p < 4; ++p) {
             fprintf(stderr, " |");

@@ -261,6 +261,22 @@ def test_model_persistent_step_kernel(NH, hs, bs, B, ctx0):
         model.close(); eng.close(); orc.close()
 
 
+def test_model_persistent_step_kernel_grid_wide_attention():
+    """Contexts beyond 32 tokens per warp of a CTA take the kernel's other attention shape (chunks spread
+    over the grid, partials merged after a grid barrier).  PA_MEGA_LOCAL_ATTN_MAX=0 (read once per process)
+    sends every context that way, so the case runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PA_MEGA_LOCAL_ATTN_MAX="0")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(here, "test_gpu_model.py"),
+                        "-k", "test_model_persistent_step_kernel and not grid_wide and not domain"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "4 passed" in r.stdout, r.stdout[-2000:]
+
+
 def test_model_persistent_step_kernel_domain():
     """Forced (model_path 2) outside its domain the persistent kernel fails loudly; auto falls back to the chain."""
     L, NH, hs, V, maxT, B = 1, 2, 64, 50, 16, 9
