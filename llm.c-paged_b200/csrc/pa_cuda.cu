@@ -117,7 +117,11 @@ void pa_cu_release(pa_handle* h) {
     cudaFree(h->d_stage);
     cudaFree(h->d_dbg);
     if (h->h_stage) cudaFreeHost(h->h_stage);
-    if (h->stream) cudaStreamDestroy((cudaStream_t)h->stream);
+    if (h->stream) {
+        cudaStreamSynchronize((cudaStream_t)h->stream);
+        pa_cu_gemm_stream_released(h->cfg.device, h->stream);
+        cudaStreamDestroy((cudaStream_t)h->stream);
+    }
     h->pool_k = h->pool_v = NULL;
 }
 
@@ -271,7 +275,14 @@ void* pa_stream_create(void) {
     if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return NULL; }
     return (void*)s;
 }
-void pa_stream_destroy(void* stream) { if (stream) cudaStreamDestroy((cudaStream_t)stream); }
+void pa_stream_destroy(void* stream) {
+    if (!stream) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    pa_cu_gemm_stream_released(dev, stream);
+    cudaStreamDestroy((cudaStream_t)stream);
+}
 int pa_stream_sync(void* stream) { CU_CHECK(cudaStreamSynchronize((cudaStream_t)stream)); return PA_OK; }
 int pa_device_sync(void) { CU_CHECK(cudaDeviceSynchronize()); return PA_OK; }
 void* pa_event_create(void) {

@@ -517,7 +517,7 @@ struct SplitWsCache {
 SplitWsCache g_ws;
 // false when the cache is full or the allocation fails (the caller then splits over a cluster instead);
 // hands out the counter set of this launch and flips to the other one for the next
-bool get_split_ws(int dev, cudaStream_t s, GemmTcParams* p) {
+bool get_split_ws(int dev, cudaStream_t s, GemmTcParams* p, bool* cooperative) {
     constexpr int BN = 128;        // sized for the widest tile
     std::lock_guard<std::mutex> lock(g_ws.mu);
     SplitWs* w = nullptr;
@@ -541,11 +541,34 @@ bool get_split_ws(int dev, cudaStream_t s, GemmTcParams* p) {
     p->ws_cnt = w->cnt + w->parity * kWsMaxCtas;
     p->ws_cnt_next = w->cnt + (1 - w->parity) * kWsMaxCtas;
     w->parity ^= 1;
+    // The CTAs of a workspace split wait for each other, which is safe while the grid has the device to itself
+    // (one stream of projections per device -- the handle's).  Once a second stream of the same device has run
+    // such launches, two grids could starve each other of SMs: from then on the launches are cooperative (the
+    // driver makes each grid resident as a whole), which costs the launch overlap (measured +8 % per step).
+    int others = 0;
+    for (int i = 0; i < g_ws.used; ++i) others += g_ws.e[i].dev == dev && g_ws.e[i].stream != s;
+    static const char* coop_env = getenv("PA_GEMM_COOP");
+    *cooperative = coop_env ? atoi(coop_env) != 0 : others > 0;
     return true;
 }
 
+}  // namespace
+/* the handle that owned `stream` is going away: its split-K workspace with it */
+extern "C" void pa_cu_gemm_stream_released(int dev, void* stream) {
+    std::lock_guard<std::mutex> lock(g_ws.mu);
+    for (int i = 0; i < g_ws.used; ++i) {
+        if (g_ws.e[i].dev == dev && g_ws.e[i].stream == (cudaStream_t)stream) {
+            cudaFree(g_ws.e[i].ws);
+            cudaFree(g_ws.e[i].cnt);
+            g_ws.e[i] = g_ws.e[--g_ws.used];
+            return;
+        }
+    }
+}
+namespace {
+
 template <int BN>
-int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams& p, int n_split, bool cluster, cudaStream_t s) {
+int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams& p, int n_split, bool cluster, bool cooperative, cudaStream_t s) {
     using Cfg = GemmCfg<BN>;
     auto fn = pa_gemm3x_kernel<BN>;
     static bool attr_done = false;
@@ -553,7 +576,10 @@ int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams
         CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
         attr_done = true;
     }
-    CU_CHECK(pa_launch_pdl(fn, dim3((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, n_split), dim3(192), Cfg::kSmem, s, cluster ? n_split : 1, tx, tw, p));
+    pa_launch_cooperative = cooperative ? 1 : 0;
+    const cudaError_t e = pa_launch_pdl(fn, dim3((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, n_split), dim3(192), Cfg::kSmem, s, cluster ? n_split : 1, tx, tw, p);
+    pa_launch_cooperative = 0;
+    CU_CHECK(e);
     return PA_OK;
 }
 
@@ -605,7 +631,7 @@ extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const
     const long long tiles = (long long)((N + BN - 1) / BN) * m_tiles;
     const int ws_cap = tiles <= sms ? (int)(sms / tiles) : 1;          // co-residency bound
     int n_split = 1;
-    bool cluster = false;
+    bool cluster = false, cooperative = false;
     if (n_split_override == 0) {
         n_split = ws_cap < kWsMaxSplit ? ws_cap : kWsMaxSplit;
         if (n_split > total_slabs / 2) n_split = total_slabs / 2;
@@ -621,7 +647,7 @@ extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const
     }
     p.ws = nullptr; p.ws_cnt = nullptr; p.ws_cnt_next = nullptr;
     if (n_split > 1 && !cluster) {
-        if (!get_split_ws(dev, (cudaStream_t)stream, &p)) {             // no workspace: clusters of 2 or 4
+        if (!get_split_ws(dev, (cudaStream_t)stream, &p, &cooperative)) {             // no workspace: clusters of 2 or 4
             if (BN == 128) n_split = 1;
             else {
                 cluster = true;
@@ -635,8 +661,9 @@ extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const
     int rc = get_map(&tx, x, M, K, x_stride, kBM);
     if (rc == PA_OK) rc = get_map(&tw, w, N, K, K, BN);
     if (rc != PA_OK) return rc;
-    rc = BN == 128 ? launch_gemm<128>(tx, tw, p, n_split, false, (cudaStream_t)stream)
-                   : launch_gemm<64>(tx, tw, p, n_split, cluster, (cudaStream_t)stream);
+    cooperative = cooperative && n_split > 1 && !cluster;
+    rc = BN == 128 ? launch_gemm<128>(tx, tw, p, n_split, false, cooperative, (cudaStream_t)stream)
+                   : launch_gemm<64>(tx, tw, p, n_split, cluster, cooperative, (cudaStream_t)stream);
     if (p.dbg) {      // ns since kernel entry: TMEM ready, first slab landed, splitter done, MMAs done, reduction done, stores issued
         unsigned long long hst[8];
         cudaDeviceSynchronize();

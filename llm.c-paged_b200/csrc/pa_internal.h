@@ -132,6 +132,7 @@ void pa_cu_prefill_tc_release(pa_handle* h);
 int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
                   int M, int N, int K, int n_dense, float* pool_k, float* pool_v, const int* slots, int C,
                   int terms, int n_split, const float* residual, int res_stride, int act, void* stream);
+void pa_cu_gemm_stream_released(int device, void* stream);      /* frees the split-K workspace kept for that stream */
 /* out = act(x.w^T + bias) + residual: tensor cores when the shape allows, else the fp32 SIMT kernel (pa_qkv.cu) */
 int pa_cu_linear(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
                  int M, int N, int K, const float* residual, int res_stride, int act, int path, void* stream);

@@ -54,6 +54,7 @@ struct pa_model {
     size_t mega_part_floats;
     unsigned* mega_bar;                    // its grid-barrier counter (monotonic over launches) ...
     unsigned mega_bar_base;                // ... and its value when the next launch starts
+    int mega_refused;                      // a cooperative launch failed once: stay on the chain (automatic choice only)
 };
 
 namespace {
@@ -176,8 +177,9 @@ int mega_step(pa_model* m, int nseq, const int* tok, const int* pos, const float
     }
     // the barrier counter only ever grows: this launch counts from where the last one stopped
     a.part = m->mega_part; a.bar = m->mega_bar; a.bar_base = m->mega_bar_base;
-    m->mega_bar_base += (unsigned)(2 + (a.local_attn ? 5 : 6) * m->L) * (unsigned)h->sm_count;
-    return pa_cu_model_mega_step(&a, s);
+    const int rc = pa_cu_model_mega_step(&a, s);
+    if (rc == PA_OK) m->mega_bar_base += (unsigned)(2 + (a.local_attn ? 5 : 6) * m->L) * (unsigned)h->sm_count;      // (only a launch that ran counts)
+    return rc;
 }
 
 }  // namespace
@@ -337,7 +339,7 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
     bool use_mega = false;
     if (model_path != 1) {
         const size_t mega_smem = (max_q == 1 && nseq <= (model_path == 2 ? PA_MEGA_MAX_SEQS : PA_MEGA_AUTO_SEQS)) ? pa_cu_model_mega_smem(nseq, C, h->cfg.head_dim, h->cfg.block_size) : 0;
-        use_mega = mega_smem && (size_t)h->smem_optin >= mega_smem + 1024;
+        use_mega = mega_smem && (size_t)h->smem_optin >= mega_smem + 1024 && !(m->mega_refused && model_path != 2);
         if (!use_mega && model_path == 2) {
             pa_set_error("pa_model_forward: the persistent step kernel takes at most %d sequences of one new token each (head_dim 64 or 128)", PA_MEGA_MAX_SEQS);
             return PA_ERR_UNSUPPORTED;
@@ -355,12 +357,18 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
         // token ids, positions and coins travel as kernel arguments, the sampled tokens come back through
         // mapped pinned memory: the step is ONE table copy, ONE launch and ONE synchronisation
         rc = mega_step(m, nseq, h_tok, h_pos, coins ? m->h_coins : nullptr, h_next, s);
-        if (rc != PA_OK) return rc;
-        h->launches += 1;
-        CU_CHECK(cudaStreamSynchronize(s));
-        pa_pdl_gate = 1;
-        memcpy(next_tokens, h_next, (size_t)nseq * sizeof(int));
-        return PA_OK;
+        if (rc == PA_OK) {
+            h->launches += 1;
+            CU_CHECK(cudaStreamSynchronize(s));
+            pa_pdl_gate = 1;
+            memcpy(next_tokens, h_next, (size_t)nseq * sizeof(int));
+            return PA_OK;
+        }
+        if (model_path == 2) return rc;
+        // chosen automatically and the cooperative launch was refused (no co-residency to be had here): the chain
+        // of per-op kernels takes this step and the following ones
+        cudaGetLastError();
+        m->mega_refused = 1;
     }
     int* d_tok = m->d_io, *d_pos = m->d_io + ntok, *d_last = m->d_io + 2 * ntok, *d_next = m->d_io + 2 * ntok + nseq;
     CU_CHECK(cudaMemcpyAsync(m->d_io, m->h_io, (size_t)(2 * ntok + nseq) * sizeof(int), cudaMemcpyHostToDevice, s));

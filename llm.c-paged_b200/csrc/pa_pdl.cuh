@@ -15,6 +15,8 @@ extern "C" int pa_pdl_gate;        /* per-step gate set by the caller of the cha
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+extern "C" int pa_launch_cooperative;      /* set around a launch whose CTAs wait for each other (split-K through the L2 workspace) */
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t pa_launch_pdl(void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                         int cluster_z, Args... args) {
@@ -23,7 +25,7 @@ static inline cudaError_t pa_launch_pdl(void (*fn)(KArgs...), dim3 grid, dim3 bl
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     int n = 0;
     if (pa_pdl_enabled && pa_pdl_gate) {
         attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -35,6 +37,11 @@ static inline cudaError_t pa_launch_pdl(void (*fn)(KArgs...), dim3 grid, dim3 bl
         attr[n].val.clusterDim.x = 1;
         attr[n].val.clusterDim.y = 1;
         attr[n].val.clusterDim.z = (unsigned)cluster_z;
+        ++n;
+    }
+    if (pa_launch_cooperative) {        // co-residency of the whole grid is checked at launch instead of assumed
+        attr[n].id = cudaLaunchAttributeCooperative;
+        attr[n].val.cooperative = 1;
         ++n;
     }
     cfg.attrs = attr;

@@ -17,6 +17,7 @@
 static __thread char g_err[512] = "";
 int pa_pdl_enabled = 1;      /* programmatic dependent launch for the step's kernel chain (pa_pdl.cuh) */
 int pa_pdl_gate = 1;
+int pa_launch_cooperative = 0;
 
 void pa_set_error(const char* fmt, ...) {
     va_list ap;

@@ -249,3 +249,38 @@ def test_matmul_bias_auto_split_k(M, N, K):
     pa.check(lib.pa_matmul_bias(dx2.ptr, 768, dw2.ptr, None, do2.ptr, 768, M, 768, 768, None), "pa_matmul_bias")
     pa.check(lib.pa_device_sync(), "sync")
     assert_close_gemm(do2.download((M, 768)), want2, "second shape")
+
+
+def test_split_k_with_two_streams_live():
+    """Two handles (two streams) of one device both running workspace-split projections: from the second
+    stream on the launches are cooperative (whole-grid residency guaranteed by the driver instead of
+    assumed); each stream has its own workspace; results unchanged and bit-identical between the two."""
+    NH, hs, bs, B = 12, 64, 16, 64
+    Cc = NH * hs
+    scs = [Scenario(NH, hs, bs, [3] * B, seed=500, extra_blocks=B + 8) for _ in range(2)]
+    try:
+        x = oa.normal((B, Cc), seed=501)
+        w = (oa.normal((3 * Cc, Cc), seed=502) * np.float32(1.0 / np.sqrt(Cc))).astype(np.float32)
+        bias = oa.normal((3 * Cc,), seed=503)
+        want = _oracle_matmul(x, w, bias)
+        outs = []
+        bufs = [(pa.DevBuf.from_numpy(x), pa.DevBuf.from_numpy(w), pa.DevBuf.from_numpy(bias), pa.DevBuf(B * Cc * 4)) for _ in scs]
+        for rep in range(3):
+            for sc, (dx, dw, db, dq) in zip(scs, bufs):
+                eng = sc.eng
+                eng.tune(pa.PA_TUNE_GEMM_PATH, 2)
+                assert eng.step_begin(sc.seq_ids, [1] * B) == 0, pa.last_error()
+                pa.check(eng.upload(), "upload")
+                pa.check(eng.qkv_append(0, dx.ptr, Cc, dw.ptr, db.ptr, dq.ptr, Cc), "qkv_append")
+            for sc, (dx, dw, db, dq) in zip(scs, bufs):
+                eng = sc.eng
+                eng.sync()
+                k, v = eng.read_pool_rows(0, eng.slot_mapping())
+                outs.append(np.concatenate([dq.download((B, Cc)), k, v], axis=1))
+                pa.check(eng.step_rollback(), "rollback")
+        for o in outs:
+            assert_close_gemm(o, want, "two streams")
+            assert np.array_equal(o.view(np.uint32), outs[0].view(np.uint32))
+    finally:
+        for sc in scs:
+            sc.close()
