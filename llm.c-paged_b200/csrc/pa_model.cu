@@ -70,26 +70,68 @@ __global__ void pa_embed_kernel(float* __restrict__ x, const int* __restrict__ t
     for (int i = threadIdx.x; i < C; i += blockDim.x) x[(size_t)s * C + i] = e[i] + ps[i];
 }
 
-// ---- layernorm_forward (paged_infer.c:49-89): one warp per row, the row held in registers -------
-__global__ void __launch_bounds__(128)
+// ---- layernorm_forward (paged_infer.c:49-89): one 128-thread CTA per row, the row held in registers ----
+// (a single warp per row leaves every latency of the load -> sum -> variance -> scale chain exposed: 5.6 us
+// for a 768-float row; four warps share it and meet twice through shared memory)
+constexpr int kLnThreads = 128, kLnPerThread = 32 * kLnMaxPerLane / kLnThreads;       // C <= 2048
+__device__ __forceinline__ void layernorm_row_block(float* __restrict__ o, const float* __restrict__ x, const float* __restrict__ weight,
+                                                    const float* __restrict__ bias, int C) {
+    __shared__ float red[2][kLnThreads / 32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float v[kLnPerThread];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kLnPerThread; ++i) {
+        const int c = tid + kLnThreads * i;
+        v[i] = c < C ? x[c] : 0.0f;
+        sum += v[i];
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) red[0][warp] = sum;
+    __syncthreads();
+    float tot = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kLnThreads / 32; ++w) tot += red[0][w];
+    const float m = tot / C;
+    float var = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kLnPerThread; ++i) {
+        const int c = tid + kLnThreads * i;
+        const float dlt = v[i] - m;
+        if (c < C) var += dlt * dlt;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+    if (lane == 0) red[1][warp] = var;
+    __syncthreads();
+    float totv = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kLnThreads / 32; ++w) totv += red[1][w];
+    const float s = 1.0f / sqrtf(totv / C + 1e-5f);              // eps, :56
+#pragma unroll
+    for (int i = 0; i < kLnPerThread; ++i) {
+        const int c = tid + kLnThreads * i;
+        if (c < C) o[c] = (s * (v[i] - m)) * weight[c] + bias[c];
+    }
+}
+__global__ void __launch_bounds__(kLnThreads)
 pa_layernorm_kernel(float* __restrict__ out, const float* __restrict__ inp, const float* __restrict__ weight,
                     const float* __restrict__ bias, int rows, int C) {
     pdl_launch_dependents();
     pdl_wait();
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    pa_layernorm_row<false>(out + (size_t)row * C, inp + (size_t)row * C, weight, bias, C, threadIdx.x & 31);
+    const int row = blockIdx.x;
+    layernorm_row_block(out + (size_t)row * C, inp + (size_t)row * C, weight, bias, C);
 }
 
 // the same over gathered input rows (final layernorm of each sequence's last position), compact output
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kLnThreads)
 pa_layernorm_rows_kernel(float* __restrict__ out, const float* __restrict__ inp, const int* __restrict__ rows_in,
                          const float* __restrict__ weight, const float* __restrict__ bias, int rows, int C) {
     pdl_launch_dependents();
     pdl_wait();
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    pa_layernorm_row<false>(out + (size_t)row * C, inp + (size_t)rows_in[row] * C, weight, bias, C, threadIdx.x & 31);
+    const int row = blockIdx.x;
+    layernorm_row_block(out + (size_t)row * C, inp + (size_t)rows_in[row] * C, weight, bias, C);
 }
 
 // ---- softmax_forward + sample_mult (paged_infer.c:259-286, :838-848) fused: one CTA per row of logits
@@ -375,10 +417,10 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
     if (coins) CU_CHECK(cudaMemcpyAsync(m->d_coins, m->h_coins, (size_t)nseq * sizeof(float), cudaMemcpyHostToDevice, s));
     CU_CHECK(pa_launch_pdl(pa_embed_kernel, dim3(ntok), dim3(256), 0, s, 1, m->x, (const int*)d_tok, (const int*)d_pos, m->wte, m->wpe, C));
     const int path = h->tune[PA_TUNE_GEMM_PATH];
-    const int ln_grid = (ntok + 3) / 4;
+    const int ln_grid = ntok;                      // one CTA per row
     long launches = 1;
     for (int l = 0; l < L; ++l) {
-        CU_CHECK(pa_launch_pdl(pa_layernorm_kernel, dim3(ln_grid), dim3(128), 0, s, 1, m->ln, (const float*)m->x, m->ln1w + (size_t)l * C, m->ln1b + (size_t)l * C, ntok, C));
+        CU_CHECK(pa_launch_pdl(pa_layernorm_kernel, dim3(ln_grid), dim3(kLnThreads), 0, s, 1, m->ln, (const float*)m->x, m->ln1w + (size_t)l * C, m->ln1b + (size_t)l * C, ntok, C));
         rc = pa_qkv_append(h, l, m->ln, C, m->qkvw + (size_t)l * 3 * C * C, m->qkvb + (size_t)l * 3 * C, m->q, C, s);
         if (rc != PA_OK) return rc;
         rc = max_q == 1 ? pa_decode(h, l, m->q, C, m->atty, C, s) : pa_prefill(h, l, m->q, C, m->atty, C, s);
@@ -386,7 +428,7 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
         // x += atty . attprojw^T + attprojb      (matmul_forward + residual_forward, :716-717)
         rc = pa_cu_linear(m->atty, C, m->attprojw + (size_t)l * C * C, m->attprojb + (size_t)l * C, m->x, C, ntok, C, C, m->x, C, 0, path, s);
         if (rc != PA_OK) return rc;
-        CU_CHECK(pa_launch_pdl(pa_layernorm_kernel, dim3(ln_grid), dim3(128), 0, s, 1, m->ln, (const float*)m->x, m->ln2w + (size_t)l * C, m->ln2b + (size_t)l * C, ntok, C));
+        CU_CHECK(pa_launch_pdl(pa_layernorm_kernel, dim3(ln_grid), dim3(kLnThreads), 0, s, 1, m->ln, (const float*)m->x, m->ln2w + (size_t)l * C, m->ln2b + (size_t)l * C, ntok, C));
         // fch = gelu(ln . fcw^T + fcb)           (:719-720)
         rc = pa_cu_linear(m->ln, C, m->fcw + (size_t)l * 4 * C * C, m->fcb + (size_t)l * 4 * C, m->fch, 4 * C, ntok, 4 * C, C, nullptr, 0, 1, path, s);
         if (rc != PA_OK) return rc;
@@ -396,7 +438,7 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
         launches += 5;
     }
     // only each sequence's last new position feeds the LM head: final layernorm over the gathered rows
-    CU_CHECK(pa_launch_pdl(pa_layernorm_rows_kernel, dim3((nseq + 3) / 4), dim3(128), 0, s, 1, m->ln, (const float*)m->x, (const int*)d_last, m->lnfw, m->lnfb, nseq, C));
+    CU_CHECK(pa_launch_pdl(pa_layernorm_rows_kernel, dim3(nseq), dim3(kLnThreads), 0, s, 1, m->ln, (const float*)m->x, (const int*)d_last, m->lnfw, m->lnfb, nseq, C));
     rc = pa_cu_linear(m->ln, C, m->wte, nullptr, m->logits, m->Vp, nseq, V, C, nullptr, 0, 0, path, s);       // logits = lnf . wte^T (:726)
     if (rc != PA_OK) return rc;
     CU_CHECK(pa_launch_pdl(pa_sample_kernel, dim3(nseq), dim3(kSampleThreads), 0, s, 1, (const float*)m->logits, m->Vp, V, (const float*)(coins ? m->d_coins : nullptr), d_next));

@@ -1,53 +1,15 @@
 /*
  * pa_model_dev.cuh -- device code shared by the per-op kernels of pa_model.cu and the persistent
- * small-batch step kernel of pa_model_mega.cu: one row of layernorm_forward on a warp, the GELU of
- * gelu_forward, and softmax_forward + sample_mult for one row of logits on a CTA.  Same statements
- * in both users, so the two routes through a decode step agree to the last bit in these ops.
+ * small-batch step kernel of pa_model_mega.cu: the GELU of gelu_forward and softmax_forward +
+ * sample_mult for one row of logits on a CTA.  Same statements in both users, so the two routes
+ * through a decode step agree to the last bit in these ops.
  */
 #pragma once
 #include <cuda_runtime.h>
 
 #include <cstdint>
 
-constexpr int kLnMaxPerLane = 64;          // layernorm keeps a row in registers: C <= 2048
-
-// kCg: read through L2 only (ld.global.cg) -- for rows another CTA of the SAME grid wrote earlier
-template <bool kCg>
-static __device__ __forceinline__ float pa_ld(const float* p) { return kCg ? __ldcg(p) : *p; }
-
-// layernorm_forward (paged_infer.c:49-89) for ONE row on one warp: mean, variance around the mean,
-// rstd = 1/sqrtf(var + 1e-5f), o = (rstd * (x - mean)) * weight + bias.  `o`, `weight` and `bias` may be shared memory.
-// kPerLane * 32 >= C bounds the registers (the loops are fully unrolled and predicated).
-template <bool kCg, int kPerLane = kLnMaxPerLane>
-static __device__ __forceinline__ void pa_layernorm_row(float* o, const float* x, const float* weight, const float* bias, int C, int lane) {
-    float v[kPerLane];
-    float sum = 0.0f;
-#pragma unroll
-    for (int i = 0; i < kPerLane; ++i) {
-        const int c = lane + 32 * i;
-        v[i] = c < C ? pa_ld<kCg>(x + c) : 0.0f;
-        sum += v[i];
-    }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    const float m = sum / C;
-    float var = 0.0f;
-#pragma unroll
-    for (int i = 0; i < kPerLane; ++i) {
-        const int c = lane + 32 * i;
-        const float dlt = v[i] - m;
-        if (c < C) var += dlt * dlt;
-    }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
-    var = var / C;
-    const float s = 1.0f / sqrtf(var + 1e-5f);                   // eps, :56
-#pragma unroll
-    for (int i = 0; i < kPerLane; ++i) {
-        const int c = lane + 32 * i;
-        if (c < C) o[c] = (s * (v[i] - m)) * weight[c] + bias[c];
-    }
-}
+constexpr int kLnMaxPerLane = 64;          // the layernorm kernels keep a row in registers: C <= 32 * 64 = 2048
 
 // gelu_forward, paged_infer.c:243-251 (tanh form)
 static __device__ __forceinline__ float pa_gelu(float v) {
