@@ -213,7 +213,7 @@ def reference_arm(args, w, quiet=False):
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "tokens_per_s": 1.0 / t}
     if not quiet:
-        print(json.dumps(line))
+        emit(line)
     return line
 
 
@@ -259,7 +259,26 @@ def cpu_baseline_sample(w, budget_s=15.0):
 
 
 # ------------------------------------------------------------------------------------ our arm
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # libraries write to stdout too (NCCL prints its version there on the first collective): everything
+    # but the JSON line goes to stderr, so stdout carries exactly one line
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -582,7 +601,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "model": model_info}
     if model_info and "ms_per_step" in model_info and model_info["gpu_launches_per_step"] > 1:
         model_info["attention_share_of_step"] = kms * L / model_info["ms_per_step"]
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
