@@ -572,7 +572,10 @@ def main():
             traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "pa_decode_stream_kernel<64,16>" + ("" if args.no_fuse else " (KV append fused)"), "achieved": achieved, "peak": peak,
+    last_ctas = lib.pa_tune_get(eng.h, 12)       # 0: the launch did not go through the stream kernel
+    kname = (f"pa_decode_stream_kernel<{hs},{bs}>" if last_ctas else
+             "pa_decode_small_kernel (one CTA per sequence and head; chosen below ~98 k token-heads, latency-bound)")
+    roofline = {"bound": "hbm", "kernel": kname + ("" if args.no_fuse else " (KV append fused)"), "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kbytes, "avg_launch_ms": kms, "launches_timed": len(dec_ms) * L,
                 "timing": f"CUDA events around the {L} back-to-back per-layer launches of a step, / {L}",

@@ -294,7 +294,7 @@ PA_API int pa_sm_count(pa_handle* h);
 
 /* ---- tuning knobs (benchmarks/tests select a kernel or a tile shape) ----------------------- */
 typedef enum pa_tune_key {
-    PA_TUNE_DECODE_PATH = 0,   /* 0 auto, 1 stream (TMA/mbarrier) kernel, 2 generic SIMT kernel */
+    PA_TUNE_DECODE_PATH = 0,   /* 0 auto, 1 stream (TMA/mbarrier) kernel, 2 generic SIMT kernel, 3 small-batch kernel (one CTA per sequence and head; auto below a measured amount of KV) */
     PA_TUNE_HEADS_PER_TILE = 1,/* 0 auto */
     PA_TUNE_STAGES = 2,        /* 0 auto */
     PA_TUNE_GRID = 3,          /* 0 auto (CTAs) */

@@ -24,10 +24,12 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "pa_internal.h"
+#include "pa_pdl.cuh"
 #include "pa_ptx.cuh"
 
 #define CU_CHECK(call)                                                                         \
@@ -870,6 +872,133 @@ int launch_rows(pa_handle* h, int layer, const float* q, int q_stride, float* ou
     return PA_OK;
 }
 
+// =============================================================================================
+// decode, small work: one CTA per (sequence, head)
+// =============================================================================================
+// A handful of sequences (the reference's own decode loop is batch 1) is a latency problem, not a
+// bandwidth one: the stream kernel's persistent grid, page scheduler and cross-CTA merge cost ~10 us
+// before the first byte matters.  Here the 16 warps of ONE CTA share a (sequence, head): chunks of
+// ceil(len / 16) tokens, hs/4 lanes per token (16-byte loads through the block table), online
+// softmax from the reference's -10000 start, the 16 partial (o, m, l) merged through shared memory
+// in chunk order.  With k_new/v_new the step's new token is read from there and its head slice is
+// stored to the page slot by this CTA (fused append).  Same arithmetic as the persistent step
+// kernel's attention (pa_model_mega.cu).
+struct SmallParams {
+    float* pool_k;
+    float* pool_v;
+    const float* q;
+    const float* k_new;      // fused append (or NULL)
+    const float* v_new;
+    float* out;
+    const int* kv_end;
+    const int* kv_start;
+    const int* slots;        // [B] slot of the new token (fused append)
+    const int* table;
+    int C, NH, hs, bs, tstride, q_stride, out_stride, new_stride;
+    float scale;
+};
+constexpr int kSmallWarps = 16;
+template <int LPT>
+__global__ void __launch_bounds__(kSmallWarps * 32)
+pa_decode_small_kernel(const SmallParams p) {
+    constexpr int TPI = 32 / LPT, UN = 4;
+    __shared__ __align__(16) float ps[kSmallWarps][LPT * 4 + 4];
+    pdl_launch_dependents();
+    pdl_wait();               // q, the step tables and the pool may belong to the previous kernel of the stream
+    const int h = blockIdx.x, s = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / LPT, li = lane % LPT;
+    const int hs = p.hs, C = p.C;
+    const int first = p.kv_start[s], last = p.kv_end[s];
+    const int chunk = (last - first + kSmallWarps - 1) / kSmallWarps;
+    const int t0 = first + warp * chunk, t1 = min(last, t0 + chunk);
+    const int* tbl = p.table + (size_t)s * p.tstride;
+    const float4 q4 = *(reinterpret_cast<const float4*>(p.q + (size_t)s * p.q_stride + h * hs) + li);
+    // the new token's K/V head slice: from the step's rows, and to its page slot
+    const float4* kn = p.k_new ? reinterpret_cast<const float4*>(p.k_new + (size_t)s * p.new_stride + h * hs) : nullptr;
+    const float4* vn = p.k_new ? reinterpret_cast<const float4*>(p.v_new + (size_t)s * p.new_stride + h * hs) : nullptr;
+    if (kn && threadIdx.x < LPT) {
+        const size_t off = (size_t)p.slots[s] * C + h * hs;
+        reinterpret_cast<float4*>(p.pool_k + off)[threadIdx.x] = kn[threadIdx.x];
+        reinterpret_cast<float4*>(p.pool_v + off)[threadIdx.x] = vn[threadIdx.x];
+    }
+    float m_run = kMaxInit, l_run = 0.0f;
+    float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int tb = t0; tb < t1; tb += TPI * UN) {
+        float4 k4[UN], v4[UN];
+#pragma unroll
+        for (int i = 0; i < UN; ++i) {
+            const int t = tb + i * TPI + sub;
+            if (t < t1) {
+                if (kn && t == last - 1) { k4[i] = kn[li]; v4[i] = vn[li]; }
+                else {
+                    const size_t off = ((size_t)tbl[t / p.bs] * p.bs + (t % p.bs)) * C + h * hs;
+                    k4[i] = __ldg(reinterpret_cast<const float4*>(p.pool_k + off) + li);
+                    v4[i] = __ldg(reinterpret_cast<const float4*>(p.pool_v + off) + li);
+                }
+            } else {
+                k4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                v4[i] = k4[i];
+            }
+        }
+        float sc[UN];
+        float m_new = m_run;
+#pragma unroll
+        for (int i = 0; i < UN; ++i) {
+            float dot = fmaf(q4.w, k4[i].w, fmaf(q4.z, k4[i].z, fmaf(q4.y, k4[i].y, q4.x * k4[i].x)));
+#pragma unroll
+            for (int d = LPT / 2; d >= 1; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
+            sc[i] = (tb + i * TPI + sub < t1) ? dot * p.scale : -INFINITY;
+            m_new = fmaxf(m_new, sc[i]);
+        }
+        const float alpha = expf(m_run - m_new);
+        l_run *= alpha; o4.x *= alpha; o4.y *= alpha; o4.z *= alpha; o4.w *= alpha;
+        m_run = m_new;
+#pragma unroll
+        for (int i = 0; i < UN; ++i) {
+            const float e = expf(sc[i] - m_new);                    // exp(-inf) = 0 for the padding
+            l_run += e;
+            o4.x = fmaf(e, v4[i].x, o4.x); o4.y = fmaf(e, v4[i].y, o4.y); o4.z = fmaf(e, v4[i].z, o4.z); o4.w = fmaf(e, v4[i].w, o4.w);
+        }
+    }
+    if (TPI > 1) {                                                  // the token sub-groups of the warp -> one partial
+#pragma unroll
+        for (int d = LPT; d < 32; d <<= 1) {
+            const float m_o = __shfl_xor_sync(0xffffffffu, m_run, d), l_o = __shfl_xor_sync(0xffffffffu, l_run, d);
+            float4 o_o;
+            o_o.x = __shfl_xor_sync(0xffffffffu, o4.x, d); o_o.y = __shfl_xor_sync(0xffffffffu, o4.y, d);
+            o_o.z = __shfl_xor_sync(0xffffffffu, o4.z, d); o_o.w = __shfl_xor_sync(0xffffffffu, o4.w, d);
+            const float m_t = fmaxf(m_run, m_o);
+            const float wa = expf(m_run - m_t), wb = expf(m_o - m_t);
+            // (lower sub-group first in both partners, so they agree bit for bit)
+            const bool lo = (lane & d) == 0;
+            const float la = lo ? l_run : l_o, lb = lo ? l_o : l_run, xa = lo ? wa : wb, xb = lo ? wb : wa;
+            l_run = fmaf(la, xa, lb * xb);
+            o4.x = fmaf(lo ? o4.x : o_o.x, xa, (lo ? o_o.x : o4.x) * xb); o4.y = fmaf(lo ? o4.y : o_o.y, xa, (lo ? o_o.y : o4.y) * xb);
+            o4.z = fmaf(lo ? o4.z : o_o.z, xa, (lo ? o_o.z : o4.z) * xb); o4.w = fmaf(lo ? o4.w : o_o.w, xa, (lo ? o_o.w : o4.w) * xb);
+            m_run = m_t;
+        }
+    }
+    if (sub == 0) {
+        reinterpret_cast<float4*>(ps[warp])[li] = o4;
+        if (li == 0) { ps[warp][hs] = m_run; ps[warp][hs + 1] = l_run; }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < hs) {
+        const int d = threadIdx.x;
+        float m_tot = kMaxInit;
+#pragma unroll
+        for (int w = 0; w < kSmallWarps; ++w) m_tot = fmaxf(m_tot, ps[w][hs]);
+        float l_tot = 0.0f, o = 0.0f;
+#pragma unroll 4
+        for (int w = 0; w < kSmallWarps; ++w) {                     // chunk order
+            const float wgt = expf(ps[w][hs] - m_tot);
+            l_tot = fmaf(ps[w][hs + 1], wgt, l_tot);
+            o = fmaf(ps[w][d], wgt, o);
+        }
+        p.out[(size_t)s * p.out_stride + h * hs + d] = o * ((l_tot == 0.0f) ? 0.0f : 1.0f / l_tot);     // :213
+    }
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -932,8 +1061,34 @@ static int decode_impl(pa_handle* h, int layer, const float* q, int q_stride, co
         pa_set_error("%s: stream kernel needs head_dim 64/128, block_size 4/8/16/32 and 16-byte aligned rows", who);
         return PA_ERR_UNSUPPORTED;
     }
+    // small work: one CTA per (sequence, head) (path 3; chosen by itself below a measured amount of KV)
+    const bool small_ok = (hs == 32 || hs == 64 || hs == 128) && (q_stride % 4 == 0) && (h->C % 4 == 0) && aligned16(q) &&
+                          (!fused || ((new_stride % 4 == 0) && aligned16(k_new) && aligned16(v_new))) && L.nseq <= 65535;
+    if (path == 3 && !small_ok) {
+        pa_set_error("%s: the small-batch kernel needs head_dim 32/64/128 and 16-byte aligned rows", who);
+        return PA_ERR_UNSUPPORTED;
+    }
+    static const long long small_max = getenv("PA_DECODE_SMALL_MAX") ? atoll(getenv("PA_DECODE_SMALL_MAX")) : 8192;       // token-heads / 12: measured crossover ~98 k (tools/decode_small_sweep.py)
+    if (small_ok && (path == 3 || (path == 0 && (long long)L.total_pages * bs * h->cfg.n_heads <= small_max * 12))) {
+        SmallParams sp;
+        sp.pool_k = h->pool_k + (size_t)layer * h->layer_stride;
+        sp.pool_v = h->pool_v + (size_t)layer * h->layer_stride;
+        sp.q = q; sp.k_new = k_new; sp.v_new = v_new; sp.out = out;
+        sp.kv_end = h->d_step + L.off_kv_end; sp.kv_start = h->d_step + L.off_kv_start;
+        sp.slots = h->d_step + L.off_slot; sp.table = h->d_step + L.off_table;
+        sp.C = h->C; sp.NH = h->cfg.n_heads; sp.hs = hs; sp.bs = bs; sp.tstride = L.tstride;
+        sp.q_stride = q_stride; sp.out_stride = out_stride; sp.new_stride = new_stride;
+        sp.scale = (float)(1.0 / sqrtf((float)hs));          // paged_infer.c:174
+        const dim3 grid(h->cfg.n_heads, L.nseq), block(kSmallWarps * 32);
+        if (hs == 64) CU_CHECK(pa_launch_pdl(pa_decode_small_kernel<16>, grid, block, 0, s, 1, sp));
+        else if (hs == 128) CU_CHECK(pa_launch_pdl(pa_decode_small_kernel<32>, grid, block, 0, s, 1, sp));
+        else CU_CHECK(pa_launch_pdl(pa_decode_small_kernel<8>, grid, block, 0, s, 1, sp));
+        h->launches++;
+        h->tune[PA_TUNE_LAST_HPG] = h->tune[PA_TUNE_LAST_STAGES] = h->tune[PA_TUNE_LAST_GRID] = 0;
+        return PA_OK;
+    }
     DecodePlan plan;
-    if (path != 2 && stream_ok && plan_decode(h, L.total_pages, L.nseq, &plan)) {
+    if (path != 2 && path != 3 && stream_ok && plan_decode(h, L.total_pages, L.nseq, &plan)) {
         DecodeParams dp;
         dp.pool_k = h->pool_k + (size_t)layer * h->layer_stride;
         dp.pool_v = h->pool_v + (size_t)layer * h->layer_stride;

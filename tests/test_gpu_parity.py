@@ -77,7 +77,7 @@ DECODE_CASES = [
 
 
 @pytest.mark.parametrize("NH,hs,bs,ctx,shuffle", DECODE_CASES)
-@pytest.mark.parametrize("path", [1, 2], ids=["stream", "generic"])
+@pytest.mark.parametrize("path", [1, 2, 3], ids=["stream", "generic", "small-batch"])
 def test_decode_matches_oracle(NH, hs, bs, ctx, shuffle, path):
     sc = Scenario(NH, hs, bs, ctx, shuffle=shuffle, seed=77)
     try:
@@ -121,11 +121,16 @@ def test_decode_dynamic_ranges(static_pct, dyn_units, grid):
         sc.close()
 
 
+@pytest.mark.parametrize("path", [0, 1, 3], ids=["auto", "stream", "small-batch"])
 @pytest.mark.parametrize("NH,hs,bs,hpg", [(12, 64, 16, 0), (12, 64, 16, 3), (25, 64, 16, 0), (4, 128, 32, 0), (12, 64, 8, 4),
                                           (2, 5, 2, 0)])
-def test_decode_append_fused(NH, hs, bs, hpg):
+def test_decode_append_fused(NH, hs, bs, hpg, path):
     """pa_decode_append = pa_append + pa_decode in one launch: the new token's K/V row is read
-    from the step's k/v rows, used, and stored to its slot (bit-exact copy); next step sees it."""
+    from the step's k/v rows, used, and stored to its slot (bit-exact copy); next step sees it.
+    Stream kernel, small-batch kernel (one CTA per sequence and head) and the automatic choice
+    (head_dim 5: append kernel + generic rows kernel)."""
+    if path != 0 and hs not in (64, 128):
+        pytest.skip("stream / small-batch kernels: head_dim 64/128")
     Cc = NH * hs
     ctx0 = [0, 1, 15, 16, 17, 31, 32, 100, 255, 256, 700]      # page boundaries on both sides
     B = len(ctx0)
@@ -133,6 +138,7 @@ def test_decode_append_fused(NH, hs, bs, hpg):
     try:
         eng, orc = sc.eng, sc.orc
         eng.tune(pa.PA_TUNE_HEADS_PER_TILE, hpg)
+        eng.tune(pa.PA_TUNE_DECODE_PATH, path)
         for step in range(4):
             qkv = oa.normal((B, 3 * Cc), seed=300 + step)
             assert eng.step_begin(sc.seq_ids, [1] * B) == 0, pa.last_error()
@@ -164,7 +170,7 @@ def test_decode_sliding_window():
         q = oa.normal((sc.B, sc.C), seed=2)
         for kv_start in ([0, 0, 0, 0], [1, 16, 32, 17], [99, 63, 0, 255], [37, 5, 31, 499]):
             want = sc.oracle_decode(q, kv_start=kv_start)
-            for path in (1, 2):
+            for path in (1, 2, 3):
                 got = sc.decode(q, kv_start=kv_start, path=path)
                 assert_close(got, want, f"window {kv_start} path={path}")
     finally:
@@ -178,7 +184,7 @@ def test_decode_large_logits_reference_value_range():
     try:
         q = oa.uniform((sc.B, sc.C), 0.0, 100.0, seed=4)
         want, truth = sc.oracle_decode(q), sc.oracle_decode_f64(q)
-        for path in (1, 2):
+        for path in (1, 2, 3):
             assert_close_illconditioned(sc.decode(q, path=path), want, truth, f"large logits path={path}")
     finally:
         sc.close()
