@@ -478,7 +478,7 @@ int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int row_stride
 // small cache of encoded maps: the same weight matrices and activation buffers come back every step
 struct MapKey { const void* ptr; int rows, K, stride, box_rows; };
 struct MapCache {
-    static constexpr int N = 32;
+    static constexpr int N = 256;      // a 12-layer model alone has 49 weight matrices x up to two tile widths
     MapKey key[N];
     CUtensorMap map[N];
     int used = 0, next = 0;
@@ -539,8 +539,7 @@ bool get_split_ws(int dev, cudaStream_t s, GemmTcParams* p, bool* cooperative) {
     }
     p->ws = w->ws;
     p->ws_cnt = w->cnt + w->parity * kWsMaxCtas;
-    p->ws_cnt_next = w->cnt + (1 - w->parity) * kWsMaxCtas;
-    w->parity ^= 1;
+    p->ws_cnt_next = w->cnt + (1 - w->parity) * kWsMaxCtas;      // (the sets swap in split_ws_launched, once the launch went through)
     // The CTAs of a workspace split wait for each other, which is safe while the grid has the device to itself
     // (one stream of projections per device -- the handle's).  Once a second stream of the same device has run
     // such launches, two grids could starve each other of SMs: from then on the launches are cooperative (the
@@ -566,6 +565,13 @@ extern "C" void pa_cu_gemm_stream_released(int dev, void* stream) {
     }
 }
 namespace {
+
+// the launch that was handed the current counter set is in the stream: the next one takes the other set
+void split_ws_launched(int dev, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_ws.mu);
+    for (int i = 0; i < g_ws.used; ++i)
+        if (g_ws.e[i].dev == dev && g_ws.e[i].stream == s) { g_ws.e[i].parity ^= 1; return; }
+}
 
 template <int BN>
 int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams& p, int n_split, bool cluster, bool cooperative, cudaStream_t s) {
@@ -664,6 +670,7 @@ extern "C" int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const
     cooperative = cooperative && n_split > 1 && !cluster;
     rc = BN == 128 ? launch_gemm<128>(tx, tw, p, n_split, false, cooperative, (cudaStream_t)stream)
                    : launch_gemm<64>(tx, tw, p, n_split, cluster, cooperative, (cudaStream_t)stream);
+    if (rc == PA_OK && p.ws) split_ws_launched(dev, (cudaStream_t)stream);
     if (p.dbg) {      // ns since kernel entry: TMEM ready, first slab landed, splitter done, MMAs done, reduction done, stores issued
         unsigned long long hst[8];
         cudaDeviceSynchronize();
