@@ -141,7 +141,7 @@ int pa_cu_linear(const float* x, int x_stride, const float* w, const float* bias
  * persistent cooperative kernel (every op of gpt2_forward for one new token per sequence) ------- */
 #define PA_MEGA_MAX_SEQS 8
 #define PA_MEGA_WARPS_PER_SM 16
-#define PA_MEGA_AUTO_SEQS 8      /* chosen by itself up to this many sequences (measured against the chain of per-op kernels: ahead up to 8 at short contexts, level at 8 x 1024) */
+#define PA_MEGA_AUTO_SEQS 6      /* chosen by itself up to this many sequences (measured against the chain of per-op kernels: 0.45 vs 0.75 ms at 2, 0.55 vs 0.85 at 4, 0.75 vs 0.78 at 6, 0.83 vs 0.79 at 8) */
 typedef struct pa_mega_args {
     /* parameters, checkpoint order (paged_infer.c:441-488) */
     const float *wte, *wpe, *ln1w, *ln1b, *qkvw, *qkvb, *attprojw, *attprojb, *ln2w, *ln2b, *fcw, *fcb, *fcprojw,
