@@ -89,6 +89,19 @@ def test_decode_matches_oracle(NH, hs, bs, ctx, shuffle, path):
         sc.close()
 
 
+def test_decode_small_batch_kernel_head_dim_32():
+    """head_dim 32 (8 lanes per token, four tokens per warp step): outside the stream kernel's domain, inside
+    the small-batch kernel's -- automatic choice, forced small-batch kernel and generic kernel agree with the oracle."""
+    sc = Scenario(4, 32, 16, [5, 100, 33, 1, 64, 257], shuffle=True, seed=21)
+    try:
+        q = oa.normal((sc.B, sc.C), seed=22)
+        want = sc.oracle_decode(q)
+        for path in (0, 3, 2):
+            assert_close(sc.decode(q, path=path), want, f"hs32 path={path}")
+    finally:
+        sc.close()
+
+
 @pytest.mark.parametrize("hpg,stages,grid", [(1, 0, 0), (2, 2, 0), (3, 3, 7), (4, 0, 1), (6, 0, 0), (12, 2, 0),
                                              (12, 4, 148), (12, 0, 1184), (0, 0, 5)])
 def test_decode_tile_shapes_and_splits(hpg, stages, grid):
