@@ -168,7 +168,6 @@ typedef struct pa_mega_args {
     unsigned bar_base;
     int sm_count;
     unsigned long long* dbg;            /* optional timeline of CTA 0 (PA_MEGA_DEBUG=1), NULL normally */
-    int exp_flags;                      /* timing experiments (PA_MEGA_EXP), 0 normally */
 } pa_mega_args;
 /* bytes of dynamic shared memory the kernel needs for this geometry, or 0 when it is outside its domain */
 size_t pa_cu_model_mega_smem(int M, int C, int hs, int block_size);

@@ -76,17 +76,16 @@ __device__ __forceinline__ void grid_wait(unsigned* bar, unsigned base, unsigned
     ++passed;
 }
 
-// The kernel body is deliberately COMPACT: every phase runs its code once per layer with eight warps
-// per SM, so the instruction stream itself has to be fetched every time -- a first version with one
-// inlined GEMV per call site and feature count (47 k instructions, 755 KB) spent ~10 us per phase on
-// instruction fetch alone.  Hence ONE loop over the projection phases with one copy of each routine,
-// run-time feature counts, and the batch bound as a template parameter.
+// The kernel body is deliberately COMPACT: every phase runs its code once per layer on a few warps
+// per scheduler, so instruction count is time -- a first version with one inlined GEMV per call site
+// and feature count (47 k instructions, 755 KB) spent ~10 us per phase.  Hence ONE loop over the
+// projection phases with one copy of each routine, and the batch bound as a template parameter.
 
 // ---- projections: out(m, n) for the M rows in shared memory and every feature n of w (N, K) -------
 // A warp pass covers `feat` (1, 2 or 4: the fewest that cover N in one pass of the grid's warps)
 // output features; its lanes interleave the 16-byte chunks of those weight rows and keep kLoads
-// loads in flight.  Load j of a batch belongs to feature j % feat and chunk j / feat; it always
-// accumulates into slot j % 4, and the slots of a feature are folded at the end.
+// loads in flight.  Load u * feat + f of a batch is chunk u of feature f; a feature's chunks
+// accumulate into 4 / feat slots (independent FMA chains) that are folded at the end.
 __device__ __forceinline__ int pick_feat_shift(int N, int K) {
     const int nw = gridDim.x * kWarps;
     int sh = N <= nw ? 0 : (N <= 2 * nw ? 1 : 2);
@@ -94,9 +93,9 @@ __device__ __forceinline__ int pick_feat_shift(int N, int K) {
     while (sh > 0 && (kLoads >> sh) * 128 < K) --sh;
     return sh;
 }
-// The weight loads of a warp's FIRST batch are issued BEFORE the grid barrier in front of the phase:
-// weights never depend on another CTA, so they stream in from HBM while the grid meets.
-// read-only, read-once: straight from L2, no L1 line to allocate
+// The weight loads of a warp's FIRST batch are issued between arriving at the grid barrier in front of
+// the phase and waiting on it: weights never depend on another CTA, so they stream in from HBM while
+// the grid meets.  Read-only, read-once: straight from L2, no L1 line to allocate.
 __device__ __forceinline__ float4 ld_weight(const float4* p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -118,12 +117,7 @@ __device__ __forceinline__ void gemv_issue_t(float4 (&wv)[kLoads], const float* 
             wv[u * FEAT + f] = (cb + 32 * u < K4 && n0 < N) ? ld_weight(row + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
-__device__ __forceinline__ void gemv_issue(float4 (&wv)[kLoads], const float* __restrict__ w, int N, int K, int sh, int n0, int cb, int noload = 0) {
-    if (noload) {
-#pragma unroll
-        for (int j = 0; j < kLoads; ++j) wv[j] = make_float4(1.f, 1.f, 1.f, 1.f);
-        return;
-    }
+__device__ __forceinline__ void gemv_issue(float4 (&wv)[kLoads], const float* __restrict__ w, int N, int K, int sh, int n0, int cb) {
     if (sh == 0) gemv_issue_t<0>(wv, w, N, K, n0, cb);
     else if (sh == 1) gemv_issue_t<1>(wv, w, N, K, n0, cb);
     else gemv_issue_t<2>(wv, w, N, K, n0, cb);
@@ -398,14 +392,6 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
     };
 #define GRID_ARRIVE() do { stamp(); grid_arrive(a.bar); } while (0)
 #define GRID_WAIT() do { grid_wait(a.bar, a.bar_base, passed); stamp(); } while (0)
-    int n_sub = 0;
-    auto substamp = [&](int ph) {   // finer timeline of layer 1's four projection phases
-        if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && (ph >> 2) == 1) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            a.dbg[2048 + n_sub++] = t;
-        }
-    };
     float4 wv[kLoads];               // a warp's first batch of weight loads for the NEXT projection, in flight across barriers
     // ... and the bias of the output this lane will finish in that first pass (lane (f, m) -> feature n0 + f)
     auto bias_issue = [&](const PhaseDesc& pd, int shift) {
@@ -428,7 +414,7 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
     GRID_ARRIVE();
     PhaseDesc d = phase_desc(a, 0);
     int sh = pick_feat_shift(d.N, d.K);
-    gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane, a.exp_flags & 1);
+    gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane);
     float bias_first = bias_issue(d, sh);
     ln_params_issue(a.ln1w, a.ln1b);
     GRID_WAIT();
@@ -439,7 +425,6 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
         float* pool_k = a.pool_k + (size_t)l * a.layer_stride;
         float* pool_v = a.pool_v + (size_t)l * a.layer_stride;
         const int N = d.N, K = d.K, K4 = K >> 2, feat = 1 << sh;
-        substamp(ph);
 
         // ---- the phase's input rows -> shared memory: layernorm of the residual stream (ln1 :703, ln2 :718,
         // lnf :724), or the previous op's output as it is (atty, fch)
@@ -491,7 +476,6 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
             }
         }
         __syncthreads();
-        substamp(ph);
 
         // ---- the projection (matmul_forward :92-114 on M rows): weight-streaming GEMV ------------------
         {
@@ -521,20 +505,13 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
                 for (int mm = 0; mm < MAXM; ++mm)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[mm][q] = 0.0f;
-                substamp(ph);
                 for (int cb = lane; cb < K4; cb += 32 * (kLoads >> sh)) {
                     if (!have) gemv_issue(wv, d.w, N, K, sh, n0, cb);
                     have = false;
-                    const int reps = (a.exp_flags & 2) ? 3 : 1;          // experiment: the same code again (instruction cache warm)
-#pragma unroll 1
-                    for (int rep = 0; rep < reps; ++rep) {
-                        if (sh == 0) gemv_fma_t<0, MAXM>(wv, xs4, cb, K4, M, acc);
-                        else if (sh == 1) gemv_fma_t<1, MAXM>(wv, xs4, cb, K4, M, acc);
-                        else gemv_fma_t<2, MAXM>(wv, xs4, cb, K4, M, acc);
-                        if (reps > 1) substamp(ph);
-                    }
+                    if (sh == 0) gemv_fma_t<0, MAXM>(wv, xs4, cb, K4, M, acc);
+                    else if (sh == 1) gemv_fma_t<1, MAXM>(wv, xs4, cb, K4, M, acc);
+                    else gemv_fma_t<2, MAXM>(wv, xs4, cb, K4, M, acc);
                 }
-                substamp(ph);
                 float v = 0.0f;
 #pragma unroll
                 for (int mm = 0; mm < MAXM; ++mm) {
@@ -552,7 +529,6 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
                         }
                     }
                 }
-                substamp(ph);
                 if (mine) {
                     const int n = n0 + f;
                     v += bv;
@@ -570,7 +546,6 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
             }
         }
 
-        substamp(ph);
         // ---- paged attention between the QKV projection and attproj (:713-715) -------------------------
         if (kind == PH_QKV) {
             GRID_ARRIVE();
@@ -589,7 +564,7 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
         if (ph + 1 < n_phases) {
             d = phase_desc(a, ph + 1);
             sh = pick_feat_shift(d.N, d.K);
-            gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane, a.exp_flags & 1);
+            gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane);
             bias_first = bias_issue(d, sh);
             // (this phase read ln_ws/ln_bs before its __syncthreads at the latest; nobody reads them again before the barrier)
             if (kind == PH_ATTPROJ) ln_params_issue(a.ln2w + (size_t)l * C, a.ln2b + (size_t)l * C);
@@ -650,7 +625,6 @@ extern "C" int pa_cu_model_mega_step(const pa_mega_args* a, void* stream) {
     const bool dbg = getenv("PA_MEGA_DEBUG") != nullptr;
     if (dbg && !d_dbg) CU_CHECK(cudaMalloc((void**)&d_dbg, 4096 * sizeof(unsigned long long)));
     args.dbg = dbg ? d_dbg : nullptr;
-    args.exp_flags = getenv("PA_MEGA_EXP") ? atoi(getenv("PA_MEGA_EXP")) : 0;      // timing experiments only (wrong results)
     CU_CHECK(cudaLaunchCooperativeKernel((const void*)fn, dim3(a->sm_count), dim3(kThreads), kargs, smem, s));
     if (dbg) {        // per phase (averaged over the layers): ns of work before the barrier, ns inside the barrier
         static unsigned long long hst[4096];
@@ -667,17 +641,6 @@ extern "C" int pa_cu_model_mega_step(const pa_mega_args* a, void* stream) {
                 work[p] += (double)(hst[2 * b] - hst[2 * b - 1]);
                 wait[p] += (double)(hst[2 * b + 1] - hst[2 * b]);
             }
-        if (args.exp_flags & 2) {
-            fprintf(stderr, "mega sub raw:");
-            for (int i = 1; i < 40; ++i) fprintf(stderr, " %lld", (long long)(hst[2048 + i] - hst[2048 + i - 1]));
-            fprintf(stderr, "\n");
-        }
-        fprintf(stderr, "mega sub (layer 1: phase start, input ready, loop entered, fma done, reduced, stored):");
-        for (int p = 0; p < 4; ++p) {
-            fprintf(stderr, " |");
-            for (int i = 1; i < 6; ++i) fprintf(stderr, " %lld", (long long)(hst[2048 + 6 * p + i] - hst[2048 + 6 * p]));
-        }
-        fprintf(stderr, "\n");
         fprintf(stderr, "mega dbg: embed barrier %lld ns;", (long long)(hst[1] - hst[0]));
         for (int p = 0; p < per_layer; ++p) fprintf(stderr, " %s %.0f+%.0f", names[p], work[p] / a->L, wait[p] / a->L);
         fprintf(stderr, "; lm head %lld+%lld; total %lld ns\n", (long long)(hst[2 * (n - 1)] - hst[2 * (n - 1) - 1]),
