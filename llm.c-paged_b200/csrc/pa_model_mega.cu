@@ -93,6 +93,12 @@ __device__ __forceinline__ int pick_feat_shift(int N, int K) {
     while (sh > 0 && (kLoads >> sh) * 128 < K) --sh;
     return sh;
 }
+// K split over a pair of neighbouring warps: when a single feature per warp would need more than one batch
+// of loads for its row (fcproj: K = 4C) and half the warps would idle anyway, warps 2i and 2i+1 of a CTA
+// take the two halves of feature i's row and add their sums through shared memory.
+__device__ __forceinline__ int pick_ksplit(int N, int K, int sh) {
+    return sh == 0 && (K >> 2) > kLoads * 32 && 2 * N <= (int)gridDim.x * kWarps && (K & 7) == 0;
+}
 // The weight loads of a warp's FIRST batch are issued between arriving at the grid barrier in front of
 // the phase and waiting on it: weights never depend on another CTA, so they stream in from HBM while
 // the grid meets.  Read-only, read-once: straight from L2, no L1 line to allocate.
@@ -106,30 +112,30 @@ __device__ __forceinline__ float4 ld_weight(const float4* p) {
 // shapes the same loop was ~900 instructions of address arithmetic and branches per pass, and at
 // two warps per scheduler those are paid at full latency.  Load u*FEAT + f = chunk u of feature f.
 template <int SH>
-__device__ __forceinline__ void gemv_issue_t(float4 (&wv)[kLoads], const float* __restrict__ w, int N, int K, int n0, int cb) {
+__device__ __forceinline__ void gemv_issue_t(float4 (&wv)[kLoads], const float* __restrict__ w, int N, int K, int k4len, int n0, int cb) {
     constexpr int FEAT = 1 << SH, UN = kLoads >> SH;
-    const int K4 = K >> 2;
 #pragma unroll
     for (int f = 0; f < FEAT; ++f) {
         const float4* row = reinterpret_cast<const float4*>(w + (size_t)min(n0 + f, N - 1) * K) + cb;
 #pragma unroll
         for (int u = 0; u < UN; ++u)
-            wv[u * FEAT + f] = (cb + 32 * u < K4 && n0 < N) ? ld_weight(row + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+            wv[u * FEAT + f] = (cb + 32 * u < k4len && n0 < N) ? ld_weight(row + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
-__device__ __forceinline__ void gemv_issue(float4 (&wv)[kLoads], const float* __restrict__ w, int N, int K, int sh, int n0, int cb) {
-    if (sh == 0) gemv_issue_t<0>(wv, w, N, K, n0, cb);
-    else if (sh == 1) gemv_issue_t<1>(wv, w, N, K, n0, cb);
-    else gemv_issue_t<2>(wv, w, N, K, n0, cb);
+// w: first float of the warp's K range in row 0; K: floats between rows; k4len: 16-byte chunks of the range
+__device__ __forceinline__ void gemv_issue(float4 (&wv)[kLoads], const float* __restrict__ w, int N, int K, int k4len, int sh, int n0, int cb) {
+    if (sh == 0) gemv_issue_t<0>(wv, w, N, K, k4len, n0, cb);
+    else if (sh == 1) gemv_issue_t<1>(wv, w, N, K, k4len, n0, cb);
+    else gemv_issue_t<2>(wv, w, N, K, k4len, n0, cb);
 }
 // acc[m][slot] += w . x for one batch; a feature's chunks spread over 4 / FEAT slots (independent FMA
 // chains), folded by the caller.  Chunks past the row carry zero weights: their x index is clamped.
 template <int SH, int MAXM>
-__device__ __forceinline__ void gemv_fma_t(const float4 (&wv)[kLoads], const float4* xs4, int cb, int K4, int M, float (&acc)[MAXM][4]) {
+__device__ __forceinline__ void gemv_fma_t(const float4 (&wv)[kLoads], const float4* xs4, int cb, int K4, int k4len, int M, float (&acc)[MAXM][4]) {
     constexpr int FEAT = 1 << SH, UN = kLoads >> SH;
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-        const int c = min(cb + 32 * u, K4 - 1);
+        const int c = min(cb + 32 * u, k4len - 1);
 #pragma unroll
         for (int mm = 0; mm < MAXM; ++mm) {
             if (mm < M) {
@@ -366,6 +372,7 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
     __shared__ PaSampleSmem<kThreads> samp;
     __shared__ StepSmem st;
     __shared__ float ln_red[2 * kWarps];
+    __shared__ float ks_buf[kWarps / 2][kMaxM];              // K split: a warp pair's second partial sums
     __shared__ __align__(16) float attn_ps[kWarps][132];     // LOCAL attention: the CTA's partials (o[hs], m, l)
     const int M = a.M, C = a.C;
     float* ln_ws = xs + (size_t)M * 4 * C;
@@ -394,9 +401,14 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
 #define GRID_WAIT() do { grid_wait(a.bar, a.bar_base, passed); stamp(); } while (0)
     float4 wv[kLoads];               // a warp's first batch of weight loads for the NEXT projection, in flight across barriers
     // ... and the bias of the output this lane will finish in that first pass (lane (f, m) -> feature n0 + f)
-    auto bias_issue = [&](const PhaseDesc& pd, int shift) {
-        const int n = (gw << shift) + (lane >> 3);
-        return (pd.bias && (lane >> 3) < (1 << shift) && n < pd.N) ? __ldg(pd.bias + n) : 0.0f;
+    auto bias_issue = [&](const PhaseDesc& pd, int shift, int ksp) {
+        const int n = (ksp ? gw >> 1 : gw << shift) + (lane >> 3);
+        return (pd.bias && (lane >> 3) < (1 << shift) && n < pd.N && !(ksp && (gw & 1))) ? __ldg(pd.bias + n) : 0.0f;
+    };
+    // the warp's first batch of the phase: feature(s) and K range as the projection loop below will take them
+    auto first_issue = [&](const PhaseDesc& pd, int shift, int ksp) {
+        const int k4 = pd.K >> 2, k4len = ksp ? k4 >> 1 : k4;
+        gemv_issue(wv, pd.w + (ksp ? (size_t)(gw & 1) * (k4len << 2) : 0), pd.N, pd.K, k4len, shift, ksp ? gw >> 1 : gw << shift, lane);
     };
     KvBatch<LPT> kb;                 // likewise the first batch of K/V for the attention phase
 
@@ -413,9 +425,9 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
     }
     GRID_ARRIVE();
     PhaseDesc d = phase_desc(a, 0);
-    int sh = pick_feat_shift(d.N, d.K);
-    gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane);
-    float bias_first = bias_issue(d, sh);
+    int sh = pick_feat_shift(d.N, d.K), ks = pick_ksplit(d.N, d.K, sh);
+    first_issue(d, sh, ks);
+    float bias_first = bias_issue(d, sh, ks);
     ln_params_issue(a.ln1w, a.ln1b);
     GRID_WAIT();
 
@@ -479,24 +491,28 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
 
         // ---- the projection (matmul_forward :92-114 on M rows): weight-streaming GEMV ------------------
         {
-            const float4* xs4 = reinterpret_cast<const float4*>(xs);
             const float* res = (kind == PH_ATTPROJ || kind == PH_FCPROJ) ? a.x : nullptr;     // residual_forward :253-257
-            bool have = true;                                // wv holds (n0 = gw * feat, cb = lane)
-            for (int n0 = gw << sh; n0 < N; n0 += nw << sh) {
+            // the warp's share: feature(s) n0.. and a K range (all of K, or one half of it with a K split)
+            const int half = ks ? (gw & 1) : 0, k4len = ks ? K4 >> 1 : K4;
+            const float* wk = d.w + (size_t)half * (k4len << 2);
+            const float4* xs4 = reinterpret_cast<const float4*>(xs) + half * k4len;
+            const int n_stride = ks ? nw >> 1 : nw << sh;
+            bool have = true;                                // wv holds the first batch of the first pass
+            for (int n0 = ks ? gw >> 1 : gw << sh; n0 < N; n0 += n_stride) {
                 // lane (f, m) finishes output (m, n0 + f): its bias and residual are requested now, used after the reduction
                 const int f = lane >> 3, m = lane & 7;
-                const bool mine = f < feat && m < M && n0 + f < N;
+                const bool mine = f < feat && m < M && n0 + f < N && half == 0;
                 const float bv = have ? bias_first : ((mine && d.bias) ? __ldg(d.bias + n0 + f) : 0.0f);
                 const float rv = (mine && res) ? __ldcg(res + (size_t)m * C + n0 + f) : 0.0f;
                 // the rows of the warp's passes after this one -> L2 while this pass computes (two passes ahead;
                 // the first pass also requests the one right after it)
                 for (int ahead = have ? 1 : 2; ahead <= 2; ++ahead) {
-                    const int np = n0 + ahead * (nw << sh);
+                    const int np = n0 + ahead * n_stride;
                     if (np < N) {
-                        const int lines = K >> 5;            // 128-byte lines per row
+                        const int lines = k4len >> 3;        // 128-byte lines of the warp's K range per row
                         for (int i = lane; i < feat * lines; i += 32) {
                             const int pf = i / lines, pl = i - pf * lines;
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(d.w + (size_t)min(np + pf, N - 1) * K + pl * 32));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(wk + (size_t)min(np + pf, N - 1) * K + pl * 32));
                         }
                     }
                 }
@@ -505,12 +521,12 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
                 for (int mm = 0; mm < MAXM; ++mm)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[mm][q] = 0.0f;
-                for (int cb = lane; cb < K4; cb += 32 * (kLoads >> sh)) {
-                    if (!have) gemv_issue(wv, d.w, N, K, sh, n0, cb);
+                for (int cb = lane; cb < k4len; cb += 32 * (kLoads >> sh)) {
+                    if (!have) gemv_issue(wv, wk, N, K, k4len, sh, n0, cb);
                     have = false;
-                    if (sh == 0) gemv_fma_t<0, MAXM>(wv, xs4, cb, K4, M, acc);
-                    else if (sh == 1) gemv_fma_t<1, MAXM>(wv, xs4, cb, K4, M, acc);
-                    else gemv_fma_t<2, MAXM>(wv, xs4, cb, K4, M, acc);
+                    if (sh == 0) gemv_fma_t<0, MAXM>(wv, xs4, cb, K4, k4len, M, acc);
+                    else if (sh == 1) gemv_fma_t<1, MAXM>(wv, xs4, cb, K4, k4len, M, acc);
+                    else gemv_fma_t<2, MAXM>(wv, xs4, cb, K4, k4len, M, acc);
                 }
                 float v = 0.0f;
 #pragma unroll
@@ -528,6 +544,15 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
                             }
                         }
                     }
+                }
+                if (ks) {                                    // the pair's second half -> first half (lane m holds row m's sum after the reduction)
+                    if (half && lane < M) {
+#pragma unroll
+                        for (int mm = 0; mm < MAXM; ++mm) if (mm == lane) ks_buf[warp >> 1][lane] = acc[mm][0];
+                    }
+                    named_bar_sync(1 + (warp >> 1), 64);
+                    if (!half && mine) v += ks_buf[warp >> 1][m];
+                    named_bar_sync(1 + (warp >> 1), 64);     // (the buffer is free again for the pair's next pass)
                 }
                 if (mine) {
                     const int n = n0 + f;
@@ -564,8 +589,9 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
         if (ph + 1 < n_phases) {
             d = phase_desc(a, ph + 1);
             sh = pick_feat_shift(d.N, d.K);
-            gemv_issue(wv, d.w, d.N, d.K, sh, gw << sh, lane);
-            bias_first = bias_issue(d, sh);
+            ks = pick_ksplit(d.N, d.K, sh);
+            first_issue(d, sh, ks);
+            bias_first = bias_issue(d, sh, ks);
             // (this phase read ln_ws/ln_bs before its __syncthreads at the latest; nobody reads them again before the barrier)
             if (kind == PH_ATTPROJ) ln_params_issue(a.ln2w + (size_t)l * C, a.ln2b + (size_t)l * C);
             else if (kind == PH_FCPROJ) {
