@@ -220,7 +220,7 @@ int mega_step(pa_model* m, int nseq, const int* tok, const int* pos, const float
     // the barrier counter only ever grows: this launch counts from where the last one stopped
     a.part = m->mega_part; a.bar = m->mega_bar; a.bar_base = m->mega_bar_base;
     const int rc = pa_cu_model_mega_step(&a, s);
-    if (rc == PA_OK) m->mega_bar_base += (unsigned)(2 + (a.local_attn ? 5 : 6) * m->L) * (unsigned)h->sm_count;      // (only a launch that ran counts)
+    if (rc == PA_OK) m->mega_bar_base += (unsigned)(2 + (a.local_attn ? 5 : 6) * m->L + (getenv("PA_MEGA_DEBUG") ? 16 : 0)) * (unsigned)h->sm_count;      // (only a launch that ran counts)
     return rc;
 }
 

@@ -601,6 +601,9 @@ pa_decode_step_mega_kernel(const pa_mega_args a) {
         }
         GRID_WAIT();
     }
+    if (a.dbg) {                     // PA_MEGA_DEBUG: 16 empty barriers back to back = the bare cost of one
+        for (int i = 0; i < 16; ++i) { GRID_ARRIVE(); GRID_WAIT(); }
+    }
     // softmax_forward + sample_mult on each row of logits
     if ((int)blockIdx.x < M)
         pa_sample_row<kThreads>(a.logits + (size_t)blockIdx.x * a.Vp, a.V, a.use_coins ? a.coins[blockIdx.x] : -1.0f, a.next + blockIdx.x, samp);
@@ -669,6 +672,7 @@ extern "C" int pa_cu_model_mega_step(const pa_mega_args* a, void* stream) {
             }
         fprintf(stderr, "mega dbg: embed barrier %lld ns;", (long long)(hst[1] - hst[0]));
         for (int p = 0; p < per_layer; ++p) fprintf(stderr, " %s %.0f+%.0f", names[p], work[p] / a->L, wait[p] / a->L);
+        fprintf(stderr, "; bare barrier %.0f ns", (double)(hst[2 * (n + 16) - 1] - hst[2 * n - 1]) / 16.0);
         fprintf(stderr, "; lm head %lld+%lld; total %lld ns\n", (long long)(hst[2 * (n - 1)] - hst[2 * (n - 1) - 1]),
                 (long long)(hst[2 * (n - 1) + 1] - hst[2 * (n - 1)]), (long long)(hst[2 * (n - 1) + 1] - hst[0]));
     }
