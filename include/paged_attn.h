@@ -205,7 +205,9 @@ PA_API int pa_model_create(pa_handle* h, const pa_model_config* cfg, const float
                            int max_batch, pa_model** out);
 PA_API void pa_model_destroy(pa_model* m);
 /* Sequence seq_ids[i] receives tokens[i] at its next position; next_tokens[i] is sampled from its
- * logits with coins[i] in [0,1) as sample_mult does (paged_infer.c:838-848), or argmax if coins is NULL. */
+ * logits with coins[i] in [0,1) as sample_mult does (paged_infer.c:838-848), or argmax if coins is NULL.
+ * Up to 6 sequences the whole step runs as ONE persistent cooperative kernel (weights streamed once,
+ * grid barriers between the ops), beyond that as a chain of per-op kernels (PA_TUNE_MODEL_PATH). */
 PA_API int pa_model_decode_step(pa_model* m, const int* seq_ids, const int* tokens, const float* coins, int nseq,
                                 int* next_tokens);
 /* General step (prompt prefill, chunked prefill, decode, or a mix): sequence seq_ids[i] receives n_new[i] >= 1
