@@ -387,9 +387,10 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
             return PA_ERR_UNSUPPORTED;
         }
     }
-    // Overlapping launches pay off while the step is a chain of latency-bound kernels (measured: +8 % at 64
-    // tokens, -3 % at 256, where early-resident successors get in the way of the cluster launches)
-    static const int pdl_max_tokens = getenv("PA_PDL_MAX_TOKENS") ? atoi(getenv("PA_PDL_MAX_TOKENS")) : 128;
+    // Overlapping launches (programmatic dependent launch) along the step's chain of kernels.  While the split-K
+    // projections were cluster launches the overlap cost time beyond 128 tokens (early-resident successors got in
+    // their way); with the workspace split it pays at every size measured (2.84 -> 2.74 ms at 256 tokens).
+    static const int pdl_max_tokens = getenv("PA_PDL_MAX_TOKENS") ? atoi(getenv("PA_PDL_MAX_TOKENS")) : (1 << 30);
     pa_pdl_gate = ntok <= pdl_max_tokens;
     int rc = pa_step_begin(h, seq_ids, n_new, nseq);
     if (rc != PA_OK) return rc;
