@@ -258,6 +258,44 @@ def cpu_baseline_sample(w, budget_s=15.0):
     return cb
 
 
+def cpu_model_sample(model, pa_mod, B, L, NH, C_, V, maxT, bs, steps=4):
+    """Whole-model decode on the host cores beside the device number: the oracle's restatement of gpt2_forward
+    (oracle/paged_oracle.c orc_model_decode_step, all layers, -O3 -Ofast -fopenmp) on the SAME weights,
+    `steps` decode steps of B sequences from an empty cache (the projections are >95 % of its work at
+    these context lengths).  Bounded: only offered for small batches."""
+    import oracle_api as oa
+    lib = pa_mod.load()
+    n = int(model.n_params)
+    params = np.empty(n, dtype=np.float32)
+    pa_mod.check(lib.pa_memcpy_d2h(params.ctypes.data, lib.pa_model_params(model.m), n * 4, None), "params d2h")
+    pa_mod.check(lib.pa_device_sync(), "sync")
+    ol = oa.load_oracle("fast")
+    pages = (steps + 2 + bs - 1) // bs + 1
+    mgrs = [oa.OrcManager(C_, bs, B * pages + 2, B, flavor="fast") for _ in range(L)]
+    arr = (C.c_void_p * L)(*[m.m for m in mgrs])
+    seq = np.arange(B, dtype=np.int32)
+    tok = np.arange(B, dtype=np.int32) + 11
+    logits = np.zeros((B, V), dtype=np.float32)
+    times = []
+    try:
+        for step in range(steps + 1):
+            pos = np.full(B, step, dtype=np.int32)
+            t0 = time.perf_counter()
+            rc = ol.orc_model_decode_step(arr, L, NH, C_, V, maxT, oa.fptr(params), oa.iptr(seq), oa.iptr(tok), oa.iptr(pos), B,
+                                          oa.fptr(logits))
+            if rc != 0:
+                raise RuntimeError(f"orc_model_decode_step rc={rc}")
+            times.append(time.perf_counter() - t0)
+            tok = logits.argmax(axis=1).astype(np.int32)
+    finally:
+        for m in mgrs:
+            m.close()
+    per = min(times[1:])
+    return {"tokens_per_s": B / per, "ms_per_step": per * 1e3, "cores": ol.orc_omp_threads(), "kind": "port",
+            "sample": f"oracle gpt2_forward restatement (all {L} layers, LM head, V={V}), best of {steps} decode steps of {B} "
+                      f"sequence(s) from an empty cache, -O3 -Ofast -fopenmp"}
+
+
 # ------------------------------------------------------------------------------------ our arm
 _REAL_STDOUT = None
 
@@ -550,6 +588,11 @@ def main():
                           "weights": "random init on the device (no checkpoint offline)",
                           "token_gather": ("NCCL all_gather of int32 next tokens, every step" if dist is not None else None),
                           "entry": "pa_model_decode_step (host token ids in, host token ids out, sync per step)"}
+            if world == 1 and B <= 8 and not args.no_cpu_baseline:
+                try:
+                    model_info["cpu_baseline"] = cpu_model_sample(model, pa, B, L, NH, C_, V, maxT, bs)
+                except Exception as ex:      # a report, never a reason to lose the line
+                    model_info["cpu_baseline"] = {"tokens_per_s": None, "sample": f"failed: {ex!r}"}
             model.close()
         except Exception as ex:
             model_info = {"error": repr(ex)}
