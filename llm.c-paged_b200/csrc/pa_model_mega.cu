@@ -4,23 +4,28 @@
  *
  * With one to eight rows every op of gpt2_forward (paged_infer.c:646-728) is a read of its weights:
  * 0.5 GB per step at GPT-2 124M = 77 us at HBM speed, while a chain of 88 dependent launches costs
- * ~9 us each whatever they do.  So the step is one grid of one CTA per SM that walks the ops in
- * order and meets at a grid barrier (one release-add + acquire-poll on a counter in L2) wherever an
- * op needs what other CTAs produced:
+ * ~9 us each whatever they do.  So the step is one grid of one 512-thread CTA per SM that walks the
+ * ops in order and meets at a grid barrier wherever an op needs what other CTAs produced:
  *
- *   embedding | per layer { [ln1 -> smem] QKV rows + KV append | attention partials | merge |
+ *   embedding | per layer { [ln1 -> smem] QKV rows + KV append | attention |
  *               [atty -> smem] attproj + residual | [ln2 -> smem] fc + GELU | [fch -> smem] fcproj + residual } |
  *   [lnf -> smem] LM head | sampler
  *
- * Projections: weight-streaming GEMV -- a warp owns 1/2/4 output features, its lanes stream those
- * weight rows with 16-byte loads (all loads of a row in flight before the first FMA), the M input
- * rows sit in shared memory (every CTA normalises / stages them for itself, so layernorm costs no
- * barrier), fp32 FMA, warp-shuffle reduction, bias / GELU / residual / page-slot scatter in the
- * epilogue -- the arithmetic of pa_gemv_kernel (pa_qkv.cu).  Attention: a warp per (sequence, head,
- * chunk of tokens) walks the block table with 16-byte loads, hs/4 lanes per token, online softmax
- * from the reference's -10000 start (paged_infer.c:187), partial (o, m, l) to a workspace; a warp
- * per (sequence, head) merges the chunks in order.  Activations written by one CTA and read by
- * another after a barrier are read through L2 (ld.global.cg).  Roofline: HBM (weights read once).
+ * Projections: weight-streaming GEMV -- a warp owns 1/2/4 output features (or, for rows of 4C
+ * floats, a pair of warps one feature), its lanes stream those weight rows with 16-byte loads that
+ * bypass L1, the M input rows sit in shared memory (every CTA normalises / stages them for itself,
+ * so layernorm costs no barrier), fp32 FMA, warp-shuffle reduction, bias / GELU / residual /
+ * page-slot scatter in the epilogue -- the arithmetic of pa_gemv_kernel (pa_qkv.cu).
+ * Attention: up to 512 tokens the warps of ONE CTA share a (sequence, head) and merge their chunks
+ * through shared memory; beyond that the chunks spread over the grid, partial (o, m, l) go to a
+ * workspace and are merged after one more barrier.  hs/4 lanes per token, 16-byte loads through the
+ * block table, online softmax from the reference's -10000 start (paged_infer.c:187).
+ * Barrier: one release-add + relaxed polls + one acquire fence on a counter in L2 that only ever
+ * grows (also across launches); between ARRIVING and WAITING a CTA requests whatever the next phase
+ * needs that no other CTA produces (weights, bias, layernorm parameters, old K/V).  Activations
+ * written by one CTA and read by another after a barrier are read through L2 (ld.global.cg).
+ * Roofline: HBM (weights read once); measured numbers and the history of the kernel in DESIGN 4.6 and
+ * profiles/r01_model_step.md.
  */
 #include <cuda_runtime.h>
 
