@@ -223,6 +223,9 @@ PA_API float* pa_model_logits(pa_model* m, int* stride);  /* device, (nseq, stri
 PA_API int pa_checkpoint_read_config(const char* path, pa_model_config* cfg);
 PA_API int pa_checkpoint_read_params(const char* path, float* params, size_t n_floats);
 PA_API int pa_checkpoint_write(const char* path, const pa_model_config* cfg, const float* params);
+/* version 2 of the same file (train_gpt2.py:266-320): weights and biases as bf16 (round to nearest even), the
+ * layernorm tensors in fp32 at the end.  pa_checkpoint_read_config / _read_params read both versions. */
+PA_API int pa_checkpoint_write_bf16(const char* path, const pa_model_config* cfg, const float* params);
 PA_API int pa_model_create_from_checkpoint(pa_handle* h, const char* path, int max_batch, pa_model** out);
 /* token stream (dataloader_*, paged_infer.c:769-818): raw int32 ids, batches of B*T (+1 target) */
 typedef struct pa_dataloader pa_dataloader;

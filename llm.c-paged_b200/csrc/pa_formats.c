@@ -24,7 +24,17 @@ static size_t ckpt_param_count(const pa_model_config* c) {
     return V * C + T * C + L * (2 * C + 3 * C * C + 3 * C + C * C + C + 2 * C + 4 * C * C + 4 * C + 4 * C * C + C) + 2 * C;
 }
 
+/* The Python writer of the reference (train_gpt2.py:298-320) knows two layouts under the same magic: version 1,
+ * every tensor fp32 in model order (the one paged_infer.c reads, :441-488), and version 2, written for the
+ * bf16 trainer: the ten weight/bias tensors as bf16 in the order wte wpe qkvw qkvb attprojw attprojb fcw fcb
+ * fcprojw fcprojb, then the six layernorm tensors in fp32 (train_gpt2.py:266-297).  Both are read here (bf16 is
+ * widened exactly); paged_infer.c itself refuses version 2 ("Bad version in model file", :444). */
+static int read_header(const char* path, pa_model_config* cfg, int* version);
 int pa_checkpoint_read_config(const char* path, pa_model_config* cfg) {
+    int version;
+    return read_header(path, cfg, &version);
+}
+static int read_header(const char* path, pa_model_config* cfg, int* version) {
     if (!path || !cfg) { pa_set_error("pa_checkpoint_read_config: NULL argument"); return PA_ERR_INVALID; }
     FILE* f = fopen(path, "rb");
     if (!f) { pa_set_error("Error opening model file %s", path); return PA_ERR_INVALID; }
@@ -33,7 +43,8 @@ int pa_checkpoint_read_config(const char* path, pa_model_config* cfg) {
     fclose(f);
     if (n != 256) { pa_set_error("model file %s: short header", path); return PA_ERR_INVALID; }
     if (hdr[0] != PA_CKPT_MAGIC) { pa_set_error("Bad magic model file"); return PA_ERR_INVALID; }          /* :443 */
-    if (hdr[1] != 1) { pa_set_error("Bad version in model file"); return PA_ERR_INVALID; }                /* :444 */
+    if (hdr[1] != 1 && hdr[1] != 2) { pa_set_error("Bad version in model file"); return PA_ERR_INVALID; } /* :444 */
+    *version = hdr[1];
     cfg->max_seq_len = hdr[2];
     cfg->vocab_size = hdr[3];
     cfg->n_layers = hdr[4];
@@ -47,9 +58,21 @@ int pa_checkpoint_read_config(const char* path, pa_model_config* cfg) {
     return PA_OK;
 }
 
+/* tensor sizes in MODEL order (wte wpe ln1w ln1b qkvw qkvb attprojw attprojb ln2w ln2b fcw fcb fcprojw fcprojb lnfw lnfb) */
+static void tensor_sizes(const pa_model_config* c, size_t sz[16]) {
+    size_t V = (size_t)c->vocab_size, T = (size_t)c->max_seq_len, L = (size_t)c->n_layers, C = (size_t)c->channels;
+    size_t s[16] = {V * C, T * C, L * C, L * C, L * 3 * C * C, L * 3 * C, L * C * C, L * C, L * C, L * C,
+                    L * 4 * C * C, L * 4 * C, L * 4 * C * C, L * C, C, C};
+    memcpy(sz, s, sizeof(s));
+}
+/* version 2 file order: model tensor index of each tensor in the file, bf16 ones first */
+static const int kV2Order[16] = {0, 1, 4, 5, 6, 7, 10, 11, 12, 13, /* fp32: */ 2, 3, 8, 9, 14, 15};
+static const int kV2Bf16 = 10;
+
 int pa_checkpoint_read_params(const char* path, float* params, size_t n_floats) {
     pa_model_config cfg;
-    int rc = pa_checkpoint_read_config(path, &cfg);
+    int version;
+    int rc = read_header(path, &cfg, &version);
     if (rc != PA_OK) return rc;
     if (!params || n_floats != ckpt_param_count(&cfg)) {
         pa_set_error("pa_checkpoint_read_params: buffer holds %zu floats, the file %zu", n_floats, ckpt_param_count(&cfg));
@@ -58,9 +81,70 @@ int pa_checkpoint_read_params(const char* path, float* params, size_t n_floats) 
     FILE* f = fopen(path, "rb");
     if (!f) { pa_set_error("Error opening model file %s", path); return PA_ERR_INVALID; }
     fseek(f, 256 * (long)sizeof(int), SEEK_SET);
-    size_t n = fread(params, sizeof(float), n_floats, f);
+    if (version == 1) {
+        size_t n = fread(params, sizeof(float), n_floats, f);
+        fclose(f);
+        if (n != n_floats) { pa_set_error("model file %s: %zu of %zu parameters", path, n, n_floats); return PA_ERR_INVALID; }
+        return PA_OK;
+    }
+    size_t sz[16], off[16], o = 0;
+    tensor_sizes(&cfg, sz);
+    for (int i = 0; i < 16; i++) { off[i] = o; o += sz[i]; }
+    for (int k = 0; k < 16; k++) {
+        const int t = kV2Order[k];
+        float* dst = params + off[t];
+        if (k < kV2Bf16) {
+            /* bf16 -> fp32 in place: read the 16-bit words into the upper half of the destination, widen from the end */
+            unsigned short* h = (unsigned short*)dst + sz[t];
+            if (fread(h, sizeof(unsigned short), sz[t], f) != sz[t]) { fclose(f); pa_set_error("model file %s: truncated bf16 tensor %d", path, t); return PA_ERR_INVALID; }
+            for (size_t i = 0; i < sz[t]; i++) {
+                unsigned int bits = (unsigned int)h[i] << 16;
+                memcpy(dst + i, &bits, sizeof(bits));          /* dst + i never overtakes h + i */
+            }
+        } else if (fread(dst, sizeof(float), sz[t], f) != sz[t]) {
+            fclose(f);
+            pa_set_error("model file %s: truncated fp32 tensor %d", path, t);
+            return PA_ERR_INVALID;
+        }
+    }
     fclose(f);
-    if (n != n_floats) { pa_set_error("model file %s: %zu of %zu parameters", path, n, n_floats); return PA_ERR_INVALID; }
+    return PA_OK;
+}
+
+/* round-to-nearest-even fp32 -> bf16, as torch's .to(torch.bfloat16) (NaN stays NaN) */
+static unsigned short bf16_rne(float x) {
+    unsigned int b;
+    memcpy(&b, &x, sizeof(b));
+    if ((b & 0x7fffffffu) > 0x7f800000u) return (unsigned short)((b >> 16) | 0x40u);
+    b += 0x7fffu + ((b >> 16) & 1u);
+    return (unsigned short)(b >> 16);
+}
+/* version 2 (bf16 weights, fp32 layernorms) in the layout of the reference's write_tensors_bf16 */
+int pa_checkpoint_write_bf16(const char* path, const pa_model_config* cfg, const float* params) {
+    if (!path || !cfg || !params) { pa_set_error("pa_checkpoint_write_bf16: NULL argument"); return PA_ERR_INVALID; }
+    FILE* f = fopen(path, "wb");
+    if (!f) { pa_set_error("cannot create %s", path); return PA_ERR_INVALID; }
+    int hdr[256];
+    memset(hdr, 0, sizeof(hdr));
+    hdr[0] = PA_CKPT_MAGIC; hdr[1] = 2;
+    hdr[2] = cfg->max_seq_len; hdr[3] = cfg->vocab_size; hdr[4] = cfg->n_layers; hdr[5] = cfg->n_heads; hdr[6] = cfg->channels;
+    int ok = fwrite(hdr, sizeof(int), 256, f) == 256;
+    size_t sz[16], off[16], o = 0;
+    tensor_sizes(cfg, sz);
+    for (int i = 0; i < 16; i++) { off[i] = o; o += sz[i]; }
+    unsigned short buf[4096];
+    for (int k = 0; k < 16 && ok; k++) {
+        const int t = kV2Order[k];
+        const float* src = params + off[t];
+        if (k >= kV2Bf16) { ok = fwrite(src, sizeof(float), sz[t], f) == sz[t]; continue; }
+        for (size_t i0 = 0; i0 < sz[t] && ok; i0 += 4096) {
+            const size_t n = sz[t] - i0 < 4096 ? sz[t] - i0 : 4096;
+            for (size_t i = 0; i < n; i++) buf[i] = bf16_rne(src[i0 + i]);
+            ok = fwrite(buf, sizeof(unsigned short), n, f) == n;
+        }
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { pa_set_error("short write to %s", path); return PA_ERR_INVALID; }
     return PA_OK;
 }
 

@@ -116,6 +116,7 @@ def load():
         "pa_checkpoint_read_config": (C.c_int, [C.c_char_p, C.POINTER(PaModelConfig)]),
         "pa_checkpoint_read_params": (C.c_int, [C.c_char_p, vp, C.c_size_t]),
         "pa_checkpoint_write": (C.c_int, [C.c_char_p, C.POINTER(PaModelConfig), vp]),
+        "pa_checkpoint_write_bf16": (C.c_int, [C.c_char_p, C.POINTER(PaModelConfig), vp]),
         "pa_model_create_from_checkpoint": (C.c_int, [vp, C.c_char_p, C.c_int, C.POINTER(vp)]),
         "pa_dataloader_open": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]),
         "pa_dataloader_reset": (None, [vp]),

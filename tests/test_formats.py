@@ -57,10 +57,57 @@ def test_checkpoint_rejects_bad_files(tmp_path):
     bad.write_bytes(hdr.tobytes())
     assert lib.pa_checkpoint_read_config(str(bad).encode(), C.byref(cfg)) == pa.PA_ERR_INVALID
     assert "Bad magic" in pa.last_error()
-    hdr[0] = 20240326; hdr[1] = 2
+    hdr[0] = 20240326; hdr[1] = 3
     bad.write_bytes(hdr.tobytes())
     assert lib.pa_checkpoint_read_config(str(bad).encode(), C.byref(cfg)) == pa.PA_ERR_INVALID
     assert "Bad version" in pa.last_error()
+
+
+def _bf16_rne(x):
+    """torch's .to(torch.bfloat16) on fp32: round to nearest even on the upper 16 bits."""
+    b = x.view(np.uint32).astype(np.uint64)
+    return ((b + 0x7fff + ((b >> 16) & 1)) >> 16).astype(np.uint16)
+
+
+def test_checkpoint_version_2_bf16_layout_of_the_reference_writer(tmp_path):
+    """Version 2 of the checkpoint (train_gpt2.py:298-320 write_model(dtype="bfloat16")): header version 2, the ten
+    weight/bias tensors as bf16 in the order of write_tensors_bf16 (train_gpt2.py:266-297), then the six layernorm
+    tensors in fp32.  The writer's bytes equal a numpy restatement of that function; the reader widens bf16 exactly
+    and returns the parameters in MODEL order."""
+    lib = pa.load()
+    maxT, V, L, NH, Cc = 24, 53, 3, 2, 16
+    cfg = pa.PaModelConfig(maxT, V, L, NH, Cc)
+    n = lib.pa_model_param_count(C.byref(cfg))
+    params = oa.normal((n,), seed=33)
+    sizes = [V * Cc, maxT * Cc, L * Cc, L * Cc, L * 3 * Cc * Cc, L * 3 * Cc, L * Cc * Cc, L * Cc, L * Cc, L * Cc,
+             L * 4 * Cc * Cc, L * 4 * Cc, L * 4 * Cc * Cc, L * Cc, Cc, Cc]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    tens = [params[offs[i]:offs[i + 1]] for i in range(16)]
+    path = str(tmp_path / "gpt2_tiny_bf16.bin").encode()
+    pa.check(lib.pa_checkpoint_write_bf16(path, C.byref(cfg), params.ctypes.data), "write bf16")
+    hdr = np.zeros(256, dtype=np.int32)
+    hdr[:7] = [20240326, 2, maxT, V, L, NH, Cc]
+    want = hdr.tobytes()
+    for t in (0, 1, 4, 5, 6, 7, 10, 11, 12, 13):                # wte wpe qkvw qkvb attprojw attprojb fcw fcb fcprojw fcprojb
+        want += _bf16_rne(tens[t]).tobytes()
+    for t in (2, 3, 8, 9, 14, 15):                              # ln1w ln1b ln2w ln2b lnfw lnfb stay fp32
+        want += tens[t].tobytes()
+    assert open(path, "rb").read() == want
+    cfg2 = pa.PaModelConfig()
+    pa.check(lib.pa_checkpoint_read_config(path, C.byref(cfg2)), "read config")
+    assert [cfg2.max_seq_len, cfg2.vocab_size, cfg2.n_layers, cfg2.n_heads, cfg2.channels] == [maxT, V, L, NH, Cc]
+    back = np.full(n, np.nan, dtype=np.float32)
+    pa.check(lib.pa_checkpoint_read_params(path, back.ctypes.data, n), "read params")
+    for t in range(16):
+        got = back[offs[t]:offs[t + 1]]
+        if t in (2, 3, 8, 9, 14, 15):
+            assert np.array_equal(got.view(np.uint32), tens[t].view(np.uint32))
+        else:
+            assert np.array_equal(got.view(np.uint32), _bf16_rne(tens[t]).astype(np.uint32) << 16)
+    # a truncated file is refused
+    trunc = tmp_path / "trunc.bin"
+    trunc.write_bytes(want[:len(want) // 2])
+    assert lib.pa_checkpoint_read_params(str(trunc).encode(), back.ctypes.data, n) == pa.PA_ERR_INVALID
 
 
 def test_dataloader_matches_reference_including_wraparound(tmp_path):
