@@ -227,7 +227,12 @@ int pa_cu_swap_page(pa_handle* h, int page, float* host_k, float* host_v, int to
         CU_CHECK(cudaMemcpy2DAsync(dk, lpitch, host_k, page_bytes, page_bytes, h->cfg.n_layers, cudaMemcpyHostToDevice, s));
         CU_CHECK(cudaMemcpy2DAsync(dv, lpitch, host_v, page_bytes, page_bytes, h->cfg.n_layers, cudaMemcpyHostToDevice, s));
     }
-    CU_CHECK(cudaStreamSynchronize(s));
+    return PA_OK;          /* enqueued on the handle's stream; pa_cu_swap_sync waits */
+}
+int pa_cu_swap_sync(pa_handle* h) {
+    if (h->host_only || !h->pool_k) return PA_OK;
+    CU_CHECK(cudaSetDevice(h->cfg.device));
+    CU_CHECK(cudaStreamSynchronize((cudaStream_t)h->stream));
     return PA_OK;
 }
 

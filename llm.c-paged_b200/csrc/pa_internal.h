@@ -118,7 +118,8 @@ void pa_cu_host_pipe_release(pa_handle* h);
 /* rows [0, rows) of page src -> page dst, K and V, every layer; stream-ordered on the handle's stream, then synchronised */
 int pa_cu_copy_page_rows(pa_handle* h, int src_page, int dst_page, int rows);
 /* one page <-> host, K and V, every layer; host layout [layer][block_size*C] for K then the same for V */
-int pa_cu_swap_page(pa_handle* h, int page, float* host_k, float* host_v, int to_host);
+int pa_cu_swap_page(pa_handle* h, int page, float* host_k, float* host_v, int to_host);     /* enqueued on the handle's stream */
+int pa_cu_swap_sync(pa_handle* h);
 
 /* ---- implemented in pa_prefill.cu / pa_prefill_tc.cu ------------------------------------- */
 /* PA_OK = launched; PA_ERR_UNSUPPORTED = shape outside the kernel's domain (use the generic rows kernel) */

@@ -205,10 +205,22 @@ int pa_page_refcount(pa_handle* h, int page) {
  * allocator's eviction first copies the victim's pages (every layer) to host memory; the sequence
  * is brought back -- into whatever pages are free then -- the next time a step names it. */
 typedef struct swap_slot {
-    float* buf;          /* [pages][2 (K,V)][n_layers][block_size*C] */
+    float* buf;          /* [pages][2 (K,V)][n_layers][block_size*C]; pinned when there is a device */
     int n_tokens;
     int n_pages;
 } swap_slot;
+
+/* Host copies live in PINNED memory: the page copies are then truly asynchronous DMA transfers on the handle's
+ * stream (pageable memory would be staged by the driver, synchronously); all pages of a sequence are enqueued
+ * back to back and waited for ONCE (a swap-out before the victim's pages are handed on -- the caller may run its
+ * kernels on another stream --, a swap-in before the host copy is released). */
+static float* swap_alloc(pa_handle* h, size_t bytes) {
+    return (float*)(h->host_only ? malloc(bytes) : pa_host_alloc(bytes));
+}
+static void swap_free(pa_handle* h, float* p) {
+    if (!p) return;
+    if (h->host_only) free(p); else pa_host_free(p);          /* (freeing pinned memory waits for the device) */
+}
 
 static swap_slot* swap_slots(pa_handle* h, int create) {
     if (!h->swap_state && create) h->swap_state = calloc((size_t)h->cfg.max_seqs, sizeof(swap_slot));
@@ -230,7 +242,7 @@ int pa_seq_swapped_tokens(pa_handle* h, int seq) {
 void pa_swap_destroy(pa_handle* h) {
     swap_slot* sl = swap_slots(h, 0);
     if (!sl) return;
-    for (int i = 0; i < h->cfg.max_seqs; i++) free(sl[i].buf);
+    for (int i = 0; i < h->cfg.max_seqs; i++) swap_free(h, sl[i].buf);
     free(sl);
     h->swap_state = NULL;
 }
@@ -243,15 +255,19 @@ int pa_seq_swap_out(pa_handle* h, int seq) {
     swap_slot* sl = swap_slots(h, 1);
     if (!sl) { pa_set_error("pa_seq_swap_out: out of host memory"); return PA_ERR_NOMEM; }
     const size_t pf = swap_page_floats(h);
-    free(sl[seq].buf);
-    sl[seq].buf = (float*)malloc((size_t)n * pf * sizeof(float));
+    swap_free(h, sl[seq].buf);
+    sl[seq].buf = swap_alloc(h, (size_t)n * pf * sizeof(float));
     if (!sl[seq].buf) { pa_set_error("pa_seq_swap_out: out of host memory (%d pages)", n); return PA_ERR_NOMEM; }
     sl[seq].n_tokens = pa_bm_context_len(m, seq);
     sl[seq].n_pages = n;
     for (int i = 0; i < n; i++) {
         float* k = sl[seq].buf + (size_t)i * pf;
         int rc = pa_cu_swap_page(h, m->prompt_block_list[seq][i], k, k + pf / 2, 1);
-        if (rc != PA_OK) { free(sl[seq].buf); sl[seq].buf = NULL; return rc; }
+        if (rc != PA_OK) { swap_free(h, sl[seq].buf); sl[seq].buf = NULL; return rc; }
+    }
+    {   /* one wait for the whole sequence: its pages may be handed to work on ANOTHER stream right away */
+        int rc = pa_cu_swap_sync(h);
+        if (rc != PA_OK) { swap_free(h, sl[seq].buf); sl[seq].buf = NULL; return rc; }
     }
     free_blocks_for_prompt(m, seq);
     return PA_OK;
@@ -267,15 +283,16 @@ void pa_swap_on_evict(pa_handle* h, int p) {
     swap_slot* sl = swap_slots(h, 1);
     if (!sl) return;
     const size_t pf = swap_page_floats(h);
-    free(sl[p].buf);
-    sl[p].buf = (float*)malloc((size_t)n * pf * sizeof(float));
+    swap_free(h, sl[p].buf);
+    sl[p].buf = swap_alloc(h, (size_t)n * pf * sizeof(float));
     if (!sl[p].buf) return;
     sl[p].n_tokens = pa_bm_context_len(m, p);
     sl[p].n_pages = n;
     for (int i = 0; i < n; i++) {
         float* k = sl[p].buf + (size_t)i * pf;
-        if (pa_cu_swap_page(h, m->prompt_block_list[p][i], k, k + pf / 2, 1) != PA_OK) { free(sl[p].buf); sl[p].buf = NULL; return; }
+        if (pa_cu_swap_page(h, m->prompt_block_list[p][i], k, k + pf / 2, 1) != PA_OK) { swap_free(h, sl[p].buf); sl[p].buf = NULL; return; }
     }
+    if (pa_cu_swap_sync(h) != PA_OK) { swap_free(h, sl[p].buf); sl[p].buf = NULL; }
 }
 
 int pa_seq_swap_in(pa_handle* h, int seq) {
@@ -296,13 +313,14 @@ int pa_seq_swap_in(pa_handle* h, int seq) {
         float* k = buf + (size_t)i * pf;
         rc = pa_cu_swap_page(h, (int)(b - m->blocks), k, k + pf / 2, 0);
     }
+    if (rc == PA_OK) rc = pa_cu_swap_sync(h);       /* the pages are in place before the host copy goes away */
     if (rc != PA_OK) {                 /* put the copy back so nothing is lost */
         free_blocks_for_prompt(m, seq);
-        free(sl[seq].buf);
+        swap_free(h, sl[seq].buf);
         sl[seq].buf = buf; sl[seq].n_pages = n; sl[seq].n_tokens = n_tokens;
         return rc;
     }
-    free(buf);
+    swap_free(h, buf);
     return PA_OK;
 }
 int pa_swap_in_if_needed(pa_handle* h, int seq) {
