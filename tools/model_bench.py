@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--gemm-path", type=int, default=0)
     ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--prefill", type=int, default=0, help="instead of decode steps: prefill prompts of this many tokens for the B sequences in ONE step")
     ap.add_argument("--model-path", type=int, default=0, help="0 auto, 1 chain of per-op kernels, 2 persistent step kernel")
     args = ap.parse_args()
     pa = ge.build(quiet=True)
@@ -46,6 +47,33 @@ def main():
     eng.tune(pa.PA_TUNE_MODEL_PATH, args.model_path)
     rng = np.random.default_rng(3)
     perm = rng.permutation(B * pages + 8)
+    if args.prefill:
+        # prompt prefill through pa_model_forward: B prompts of `prefill` tokens in one step (causal prefill kernel,
+        # projections at B * prefill rows, KV append fused into the QKV projection), sequences freed after every step
+        P = args.prefill
+        eng.close()
+        pages = (P + bs - 1) // bs + 1
+        eng = pa.PagedAttn(bs, B * pages + 8, B, NH, hs, n_layers=L, device=0, max_batch_tokens=B * P)
+        eng.tune(pa.PA_TUNE_GEMM_PATH, args.gemm_path)
+        model = pa.Model(eng, max(1024, P + 8), 50257, params=None, seed=1, max_batch=B * P)
+        seq = np.arange(B, dtype=np.int32)
+        toks = rng.integers(0, 50257, size=B * P).astype(np.int32)
+
+        def pstep():
+            nxt = model.forward(seq, [P] * B, toks, None)
+            for s in range(B):
+                eng.seq_free(s)
+            return nxt
+        for _ in range(2):
+            pstep()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pstep()
+        dt = (time.perf_counter() - t0) / args.steps
+        print(json.dumps({"tool": "model_bench", "mode": "prefill", "shape": args.shape, "B": B, "prompt": P, "layers": L,
+                          "ms_per_step": dt * 1e3, "prompt_tokens_per_s": B * P / dt, "gemm_path": args.gemm_path}))
+        model.close(); eng.close()
+        return
     for s in range(B):
         assert eng.seq_adopt(s, perm[s * pages: s * pages + (ctx - 1 + bs - 1) // bs], ctx - 1) == 0, pa.last_error()
     V = 50257
