@@ -63,6 +63,8 @@ typedef struct BlockManager { /* block_manager.c:17-23 */
     int* refcount;                /* [max_blocks] holders of a page: sequences (+1 if the prefix cache holds it); 0 = free.
                                      Always 0/1 unless pa_seq_fork / pa_prefix_* are used */
     void* prefix_cache;           /* opaque (pa_sharing.c), NULL until pa_prefix_insert */
+    unsigned char* pinned;        /* [max_prompts] 1 while the sequence belongs to the step being built: the LRU never
+                                     evicts it (all 0 outside pa_step_begin*, so the reference trace is unchanged) */
 } BlockManager;
 
 typedef enum pa_status {
@@ -150,7 +152,12 @@ PA_API const char* pa_version(void);
 /* Sequence seq_ids[i] receives n_new[i] tokens.  For each token run the page choice of
  * add_to_cache (paged_infer.c:518-529: current page, new page if none/full, else LRU touch),
  * crossing page boundaries when needed (extension), and record slot = page*block_size + row.
- * Builds the step tables (context lengths, page prefix sums, slot mapping, block-table rows). */
+ * Builds the step tables (context lengths, page prefix sums, slot mapping, block-table rows).
+ * The sequences of the step are pinned while its pages are placed: the whole-prompt LRU eviction may
+ * take any OTHER sequence, never one of the step (nor the requester itself, which the single-prompt
+ * reference would evict, block_manager.c:157): when only they are left the call fails with
+ * PA_ERR_NO_BLOCKS and every sequence of the step is back at the length it had before the call.
+ * A sequence id may appear once per step. */
 PA_API int pa_step_begin(pa_handle* h, const int* seq_ids, const int* n_new, int nseq);
 /* Optional sliding window: row i attends cached tokens [kv_start[i], ctx) (reference `offset`). */
 PA_API int pa_step_set_kv_start(pa_handle* h, const int* kv_start);
@@ -286,6 +293,7 @@ PA_API int pa_prefix_cached_pages(pa_handle* h);
 PA_API int pa_set_evict_swap(pa_handle* h, int enable);
 PA_API int pa_seq_swap_out(pa_handle* h, int seq_id);       /* explicit */
 PA_API int pa_seq_swap_in(pa_handle* h, int seq_id);
+PA_API int pa_swap_failures(pa_handle* h);                  /* evictions whose host copy could not be made (sequence dropped; also on stderr) */
 PA_API int pa_seq_swapped_tokens(pa_handle* h, int seq_id);  /* tokens held in the host copy, 0 if resident or unknown */
 PA_API int pa_page_refcount(pa_handle* h, int page);
 

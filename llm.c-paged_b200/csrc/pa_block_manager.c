@@ -35,7 +35,8 @@ BlockManager* pa_bm_create(pa_handle* owner, int channels, int block_size, int m
     m->prompt_block_list = (int**)calloc((size_t)max_prompts, sizeof(int*));
     m->prompt_block_count = (int*)calloc((size_t)max_prompts, sizeof(int));
     m->refcount = (int*)calloc((size_t)max_blocks, sizeof(int));
-    if (!m->blocks || !m->block_table || !m->prompt_block_list || !m->prompt_block_count || !m->refcount) {
+    m->pinned = (unsigned char*)calloc((size_t)max_prompts, 1);
+    if (!m->blocks || !m->block_table || !m->prompt_block_list || !m->prompt_block_count || !m->refcount || !m->pinned) {
         pa_bm_destroy(m);
         return NULL;
     }
@@ -48,6 +49,7 @@ void pa_bm_destroy(BlockManager* m) {
     if (!m) return;
     pa_share_destroy(m);
     free(m->refcount);
+    free(m->pinned);
     free(m->blocks);
     free(m->block_table);
     free(m->prompt_block_list);
@@ -120,7 +122,8 @@ int find_least_recently_used_block(BlockManager* m) {
     int lowest = m->lru_epoch;
     for (int i = 0; i < m->max_blocks; i++) {
         const KVBlock* b = &m->blocks[i];
-        if (b->prompt_id >= 0 && b->lru_counter < lowest) {      /* (pages held only by the prefix cache are not a prompt's) */
+        /* (pages held only by the prefix cache are not a prompt's; a sequence of the step being built is pinned) */
+        if (b->prompt_id >= 0 && b->lru_counter < lowest && !m->pinned[b->prompt_id]) {
             lowest = b->lru_counter;
             victim = i;
         }

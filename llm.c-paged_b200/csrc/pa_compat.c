@@ -8,6 +8,7 @@
  * host memory (as in the reference, staged through pinned memory inside the call) or device
  * memory.  Calls are synchronous like the reference's.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -30,23 +31,40 @@ void pa_set_default_geometry(int block_size, int max_blocks, int max_prompts) {
 }
 int pa_default_block_size(void) { return env_int("PA_BLOCK_SIZE", g_block_size); }
 
-/* ---- registry: attention_paged receives page pointers, not a manager ----------------------- */
-#define PA_MAX_LIVE 64
-static pa_handle* g_live[PA_MAX_LIVE];
+/* ---- registry: attention_paged receives page pointers, not a manager -----------------------
+ * A growable array behind a mutex: managers may be created and destroyed from different host threads
+ * (each manager itself is driven by one thread, like the reference's). */
+static pthread_mutex_t g_live_lock = PTHREAD_MUTEX_INITIALIZER;
+static pa_handle** g_live = NULL;
+static int g_live_n = 0, g_live_cap = 0;
 
-static void registry_add(pa_handle* h) {
-    for (int i = 0; i < PA_MAX_LIVE; i++) if (!g_live[i]) { g_live[i] = h; return; }
+static int registry_add(pa_handle* h) {
+    int ok = 1;
+    pthread_mutex_lock(&g_live_lock);
+    if (g_live_n == g_live_cap) {
+        int cap = g_live_cap ? 2 * g_live_cap : 16;
+        pa_handle** p = (pa_handle**)realloc(g_live, (size_t)cap * sizeof(*p));
+        if (p) { g_live = p; g_live_cap = cap; } else ok = 0;
+    }
+    if (ok) g_live[g_live_n++] = h;
+    pthread_mutex_unlock(&g_live_lock);
+    return ok;
 }
 static void registry_remove(pa_handle* h) {
-    for (int i = 0; i < PA_MAX_LIVE; i++) if (g_live[i] == h) g_live[i] = NULL;
+    pthread_mutex_lock(&g_live_lock);
+    for (int i = 0; i < g_live_n; i++)
+        if (g_live[i] == h) { g_live[i] = g_live[--g_live_n]; break; }
+    pthread_mutex_unlock(&g_live_lock);
 }
 static pa_handle* registry_find_by_page(const float* key_page) {
-    for (int i = 0; i < PA_MAX_LIVE; i++) {
+    pa_handle* found = NULL;
+    pthread_mutex_lock(&g_live_lock);
+    for (int i = 0; i < g_live_n && !found; i++) {
         pa_handle* h = g_live[i];
-        if (!h || !h->pool_k) continue;
-        if (key_page >= h->pool_k && key_page < h->pool_k + h->layer_stride * h->cfg.n_layers) return h;
+        if (h->pool_k && key_page >= h->pool_k && key_page < h->pool_k + h->layer_stride * h->cfg.n_layers) found = h;
     }
-    return NULL;
+    pthread_mutex_unlock(&g_live_lock);
+    return found;
 }
 
 BlockManager* create_block_manager(int channels) {
@@ -67,7 +85,11 @@ BlockManager* create_block_manager(int channels) {
         fprintf(stderr, "create_block_manager: %s\n", pa_last_error());
         return NULL;
     }
-    registry_add(h);
+    if (!registry_add(h)) {
+        fprintf(stderr, "create_block_manager: out of host memory\n");
+        pa_destroy(h);
+        return NULL;
+    }
     return h->mgr;
 }
 
@@ -130,26 +152,42 @@ void attention_paged(float* out, float* preatt, float* att, float* inp,
     const int bs = h->mgr->block_size;
     const size_t page_floats = (size_t)bs * C;
     const int n_pages = (T - 1 + offset) / bs + 1;        /* pages the reference touches (:190) */
-    int* table = (int*)malloc((size_t)n_pages * sizeof(int));
-    const int** rows = (const int**)malloc((size_t)B * sizeof(int*));
-    int* ints = (int*)malloc((size_t)B * 4 * sizeof(int));
-    if (!table || !rows || !ints) { fprintf(stderr, "attention_paged: out of memory\n"); goto done; }
+    /* scratch lives in the handle and only ever grows: no allocation per call on the decode loop */
+    const size_t need_ints = (size_t)n_pages + (size_t)B * 4;
+    if (need_ints > h->compat_ints_cap) {
+        int* p = (int*)realloc(h->compat_ints, need_ints * 2 * sizeof(int));
+        if (!p) { fprintf(stderr, "attention_paged: out of memory\n"); return; }
+        h->compat_ints = p; h->compat_ints_cap = need_ints * 2;
+    }
+    if ((size_t)B > h->compat_rows_cap) {
+        const int** p = (const int**)realloc((void*)h->compat_rows, (size_t)B * 2 * sizeof(int*));
+        if (!p) { fprintf(stderr, "attention_paged: out of memory\n"); return; }
+        h->compat_rows = p; h->compat_rows_cap = (size_t)B * 2;
+    }
+    int* table = h->compat_ints;
+    int* ints = h->compat_ints + n_pages;
+    const int** rows = h->compat_rows;
     for (int i = 0; i < n_pages; i++) {
         size_t koff = (size_t)(key_blocks[i] - h->pool_k), voff = (size_t)(value_blocks[i] - h->pool_v);
         if (koff % page_floats || koff != voff || koff / page_floats >= (size_t)h->cfg.max_blocks) {
             fprintf(stderr, "attention_paged: page %d is not a (keys, values) pair of this pool\n", i);
-            goto done;
+            return;
         }
         table[i] = (int)(koff / page_floats);
     }
     /* key_blocks/value_blocks are shared by every b (:190 has no b) */
     int* np = ints, *ks = ints + B, *ke = ints + 2 * B, *nq = ints + 3 * B;
     for (int b = 0; b < B; b++) { rows[b] = table; np[b] = n_pages; ks[b] = offset; ke[b] = offset + T; nq[b] = T; }
-    h->cfg.n_heads = NH;
-    h->cfg.head_dim = C / NH;
+    /* create_block_manager(channels) cannot know the head count (block_manager.c:38): the manager learns it
+     * from the first attention_paged and keeps it (a compat handle sized its workspace for any NH dividing C) */
+    if (h->cfg.n_heads != NH) {
+        if (!h->compat) { fprintf(stderr, "attention_paged: NH=%d does not match the handle (%d heads)\n", NH, h->cfg.n_heads); return; }
+        h->cfg.n_heads = NH;
+        h->cfg.head_dim = C / NH;
+    }
     if (pa_step_begin_raw(h, B, rows, np, ks, ke, nq) != PA_OK || pa_step_upload(h, h->stream) != PA_OK) {
         fprintf(stderr, "attention_paged: %s\n", pa_last_error());
-        goto done;
+        return;
     }
     {
         const size_t n_in = (size_t)B * T * 3 * C, n_out = (size_t)B * T * C;
@@ -157,32 +195,30 @@ void attention_paged(float* out, float* preatt, float* att, float* inp,
         const float* d_in = inp;
         float* d_out = out;
         if (!in_dev || !out_dev) {
-            if (pa_cu_ensure_stage(h, n_in + n_out) != PA_OK) { fprintf(stderr, "attention_paged: %s\n", pa_last_error()); goto done; }
+            if (pa_cu_ensure_stage(h, n_in + n_out) != PA_OK) { fprintf(stderr, "attention_paged: %s\n", pa_last_error()); return; }
         }
         if (!in_dev) {
             memcpy(h->h_stage, inp, n_in * sizeof(float));
             if (pa_memcpy_h2d(h->d_stage, h->h_stage, n_in * sizeof(float), h->stream) != PA_OK) {
                 fprintf(stderr, "attention_paged: %s\n", pa_last_error());
-                goto done;
+                return;
             }
             d_in = h->d_stage;
         }
         if (!out_dev) d_out = h->d_stage + n_in;
         if (pa_prefill(h, 0, d_in, 3 * C, d_out, C, h->stream) != PA_OK) {
             fprintf(stderr, "attention_paged: %s\n", pa_last_error());
-            goto done;
+            return;
         }
         if (!out_dev) {
             if (pa_memcpy_d2h(h->h_stage + n_in, d_out, n_out * sizeof(float), h->stream) != PA_OK ||
                 pa_stream_sync(h->stream) != PA_OK) {
                 fprintf(stderr, "attention_paged: %s\n", pa_last_error());
-                goto done;
+                return;
             }
             memcpy(out, h->h_stage + n_in, n_out * sizeof(float));
         } else if (pa_stream_sync(h->stream) != PA_OK) {
             fprintf(stderr, "attention_paged: %s\n", pa_last_error());
         }
     }
-done:
-    free(table); free(rows); free(ints);
 }

@@ -63,6 +63,7 @@ int pa_cu_init(pa_handle* h) {
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+    h->max_pitch = prop.memPitch;
     cudaStream_t s;
     CU_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     h->stream = (void*)s;
@@ -220,12 +221,30 @@ int pa_cu_swap_page(pa_handle* h, int page, float* host_k, float* host_v, int to
     const size_t lpitch = h->layer_stride * sizeof(float);
     float* dk = h->pool_k + (size_t)page * h->cfg.block_size * h->C;
     float* dv = h->pool_v + (size_t)page * h->cfg.block_size * h->C;
-    if (to_host) {
-        CU_CHECK(cudaMemcpy2DAsync(host_k, page_bytes, dk, lpitch, page_bytes, h->cfg.n_layers, cudaMemcpyDeviceToHost, s));
-        CU_CHECK(cudaMemcpy2DAsync(host_v, page_bytes, dv, lpitch, page_bytes, h->cfg.n_layers, cudaMemcpyDeviceToHost, s));
+    /* one 2-D copy moves a page of every layer (pitch = layer stride) while the pitch is one the runtime
+     * accepts (cudaDeviceProp::memPitch, ~2 GiB: pools beyond ~700 k tokens at C = 768 exceed it); beyond
+     * that, one plain copy per layer */
+    if (lpitch <= h->max_pitch) {
+        if (to_host) {
+            CU_CHECK(cudaMemcpy2DAsync(host_k, page_bytes, dk, lpitch, page_bytes, h->cfg.n_layers, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(cudaMemcpy2DAsync(host_v, page_bytes, dv, lpitch, page_bytes, h->cfg.n_layers, cudaMemcpyDeviceToHost, s));
+        } else {
+            CU_CHECK(cudaMemcpy2DAsync(dk, lpitch, host_k, page_bytes, page_bytes, h->cfg.n_layers, cudaMemcpyHostToDevice, s));
+            CU_CHECK(cudaMemcpy2DAsync(dv, lpitch, host_v, page_bytes, page_bytes, h->cfg.n_layers, cudaMemcpyHostToDevice, s));
+        }
     } else {
-        CU_CHECK(cudaMemcpy2DAsync(dk, lpitch, host_k, page_bytes, page_bytes, h->cfg.n_layers, cudaMemcpyHostToDevice, s));
-        CU_CHECK(cudaMemcpy2DAsync(dv, lpitch, host_v, page_bytes, page_bytes, h->cfg.n_layers, cudaMemcpyHostToDevice, s));
+        const size_t pf = page_bytes / sizeof(float);
+        for (int l = 0; l < h->cfg.n_layers; l++) {
+            float* lk = dk + (size_t)l * h->layer_stride;
+            float* lv = dv + (size_t)l * h->layer_stride;
+            if (to_host) {
+                CU_CHECK(cudaMemcpyAsync(host_k + l * pf, lk, page_bytes, cudaMemcpyDeviceToHost, s));
+                CU_CHECK(cudaMemcpyAsync(host_v + l * pf, lv, page_bytes, cudaMemcpyDeviceToHost, s));
+            } else {
+                CU_CHECK(cudaMemcpyAsync(lk, host_k + l * pf, page_bytes, cudaMemcpyHostToDevice, s));
+                CU_CHECK(cudaMemcpyAsync(lv, host_v + l * pf, page_bytes, cudaMemcpyHostToDevice, s));
+            }
+        }
     }
     return PA_OK;          /* enqueued on the handle's stream; pa_cu_swap_sync waits */
 }

@@ -47,6 +47,7 @@ struct pa_handle {
     pa_step_layout step;
     int* step_seq_ids;            /* host [max_seqs] */
     int* step_n_new;              /* host [max_seqs] */
+    int* step_pre_len;            /* host [max_seqs] context length of each sequence before the step being built */
     int* slot_scratch;            /* host [max_batch_tokens] */
     /* decode split workspace */
     float* d_ws;
@@ -61,6 +62,7 @@ struct pa_handle {
     int sm_count;
     int smem_optin;
     int smem_per_sm;
+    size_t max_pitch;             /* cudaDeviceProp::memPitch */
     int tune[32];
     long launches;
     void* d_dbg;                  /* optional per-CTA timeline of the last decode launch */
@@ -69,13 +71,20 @@ struct pa_handle {
     int max_heads;                /* heads the split workspace was sized for */
     void* tc_state;               /* TMA tensor maps of the pool (pa_prefill_tc.cu), lazily built */
     void* host_pipe;              /* copy streams + events of pa_decode_step_host_async (pa_kernels.cu) */
+    int* compat_ints;             /* attention_paged scratch (page indices + per-row ints), grown on demand, kept */
+    size_t compat_ints_cap;
+    const int** compat_rows;
+    size_t compat_rows_cap;
     int swap_enabled;             /* extension: evicted sequences are swapped out to host memory instead of dropped */
     void* swap_state;             /* pa_sharing.c */
+    int swap_failures;            /* evictions whose host copy could not be made (the sequence was dropped, as the reference does) */
 };
 
 void pa_set_error(const char* fmt, ...);
-extern int pa_pdl_enabled;
-extern int pa_pdl_gate;
+/* launch switches of the CALLING THREAD (one host thread drives a handle): set from the handle at every
+ * public entry that launches kernels, so two handles on two threads never see each other's settings */
+extern __thread int pa_pdl_enabled;
+extern __thread int pa_pdl_gate;
 
 /* ---- implemented in pa_block_manager.c (plain C, integer only) ------------------------- */
 BlockManager* pa_bm_create(pa_handle* owner, int channels, int block_size, int max_blocks,

@@ -1016,6 +1016,7 @@ static int check_compute(pa_handle* h, int layer, const char* who) {
     if (h->step.nseq < 1) { pa_set_error("%s: no step (call pa_step_begin)", who); return PA_ERR_INVALID; }
     if (!h->step.uploaded) { pa_set_error("%s: step tables not uploaded (call pa_step_upload)", who); return PA_ERR_INVALID; }
     if (cudaSetDevice(h->cfg.device) != cudaSuccess) { pa_set_error("%s: cudaSetDevice failed", who); return PA_ERR_CUDA; }
+    pa_pdl_enabled = h->tune[PA_TUNE_NO_PDL] ? 0 : 1;      // this thread's launches follow THIS handle's switch
     return PA_OK;
 }
 

@@ -338,8 +338,18 @@ float* pa_model_logits(pa_model* m, int* stride) {
  * projection with fused KV append -> paged attention (decode kernel when every sequence has one
  * new token, else the causal prefill kernel) -> attproj (+residual) -> ln2 -> fc (+GELU) -> fcproj
  * (+residual); final layernorm, LM head and sampler on the last rows only. */
+static int model_forward_impl(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins, int nseq,
+                              int* next_tokens);
+
 int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins, int nseq,
                      int* next_tokens) {
+    const int rc = model_forward_impl(m, seq_ids, n_new, tokens, coins, nseq, next_tokens);
+    pa_pdl_gate = 1;          // whatever path the step left by, the gate does not outlive it
+    return rc;
+}
+
+static int model_forward_impl(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins, int nseq,
+                              int* next_tokens) {
     if (!m || !seq_ids || !n_new || !tokens || !next_tokens || nseq < 1) {
         pa_set_error("pa_model_forward: bad arguments");
         return PA_ERR_INVALID;
@@ -358,24 +368,34 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
         return PA_ERR_INVALID;
     }
     const int ntok = (int)ntok_ll;
+    for (int row = 0; row < ntok; ++row)
+        if (tokens[row] < 0 || tokens[row] >= V) { pa_set_error("pa_model_forward: token %d out of range", tokens[row]); return PA_ERR_INVALID; }
+    CU_CHECK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)h->stream;
+    pa_pdl_enabled = h->tune[PA_TUNE_NO_PDL] ? 0 : 1;
+    // The page choice comes FIRST: pa_step_begin may bring a swapped-out sequence back (its cached length is 0
+    // until then), so the positions of the new tokens are only known from the step tables it builds:
+    // position of a sequence's first new token = kv_end - n_new.
+    int rc = pa_step_begin(h, seq_ids, n_new, nseq);
+    if (rc != PA_OK) return rc;
     // host io layout: tokens[ntok] | positions[ntok] | last_row[nseq] | next[nseq]
     int* h_tok = m->h_io, *h_pos = m->h_io + ntok, *h_last = m->h_io + 2 * ntok, *h_next = m->h_io + 2 * ntok + nseq;
     for (int i = 0, row = 0; i < nseq; ++i) {
-        const int pos0 = pa_seq_len(h, seq_ids[i]);
-        if (pos0 < 0 || pos0 + n_new[i] > m->maxT) {
-            pa_set_error("pa_model_forward: sequence %d would reach position %d of %d", seq_ids[i], pos0 + n_new[i], m->maxT);
+        const int end = h->h_step[h->step.off_kv_end + i];
+        const int pos0 = end - n_new[i];
+        if (pos0 < 0 || pos0 != h->step_pre_len[i] || end > m->maxT) {
+            if (end > m->maxT) pa_set_error("pa_model_forward: sequence %d would reach position %d of %d", seq_ids[i], end, m->maxT);
+            else pa_set_error("pa_model_forward: sequence %d changed length while the step was built (%d cached, %d new, %d before)", seq_ids[i], end, n_new[i], h->step_pre_len[i]);
+            pa_step_rollback(h);
             return PA_ERR_INVALID;
         }
         for (int j = 0; j < n_new[i]; ++j, ++row) {
-            if (tokens[row] < 0 || tokens[row] >= V) { pa_set_error("pa_model_forward: token %d out of range", tokens[row]); return PA_ERR_INVALID; }
             h_tok[row] = tokens[row];
             h_pos[row] = pos0 + j;
         }
         h_last[i] = row - 1;
         if (coins) m->h_coins[i] = coins[i];
     }
-    CU_CHECK(cudaSetDevice(h->cfg.device));
-    cudaStream_t s = (cudaStream_t)h->stream;
     // A handful of sequences with one new token each: the whole step is ONE persistent kernel (pa_model_mega.cu)
     const int model_path = h->tune[PA_TUNE_MODEL_PATH];
     bool use_mega = false;
@@ -384,6 +404,7 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
         use_mega = mega_smem && (size_t)h->smem_optin >= mega_smem + 1024 && !(m->mega_refused && model_path != 2);
         if (!use_mega && model_path == 2) {
             pa_set_error("pa_model_forward: the persistent step kernel takes at most %d sequences of one new token each (head_dim 64 or 128)", PA_MEGA_MAX_SEQS);
+            pa_step_rollback(h);
             return PA_ERR_UNSUPPORTED;
         }
     }
@@ -392,8 +413,6 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
     // their way); with the workspace split it pays at every size measured (2.84 -> 2.74 ms at 256 tokens).
     static const int pdl_max_tokens = getenv("PA_PDL_MAX_TOKENS") ? atoi(getenv("PA_PDL_MAX_TOKENS")) : (1 << 30);
     pa_pdl_gate = ntok <= pdl_max_tokens;
-    int rc = pa_step_begin(h, seq_ids, n_new, nseq);
-    if (rc != PA_OK) return rc;
     rc = pa_step_upload(h, s);
     if (rc != PA_OK) return rc;
     if (use_mega) {
@@ -403,7 +422,6 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
         if (rc == PA_OK) {
             h->launches += 1;
             CU_CHECK(cudaStreamSynchronize(s));
-            pa_pdl_gate = 1;
             memcpy(next_tokens, h_next, (size_t)nseq * sizeof(int));
             return PA_OK;
         }
@@ -446,7 +464,6 @@ int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const in
     h->launches += launches + 3;        // (pa_qkv_append / pa_decode / pa_prefill count themselves)
     CU_CHECK(cudaMemcpyAsync(h_next, d_next, (size_t)nseq * sizeof(int), cudaMemcpyDeviceToHost, s));
     CU_CHECK(cudaStreamSynchronize(s));
-    pa_pdl_gate = 1;
     memcpy(next_tokens, h_next, (size_t)nseq * sizeof(int));
     return PA_OK;
 }

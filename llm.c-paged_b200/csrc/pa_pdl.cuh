@@ -9,13 +9,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
-extern "C" int pa_pdl_enabled;     /* 1 by default; PA_TUNE_NO_PDL switches it off (pa_step.c) */
-extern "C" int pa_pdl_gate;        /* per-step gate set by the caller of the chain (pa_model_forward) */
+extern "C" __thread int pa_pdl_enabled;     /* per host thread; set from the handle's PA_TUNE_NO_PDL at each launching entry */
+extern "C" __thread int pa_pdl_gate;        /* per-step gate set by the caller of the chain (pa_model_forward) */
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-extern "C" int pa_launch_cooperative;      /* set around a launch whose CTAs wait for each other (split-K through the L2 workspace) */
+extern "C" __thread int pa_launch_cooperative;      /* set around a launch whose CTAs wait for each other (split-K through the L2 workspace) */
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t pa_launch_pdl(void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,

@@ -279,6 +279,7 @@ int pa_qkv_append(pa_handle* h, int layer, const float* x, int x_stride, const f
     if (!x || !w || !q_out || x_stride < h->C || q_stride < h->C) { pa_set_error("pa_qkv_append: bad arguments"); return PA_ERR_INVALID; }
     if (L.ntok == 0) return PA_OK;
     CU_CHECK(cudaSetDevice(h->cfg.device));
+    pa_pdl_enabled = h->tune[PA_TUNE_NO_PDL] ? 0 : 1;
     QkvParams p;
     p.x = x; p.in_rows = nullptr; p.w = w; p.bias = bias;
     p.out = q_out; p.out_rows = nullptr;

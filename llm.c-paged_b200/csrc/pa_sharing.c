@@ -15,6 +15,7 @@
  * through it, block_manager.c:104-113) or PA_OWNER_CACHE.
  */
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -129,7 +130,11 @@ int pa_seq_fork(pa_handle* h, int src, int dst) {
     }
     m->prompt_block_count[dst] = shared;
     if (shared < n) {
-        KVBlock* b = request_block(m, dst);       /* may evict (never src or dst pages that are shared: they have other holders) */
+        /* may evict another sequence -- never src or dst: both are pinned while the page for the copy is found */
+        const unsigned char pin_src = m->pinned[src], pin_dst = m->pinned[dst];
+        m->pinned[src] = m->pinned[dst] = 1;
+        KVBlock* b = request_block(m, dst);
+        m->pinned[src] = pin_src; m->pinned[dst] = pin_dst;
         if (!b || m->prompt_block_count[src] != n || m->prompt_block_list[src][n - 1] != last) {
             pa_set_error("pa_seq_fork: no page for the copy of the last page");
             free_blocks_for_prompt(m, dst);
@@ -273,27 +278,34 @@ int pa_seq_swap_out(pa_handle* h, int seq) {
     return PA_OK;
 }
 
-/* allocator hook: the victim is about to lose its pages; keep a host copy (errors degrade to the
- * reference's behaviour: the sequence is simply dropped) */
+/* allocator hook: the victim is about to lose its pages; keep a host copy.  A copy that cannot be made
+ * degrades to the reference's behaviour (the sequence is dropped and must be prefilled again) -- loudly:
+ * stderr like the reference's allocator messages, and counted in pa_swap_failures(). */
+static void swap_failed(pa_handle* h, int p, swap_slot* sl, const char* why) {
+    if (sl && sl[p].buf) { swap_free(h, sl[p].buf); sl[p].buf = NULL; }
+    h->swap_failures++;
+    fprintf(stderr, "Swap-out of prompt %d failed (%s); its KV is dropped.\n", p, why);
+}
 void pa_swap_on_evict(pa_handle* h, int p) {
     if (bad_seq(h, p)) return;
     BlockManager* m = h->mgr;
     const int n = m->prompt_block_count[p];
     if (n == 0) return;
     swap_slot* sl = swap_slots(h, 1);
-    if (!sl) return;
+    if (!sl) { swap_failed(h, p, NULL, "out of host memory"); return; }
     const size_t pf = swap_page_floats(h);
     swap_free(h, sl[p].buf);
     sl[p].buf = swap_alloc(h, (size_t)n * pf * sizeof(float));
-    if (!sl[p].buf) return;
+    if (!sl[p].buf) { swap_failed(h, p, sl, "out of host memory"); return; }
     sl[p].n_tokens = pa_bm_context_len(m, p);
     sl[p].n_pages = n;
     for (int i = 0; i < n; i++) {
         float* k = sl[p].buf + (size_t)i * pf;
-        if (pa_cu_swap_page(h, m->prompt_block_list[p][i], k, k + pf / 2, 1) != PA_OK) { swap_free(h, sl[p].buf); sl[p].buf = NULL; return; }
+        if (pa_cu_swap_page(h, m->prompt_block_list[p][i], k, k + pf / 2, 1) != PA_OK) { swap_failed(h, p, sl, pa_last_error()); return; }
     }
-    if (pa_cu_swap_sync(h) != PA_OK) { swap_free(h, sl[p].buf); sl[p].buf = NULL; }
+    if (pa_cu_swap_sync(h) != PA_OK) swap_failed(h, p, sl, pa_last_error());
 }
+int pa_swap_failures(pa_handle* h) { return h ? h->swap_failures : PA_ERR_INVALID; }
 
 int pa_seq_swap_in(pa_handle* h, int seq) {
     if (bad_seq(h, seq)) { pa_set_error("pa_seq_swap_in: bad sequence id"); return PA_ERR_INVALID; }

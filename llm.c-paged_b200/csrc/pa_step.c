@@ -15,9 +15,9 @@
 #include "pa_internal.h"
 
 static __thread char g_err[512] = "";
-int pa_pdl_enabled = 1;      /* programmatic dependent launch for the step's kernel chain (pa_pdl.cuh) */
-int pa_pdl_gate = 1;
-int pa_launch_cooperative = 0;
+__thread int pa_pdl_enabled = 1;      /* programmatic dependent launch for the step's kernel chain (pa_pdl.cuh) */
+__thread int pa_pdl_gate = 1;
+__thread int pa_launch_cooperative = 0;
 
 void pa_set_error(const char* fmt, ...) {
     va_list ap;
@@ -61,9 +61,10 @@ static int create_impl(const pa_config* cfg, pa_handle** out, int compat) {
     h->layer_stride = (size_t)cfg->max_blocks * cfg->block_size * h->C;
     h->step_seq_ids = (int*)calloc((size_t)cfg->max_seqs, sizeof(int));
     h->step_n_new = (int*)calloc((size_t)cfg->max_seqs, sizeof(int));
+    h->step_pre_len = (int*)calloc((size_t)cfg->max_seqs, sizeof(int));
     h->slot_scratch = (int*)calloc((size_t)h->cfg.max_batch_tokens + 1, sizeof(int));
     h->mgr = pa_bm_create(h, h->C, cfg->block_size, cfg->max_blocks, cfg->max_seqs, h->cfg.max_blocks_per_seq);
-    if (!h->mgr || !h->step_seq_ids || !h->step_n_new || !h->slot_scratch) {
+    if (!h->mgr || !h->step_seq_ids || !h->step_n_new || !h->step_pre_len || !h->slot_scratch) {
         pa_set_error("pa_create: out of host memory");
         pa_destroy(h);
         return PA_ERR_NOMEM;
@@ -84,7 +85,10 @@ void pa_destroy(pa_handle* h) {
     pa_bm_destroy(h->mgr);
     free(h->step_seq_ids);
     free(h->step_n_new);
+    free(h->step_pre_len);
     free(h->slot_scratch);
+    free(h->compat_ints);
+    free((void*)h->compat_rows);
     free(h);
 }
 
@@ -100,7 +104,6 @@ int pa_tune_set(pa_handle* h, int key, int value) {
     if (!h || key < 0 || key >= PA_TUNE_MAX || key == PA_TUNE_COUNT_LAUNCHES ||
         (key >= PA_TUNE_LAST_HPG && key <= PA_TUNE_LAST_GRID)) return PA_ERR_INVALID;
     h->tune[key] = value;
-    if (key == PA_TUNE_NO_PDL) pa_pdl_enabled = value ? 0 : 1;
     return PA_OK;
 }
 int pa_tune_get(pa_handle* h, int key) {
@@ -186,6 +189,35 @@ static int build_tables(pa_handle* h, int nseq, int ntok, const int* kv_start_in
     return PA_OK;
 }
 
+/* The sequences of the step being built are PINNED while pages are placed: the whole-prompt LRU eviction
+ * inside request_block (block_manager.c:104-113) must never take a sequence whose slots were already
+ * handed out in this step, nor the requester itself.  Returns PA_ERR_INVALID on a duplicate id. */
+static int pin_step(pa_handle* h, const int* seq_ids, int nseq, const char* who) {
+    unsigned char* pinned = h->mgr->pinned;
+    for (int i = 0; i < nseq; i++) {
+        if (pinned[seq_ids[i]]) {
+            for (int j = 0; j < i; j++) pinned[seq_ids[j]] = 0;
+            pa_set_error("%s: sequence %d is named twice in one step", who, seq_ids[i]);
+            return PA_ERR_INVALID;
+        }
+        pinned[seq_ids[i]] = 1;
+    }
+    return PA_OK;
+}
+static void unpin_step(pa_handle* h, const int* seq_ids, int nseq) {
+    for (int i = 0; i < nseq; i++) h->mgr->pinned[seq_ids[i]] = 0;
+}
+
+/* a step that failed part-way leaves no trace in the sequences it had already touched: rows [0, upto]
+ * go back to the length they had before the step (pages allocated for tokens that will never be written
+ * return to the pool) */
+static void undo_partial_step(pa_handle* h, int upto) {
+    for (int j = 0; j <= upto; j++) {
+        int p = h->step_seq_ids[j];
+        if (pa_bm_context_len(h->mgr, p) > h->step_pre_len[j]) pa_seq_truncate(h, p, h->step_pre_len[j]);
+    }
+}
+
 int pa_step_begin(pa_handle* h, const int* seq_ids, const int* n_new, int nseq) {
     int rc = check_batch(h, seq_ids, nseq, "pa_step_begin");
     if (rc != PA_OK) return rc;
@@ -201,24 +233,32 @@ int pa_step_begin(pa_handle* h, const int* seq_ids, const int* n_new, int nseq) 
         pa_set_error("pa_step_begin: %lld new tokens > max_batch_tokens %d", ntok, h->cfg.max_batch_tokens);
         return PA_ERR_INVALID;
     }
+    rc = pin_step(h, seq_ids, nseq, "pa_step_begin");
+    if (rc != PA_OK) return rc;
     /* slot mapping goes to a scratch area first (table size is unknown until pages are placed) */
     int* slots = h->slot_scratch;
     int tok = 0;
-    for (int i = 0; i < nseq; i++) {
+    for (int i = 0; i < nseq && rc == PA_OK; i++) {
         int p = seq_ids[i];
         h->step_seq_ids[i] = p;
         h->step_n_new[i] = n_new[i];
         if (h->swap_enabled) {                       /* extension: a swapped-out sequence comes back before it grows */
-            int rcs = pa_swap_in_if_needed(h, p);
-            if (rcs != PA_OK) { h->step.nseq = 0; return rcs; }
+            rc = pa_swap_in_if_needed(h, p);
+            if (rc != PA_OK) { h->step_pre_len[i] = pa_bm_context_len(m, p); undo_partial_step(h, i - 1); break; }
         }
+        h->step_pre_len[i] = pa_bm_context_len(m, p);
         int left = n_new[i];
         while (left > 0) {
             int idx = pa_bm_choose_page(m, p);
             if (idx < 0) {
-                pa_set_error("pa_step_begin: No blocks available (sequence %d)", p);
-                h->step.nseq = 0;
-                return PA_ERR_NO_BLOCKS;
+                /* the pool is exhausted and every page left belongs to a sequence of this very step (or the
+                 * per-sequence cap is reached): evicting one of them -- or the requester, as the single-prompt
+                 * reference would (block_manager.c:157) -- would leave slots of this step pointing into pages
+                 * their sequence no longer owns, so this is an error */
+                pa_set_error("pa_step_begin: No blocks available (sequence %d; the sequences of a step are never evicted for it)", p);
+                undo_partial_step(h, i);
+                rc = PA_ERR_NO_BLOCKS;
+                break;
             }
             KVBlock* b = &m->blocks[idx];
             int take = bs - b->filled;
@@ -228,6 +268,8 @@ int pa_step_begin(pa_handle* h, const int* seq_ids, const int* n_new, int nseq) 
             left -= take;
         }
     }
+    unpin_step(h, seq_ids, nseq);
+    if (rc != PA_OK) { h->step.nseq = 0; return rc; }
     return build_tables(h, nseq, tok, NULL);
 }
 
@@ -291,14 +333,16 @@ int pa_step_begin_raw(pa_handle* h, int nseq, const int* const* tables, const in
 int pa_step_begin_readonly(pa_handle* h, const int* seq_ids, int nseq) {
     int rc = check_batch(h, seq_ids, nseq, "pa_step_begin_readonly");
     if (rc != PA_OK) return rc;
-    for (int i = 0; i < nseq; i++) {
+    rc = pin_step(h, seq_ids, nseq, "pa_step_begin_readonly");      /* a swap-in below must not evict another row of this step */
+    if (rc != PA_OK) return rc;
+    for (int i = 0; i < nseq && rc == PA_OK; i++) {
         h->step_seq_ids[i] = seq_ids[i];
         h->step_n_new[i] = 0;
-        if (h->swap_enabled) {
-            int rcs = pa_swap_in_if_needed(h, seq_ids[i]);
-            if (rcs != PA_OK) return rcs;
-        }
+        if (h->swap_enabled) rc = pa_swap_in_if_needed(h, seq_ids[i]);
+        h->step_pre_len[i] = pa_bm_context_len(h->mgr, seq_ids[i]);
     }
+    unpin_step(h, seq_ids, nseq);
+    if (rc != PA_OK) { h->step.nseq = 0; return rc; }
     return build_tables(h, nseq, 0, NULL);
 }
 

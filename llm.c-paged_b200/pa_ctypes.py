@@ -38,7 +38,8 @@ class BlockManager(C.Structure):
     _fields_ = [("C", C.c_int), ("blocks", C.POINTER(KVBlock)), ("prompt_block_list", C.POINTER(c_int_p)),
                 ("prompt_block_count", c_int_p), ("lru_epoch", C.c_int),
                 ("block_size", C.c_int), ("max_blocks", C.c_int), ("max_prompts", C.c_int),
-                ("table_stride", C.c_int), ("block_table", c_int_p), ("pa", vp)]
+                ("table_stride", C.c_int), ("block_table", c_int_p), ("pa", vp),
+                ("refcount", c_int_p), ("prefix_cache", vp), ("pinned", C.POINTER(C.c_ubyte))]
 
 
 class PaConfig(C.Structure):
@@ -134,6 +135,7 @@ def load():
         "pa_seq_swap_out": (C.c_int, [vp, C.c_int]),
         "pa_seq_swap_in": (C.c_int, [vp, C.c_int]),
         "pa_seq_swapped_tokens": (C.c_int, [vp, C.c_int]),
+        "pa_swap_failures": (C.c_int, [vp]),
         "pa_prefix_insert": (C.c_int, [vp, C.c_int, c_int_p, C.c_int]),
         "pa_prefix_match": (C.c_int, [vp, C.c_int, c_int_p, C.c_int]),
         "pa_prefix_cached_pages": (C.c_int, [vp]),
