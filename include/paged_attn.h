@@ -222,8 +222,47 @@ PA_API int pa_model_decode_step(pa_model* m, const int* seq_ids, const int* toke
  * max_batch of pa_model_create bounds the tokens of one step. */
 PA_API int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins,
                             int nseq, int* next_tokens);
+/* The same step in two halves: _async enqueues everything on the handle's stream and returns without a host
+ * synchronisation; pa_model_wait synchronises and hands out the sampled tokens (next_tokens may be NULL).
+ * A host driving several GPUs queues every GPU's step before it waits for any (pa_group_model_step). */
+PA_API int pa_model_forward_async(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins,
+                                  int nseq);
+PA_API int pa_model_wait(pa_model* m, int* next_tokens);
+PA_API int* pa_model_next_tokens_dev(pa_model* m);        /* device: sampled tokens of the step in flight / last step, [nseq] */
+PA_API void pa_model_want_device_tokens(pa_model* m, int on); /* keep them in device memory too (the persistent kernel otherwise writes mapped host memory only) */
+PA_API pa_handle* pa_model_handle(pa_model* m);
 PA_API float* pa_model_params(pa_model* m);               /* device */
 PA_API float* pa_model_logits(pa_model* m, int* stride);  /* device, (nseq, stride) of the last step */
+
+/* ---- multi-GPU: sequences sharded over the GPUs of one box, each GPU with its own block manager,
+ * page pool and tables; the attention needs no collective.  The ONE exchange is the all-gather of the
+ * sampled tokens (or of last-position logits) after the sampler: plain ncclAllGather enqueued on each
+ * handle's stream behind the sampler kernel, no host synchronisation in between.  NCCL (libnccl.so.2) is
+ * opened on first use, not linked.  Only precedent in the reference: Python DDP, train_gpt2.py:400-412. */
+typedef struct pa_group pa_group;
+#define PA_COMM_ID_BYTES 128
+/* (a) ONE process drives n GPUs: a handle + stream per device (devices[i], or 0..n-1 when NULL; cfg->device is
+ * ignored) and one communicator per handle (ncclCommInitAll).  pa_group_destroy destroys the handles too. */
+PA_API int pa_group_create(const pa_config* cfg, int n_gpus, const int* devices, pa_group** out);
+/* (b) one process per GPU (torchrun, MPI): rank 0 makes the id, the launcher distributes its 128 bytes, every
+ * rank joins with its own handle (ncclCommInitRank).  The handle stays the caller's. */
+PA_API int pa_comm_unique_id(void* id128);
+PA_API int pa_group_join(pa_handle* h, const void* id128, int rank, int world, pa_group** out);
+PA_API void pa_group_destroy(pa_group* g);
+PA_API int pa_group_size(pa_group* g);                    /* ranks in the group */
+PA_API int pa_group_local_count(pa_group* g);             /* members driven by this process: n (a) or 1 (b) */
+PA_API int pa_group_rank(pa_group* g, int i);             /* rank of local member i */
+PA_API pa_handle* pa_group_handle(pa_group* g, int i);    /* handle of local member i */
+/* all-gather on the members' streams: send[i] = n_per_rank int32 (device memory of member i), recv[i] =
+ * size * n_per_rank int32 there, rank-major.  Stream-ordered; returns without synchronising. */
+PA_API int pa_group_gather_tokens(pa_group* g, const int* const* send, int* const* recv, int n_per_rank);
+PA_API int pa_group_gather_logits(pa_group* g, const float* const* send, float* const* recv, size_t n_floats_per_rank);
+/* One decode step of the whole group: model i (on member i's handle) takes one token per sequence, the sampled
+ * tokens of all ranks are gathered behind the samplers, the host waits once per member.
+ * all_next: size * nseq ints, rank-major. */
+PA_API int pa_group_model_step(pa_group* g, pa_model* const* models, const int* const* seq_ids, const int* const* tokens,
+                               const float* const* coins, int nseq, int* all_next);
+PA_API int pa_nccl_version(void);                         /* e.g. 22809; 0 when NCCL cannot be opened */
 
 /* ---- the reference's on-disk formats (host only, no device needed) ---------------- */
 /* checkpoint gpt2_124M.bin (reader paged_infer.c:436-502): 256 x int32 header + 16 fp32 tensors */
@@ -345,6 +384,9 @@ PA_API void pa_host_free(void* p);
 PA_API int pa_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);
 PA_API int pa_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);
 PA_API int pa_memset(void* dst, int value, size_t bytes, void* stream);
+/* N(mean, stdv) written by the device from a counter-based hash of (seed, index): synthetic pools of any size
+ * without a host copy; element i is a pure function of (seed, i) */
+PA_API int pa_fill_normal(float* dev, size_t n, float stdv, float mean, unsigned long long seed, void* stream);
 PA_API void* pa_stream_create(void);
 PA_API void pa_stream_destroy(void* stream);
 PA_API int pa_stream_sync(void* stream);

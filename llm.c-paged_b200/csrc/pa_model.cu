@@ -55,6 +55,10 @@ struct pa_model {
     unsigned* mega_bar;                    // its grid-barrier counter (monotonic over launches) ...
     unsigned mega_bar_base;                // ... and its value when the next launch starts
     int mega_refused;                      // a cooperative launch failed once: stay on the chain (automatic choice only)
+    int next_on_device;                    // the step's sampled tokens are wanted in device memory too (pa_group gathers them with NCCL)
+    int* d_next_cur;                       // device: sampled tokens of the step in flight ...
+    int* h_next_cur;                       // ... their pinned host copy ...
+    int nseq_cur;                          // ... and how many (0: no step in flight)
 };
 
 namespace {
@@ -315,6 +319,17 @@ int pa_model_create(pa_handle* h, const pa_model_config* cfg, const float* param
     return PA_OK;
 }
 
+/* N(mean, stdv) from the counter-based hash above, written by the device: synthetic pools and activations of
+ * any size without a host copy (a 160 GB pool is filled at HBM speed instead of over PCIe); the same
+ * (seed, index) always gives the same value, so a checker can regenerate any element on the host side */
+int pa_fill_normal(float* dev, size_t n, float stdv, float mean, unsigned long long seed, void* stream) {
+    if (!dev) { pa_set_error("pa_fill_normal: NULL pointer"); return PA_ERR_INVALID; }
+    if (n == 0) return PA_OK;
+    pa_init_normal_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(dev, n, stdv, mean, (uint64_t)seed);
+    CU_CHECK(cudaGetLastError());
+    return PA_OK;
+}
+
 void pa_model_destroy(pa_model* m) {
     if (!m) return;
     cudaFree(m->params); cudaFree(m->x); cudaFree(m->ln); cudaFree(m->q); cudaFree(m->atty); cudaFree(m->fch);
@@ -338,19 +353,40 @@ float* pa_model_logits(pa_model* m, int* stride) {
  * projection with fused KV append -> paged attention (decode kernel when every sequence has one
  * new token, else the causal prefill kernel) -> attproj (+residual) -> ln2 -> fc (+GELU) -> fcproj
  * (+residual); final layernorm, LM head and sampler on the last rows only. */
-static int model_forward_impl(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins, int nseq,
-                              int* next_tokens);
+static int model_forward_impl(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins, int nseq);
 
-int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins, int nseq,
-                     int* next_tokens) {
-    const int rc = model_forward_impl(m, seq_ids, n_new, tokens, coins, nseq, next_tokens);
+/* Enqueue the whole step on the handle's stream and return: no host synchronisation.  pa_model_wait
+ * finishes it.  A host driving several GPUs queues every GPU's step (and the NCCL gather behind it,
+ * pa_group_model_step) before it waits for any of them. */
+int pa_model_forward_async(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins, int nseq) {
+    if (m && m->nseq_cur) { pa_set_error("pa_model_forward_async: the previous step was not finished with pa_model_wait"); return PA_ERR_INVALID; }
+    const int rc = model_forward_impl(m, seq_ids, n_new, tokens, coins, nseq);
     pa_pdl_gate = 1;          // whatever path the step left by, the gate does not outlive it
     return rc;
 }
+int pa_model_wait(pa_model* m, int* next_tokens) {
+    if (!m || !m->nseq_cur) { pa_set_error("pa_model_wait: no step in flight"); return PA_ERR_INVALID; }
+    const int n = m->nseq_cur;
+    m->nseq_cur = 0;
+    CU_CHECK(cudaSetDevice(m->h->cfg.device));
+    CU_CHECK(cudaStreamSynchronize((cudaStream_t)m->h->stream));
+    if (next_tokens) memcpy(next_tokens, m->h_next_cur, (size_t)n * sizeof(int));
+    return PA_OK;
+}
+int* pa_model_next_tokens_dev(pa_model* m) { return m ? m->d_next_cur : nullptr; }
+void pa_model_want_device_tokens(pa_model* m, int on) { if (m) m->next_on_device = on ? 1 : 0; }
+pa_handle* pa_model_handle(pa_model* m) { return m ? m->h : nullptr; }
 
-static int model_forward_impl(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins, int nseq,
-                              int* next_tokens) {
-    if (!m || !seq_ids || !n_new || !tokens || !next_tokens || nseq < 1) {
+int pa_model_forward(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins, int nseq,
+                     int* next_tokens) {
+    if (!next_tokens) { pa_set_error("pa_model_forward: bad arguments"); return PA_ERR_INVALID; }
+    const int rc = pa_model_forward_async(m, seq_ids, n_new, tokens, coins, nseq);
+    if (rc != PA_OK) return rc;
+    return pa_model_wait(m, next_tokens);
+}
+
+static int model_forward_impl(pa_model* m, const int* seq_ids, const int* n_new, const int* tokens, const float* coins, int nseq) {
+    if (!m || !seq_ids || !n_new || !tokens || nseq < 1) {
         pa_set_error("pa_model_forward: bad arguments");
         return PA_ERR_INVALID;
     }
@@ -418,11 +454,13 @@ static int model_forward_impl(pa_model* m, const int* seq_ids, const int* n_new,
     if (use_mega) {
         // token ids, positions and coins travel as kernel arguments, the sampled tokens come back through
         // mapped pinned memory: the step is ONE table copy, ONE launch and ONE synchronisation
-        rc = mega_step(m, nseq, h_tok, h_pos, coins ? m->h_coins : nullptr, h_next, s);
+        // (with next_on_device they go to device memory first -- NCCL gathers from there -- and are copied back)
+        int* d_next_mega = m->d_io + 2 * ntok + nseq;
+        rc = mega_step(m, nseq, h_tok, h_pos, coins ? m->h_coins : nullptr, m->next_on_device ? d_next_mega : h_next, s);
         if (rc == PA_OK) {
             h->launches += 1;
-            CU_CHECK(cudaStreamSynchronize(s));
-            memcpy(next_tokens, h_next, (size_t)nseq * sizeof(int));
+            if (m->next_on_device) CU_CHECK(cudaMemcpyAsync(h_next, d_next_mega, (size_t)nseq * sizeof(int), cudaMemcpyDeviceToHost, s));
+            m->d_next_cur = d_next_mega; m->h_next_cur = h_next; m->nseq_cur = nseq;
             return PA_OK;
         }
         if (model_path == 2) return rc;
@@ -463,8 +501,7 @@ static int model_forward_impl(pa_model* m, const int* seq_ids, const int* n_new,
     CU_CHECK(pa_launch_pdl(pa_sample_kernel, dim3(nseq), dim3(kSampleThreads), 0, s, 1, (const float*)m->logits, m->Vp, V, (const float*)(coins ? m->d_coins : nullptr), d_next));
     h->launches += launches + 3;        // (pa_qkv_append / pa_decode / pa_prefill count themselves)
     CU_CHECK(cudaMemcpyAsync(h_next, d_next, (size_t)nseq * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU_CHECK(cudaStreamSynchronize(s));
-    memcpy(next_tokens, h_next, (size_t)nseq * sizeof(int));
+    m->d_next_cur = d_next; m->h_next_cur = h_next; m->nseq_cur = nseq;
     return PA_OK;
 }
 

@@ -112,6 +112,24 @@ def load():
         "pa_model_destroy": (None, [vp]),
         "pa_model_decode_step": (C.c_int, [vp, c_int_p, c_int_p, vp, C.c_int, c_int_p]),
         "pa_model_forward": (C.c_int, [vp, c_int_p, c_int_p, c_int_p, vp, C.c_int, c_int_p]),
+        "pa_model_forward_async": (C.c_int, [vp, c_int_p, c_int_p, c_int_p, vp, C.c_int]),
+        "pa_model_wait": (C.c_int, [vp, c_int_p]),
+        "pa_model_next_tokens_dev": (vp, [vp]),
+        "pa_model_want_device_tokens": (None, [vp, C.c_int]),
+        "pa_model_handle": (vp, [vp]),
+        "pa_group_create": (C.c_int, [C.POINTER(PaConfig), C.c_int, c_int_p, C.POINTER(vp)]),
+        "pa_comm_unique_id": (C.c_int, [vp]),
+        "pa_group_join": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
+        "pa_group_destroy": (None, [vp]),
+        "pa_group_size": (C.c_int, [vp]),
+        "pa_group_local_count": (C.c_int, [vp]),
+        "pa_group_rank": (C.c_int, [vp, C.c_int]),
+        "pa_group_handle": (vp, [vp, C.c_int]),
+        "pa_group_gather_tokens": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_int]),
+        "pa_group_gather_logits": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t]),
+        "pa_group_model_step": (C.c_int, [vp, C.POINTER(vp), C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(vp), C.c_int, c_int_p]),
+        "pa_nccl_version": (C.c_int, []),
+        "pa_fill_normal": (C.c_int, [vp, C.c_size_t, C.c_float, C.c_float, C.c_ulonglong, vp]),
         "pa_model_params": (vp, [vp]),
         "pa_model_logits": (vp, [vp, c_int_p]),
         "pa_checkpoint_read_config": (C.c_int, [C.c_char_p, C.POINTER(PaModelConfig)]),

@@ -121,3 +121,50 @@ def test_plain_c_generate_example_matches_oracle_generation():
     finally:
         for m in mgrs:
             m.close()
+
+
+def _multi_tokens(stdout):
+    got = {}
+    for line in stdout.splitlines():
+        m = re.match(r"rank (\d+) sequence (\d+):((?: \d+)+)", line)
+        if m:
+            got[(int(m.group(1)), int(m.group(2)))] = [int(t) for t in m.group(3).split()]
+    return got
+
+
+def test_plain_c_multi_gpu_example_rank0_equals_single_gpu_generation():
+    """examples/generate_multi.c (gcc only): ONE process drives a pa_group; the sampled tokens travel through
+    pa_group_model_step (forward enqueued, all-gather on the handle's stream, one wait).  With one GPU the
+    group's rank 0 must generate exactly what examples/generate.c generates (already pinned to the oracle)."""
+    single = subprocess.run([os.path.join(ge.ROOT, "examples", "generate")], capture_output=True, text=True, timeout=180)
+    assert single.returncode == 0, single.stderr
+    want = {}
+    for line in single.stdout.splitlines():
+        m = re.match(r"sequence (\d+):((?: \d+)+)", line)
+        if m:
+            want[(0, int(m.group(1)))] = [int(t) for t in m.group(2).split()]
+    exe = os.path.join(ge.ROOT, "examples", "generate_multi")
+    assert os.path.exists(exe), "build() should have produced the example"
+    r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert _multi_tokens(r.stdout) == want and len(want) == 4
+
+
+def test_plain_c_multi_gpu_example_sharded_over_all_gpus():
+    """With n GPUs: rank r's lines (printed from the NCCL-gathered buffer) equal what one GPU playing rank r
+    alone generates.  Needs >= 2 GPUs (`gpurun --gpus 2`); the driver's 1-GPU test box skips it."""
+    pa = ge.load_binding()
+    n = min(pa.load().pa_device_count(), 8)
+    if n < 2:
+        pytest.skip("one GPU visible")
+    exe = os.path.join(ge.ROOT, "examples", "generate_multi")
+    r = subprocess.run([exe, str(n)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr + r.stdout
+    got = _multi_tokens(r.stdout)
+    assert len(got) == 4 * n
+    assert f"group: {n} GPU(s)" in r.stdout and "NCCL 2" in r.stdout
+    for rank in range(n):
+        alone = subprocess.run([exe, "1", str(rank)], capture_output=True, text=True, timeout=180)
+        assert alone.returncode == 0, alone.stderr
+        want = _multi_tokens(alone.stdout)
+        assert {k: v for k, v in got.items() if k[0] == rank} == want, rank

@@ -35,6 +35,16 @@ def make_params(V, maxT, L, Cc, seed):
     return np.concatenate(parts).astype(np.float32)
 
 
+def assert_sampler_boundary_case(probs_row, coin, got, want, where):
+    """A sampled token may differ from sample_mult's (paged_infer.c:838-848) only when the coin sits on a boundary
+    of the cdf: fp32 partial sums taken in another order move the cdf by ~1e-6, so the crossing may land on a
+    neighbour -- or skip over tokens of negligible probability.  Both crossings must lie within 1e-5 of cdf mass
+    of the coin."""
+    cdf = np.cumsum(probs_row.astype(np.float64))
+    lo, hi = sorted((int(got), int(want)))
+    assert abs(cdf[lo] - coin) < 1e-5 and cdf[hi - 1] - cdf[lo] < 1e-5, (where, got, want, coin, cdf[lo], cdf[hi - 1])
+
+
 class OracleModel:
     def __init__(self, L, NH, Cc, V, maxT, bs, max_blocks, max_seqs, params):
         self.ol = oa.load_oracle()
@@ -98,10 +108,8 @@ def test_model_decode_steps_match_oracle(L, NH, hs, V, bs, gemm_path, model_path
             for i in range(len(active)):
                 row = np.ascontiguousarray(probs[i])
                 want_tok = ol.orc_sample_mult(oa.fptr(row), V, float(coins[i]))
-                if got_next[i] != want_tok:          # only legitimate when the coin sits on a boundary of the cdf
-                    cdf = np.cumsum(row.astype(np.float64))
-                    lo, hi = sorted((int(got_next[i]), int(want_tok)))
-                    assert abs(cdf[lo] - coins[i]) < 1e-5 and hi - lo <= 2, (step, i, got_next[i], want_tok, coins[i])
+                if got_next[i] != want_tok:
+                    assert_sampler_boundary_case(row, coins[i], got_next[i], want_tok, (step, i))
             tokens[active] = got_next
             pos[active] += 1
             # block tables stay bit-exact with the oracle's allocator (one table drives all layers)
@@ -296,3 +304,166 @@ def test_model_persistent_step_kernel_domain():
         assert eng.launches() - l0 > 1 and len(nxt) == B
     finally:
         model.close(); eng.close()
+
+
+def _fill_context(eng, orc, L, bs, Cc, ctx, seed):
+    """Give sequence s ctx[s] cached tokens of random K/V in every layer, in the device pools and in the
+    oracle's per-layer managers alike (the caches of a model that has already decoded ctx tokens)."""
+    rng = np.random.default_rng(seed)
+    for s, n in enumerate(ctx):
+        if n <= 0:
+            continue
+        assert eng.step_begin([s], [n]) == 0, pa.last_error()
+        slots = np.array(eng.slot_mapping())
+        pages = [orc.mgrs[0].request_block(s) for _ in range(0, n, bs)]
+        for l in range(1, L):
+            assert [orc.mgrs[l].request_block(s) for _ in range(0, n, bs)] == pages
+        for l in range(L):
+            kv = rng.standard_normal((n, 2, Cc), dtype=np.float32)
+            eng.write_pool_rows(l, slots, np.ascontiguousarray(kv[:, 0]), np.ascontiguousarray(kv[:, 1]))
+            for j, idx in enumerate(pages):
+                k, v = orc.mgrs[l].page_arrays(idx)
+                m = min(bs, n - j * bs)
+                k[:m], v[:m] = kv[j * bs:j * bs + m, 0], kv[j * bs:j * bs + m, 1]
+                orc.mgrs[l].set_filled(idx, m)
+
+
+@pytest.mark.parametrize("B,ctx_kind", [(64, "fixed1000"), (256, "mixed")], ids=["cfg2-64x1000", "cfg3-256-mixed"])
+def test_model_step_at_the_benchmarked_shape(B, ctx_kind):
+    """The whole-model step at the shape bench.py times: GPT-2 124M width and vocabulary
+    (C = 768, 12 heads, V = 50257 -- the 393-tile LM head, the split-K attproj/fcproj, the 512-thread sampler
+    over 50257 logits), 64 sequences at ~1000 tokens of context (cfg2: 64-column GEMM tiles, stream decode
+    kernel) and 256 sequences at mixed contexts (cfg3: 128-column tiles for fc and the LM head); L = 2 keeps
+    the oracle affordable.  Logits within L * 1e-5 of the oracle chain, sampled tokens equal, tables bit-exact."""
+    L, NH, hs, V, bs = 2, 12, 64, 50257, 16
+    Cc, maxT = NH * hs, 1032
+    rng = np.random.default_rng(17)
+    ctx = [1000] * B if ctx_kind == "fixed1000" else rng.integers(16, 200, size=B).tolist()
+    pages = sum((c + 4 + bs - 1) // bs for c in ctx) + 8
+    params = make_params(V, maxT, L, Cc, seed=900)
+    eng = pa.PagedAttn(bs, pages, B, NH, hs, n_layers=L, device=0, max_batch_tokens=max(max(ctx), B))
+    model = pa.Model(eng, maxT, V, params=params, max_batch=B)
+    orc = OracleModel(L, NH, Cc, V, maxT, bs, pages, B, params)
+    ol = oa.load_oracle()
+    try:
+        _fill_context(eng, orc, L, bs, Cc, ctx, seed=3)
+        seqs = list(range(B))
+        tokens = rng.integers(0, V, size=B).astype(np.int32)
+        pos = np.array(ctx, dtype=np.int32)
+        worst = 0.0
+        for step in range(2):
+            coins = rng.random(B).astype(np.float32)
+            l0 = eng.launches()
+            got_next = model.decode_step(seqs, tokens, coins)
+            assert eng.launches() - l0 > 1, "this batch size runs the chain of per-op kernels"
+            assert eng.lib.pa_tune_get(eng.h, pa.PA_TUNE_LAST_GRID) > 0, "decode attention went through the stream kernel"
+            got = model.logits(B)
+            want = orc.step(seqs, tokens, pos)
+            err = np.abs(got.astype(np.float64) - want).max() / np.abs(want).max()
+            worst = max(worst, err)
+            assert np.isfinite(got).all() and err <= LOGIT_TOL_PER_LAYER * L, f"step {step}: logits err {err:.3e}"
+            probs = np.zeros_like(want)
+            ol.orc_softmax_forward(oa.fptr(probs), oa.fptr(want), B, 1, V)
+            for i in range(B):
+                row = np.ascontiguousarray(probs[i])
+                want_tok = ol.orc_sample_mult(oa.fptr(row), V, float(coins[i]))
+                if got_next[i] != want_tok:
+                    assert_sampler_boundary_case(row, coins[i], got_next[i], want_tok, (step, i))
+            tokens = got_next.astype(np.int32)
+            pos += 1
+            for s in (0, B // 2, B - 1):
+                assert list(eng.table(s)) == list(orc.mgrs[0].table(s))
+        print(f"benchmark shape B={B} {ctx_kind}: worst logits err {worst:.2e}")
+    finally:
+        model.close(); eng.close(); orc.close()
+
+
+def test_model_step_positions_follow_a_swapped_in_sequence():
+    """a swapped-out sequence reports length 0 until pa_step_begin brings it back; the model step
+    must embed its new token at the position AFTER the swapped-in context (positions come from the step tables)."""
+    L, NH, hs, V, maxT, bs, B = 2, 2, 64, 131, 64, 4, 2
+    Cc = NH * hs
+    params = make_params(V, maxT, L, Cc, seed=600)
+    outs = []
+    for swap in (False, True):
+        eng = pa.PagedAttn(bs, 32, B, NH, hs, n_layers=L, device=0, max_batch_tokens=8)
+        eng.tune(pa.PA_TUNE_MODEL_PATH, 1)
+        model = pa.Model(eng, maxT, V, params=params, max_batch=8)
+        try:
+            tok = np.array([7, 19], dtype=np.int32)
+            for _ in range(9):
+                tok = model.decode_step([0, 1], tok, None)
+            if swap:
+                assert eng.lib.pa_set_evict_swap(eng.h, 1) == 0
+                assert eng.lib.pa_seq_swap_out(eng.h, 0) == 0
+                assert eng.seq_len(0) == 0 and eng.lib.pa_seq_swapped_tokens(eng.h, 0) == 9
+            nxt = model.decode_step([0, 1], tok, None)
+            assert eng.seq_len(0) == 10 and eng.seq_len(1) == 10
+            outs.append((nxt.copy(), model.logits(2).copy()))
+        finally:
+            model.close(); eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32)), "logits differ after a swap-in: wrong positions"
+
+
+def test_model_step_beyond_max_seq_len_is_refused_and_rolled_back():
+    L, NH, hs, V, maxT, B = 1, 2, 64, 50, 6, 2
+    eng = pa.PagedAttn(4, 16, B, NH, hs, n_layers=L, device=0, max_batch_tokens=8)
+    model = pa.Model(eng, maxT, V, params=None, seed=3, max_batch=8)
+    try:
+        model.forward([0, 1], [5, 2], np.arange(7, dtype=np.int32), None)
+        assert eng.seq_len(0) == 5 and eng.seq_len(1) == 2
+        with pytest.raises(Exception):
+            model.forward([1, 0], [1, 2], np.arange(3, dtype=np.int32), None)      # sequence 0 would reach 7 > maxT
+        assert eng.seq_len(0) == 5 and eng.seq_len(1) == 2, "the refused step left tokens behind"
+        model.forward([0, 1], [1, 1], np.arange(2, dtype=np.int32), None)
+        assert eng.seq_len(0) == 6 and eng.seq_len(1) == 3
+    finally:
+        model.close(); eng.close()
+
+
+def test_group_of_one_gathers_through_the_library():
+    """pa_group_create(1) / pa_group_join(world 1): the group calls work without NCCL traffic (the gather of a
+    group of one is a copy on the handle's stream) and pa_group_model_step returns what pa_model_decode_step
+    returns -- through the async half-steps (forward enqueued, tokens kept on the device, one wait)."""
+    L, NH, hs, V, maxT, B = 2, 2, 64, 131, 32, 5
+    Cc = NH * hs
+    params = make_params(V, maxT, L, Cc, seed=77)
+    lib = pa.load()
+    cfg = pa.PaConfig(16, 32, B, 0, L, NH, hs, 0, B)
+    for model_path in (1, 0):          # chain, and the persistent kernel (tokens land in device memory for the gather)
+        g = C.c_void_p()
+        pa.check(lib.pa_group_create(C.byref(cfg), 1, None, C.byref(g)), "group create")
+        assert lib.pa_group_size(g) == 1 and lib.pa_group_local_count(g) == 1 and lib.pa_group_rank(g, 0) == 0
+        h = lib.pa_group_handle(g, 0)
+        lib.pa_tune_set(h, pa.PA_TUNE_MODEL_PATH, model_path)
+        mcfg = pa.PaModelConfig(maxT, V, L, NH, Cc)
+        m = C.c_void_p()
+        pa.check(lib.pa_model_create(h, C.byref(mcfg), params.ctypes.data, 1, B, C.byref(m)), "model")
+        eng = pa.PagedAttn(16, 32, B, NH, hs, n_layers=L, device=0, max_batch_tokens=B)
+        eng.tune(pa.PA_TUNE_MODEL_PATH, model_path)
+        ref = pa.Model(eng, maxT, V, params=params, max_batch=B)
+        try:
+            seq = np.arange(B, dtype=np.int32)
+            tok = np.array([3, 9, 27, 81, 100], dtype=np.int32)
+            rng = np.random.default_rng(1)
+            for _ in range(6):
+                coins = rng.random(B).astype(np.float32)
+                want = ref.decode_step(seq, tok, coins)
+                out = np.zeros(B, dtype=np.int32)
+                models = (C.c_void_p * 1)(m)
+                seqs = (pa.c_int_p * 1)(pa.iptr(seq)); toks = (pa.c_int_p * 1)(pa.iptr(tok))
+                cs = (C.c_void_p * 1)(coins.ctypes.data)
+                pa.check(lib.pa_group_model_step(g, models, seqs, toks, cs, B, pa.iptr(out)), "group step")
+                assert np.array_equal(out, want)
+                tok = want.astype(np.int32)
+            # a second step before the wait is refused
+            ones = np.ones(B, dtype=np.int32)
+            assert lib.pa_model_forward_async(m, pa.iptr(seq), pa.iptr(ones), pa.iptr(tok), None, B) == 0
+            assert lib.pa_model_forward_async(m, pa.iptr(seq), pa.iptr(ones), pa.iptr(tok), None, B) == pa.PA_ERR_INVALID
+            assert lib.pa_model_wait(m, pa.iptr(out)) == 0
+            assert lib.pa_model_wait(m, pa.iptr(out)) == pa.PA_ERR_INVALID
+        finally:
+            ref.close(); eng.close()
+            lib.pa_model_destroy(m)
+            lib.pa_group_destroy(g)

@@ -176,6 +176,50 @@ def test_decode_append_fused(NH, hs, bs, hpg, path):
         sc.close()
 
 
+@pytest.mark.parametrize("hpg", [0, 8, 4, 1], ids=["auto", "hpg8", "hpg4", "hpg1"])
+def test_decode_cfg5_shape_column_slices(hpg):
+    """BASELINE configs[4] at the shape bench.py times (`long`): 32 heads x head_dim 128 (C = 4096), block 16,
+    32k-token context.  A whole page (256 KiB) does not fit the ring, so the stream kernel's tile is a
+    COLUMN SLICE of hpg heads, one bulk copy per row (pa_kernels.cu, the `hpg < NH` path at head_dim 128);
+    the plan bench.py reports is hpg 8.  Contexts: 32768 (2048 pages), 5 (one partial page), 4097 (one
+    token into page 257).  Read-only decode and the fused append, launch after launch."""
+    NH, hs, bs = 32, 128, 16
+    Cc = NH * hs
+    ctx = [32768, 5, 4097]
+    sc = Scenario(NH, hs, bs, ctx, shuffle=True, seed=55, extra_blocks=16)
+    try:
+        q = oa.normal((sc.B, sc.C), seed=56)
+        want = sc.oracle_decode(q)
+        for rep in range(2):
+            got = sc.decode(q, path=1, hpg=hpg)
+            assert_close(got, want, f"cfg5 shape hpg={hpg} rep={rep}")
+        if hpg:
+            assert sc.eng.lib.pa_tune_get(sc.eng.h, pa.PA_TUNE_LAST_HPG) == hpg
+        else:
+            assert sc.eng.lib.pa_tune_get(sc.eng.h, pa.PA_TUNE_LAST_HPG) in (1, 2, 4, 8), "auto plan is a column slice at C=4096"
+        # fused append: contexts grow to 32769 / 6 / 4098 (the first crosses into a new page)
+        eng, orc = sc.eng, sc.orc
+        B = sc.B
+        for step in range(2):
+            qkv = oa.normal((B, 3 * Cc), seed=400 + step)
+            assert eng.step_begin(sc.seq_ids, [1] * B) == 0, pa.last_error()
+            pa.check(eng.upload(), "upload")
+            for s_ in range(B):
+                orc.add_to_cache(qkv[s_][None, None, :], 1, 1, 1, prompt=s_)
+            want = orc.decode_batch(sc.seq_ids, NH, qkv[:, :Cc])
+            d = pa.DevBuf.from_numpy(qkv)
+            o = pa.DevBuf(B * Cc * 4)
+            pa.check(eng.decode_append(0, d.ptr, d.ptr + Cc * 4, d.ptr + 2 * Cc * 4, 3 * Cc, o.ptr, Cc), "decode_append")
+            eng.sync()
+            assert_close(o.download((B, Cc)), want, f"cfg5 shape fused hpg={hpg} step {step}")
+            k, v = eng.read_pool_rows(0, eng.slot_mapping())
+            assert np.array_equal(k.view(np.uint32), qkv[:, Cc:2 * Cc].view(np.uint32))
+            assert np.array_equal(v.view(np.uint32), qkv[:, 2 * Cc:].view(np.uint32))
+            d.free(); o.free()
+    finally:
+        sc.close()
+
+
 def test_decode_sliding_window():
     """Reference `offset` (paged_infer.c:190,1057): row attends cached tokens [kv_start, ctx)."""
     sc = Scenario(12, 64, 16, [100, 64, 33, 500], shuffle=True, seed=9)
