@@ -474,7 +474,7 @@ def run_workload(cx, wid, w, primary):
             eng.tune(pa.PA_TUNE_STATIC_PCT, args.static_pct)
             eng.tune(pa.PA_TUNE_DYN_UNITS, args.dyn_units)
         eng.tune(pa.PA_TUNE_NO_PDL, 1 if args.no_pdl else 0)
-        eng.tune(pa.PA_TUNE_NO_ZEROCOPY, 1 if args.no_zerocopy else 0)
+        eng.tune(pa.PA_TUNE_NO_ZEROCOPY, args.host_mode)
         rng = np.random.default_rng(1234 + rank)
         stream = lib.pa_stream_create()
         seq_ids = np.arange(B, dtype=np.int32)
@@ -499,11 +499,16 @@ def run_workload(cx, wid, w, primary):
                 if n_tok > 0:
                     assert eng.seq_adopt(s, blocks[:n_pg], n_tok) == 0, pa.last_error()
 
-        qkv_host = lib.pa_host_alloc(B * 3 * C_ * 4)
-        out_host = lib.pa_host_alloc(B * C_ * 4)
-        qkv_np = np.ctypeslib.as_array(C.cast(qkv_host, C.POINTER(C.c_float)), (B, 3 * C_))
-        qkv_np[:] = rng.standard_normal((B, 3 * C_), dtype=np.float32)
-        out_np = np.ctypeslib.as_array(C.cast(out_host, C.POINTER(C.c_float)), (B, C_))
+        # host buffers of the e2e entry: every layer has its own q|k|v rows (L x B x 3C) and its own output rows
+        # (L x B x C) in pinned memory, so h2d/d2h_bytes_per_step are bytes that really cross PCIe each step; the
+        # rows are the same for every layer (and equal to the device-resident arm's), so one oracle row checks both
+        qkv_host = lib.pa_host_alloc(L * B * 3 * C_ * 4)
+        out_host = lib.pa_host_alloc(L * B * C_ * 4)
+        qkv_all = np.ctypeslib.as_array(C.cast(qkv_host, C.POINTER(C.c_float)), (L, B, 3 * C_))
+        qkv_all[:] = rng.standard_normal((B, 3 * C_), dtype=np.float32)[None]
+        qkv_np = qkv_all[0]
+        out_all = np.ctypeslib.as_array(C.cast(out_host, C.POINTER(C.c_float)), (L, B, C_))
+        out_np = out_all[L - 1]
         d_qkv = pa.DevBuf.from_numpy(qkv_np)
         d_out = pa.DevBuf(B * C_ * 4)
 
@@ -575,44 +580,91 @@ def run_workload(cx, wid, w, primary):
                    tokens_per_s=world * B / (ms_per_step * 1e-3), gpu_launches=int(launches), step_bytes=step_bytes,
                    batch_per_gpu=B, layers=L, ctx_mean=sum(ctx) / len(ctx))
 
-        # ---- e2e: host buffers through pa_decode_step_host_async ------------------------------
+        # ---- e2e: host buffers through the host-buffer entry of the C ABI --------------------------
+        # Every step: pa_step_begin (tables), ONE call queueing all layers (the kernels pull the pinned host q|k|v rows
+        # over PCIe and store their outputs to pinned host memory), a completion ticket, and the host READS the step's
+        # result.  The host queues step n+1 before it waits for step n's ticket (the attention path's inputs are the
+        # host's rows, never its own previous outputs), so the device does not idle during the host's turnaround; the
+        # one-sync-per-step variant is timed beside it.
+        e2e_step = None
         if not args.no_e2e:
-            def e2e_step(keep=False):
+            out_host2 = lib.pa_host_alloc(L * B * C_ * 4)
+            out_np2 = np.ctypeslib.as_array(C.cast(out_host2, C.POINTER(C.c_float)), (L, B, C_))[L - 1]
+            outs = [(out_host, out_np), (out_host2, out_np2)]
+            in_stride, out_stride = B * 3 * C_, B * C_
+
+            def e2e_queue(buf):
                 pa.check(eng.step_begin(seq_ids, ones), "step_begin")
-                for layer in range(L):      # the layers of a step are queued behind each other, one sync per step
-                    pa.check(eng.decode_step_host_async(layer, qkv_host, out_host), "decode_step_host_async")
+                pa.check(lib.pa_decode_step_host_layers_async(eng.h, qkv_host, in_stride, outs[buf][0], out_stride), "decode_step_host_layers_async")
+                t = lib.pa_decode_step_host_mark(eng.h)
+                pa.check(min(t, 0), "mark")
+                rollback()                      # host-side integer state only: the queued kernels carry their tables
+                return t
+
+            def e2e_step(keep=False):           # one step, waited for at once (verification, and the per-step-sync timing)
+                pa.check(eng.step_begin(seq_ids, ones), "step_begin")
+                pa.check(lib.pa_decode_step_host_layers_async(eng.h, qkv_host, in_stride, out_host, out_stride), "decode_step_host_layers_async")
                 pa.check(lib.pa_decode_step_host_sync(eng.h), "sync")
                 if not keep:
                     rollback()
                 return float(out_np[0, 0])      # the step's result is read on the host
+
+            def e2e_run(k, pipelined):
+                hs_ = lib.pa_stream_of(eng.h)
+                cx.barrier()
+                lib.pa_event_record(e0, hs_)
+                t0 = time.perf_counter()
+                acc = 0.0
+                if pipelined:
+                    prev = None
+                    for i in range(k):
+                        t = e2e_queue(i & 1)
+                        if prev is not None:
+                            pa.check(lib.pa_decode_step_host_wait(eng.h, prev[0]), "wait")
+                            acc += float(outs[prev[1]][1][0, 0])         # step i-1's result, read while step i runs
+                        prev = (t, i & 1)
+                    pa.check(lib.pa_decode_step_host_wait(eng.h, prev[0]), "wait")
+                    acc += float(outs[prev[1]][1][0, 0])
+                else:
+                    for _ in range(k):
+                        acc += e2e_step()
+                lib.pa_event_record(e1, hs_)
+                cx.barrier()
+                wall = time.perf_counter() - t0
+                return cx.allmax(max(lib.pa_event_elapsed_ms(e0, e1), 0.0)) / k, wall * 1e3 / k
             k_e2e = max(5, min(steps, 50))
             for _ in range(3):
                 e2e_step()
-            cx.barrier()
-            hs_ = lib.pa_stream_of(eng.h)
-            lib.pa_event_record(e0, hs_)
-            t0 = time.perf_counter()
-            for _ in range(k_e2e):
-                e2e_step()
-            lib.pa_event_record(e1, hs_)
-            cx.barrier()
-            wall = time.perf_counter() - t0
-            ms_e2e = cx.allmax(max(lib.pa_event_elapsed_ms(e0, e1), 0.0)) / k_e2e
+            e2e_run(4, True)
+            ms_sync, wall_sync = e2e_run(k_e2e, False)
+            ms_e2e, wall = e2e_run(k_e2e, True)
             table_bytes = (4 * B + 2 + B + 4 + B * ((max(pages) + 3) & ~3)) * 4
             res["e2e"] = {"value": world * step_bytes / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
                           "h2d_bytes_per_step": L * B * 3 * C_ * 4 + table_bytes, "d2h_bytes_per_step": L * B * C_ * 4,
                           "ms_per_step": ms_e2e, "steps": k_e2e, "tokens_per_s": world * B / (ms_e2e * 1e-3),
-                          "entry": "pa_decode_step_host_async per layer + one stream sync per step: host q|k|v rows in pinned memory are " +
-                                   ("copied H2D, then fused append+decode, then D2H copy" if args.no_zerocopy else
-                                    "pulled over PCIe by the kernel's bulk copies, outputs stored to pinned host memory by the kernel"),
-                          "wall_ms_per_step": wall * 1e3 / k_e2e}
+                          "entry": "per step: pa_step_begin + pa_decode_step_host_layers_async (one call queues every layer) + "
+                                   "pa_decode_step_host_mark; the host queues step n+1, then waits for step n's ticket "
+                                   "(pa_decode_step_host_wait) and reads its output rows; " +
+                                   {0: ("the step's pinned host q|k|v rows (every layer's) go H2D in one copy and its output rows D2H in one "
+                                        "copy, on copy streams beside the kernels (double buffered)" if L * B * 3 * C_ * 4 / 1e6 * 4.0 < L * 7.0 else
+                                        "host q|k|v rows in pinned memory are pulled over PCIe by the kernel's bulk copies, outputs stored to "
+                                        "pinned host memory by the kernel (zero-copy: chosen by the library for steps whose staged copies "
+                                        "would cost more HBM write interference than the per-layer PCIe latency they save)"),
+                                    1: "per-layer staged copies on copy streams",
+                                    2: "host q|k|v rows in pinned memory are pulled over PCIe by the kernel's bulk copies, outputs stored "
+                                       "to pinned host memory by the kernel (zero-copy)",
+                                    3: "whole-step staged copies"}[args.host_mode],
+                          "wall_ms_per_step": wall,
+                          "sync_per_step": {"value": world * step_bytes / (ms_sync * 1e-3) / 1e9, "ms_per_step": ms_sync,
+                                            "wall_ms_per_step": wall_sync,
+                                            "entry": "the same with one full stream synchronisation per step before the next is queued"}}
+            res["e2e"]["frac_of_measured_peak"] = res["e2e"]["value"] / world / peaks()[0]
         else:
             res["e2e"] = None
 
         # ---- verified: output rows of THIS configuration against the CPU oracle ------------------
         if not args.no_verify:
-            res["verified"] = verify_attention(cx, eng, w, ctx, step, e2e_step if not args.no_e2e else None, rollback,
-                                               qkv_np, d_out, out_np)
+            res["verified"] = verify_attention(cx, eng, w, ctx, step, e2e_step, rollback, qkv_np, d_out, out_np)
 
         # ---- roofline of the dominant kernel ---------------------------------------------------
         peak, peak_src = peaks()
@@ -648,6 +700,8 @@ def run_workload(cx, wid, w, primary):
                 res["model"] = {"error": repr(ex)}
         lib.pa_host_free(qkv_host)
         lib.pa_host_free(out_host)
+        if not args.no_e2e:
+            lib.pa_host_free(out_host2)
         lib.pa_stream_destroy(stream)
     finally:
         eng.close()
@@ -825,7 +879,9 @@ def model_section(cx, eng, w, ctx, kms):
         # verified: the logits row of sequence 0 of a step of THIS configuration against the oracle's gpt2_forward
         # restatement fed with the device's own weights and that sequence's cached pages of every layer
         if not args.no_verify and rank == 0:
-            info["verified"] = verify_model(cx, eng, model, w, ctx, model_step, seq_ids, toks)
+            # (a LOCAL step: the other ranks do not take part, so it must not contain the collective)
+            info["verified"] = verify_model(cx, eng, model, w, ctx, lambda keep=False: model.decode_step(seq_ids, toks, coins),
+                                            seq_ids, toks)
         if world == 1 and B <= 8 and not args.no_cpu_baseline:
             try:
                 info["cpu_baseline"] = cpu_model_sample(model, pa, B, L, NH, C_, V, maxT, bs)
@@ -921,7 +977,7 @@ def main():
     ap.add_argument("--static-pct", type=int, default=0)
     ap.add_argument("--dyn-units", type=int, default=0)
     ap.add_argument("--no-pdl", action="store_true")
-    ap.add_argument("--no-zerocopy", action="store_true", help="e2e: stage pinned host buffers with copies")
+    ap.add_argument("--host-mode", type=int, default=0, help="e2e (PA_TUNE_NO_ZEROCOPY): 0 auto = whole-step staged copies, 1 per-layer staged, 2 zero-copy, 3 whole-step staged")
     ap.add_argument("--timeline", default="", help="write a per-CTA timeline of one decode launch to this file")
     ap.add_argument("--no-fuse", action="store_true", help="separate KV-append kernel instead of the fused decode+append")
     args = ap.parse_args()

@@ -300,6 +300,20 @@ PA_API int pa_decode_step_host(pa_handle* h, int layer, const float* qkv_host, f
  * overlap the neighbouring layers' kernels. */
 PA_API int pa_decode_step_host_async(pa_handle* h, int layer, const float* qkv_host, float* out_host);
 PA_API int pa_decode_step_host_sync(pa_handle* h);
+/* every layer of the step in one call: layer l reads qkv_host + l * qkv_layer_stride floats (0: the same rows for
+ * every layer) and writes out_host + l * out_layer_stride.  With pinned buffers the step is staged as a whole: ONE
+ * host-to-device copy of its inputs and ONE device-to-host copy of its outputs on copy streams of their own, double
+ * buffered, so the copies of neighbouring steps run beside the kernels and the kernels never wait on PCIe. */
+PA_API int pa_decode_step_host_layers_async(pa_handle* h, const float* qkv_host, size_t qkv_layer_stride, float* out_host,
+                                            size_t out_layer_stride);
+/* Completion tickets: pa_decode_step_host_mark returns a ticket (> 0) for everything queued so far on this handle;
+ * pa_decode_step_host_wait blocks until that work -- kernels and output copies -- is done, and only that.  The host
+ * queues step n+1 (pa_step_begin builds its tables in the next pinned buffer of the ring; the layers follow on the
+ * stream) BEFORE it waits for step n's outputs, so the device never idles while the host turns a step around.
+ * The attention path has no dependency of a step on its predecessor's outputs: its inputs are the host's q|k|v rows.
+ * A ticket stays valid until 8 newer ones were made. */
+PA_API int pa_decode_step_host_mark(pa_handle* h);
+PA_API int pa_decode_step_host_wait(pa_handle* h, int ticket);
 
 /* ---- sequence bookkeeping ----------------------------------------------------------------- */
 PA_API int pa_seq_len(pa_handle* h, int seq_id);                 /* cached tokens */
@@ -355,7 +369,7 @@ typedef enum pa_tune_key {
     PA_TUNE_DYN_UNITS = 6,     /* 0 auto: pages per dynamically claimed range */
     PA_TUNE_DEBUG_TIMELINE = 7,/* 1: the stream decode kernel records a per-CTA timeline (pa_debug_timeline) */
     PA_TUNE_NO_PDL = 8,        /* 1: launch the decode kernel without programmatic dependent launch */
-    PA_TUNE_NO_ZEROCOPY = 9,   /* 1: pa_decode_step_host stages pinned buffers with copies instead of mapping them */
+    PA_TUNE_NO_ZEROCOPY = 9,   /* host-buffer entries, pinned buffers: 0 auto (one layer per call: zero-copy, the kernel reads / writes the mapped host rows itself; pa_decode_step_host_layers_async: whole-step staging, one input and one output copy per step on copy streams beside the kernels), 1 per-layer staged copies, 2 zero-copy always, 3 whole-step staging or fail */
     PA_TUNE_LAST_HPG = 10,     /* read-only: heads per tile, ring stages and CTAs of the last stream-decode launch */
     PA_TUNE_LAST_STAGES = 11,  /*            (0 when the last decode ran on the generic kernel) */
     PA_TUNE_LAST_GRID = 12,

@@ -577,11 +577,8 @@ template <int BN>
 int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmTcParams& p, int n_split, bool cluster, bool cooperative, cudaStream_t s) {
     using Cfg = GemmCfg<BN>;
     auto fn = pa_gemm3x_kernel<BN>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
-        attr_done = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};       // per instantiation; one bit per device
+    CU_CHECK(pa_optin_smem(attr_done, fn, (int)Cfg::kSmem));
     pa_launch_cooperative = cooperative ? 1 : 0;
     const cudaError_t e = pa_launch_pdl(fn, dim3((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, n_split), dim3(192), Cfg::kSmem, s, cluster ? n_split : 1, tx, tw, p);
     pa_launch_cooperative = 0;

@@ -641,15 +641,19 @@ extern "C" int pa_cu_model_mega_step(const pa_mega_args* a, void* stream) {
     if (!smem) return PA_ERR_UNSUPPORTED;
     MegaKernel fn = pick_kernel(a->M, a->C, a->hs);
     // (each instantiation needs its own opt-in for more than 48 KB of dynamic shared memory)
-    static MegaKernel attr_fn[32];
-    static size_t attr_smem[32];
+    // (and the opt-in is per device: one process may drive several GPUs)
+    int cur_dev = 0;
+    CU_CHECK(cudaGetDevice(&cur_dev));
+    static MegaKernel attr_fn[64];
+    static size_t attr_smem[64];
+    static int attr_dev[64];
     static int attr_n = 0;
     int ai = 0;
-    while (ai < attr_n && attr_fn[ai] != fn) ++ai;
+    while (ai < attr_n && !(attr_fn[ai] == fn && attr_dev[ai] == cur_dev)) ++ai;
     if (ai == attr_n || attr_smem[ai] < smem) {
         CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (ai == attr_n && attr_n < 32) ++attr_n;
-        if (ai < 32) { attr_fn[ai] = fn; attr_smem[ai] = smem; }
+        if (ai == attr_n && attr_n < 64) ++attr_n;
+        if (ai < 64) { attr_fn[ai] = fn; attr_smem[ai] = smem; attr_dev[ai] = cur_dev; }
     }
     cudaStream_t s = (cudaStream_t)stream;
     pa_mega_args args = *a;

@@ -9,6 +9,23 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
+// More than 48 KB of dynamic shared memory is a per-DEVICE opt-in of a kernel: `done` is the call site's (one
+// per kernel instantiation) bit mask of the devices that already have it.  One process may drive several GPUs
+// (pa_group_create), so a process-wide "done once" flag is not enough.
+template <typename F>
+static inline cudaError_t pa_optin_smem(std::atomic<unsigned long long>& done, F fn, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_relaxed) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_relaxed);
+    return e;
+}
+
 extern "C" __thread int pa_pdl_enabled;     /* per host thread; set from the handle's PA_TUNE_NO_PDL at each launching entry */
 extern "C" __thread int pa_pdl_gate;        /* per-step gate set by the caller of the chain (pa_model_forward) */
 

@@ -21,6 +21,7 @@
 #include <cstdint>
 
 #include "pa_internal.h"
+#include "pa_pdl.cuh"
 #include "pa_ptx.cuh"
 
 #define CU_CHECK(call)                                                                         \
@@ -297,11 +298,8 @@ template <int HS, int BM, int BN>
 int launch_tiled(const PrefillParams& pp, int n_tiles, cudaStream_t s) {
     using Cfg = PrefillCfg<HS, BM, BN>;
     auto fn = pa_prefill_tiled_kernel<HS, BM, BN>;
-    static bool attr_done = false;     // per process and instantiation; the value never changes
-    if (!attr_done) {
-        CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
-        attr_done = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};       // per instantiation; one bit per device
+    CU_CHECK(pa_optin_smem(attr_done, fn, (int)Cfg::kSmem));
     PrefillParams p = pp;
     p.n_tiles = n_tiles;
     fn<<<(unsigned)((long long)n_tiles * p.NH), Cfg::kThreads, Cfg::kSmem, s>>>(p);

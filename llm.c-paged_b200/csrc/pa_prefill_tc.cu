@@ -36,6 +36,7 @@
 #include <type_traits>
 
 #include "pa_internal.h"
+#include "pa_pdl.cuh"
 #include "pa_ptx.cuh"
 
 #define CU_CHECK(call)                                                                         \
@@ -460,11 +461,8 @@ template <int HS, int BN, int NWG, int NST, int SBUF>
 int launch_tc(const TcState* st, const TcParams& p, cudaStream_t s) {
     using Cfg = TcCfg<HS, BN, NWG, NST, SBUF>;
     auto fn = pa_prefill_tc_kernel<HS, BN, NWG, NST, SBUF>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
-        attr_done = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};       // per instantiation; one bit per device
+    CU_CHECK(pa_optin_smem(attr_done, fn, (int)Cfg::kSmem));
     fn<<<(unsigned)((long long)p.n_tiles * p.NH), Cfg::kThreads, Cfg::kSmem, s>>>(st->tm_k, st->tm_v, p);
     CU_CHECK(cudaGetLastError());
     return PA_OK;

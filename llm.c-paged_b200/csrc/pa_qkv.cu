@@ -244,11 +244,8 @@ bool gemv_ok(const QkvParams& p) {
            (size_t)p.M * p.K * sizeof(float) <= 96 * 1024;
 }
 int launch_gemv(const QkvParams& p, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        CU_CHECK(cudaFuncSetAttribute(pa_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_done = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};       // one bit per device
+    CU_CHECK(pa_optin_smem(attr_done, pa_gemv_kernel, 96 * 1024));
     const int groups = (p.N + kGemvFeat - 1) / kGemvFeat;            // warp passes needed
     int blocks = (groups + 7) / 8;
     if (blocks > 592) blocks = 592;                                   // 4 CTAs per SM: the rest loops

@@ -107,6 +107,9 @@ def load():
         "pa_decode_step_host": (C.c_int, [vp, C.c_int, vp, vp]),
         "pa_decode_step_host_async": (C.c_int, [vp, C.c_int, vp, vp]),
         "pa_decode_step_host_sync": (C.c_int, [vp]),
+        "pa_decode_step_host_layers_async": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t]),
+        "pa_decode_step_host_mark": (C.c_int, [vp]),
+        "pa_decode_step_host_wait": (C.c_int, [vp, C.c_int]),
         "pa_model_param_count": (C.c_size_t, [C.POINTER(PaModelConfig)]),
         "pa_model_create": (C.c_int, [vp, C.POINTER(PaModelConfig), vp, C.c_ulonglong, C.c_int, C.POINTER(vp)]),
         "pa_model_destroy": (None, [vp]),

@@ -457,6 +457,71 @@ def test_decode_step_host_async_matches_sync():
         sc.close()
 
 
+def test_decode_step_host_layers_pipelined_with_tickets():
+    """pa_decode_step_host_layers_async (every layer of a step in one call) in its three modes -- whole-step staged
+    copies (auto for a small step / forced), zero-copy -- with the host running one step AHEAD: step n+1 is queued
+    (new tables, new layers) before step n's ticket is waited for.  Every step's output rows equal what the
+    device-resident pa_decode_append gives for the same step; strided per-layer rows; stale tickets are refused."""
+    import ctypes as Ct
+    NH, hs, bs, B, L = 4, 64, 16, 6, 3
+    Cc = NH * hs
+    n_steps = 5
+    lib = pa.load()
+    in_stride, out_stride = B * 3 * Cc + 64, B * Cc + 32          # padded layer strides: the 2-D copy path
+    hin = lib.pa_host_alloc(n_steps * L * in_stride * 4)
+    hout = lib.pa_host_alloc(n_steps * L * out_stride * 4)
+    ins = np.ctypeslib.as_array(Ct.cast(hin, Ct.POINTER(Ct.c_float)), (n_steps, L, in_stride))
+    outs = np.ctypeslib.as_array(Ct.cast(hout, Ct.POINTER(Ct.c_float)), (n_steps, L, out_stride))
+    ins[:] = oa.normal((n_steps, L, in_stride), seed=123)
+    try:
+        want = None
+        for mode in ("device", 0, 3, 2, 1):
+            sc = Scenario(NH, hs, bs, [33, 1, 16, 70, 5, 48], n_layers=L, layer=0, seed=77, extra_blocks=32)
+            eng = sc.eng
+            try:
+                got = np.zeros((n_steps, L, B, Cc), dtype=np.float32)
+                if mode == "device":
+                    for st in range(n_steps):
+                        assert eng.step_begin(sc.seq_ids, [1] * B) == 0, pa.last_error()
+                        pa.check(eng.upload(), "upload")
+                        for l in range(L):
+                            d = pa.DevBuf.from_numpy(np.ascontiguousarray(ins[st, l, :B * 3 * Cc].reshape(B, 3 * Cc)))
+                            o = pa.DevBuf(B * Cc * 4)
+                            pa.check(eng.decode_append(l, d.ptr, d.ptr + Cc * 4, d.ptr + 2 * Cc * 4, 3 * Cc, o.ptr, Cc), "decode_append")
+                            eng.sync()
+                            got[st, l] = o.download((B, Cc))
+                            d.free(); o.free()
+                    want = got
+                    continue
+                eng.tune(pa.PA_TUNE_NO_ZEROCOPY, mode)
+                outs[:] = np.nan
+                tickets = []
+                for st in range(n_steps):
+                    assert eng.step_begin(sc.seq_ids, [1] * B) == 0, pa.last_error()
+                    pa.check(lib.pa_decode_step_host_layers_async(eng.h, ins[st].ctypes.data, in_stride, outs[st].ctypes.data, out_stride),
+                             f"layers_async mode {mode}")
+                    t = lib.pa_decode_step_host_mark(eng.h)
+                    assert t > 0
+                    tickets.append(t)
+                    if st >= 1:                      # one step behind: wait for step st-1 while step st runs
+                        pa.check(lib.pa_decode_step_host_wait(eng.h, tickets[st - 1]), "wait")
+                        got[st - 1] = outs[st - 1, :, :B * Cc].reshape(L, B, Cc)
+                pa.check(lib.pa_decode_step_host_wait(eng.h, tickets[-1]), "wait")
+                got[-1] = outs[-1, :, :B * Cc].reshape(L, B, Cc)
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"host mode {mode}"
+                assert np.isnan(outs[:, :, B * Cc:]).all(), "the padding between the layers' output rows was written"
+                assert lib.pa_decode_step_host_wait(eng.h, tickets[-1] + 1) == pa.PA_ERR_INVALID      # never made
+                for _ in range(9):
+                    lib.pa_decode_step_host_mark(eng.h)
+                assert lib.pa_decode_step_host_wait(eng.h, tickets[0]) == pa.PA_ERR_INVALID            # too old
+                pa.check(lib.pa_decode_step_host_sync(eng.h), "sync")
+            finally:
+                sc.close()
+    finally:
+        lib.pa_host_free(hin)
+        lib.pa_host_free(hout)
+
+
 # --------------------------------------------------------------------------------- prefill rows
 def _run_prefill(NH, hs, bs, before, n_new, path, seed=61, kv_start=None, dist="normal", shuffle=False, nwg=0, bn=0):
     """Append + causal rows for a mixed batch; returns (got, want32, scenario-free copies)."""
