@@ -833,11 +833,16 @@ def model_section(cx, eng, w, ctx, kms):
             seqs = (pa.c_int_p * 1)(pa.iptr(seq_ids))
             tokp = (pa.c_int_p * 1)(pa.iptr(toks))
             coinp = (C.c_void_p * 1)(coins.ctypes.data)
+            nxt_local = np.zeros(B, dtype=np.int32)
+            nxtp = (pa.c_int_p * 1)(pa.iptr(nxt_local))
 
         def model_step(keep=False):
             if group is not None:
-                pa.check(lib.pa_group_model_step(group, models, seqs, tokp, coinp, B, pa.iptr(all_next)), "pa_group_model_step")
-                nxt = all_next[rank * B:(rank + 1) * B]
+                # own tokens back after one wait; the all-gather of this step's tokens runs on a side stream beside the
+                # next step and is handed out by the next call (all_next: the previous step's tokens of every rank)
+                pa.check(min(lib.pa_group_model_step_overlapped(group, models, seqs, tokp, coinp, B, nxtp, pa.iptr(all_next)), 0),
+                         "pa_group_model_step_overlapped")
+                nxt = nxt_local
             else:
                 nxt = model.decode_step(seq_ids, toks, coins)
             if not keep:
@@ -854,12 +859,23 @@ def model_section(cx, eng, w, ctx, kms):
         t0 = time.perf_counter()
         for _ in range(k_model):
             model_step()
+        if group is not None:
+            pa.check(min(lib.pa_group_gather_flush(group, pa.iptr(all_next)), 0), "pa_group_gather_flush")     # the last step's gather, inside the timed region
         lib.pa_event_record(e1, hs_)
         cx.barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3 / k_model
         ms_model = cx.allmax(max(lib.pa_event_elapsed_ms(e0, e1) / k_model, wall_ms))
         per_step = (eng.launches() - l0) / k_model
         persistent = per_step <= (2.0 if group is not None else 1.0)
+        if group is not None:
+            # the blocking variant beside it: the gather on the handle's stream, waited for inside the step
+            cx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(k_model):
+                pa.check(lib.pa_group_model_step(group, models, seqs, tokp, coinp, B, pa.iptr(all_next)), "pa_group_model_step")
+                pa.check(eng.step_rollback(), "rollback")
+            cx.barrier()
+            blocking_ms = cx.allmax((time.perf_counter() - t0) * 1e3 / k_model)
         info = {"tokens_per_s": world * B / (ms_model * 1e-3), "ms_per_step": ms_model, "steps": k_model,
                 "vocab": V, "layers": L, "gpu_launches_per_step": per_step,
                 "path": ("ONE persistent cooperative kernel for the whole step (pa_model_mega.cu: weight-streaming "
@@ -869,11 +885,19 @@ def model_section(cx, eng, w, ctx, kms):
                 "projections": ("fp32 FMA weight-streaming GEMV with bias/GELU/residual epilogues" if persistent else
                                 "tcgen05 3xTF32 (fp32-accurate) GEMMs with bias/GELU/residual epilogues"),
                 "weights": "random init on the device (no checkpoint offline)",
-                "token_gather": (f"ncclAllGather of int32 next tokens inside the library (pa_group_model_step, NCCL "
-                                 f"{lib.pa_nccl_version()}), enqueued on the handle's stream behind the sampler, every step"
+                "token_gather": (f"ncclAllGather of int32 next tokens inside the library (pa_group_model_step_overlapped, NCCL "
+                                 f"{lib.pa_nccl_version()}), every step, on a side stream behind the sampler: a rank's next step consumes "
+                                 f"only its own tokens, the gathered tokens of step n are handed out while step n+1 runs"
                                  if group is not None else None),
-                "entry": ("pa_group_model_step" if group is not None else "pa_model_decode_step") +
+                "entry": ("pa_group_model_step_overlapped" if group is not None else "pa_model_decode_step") +
                          " (host token ids in, host token ids out, one sync per step)"}
+        if group is not None:
+            info["blocking_gather_ms_per_step"] = blocking_ms
+            info["overlapped_gather_ms_per_step"] = ms_model
+            if blocking_ms < ms_model:       # a handful of sequences (one persistent kernel per step, which owns every SM): the
+                # side-stream collective only gets in its way -- the blocking pa_group_model_step is the faster entry there
+                info.update(ms_per_step=blocking_ms, tokens_per_s=world * B / (blocking_ms * 1e-3),
+                            entry="pa_group_model_step (host token ids in, host token ids out, gather on the handle's stream, one sync per step)")
         if not persistent:
             info["attention_share_of_step"] = kms * L / ms_model
         # verified: the logits row of sequence 0 of a step of THIS configuration against the oracle's gpt2_forward

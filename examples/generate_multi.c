@@ -91,13 +91,21 @@ int main(int argc, char** argv) {
         CHECK(pa_model_forward_async(models[i], seq_ids[i], n_new, prompts[i], coins[i], B));
     }
     for (int i = 0; i < n; i++) CHECK(pa_model_wait(models[i], next[i]));
-    for (int i = 0; i < n; i++) for (int b = 0; b < B; b++) all_next[i * B + b] = next[i][b];
-    /* decode: one group step per token; the sampled tokens of ALL ranks come back gathered */
-    for (int t = PROMPT_SIZE; t < TOTAL; t++) {
-        for (int i = 0; i < n; i++)
-            for (int b = 0; b < B; b++) { gen[i][b][t] = all_next[i * B + b]; next[i][b] = all_next[i * B + b]; coins[i][b] = random_f32(&rng[i]); }
-        if (t + 1 < TOTAL) CHECK(pa_group_model_step(group, models, seq_ptr, tok_ptr, coin_ptr, B, all_next));
+    for (int i = 0; i < n; i++) for (int b = 0; b < B; b++) gen[i][b][PROMPT_SIZE] = next[i][b];      /* the prefill's token: local, no gather */
+    /* decode: one group step per token.  A rank's next step needs only its OWN sampled tokens (next[i], handed back
+     * after one wait); the all-gather of a step's tokens runs on a side stream beside the NEXT step and comes out of
+     * the next call -- gen[][][t] for t > PROMPT_SIZE is filled FROM THE GATHERED BUFFER, one step late. */
+    int* next_ptr[MAX_GPUS];
+    for (int i = 0; i < n; i++) next_ptr[i] = next[i];
+    for (int t = PROMPT_SIZE + 1; t < TOTAL; t++) {
+        for (int i = 0; i < n; i++) for (int b = 0; b < B; b++) coins[i][b] = random_f32(&rng[i]);
+        int have = pa_group_model_step_overlapped(group, models, seq_ptr, tok_ptr, coin_ptr, B, next_ptr, all_next);
+        CHECK(have);
+        if (have > 0)       /* the tokens of position t - 1, every rank's */
+            for (int i = 0; i < n; i++) for (int b = 0; b < B; b++) gen[i][b][t - 1] = all_next[i * B + b];
     }
+    CHECK(pa_group_gather_flush(group, all_next));
+    for (int i = 0; i < n; i++) for (int b = 0; b < B; b++) gen[i][b][TOTAL - 1] = all_next[i * B + b];
     clock_gettime(CLOCK_MONOTONIC, &t1);
     for (int i = 0; i < n; i++)
         for (int b = 0; b < B; b++) {

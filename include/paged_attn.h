@@ -262,6 +262,15 @@ PA_API int pa_group_gather_logits(pa_group* g, const float* const* send, float* 
  * all_next: size * nseq ints, rank-major. */
 PA_API int pa_group_model_step(pa_group* g, pa_model* const* models, const int* const* seq_ids, const int* const* tokens,
                                const float* const* coins, int nseq, int* all_next);
+/* The same step with the gather OFF the critical path: a rank's next step consumes only its OWN sampled tokens
+ * (next_local[i]: nseq ints of local member i, handed back after ONE wait on its stream); the all-gather runs on
+ * a side stream behind the sampler, beside the next step's kernels, and its result comes out of the NEXT call
+ * (gathered_prev: size * nseq ints of the previous step, rank-major; may be NULL) or of pa_group_gather_flush.
+ * Returns how many sequences per rank gathered_prev holds (0 on the first call), or a negative pa_status. */
+PA_API int pa_group_model_step_overlapped(pa_group* g, pa_model* const* models, const int* const* seq_ids,
+                                          const int* const* tokens, const float* const* coins, int nseq,
+                                          int* const* next_local, int* gathered_prev);
+PA_API int pa_group_gather_flush(pa_group* g, int* gathered);   /* waits for the gather in flight; returns its nseq (0: none) */
 PA_API int pa_nccl_version(void);                         /* e.g. 22809; 0 when NCCL cannot be opened */
 
 /* ---- the reference's on-disk formats (host only, no device needed) ---------------- */

@@ -108,6 +108,17 @@ struct pa_group {
     // per local member: device + pinned buffers of world * cap ints for the gathered tokens
     std::vector<int*> d_all, h_all;
     int cap = 0;
+    // overlapped gather (pa_group_model_step_overlapped): per member a side stream, and per step parity a staging
+    // copy of the member's own tokens, a gathered buffer (device + pinned) and two events
+    struct Side {
+        cudaStream_t stream = nullptr;
+        int* d_local[2] = {nullptr, nullptr};
+        int* d_all[2] = {nullptr, nullptr};
+        int* h_all[2] = {nullptr, nullptr};
+        cudaEvent_t sampled[2] = {nullptr, nullptr}, gathered[2] = {nullptr, nullptr};
+    };
+    std::vector<Side> side;
+    int side_cap = 0, parity = 0, pending = -1, pending_nseq = 0;      // pending: parity of a gather in flight, -1 none
 };
 
 extern "C" {
@@ -215,6 +226,18 @@ void pa_group_destroy(pa_group* g) {
         if (i < g->comms.size() && g->comms[i]) g_nccl.CommDestroy(g->comms[i]);
         if (i < g->d_all.size() && g->d_all[i]) cudaFree(g->d_all[i]);
         if (i < g->h_all.size() && g->h_all[i]) cudaFreeHost(g->h_all[i]);
+        if (i < g->side.size()) {
+            pa_group::Side& sd = g->side[i];
+            if (sd.stream) cudaStreamSynchronize(sd.stream);
+            for (int b = 0; b < 2; ++b) {
+                if (sd.d_local[b]) cudaFree(sd.d_local[b]);
+                if (sd.d_all[b]) cudaFree(sd.d_all[b]);
+                if (sd.h_all[b]) cudaFreeHost(sd.h_all[b]);
+                if (sd.sampled[b]) cudaEventDestroy(sd.sampled[b]);
+                if (sd.gathered[b]) cudaEventDestroy(sd.gathered[b]);
+            }
+            if (sd.stream) cudaStreamDestroy(sd.stream);
+        }
         if (g->owns_handles) pa_destroy(h);
     }
     delete g;
@@ -297,6 +320,121 @@ int pa_group_model_step(pa_group* g, pa_model* const* models, const int* const* 
     }
     if (rc == PA_OK) memcpy(all_next, g->h_all[0], (size_t)g->world * nseq * sizeof(int));
     return rc;
+}
+
+
+static int side_buffers(pa_group* g, int cap) {
+    const int n = (int)g->members.size();
+    if ((int)g->side.size() != n) g->side.assign(n, pa_group::Side());
+    if (cap <= g->side_cap) return PA_OK;
+    for (int i = 0; i < n; ++i) {
+        pa_group::Side& sd = g->side[i];
+        CU_CHECK(cudaSetDevice(g->members[i]->cfg.device));
+        if (!sd.stream) CU_CHECK(cudaStreamCreateWithFlags(&sd.stream, cudaStreamNonBlocking));
+        CU_CHECK(cudaStreamSynchronize(sd.stream));
+        CU_CHECK(cudaStreamSynchronize((cudaStream_t)g->members[i]->stream));
+        for (int b = 0; b < 2; ++b) {
+            if (sd.d_local[b]) cudaFree(sd.d_local[b]);
+            if (sd.d_all[b]) cudaFree(sd.d_all[b]);
+            if (sd.h_all[b]) cudaFreeHost(sd.h_all[b]);
+            sd.d_local[b] = sd.d_all[b] = sd.h_all[b] = nullptr;
+            CU_CHECK(cudaMalloc((void**)&sd.d_local[b], (size_t)cap * sizeof(int)));
+            CU_CHECK(cudaMalloc((void**)&sd.d_all[b], (size_t)g->world * cap * sizeof(int)));
+            CU_CHECK(cudaMallocHost((void**)&sd.h_all[b], (size_t)g->world * cap * sizeof(int)));
+            if (!sd.sampled[b]) CU_CHECK(cudaEventCreateWithFlags(&sd.sampled[b], cudaEventDisableTiming));
+            if (!sd.gathered[b]) CU_CHECK(cudaEventCreateWithFlags(&sd.gathered[b], cudaEventDisableTiming));
+        }
+    }
+    g->side_cap = cap;
+    return PA_OK;
+}
+
+/* wait for the all-gather still in flight (if any) and hand out its tokens: size * nseq ints, rank-major */
+int pa_group_gather_flush(pa_group* g, int* gathered) {
+    if (!g) { pa_set_error("pa_group_gather_flush: NULL group"); return PA_ERR_INVALID; }
+    if (g->pending < 0) return 0;
+    const int b = g->pending, nseq = g->pending_nseq;
+    g->pending = -1;
+    for (size_t i = 0; i < g->members.size(); ++i) {
+        CU_CHECK(cudaSetDevice(g->members[i]->cfg.device));
+        CU_CHECK(cudaEventSynchronize(g->side[i].gathered[b]));
+    }
+    if (gathered) memcpy(gathered, g->side[0].h_all[b], (size_t)g->world * nseq * sizeof(int));
+    return nseq;
+}
+
+/* The decode step of the whole group with the gather OFF the critical path.  A rank's next step consumes only its
+ * OWN sampled tokens; the tokens of the other ranks are output (detokenising, logging, stop conditions).  So: every
+ * local member's model takes its step and hands back its own tokens (next_local[i], nseq ints) after ONE wait on
+ * its stream; the all-gather of those tokens runs on a side stream behind the sampler -- beside the NEXT step's
+ * kernels -- and its result is handed out by the next call (gathered_prev: size * nseq ints of the PREVIOUS step,
+ * rank-major; untouched on the first call) or by pa_group_gather_flush.  Returns the number of sequences per rank
+ * that gathered_prev holds (0 on the first call), or a negative pa_status. */
+int pa_group_model_step_overlapped(pa_group* g, pa_model* const* models, const int* const* seq_ids, const int* const* tokens,
+                                   const float* const* coins, int nseq, int* const* next_local, int* gathered_prev) {
+    if (!g || !models || !seq_ids || !tokens || nseq < 1 || !next_local) { pa_set_error("pa_group_model_step_overlapped: bad arguments"); return PA_ERR_INVALID; }
+    const int n = (int)g->members.size();
+    int rc = side_buffers(g, nseq);
+    if (rc != PA_OK) return rc;
+    const int b = g->parity;
+    std::vector<int> ones(nseq, 1);
+    for (int i = 0; i < n; ++i) {
+        if (!models[i] || pa_model_handle(models[i]) != g->members[i]) { pa_set_error("pa_group_model_step_overlapped: model %d does not belong to member %d", i, i); return PA_ERR_INVALID; }
+        pa_model_want_device_tokens(models[i], 1);
+        rc = pa_model_forward_async(models[i], seq_ids[i], ones.data(), tokens[i], coins ? coins[i] : nullptr, nseq);
+        if (rc != PA_OK) {
+            for (int j = 0; j < i; ++j) pa_model_wait(models[j], nullptr);
+            return rc;
+        }
+        // the member's own tokens leave the model's buffer (the next step's sampler overwrites it) on the main stream ...
+        pa_group::Side& sd = g->side[i];
+        cudaStream_t ms = (cudaStream_t)g->members[i]->stream;
+        if (cudaSetDevice(g->members[i]->cfg.device) != cudaSuccess ||
+            cudaMemcpyAsync(sd.d_local[b], pa_model_next_tokens_dev(models[i]), (size_t)nseq * sizeof(int), cudaMemcpyDeviceToDevice, ms) != cudaSuccess ||
+            cudaEventRecord(sd.sampled[b], ms) != cudaSuccess || cudaStreamWaitEvent(sd.stream, sd.sampled[b], 0) != cudaSuccess) {
+            pa_set_error("pa_group_model_step_overlapped: staging the sampled tokens failed");
+            for (int j = 0; j <= i; ++j) pa_model_wait(models[j], nullptr);
+            return PA_ERR_CUDA;
+        }
+    }
+    // ... and are gathered on the side streams
+    if (g->world == 1) {
+        rc = cudaMemcpyAsync(g->side[0].d_all[b], g->side[0].d_local[b], (size_t)nseq * sizeof(int), cudaMemcpyDeviceToDevice, g->side[0].stream) == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+    } else {
+        if (n > 1) g_nccl.GroupStart();
+        for (int i = 0; i < n && rc == PA_OK; ++i) {
+            ncclResult_t r = g_nccl.AllGather(g->side[i].d_local[b], g->side[i].d_all[b], (size_t)nseq, ncclInt32, g->comms[i], g->side[i].stream);
+            if (r != ncclSuccess) { pa_set_error("pa_group_model_step_overlapped: ncclAllGather: %s", g_nccl.GetErrorString(r)); rc = PA_ERR_CUDA; }
+            g->members[i]->launches++;
+        }
+        if (n > 1) g_nccl.GroupEnd();
+    }
+    for (int i = 0; i < n && rc == PA_OK; ++i) {
+        pa_group::Side& sd = g->side[i];
+        if (cudaSetDevice(g->members[i]->cfg.device) != cudaSuccess ||
+            cudaMemcpyAsync(sd.h_all[b], sd.d_all[b], (size_t)g->world * nseq * sizeof(int), cudaMemcpyDeviceToHost, sd.stream) != cudaSuccess ||
+            cudaEventRecord(sd.gathered[b], sd.stream) != cudaSuccess) {
+            pa_set_error("pa_group_model_step_overlapped: copy of the gathered tokens failed");
+            rc = PA_ERR_CUDA;
+        }
+    }
+    // the PREVIOUS step's gather has had this whole step's queueing time (and its own step) to finish
+    int got_prev = 0;
+    if (rc == PA_OK) {
+        const int prev_pending = g->pending;
+        got_prev = pa_group_gather_flush(g, gathered_prev);
+        if (got_prev < 0) rc = got_prev;
+        (void)prev_pending;
+    }
+    for (int i = 0; i < n; ++i) {
+        const int rw = pa_model_wait(models[i], next_local[i]);
+        if (rc == PA_OK) rc = rw;
+    }
+    if (rc != PA_OK) return rc;
+    g->pending = b;
+    g->pending_nseq = nseq;
+    g->parity ^= 1;
+    return got_prev;
 }
 
 }  // extern "C"

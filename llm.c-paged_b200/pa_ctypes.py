@@ -131,6 +131,9 @@ def load():
         "pa_group_gather_tokens": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_int]),
         "pa_group_gather_logits": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.c_size_t]),
         "pa_group_model_step": (C.c_int, [vp, C.POINTER(vp), C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(vp), C.c_int, c_int_p]),
+        "pa_group_model_step_overlapped": (C.c_int, [vp, C.POINTER(vp), C.POINTER(c_int_p), C.POINTER(c_int_p), C.POINTER(vp), C.c_int,
+                                                     C.POINTER(c_int_p), c_int_p]),
+        "pa_group_gather_flush": (C.c_int, [vp, c_int_p]),
         "pa_nccl_version": (C.c_int, []),
         "pa_fill_normal": (C.c_int, [vp, C.c_size_t, C.c_float, C.c_float, C.c_ulonglong, vp]),
         "pa_model_params": (vp, [vp]),

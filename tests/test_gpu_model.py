@@ -459,6 +459,25 @@ def test_group_of_one_gathers_through_the_library():
                 pa.check(lib.pa_group_model_step(g, models, seqs, toks, cs, B, pa.iptr(out)), "group step")
                 assert np.array_equal(out, want)
                 tok = want.astype(np.int32)
+            # the overlapped variant: own tokens at once, the gathered ones a call later (or from the flush)
+            got_local = np.zeros(B, dtype=np.int32)
+            prev = np.full(B, -1, dtype=np.int32)
+            nxtp = (pa.c_int_p * 1)(pa.iptr(got_local))
+            history = []
+            for k in range(4):
+                coins = rng.random(B).astype(np.float32)
+                cs = (C.c_void_p * 1)(coins.ctypes.data)
+                toks = (pa.c_int_p * 1)(pa.iptr(tok))
+                want = ref.decode_step(seq, tok, coins)
+                have = lib.pa_group_model_step_overlapped(g, models, seqs, toks, cs, B, nxtp, pa.iptr(prev))
+                assert have == (0 if k == 0 else B), have
+                assert np.array_equal(got_local, want)
+                if k > 0:
+                    assert np.array_equal(prev, history[-1])
+                history.append(want.copy())
+                tok = want.astype(np.int32)
+            assert lib.pa_group_gather_flush(g, pa.iptr(prev)) == B and np.array_equal(prev, history[-1])
+            assert lib.pa_group_gather_flush(g, pa.iptr(prev)) == 0
             # a second step before the wait is refused
             ones = np.ones(B, dtype=np.int32)
             assert lib.pa_model_forward_async(m, pa.iptr(seq), pa.iptr(ones), pa.iptr(tok), None, B) == 0
