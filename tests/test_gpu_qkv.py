@@ -284,3 +284,40 @@ def test_split_k_with_two_streams_live():
     finally:
         for sc in scs:
             sc.close()
+
+
+@pytest.mark.timeout(180)
+def test_split_k_spin_wait_beside_a_busy_foreign_stream():
+    """the CTAs of a workspace-split projection wait for each other under a NON-cooperative launch, and
+    the library only counts its own streams when it decides to launch cooperatively.  A caller's foreign stream that
+    keeps the device busy (here: back-to-back device-side fills of a 1 GiB buffer on a stream the library knows
+    nothing about -- 1184-CTA grids that hold SM slots but always finish) must delay the waiting CTAs, never deadlock
+    them: a chain of 200 split projections queued beside it finishes, with bit-identical results to a quiet device.
+    (pytest-timeout turns a hang into a failure.)"""
+    lib = pa.load()
+    M, N, K = 64, 768, 3072          # fcproj at 64 rows: 12 tiles x 12 splits = 144 spinning CTAs
+    x = oa.normal((M, K), seed=801)
+    w = (oa.normal((N, K), seed=802) * np.float32(1.0 / np.sqrt(K))).astype(np.float32)
+    bias = oa.normal((N,), seed=803)
+    want = _oracle_matmul(x, w, bias)
+    dx, dw, db, do = pa.DevBuf.from_numpy(x), pa.DevBuf.from_numpy(w), pa.DevBuf.from_numpy(bias), pa.DevBuf(M * N * 4)
+    ours, foreign = lib.pa_stream_create(), lib.pa_stream_create()
+    junk_floats = 1 << 28
+    junk = lib.pa_dev_alloc(junk_floats * 4)
+    try:
+        pa.check(lib.pa_matmul_bias(dx.ptr, K, dw.ptr, db.ptr, do.ptr, N, M, N, K, ours), "quiet")
+        pa.check(lib.pa_stream_sync(ours), "sync")
+        quiet = do.download((M, N))
+        assert_close_gemm(quiet, want, "quiet device")
+        for rep in range(40):
+            pa.check(lib.pa_fill_normal(junk, junk_floats, 1.0, 0.0, rep, foreign), "foreign fill")
+        for rep in range(200):
+            pa.check(lib.pa_matmul_bias(dx.ptr, K, dw.ptr, db.ptr, do.ptr, N, M, N, K, ours), "busy")
+        pa.check(lib.pa_stream_sync(ours), "sync ours")
+        busy = do.download((M, N))
+        pa.check(lib.pa_stream_sync(foreign), "sync foreign")
+        assert np.array_equal(busy.view(np.uint32), quiet.view(np.uint32))
+    finally:
+        lib.pa_dev_free(junk)
+        lib.pa_stream_destroy(ours)
+        lib.pa_stream_destroy(foreign)
