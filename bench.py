@@ -673,10 +673,12 @@ def run_workload(cx, wid, w, primary):
         achieved = kbytes / (kms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath):       # the ncu --set full figure of this kernel AT THIS SHAPE (entries carry the shape's algorithmic bytes)
             try:
-                tj = json.load(open(tpath))
-                traffic = (tj.get(wid) or tj.get({"cfg4": "xl", "cfg5": "long"}.get(wid, wid)) or {}).get("dram_bytes_per_launch")
+                for key, ent in json.load(open(tpath)).items():
+                    if isinstance(ent, dict) and abs(ent.get("algorithmic_bytes_per_launch", 0) - kbytes) <= 0.01 * kbytes:
+                        traffic = ent.get("dram_bytes_per_launch")
+                        break
             except Exception:
                 traffic = None
         last_ctas = lib.pa_tune_get(eng.h, 12)       # 0: the launch did not go through the stream kernel

@@ -112,6 +112,7 @@ void pa_cu_release(pa_handle* h) {
     }
     if (h->host_only) return;
     pa_cu_prefill_tc_release(h);
+    pa_cu_prefill_tc3_release(h);
     pa_cu_host_pipe_release(h);
     cudaFree(h->pool_k); cudaFree(h->pool_v);
     cudaFree(h->d_step); cudaFree(h->d_ws); cudaFree(h->d_counters);

@@ -70,6 +70,7 @@ struct pa_handle {
     void* decode_attr_fn;         /* kernel whose dynamic-smem attribute has been raised */
     int max_heads;                /* heads the split workspace was sized for */
     void* tc_state;               /* TMA tensor maps of the pool (pa_prefill_tc.cu), lazily built */
+    void* tc3_state;              /* the same for the fp32-accurate 3xTF32 prefill (pa_prefill_tc3.cu) */
     void* host_pipe;              /* copy streams + events of pa_decode_step_host_async (pa_kernels.cu) */
     int* compat_ints;             /* attention_paged scratch (page indices + per-row ints), grown on demand, kept */
     size_t compat_ints_cap;
@@ -137,6 +138,9 @@ int pa_cu_prefill_tiled(pa_handle* h, int layer, const float* q, int q_stride, f
 int pa_cu_prefill_tc(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride,
                      void* stream);
 void pa_cu_prefill_tc_release(pa_handle* h);
+/* fp32-accurate tensor-core prefill (tcgen05 3xTF32, tolerance 1e-5) */
+int pa_cu_prefill_tc3(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream);
+void pa_cu_prefill_tc3_release(pa_handle* h);
 
 /* ---- implemented in pa_gemm_tc.cu: fp32-accurate (3xTF32) tensor-core GEMM ---------------- */
 int pa_cu_gemm_tc(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,

@@ -1181,6 +1181,17 @@ int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out
             pa_set_error("pa_prefill: tcgen05 kernel needs head_dim 64/128, block_size 8..128 (power of two), 16-byte aligned rows");
         return rc;
     }
+    // fp32-accurate tensor-core kernel (tcgen05 3xTF32, tolerance 1e-5): forced with 4; chosen by itself (0) when the
+    // step has enough query rows for 128-row tiles to pay (measured crossover against the tiled SIMT kernel)
+    static const int tc3_min_rows = getenv("PA_PREFILL_TC3_MIN_ROWS") ? atoi(getenv("PA_PREFILL_TC3_MIN_ROWS")) : 256;
+    if (path == 4 || (path == 0 && h->step.ntok >= tc3_min_rows && h->step.max_q >= 32)) {
+        rc = pa_cu_prefill_tc3(h, layer, q, q_stride, out, out_stride, (void*)s);
+        if (rc != PA_ERR_UNSUPPORTED) return rc;
+        if (path == 4) {
+            pa_set_error("pa_prefill: the 3xTF32 tcgen05 kernel needs head_dim 64/128, block_size 8..64 (head_dim 128: 8..32; a power of two), 16-byte aligned rows");
+            return rc;
+        }
+    }
     if (path != 2) {
         rc = pa_cu_prefill_tiled(h, layer, q, q_stride, out, out_stride, 1, (void*)s);
         if (rc != PA_ERR_UNSUPPORTED) return rc;

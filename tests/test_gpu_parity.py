@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle_api as oa
-from gpu_common import assert_close_tc, Scenario, assert_close, assert_close_illconditioned, pa
+from gpu_common import assert_close_tc, assert_close_tc3, Scenario, assert_close, assert_close_illconditioned, pa
 
 pytestmark = pytest.mark.gpu
 
@@ -600,6 +600,45 @@ def test_prefill_tcgen05_tf32(NH, hs, bs, before, n_new, nwg, bn):
     got, want = _run_prefill(NH, hs, bs, before, n_new, 3, shuffle=True, nwg=nwg, bn=bn)
     err = assert_close_tc(got, want, "tcgen05 prefill")
     print(f"tcgen05 tf32 prefill hs={hs} bs={bs} nwg={nwg} bn={bn}: max rel err {err:.2e}")
+
+
+@pytest.mark.parametrize("NH,hs,bs,before,n_new", [
+    (3, 64, 16, [0, 100, 0, 17, 300], [300, 129, 128, 1, 257]),     # several q tiles, diagonal + tail tiles, a 1-row sequence
+    (2, 128, 16, [0, 77, 0], [200, 65, 64]),
+    (2, 64, 8, [3, 0], [130, 70]),
+    (2, 64, 32, [0, 500], [1000, 3]),
+    (2, 64, 64, [0, 130], [260, 33]),                                # a page = a whole key tile
+    (1, 128, 32, [0], [129]),
+    (1, 128, 8, [1000], [700]),                                      # chunk on top of a long cache, head_dim 128
+    (12, 64, 16, [0], [2048]),                                       # GPT-2 124M heads, a 2048-token prompt
+])
+def test_prefill_tcgen05_3xtf32_is_fp32_accurate(NH, hs, bs, before, n_new):
+    """The fp32-ACCURATE tensor-core prefill (pa_prefill_tc3.cu: tcgen05 kind::tf32 with the 3xTF32 split, fresh
+    TMEM accumulators per key tile, register accumulation across tiles, expf) against the fp32 oracle at the
+    path's tolerance: max|a-b|/max|ref| <= 1e-5 and allclose(rtol 1e-5, atol 3e-6) (gpu_common.assert_close_tc3)."""
+    got, want = _run_prefill(NH, hs, bs, before, n_new, 4, shuffle=True)
+    err = assert_close_tc3(got, want, "tcgen05 3xTF32 prefill")
+    print(f"tcgen05 3xtf32 prefill NH={NH} hs={hs} bs={bs}: max rel err {err:.2e}")
+
+
+def test_prefill_tcgen05_3xtf32_window_large_logits_and_domain():
+    got, want = _run_prefill(2, 64, 16, [150, 70], [90, 140], 4, kv_start=[37, 64])
+    assert_close_tc3(got, want, "3xTF32 prefill, window")
+    # the reference test's U[0,100) inputs (logits ~1e5): as well conditioned as the fp32 kernels are (see gpu_common)
+    got_t, want = _run_prefill(2, 64, 16, [0, 20], [70, 40], 4, dist="uniform")
+    got_r, _ = _run_prefill(2, 64, 16, [0, 20], [70, 40], 2, dist="uniform")
+    assert np.isfinite(got_t).all()
+    ref_gap = np.abs(got_r.astype(np.float64) - want).max()
+    assert np.abs(got_t.astype(np.float64) - want).max() <= max(4 * ref_gap, 1e-2)
+    with pytest.raises(pa.PagedAttnError):          # block size 4 < one swizzle group: forced path fails loudly
+        _run_prefill(2, 64, 4, [0], [40], 4)
+    with pytest.raises(pa.PagedAttnError):          # head_dim 128: pages above 32 tokens exceed the 32-key tile
+        _run_prefill(1, 128, 64, [0], [129], 4)
+    # the automatic choice (path 0) takes it for large steps and the SIMT kernel for small ones: same answers
+    big, want_big = _run_prefill(2, 64, 16, [0, 10], [300, 200], 0)
+    assert_close_tc3(big, want_big, "auto, large step")
+    small, want_small = _run_prefill(2, 64, 16, [0, 10], [20, 9], 0)
+    assert_close(small, want_small, "auto, small step")
 
 
 def test_prefill_tcgen05_window_and_unsupported_shapes():

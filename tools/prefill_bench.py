@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 SHAPES = {"124m": (12, 64), "xl": (25, 64), "long": (32, 128)}
-PATH_NAMES = {0: "auto", 1: "tiled fp32 SIMT", 2: "generic rows", 3: "tcgen05 tf32"}
+PATH_NAMES = {0: "auto", 1: "tiled fp32 SIMT", 2: "generic rows", 3: "tcgen05 tf32", 4: "tcgen05 3xtf32 (fp32-accurate)"}
 
 
 def main():
