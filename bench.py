@@ -756,7 +756,7 @@ def prefill_section(cx, eng, w, ctx, perm, pages, stream):
     d_o = pa.DevBuf(B * chunk * C_ * 4)
     seq_ids = np.arange(B, dtype=np.int32)
     out = {}
-    paths = [(0, "fp32 (default path, tolerance 1e-5)")]
+    paths = [(0, "default: tcgen05 3xTF32, fp32-accurate (tolerance 1e-5)")]
     if not args.no_tc_prefill:
         paths.append((3, "tcgen05 TF32 (opt-in, tolerance 5e-3)"))
     e0, e1 = lib.pa_event_create(), lib.pa_event_create()
@@ -798,16 +798,70 @@ def prefill_section(cx, eng, w, ctx, perm, pages, stream):
                "tflops_per_gpu": flops / (ms * 1e-3) / 1e12, "prompt_tokens_per_s": cx.world * B * n_tok / (ms * 1e-3),
                "verified_last_row_max_rel_err": check, "tolerance": tol,
                "verified_against": "the closer of the oracle's fp32 last-row restatement and its fp64 evaluation (32k-term fp32 sums)"}
-        if path == 3:
-            ent["frac_of_dense_tf32_peak"] = ent["tflops_per_gpu"] / (tp / 2.0)
-            ent["peak_note"] = f"dense TF32 peak taken as half of the {tp_src} = {tp / 2:.0f} TFLOP/s"
-        else:
-            ent["frac_of_fp32_ffma_peak"] = ent["tflops_per_gpu"] / 74.5
-            ent["peak_note"] = "fp32 FFMA peak 148 SMs x 128 lanes x 2 flop x 1.965 GHz = 74.5 TFLOP/s"
+        ent["frac_of_dense_tf32_peak"] = ent["tflops_per_gpu"] / (tp / 2.0)
+        ent["peak_note"] = (f"dense TF32 peak taken as half of the {tp_src} = {tp / 2:.0f} TFLOP/s" +
+                            ("; the 3xTF32 split issues three MMAs per product, so its ceiling is a third of that" if path == 0 else ""))
         out["fp32" if path == 0 else "tf32"] = ent
     eng.tune(pa.PA_TUNE_PREFILL_PATH, 0)
     d_in.free()
     d_o.free()
+    return out
+
+
+def prefill_headline(cx):
+    """Prompt prefill at the GPT-2 124M head shape (12 heads x 64, block 16): 16 prompts x 2048 tokens, one layer,
+    KV append + causal multi-row paged attention per pass; the default path (tcgen05 3xTF32, fp32-accurate), the fp32
+    SIMT kernel it replaced as default, and the opt-in plain-TF32 kernel.  The last prompt row of sequence 0 is checked
+    against the oracle for each."""
+    args, pa, lib = cx.args, cx.pa, cx.lib
+    NH, hs, bs, B, T = 12, 64, 16, 16, 2048
+    C_ = NH * hs
+    pages = (T + bs - 1) // bs + 1
+    eng = pa.PagedAttn(bs, B * pages + 8, B, NH, hs, n_layers=1, device=cx.local_rank, max_batch_tokens=B * T)
+    out = {"shape": f"{B} prompts x {T} tokens, {NH} heads x head_dim {hs}, block {bs}, 1 layer (append + prefill per pass)"}
+    try:
+        d_in, d_o = pa.DevBuf(B * T * 3 * C_ * 4), pa.DevBuf(B * T * C_ * 4)
+        hstream = lib.pa_stream_of(eng.h)
+        pa.check(lib.pa_fill_normal(d_in.ptr, B * T * 3 * C_, 1.0, 0.0, 4242 + cx.rank, hstream), "fill")
+        seq_ids = np.arange(B, dtype=np.int32)
+        e0, e1 = lib.pa_event_create(), lib.pa_event_create()
+        keys_seen = B * T * (T + 1) // 2
+        flops = 4.0 * hs * NH * keys_seen
+        tp, tp_src = tensor_peak()
+        for path, key, label, tol in ((0, "default", "tcgen05 3xTF32, fp32-accurate (automatic choice)", VERIFY_TOL),
+                                      (1, "simt", "tiled fp32 SIMT (PA_TUNE_PREFILL_PATH=1)", VERIFY_TOL),
+                                      (3, "tf32", "tcgen05 plain TF32 (opt-in, PA_TUNE_PREFILL_PATH=3)", 5e-3)):
+            eng.tune(pa.PA_TUNE_PREFILL_PATH, path)
+            ms = []
+            check = None
+            for it in range(3 + 5):
+                pa.check(eng.step_begin(seq_ids, np.full(B, T, dtype=np.int32)), "step_begin")
+                pa.check(eng.upload(hstream), "upload")
+                lib.pa_event_record(e0, hstream)
+                pa.check(eng.append(0, d_in.ptr + C_ * 4, d_in.ptr + 2 * C_ * 4, 3 * C_, hstream), "append")
+                pa.check(eng.prefill(0, d_in.ptr, 3 * C_, d_o.ptr, C_, hstream), "prefill")
+                lib.pa_event_record(e1, hstream)
+                pa.check(lib.pa_stream_sync(hstream), "sync")
+                if it >= 3:
+                    ms.append(lib.pa_event_elapsed_ms(e0, e1))
+                if it == 7 and not args.no_verify:
+                    q_last = d_in.download((1, 3 * C_), offset_bytes=(T - 1) * 3 * C_ * 4)[0]
+                    o_last = d_o.download((1, C_), offset_bytes=(T - 1) * C_ * 4)[0]
+                    check = min(row_err(o_last, oracle_row(cx, eng, 0, 0, q_last, NH, hs, bs)))
+                pa.check(eng.step_rollback(), "rollback")
+            if check is not None and not (check <= tol):
+                raise SystemExit(f"bench.py: VERIFICATION FAILED for the prefill ({label}): {check:.3e} > {tol}")
+            t = cx.allmax(float(np.median(ms)))
+            out[key] = {"path": label, "ms": t, "tflops_per_gpu": flops / (t * 1e-3) / 1e12,
+                        "prompt_tokens_per_s": cx.world * B * T / (t * 1e-3), "verified_last_row_max_rel_err": check, "tolerance": tol,
+                        "frac_of_dense_tf32_peak": flops / (t * 1e-3) / 1e12 / (tp / 2.0)}
+        out["peak_note"] = (f"dense TF32 peak taken as half of the {tp_src} = {tp / 2:.0f} TFLOP/s; the 3xTF32 split issues three "
+                            f"MMAs per product (ceiling: a third of it); fp32 FFMA peak for the SIMT kernel: 74.5 TFLOP/s")
+        out["flops"] = "4 * head_dim per (query row, visible key, head): QK^T and PV, causal"
+        d_in.free()
+        d_o.free()
+    finally:
+        eng.close()
     return out
 
 
@@ -995,6 +1049,7 @@ def main():
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of the timed configuration's output rows")
     ap.add_argument("--no-model", action="store_true", help="skip the whole-model decode step section (SURVEY 8f.2)")
     ap.add_argument("--no-tc-prefill", action="store_true", help="cfg5: skip the opt-in tcgen05 TF32 prefill pass")
+    ap.add_argument("--no-prefill", action="store_true", help="skip the prompt-prefill section of the headline line")
     ap.add_argument("--no-clock-hold", action="store_true", help="skip the untimed >=1.5 s continuation (ncu runs)")
     ap.add_argument("--hpg", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
@@ -1043,6 +1098,15 @@ def main():
 
     head = run_workload(cx, wid, w, primary=True)
 
+    prefill = None
+    if wid == "cfg2" and not args.no_prefill:
+        try:
+            prefill = prefill_headline(cx)
+        except SystemExit:
+            raise
+        except Exception as ex:
+            prefill = {"error": repr(ex)}
+
     others = {}
     if args.configs != "none" and (args.configs != "all" or wid == "cfg2"):
         want = ["cfg1", "cfg3", "cfg4", "cfg5"] if args.configs == "all" else [ALIASES.get(c, c) for c in args.configs.split(",") if c]
@@ -1081,7 +1145,7 @@ def main():
             "tokens_per_s": head["tokens_per_s"], "frac_of_measured_peak": head["frac_of_measured_peak"],
             "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
             "roofline": head["roofline"], "verified": head.get("verified"), "cpu_baseline": cpu_baseline,
-            "model": head.get("model"), "prefill": head.get("prefill")}
+            "model": head.get("model"), "prefill": prefill if prefill is not None else head.get("prefill")}
     if others:
         for r in others.values():
             r.pop("clocks", None)

@@ -3,7 +3,7 @@
 # then the launch list / the --set full capture of the dominant kernel.  Outputs under gpurun_out/.
 set -uo pipefail
 OUT=gpurun_out
-COMMON="--configs none --no-cpu-baseline --no-clock-hold --no-verify --no-e2e"
+COMMON="--configs none --no-cpu-baseline --no-clock-hold --no-verify --no-e2e --no-prefill"
 CMD2="python bench.py --steps 3 --warmup 3 $COMMON"
 CMD4="python bench.py --workload cfg4 --steps 1 --warmup 3 $COMMON --no-model"
 CMD5="python bench.py --workload cfg5 --steps 1 --warmup 3 $COMMON --no-model --no-tc-prefill"
