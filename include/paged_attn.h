@@ -168,6 +168,10 @@ PA_API const int* pa_step_context_lens(pa_handle* h, int* nseq);
 PA_API const int* pa_step_block_table(pa_handle* h, int* nseq, int* stride);
 /* Mirror the step tables to HBM: ONE cudaMemcpyAsync from pinned memory. */
 PA_API int pa_step_upload(pa_handle* h, void* stream);
+/* Bounds check of the step tables (every page index inside the pool, every slot inside it, windows and prefix sums
+ * consistent): all addresses the kernels form into the KV pool derive from these.  pa_step_upload runs it on every
+ * step when the environment has PA_VALIDATE_STEP=1. */
+PA_API int pa_step_validate(pa_handle* h);
 
 /* ---- kernels (device pointers, caller's stream; NULL stream = the handle's own) ----------- */
 /* KV append: token j of the step (order of pa_step_begin) has K at k+j*row_stride, V likewise. */

@@ -1367,7 +1367,7 @@ int pa_decode_step_host_layers_async(pa_handle* h, const float* qkv_host, size_t
                                    n * 3 * C * sizeof(float), (size_t)L, cudaMemcpyHostToDevice, hp->h2d));
     }
     CU_CHECK(cudaEventRecord(ev_in, hp->h2d));
-    if (!h->step.uploaded) { rc = pa_cu_step_upload(h, s); if (rc != PA_OK) return rc; }
+    if (!h->step.uploaded) { rc = pa_step_upload(h, s); if (rc != PA_OK) return rc; }
     CU_CHECK(cudaStreamWaitEvent(s, ev_in, 0));
     for (int l = 0; l < L; ++l) {
         const float* in_l = hp->st_in[b] + (qkv_layer_stride ? (size_t)l * n * 3 * C : 0);
@@ -1395,7 +1395,7 @@ static int decode_step_host_impl(pa_handle* h, int layer, const float* qkv_host,
     const size_t C = h->C, n = L.nseq;
     cudaStream_t s = (cudaStream_t)h->stream;
     int rc;
-    if (!h->step.uploaded) { rc = pa_cu_step_upload(h, s); if (rc != PA_OK) return rc; }
+    if (!h->step.uploaded) { rc = pa_step_upload(h, s); if (rc != PA_OK) return rc; }
     const HostPipe::Alias a_in = host_alias(h, qkv_host), a_out = host_alias(h, out_host);
     const bool in_pinned = a_in.pinned, out_pinned = a_out.pinned;
     const float* in_alias = (const float*)a_in.dev;

@@ -385,9 +385,49 @@ const int* pa_step_block_table(pa_handle* h, int* nseq, int* stride) {
     return h->h_step + h->step.off_table;
 }
 
+/* Every address a kernel forms into the KV pool comes from these tables (page index * page size + row, slot * C)
+ * inside loops bounded by kv_start / kv_end: checking the tables bounds the kernels' pool accesses.  Run on every
+ * upload when PA_VALIDATE_STEP=1 (the test suite sets it; compute-sanitizer is closed on the B200 pool this was
+ * developed on), O(batch x pages) integer compares. */
+int pa_step_validate(pa_handle* h) {
+    if (!h || h->step.nseq < 1 || !h->h_step) { pa_set_error("pa_step_validate: no step"); return PA_ERR_INVALID; }
+    const pa_step_layout* L = &h->step;
+    const int* buf = h->h_step;
+    const int bs = h->mgr->block_size, mb = h->mgr->max_blocks;
+    int cum = 0, qrow = 0;
+    for (int i = 0; i < L->nseq; i++) {
+        const int end = buf[L->off_kv_end + i], start = buf[L->off_kv_start + i];
+        if (start < 0 || start > end) { pa_set_error("pa_step_validate: row %d window [%d, %d)", i, start, end); return PA_ERR_INVALID; }
+        const int pages = (end + bs - 1) / bs;
+        if (pages > L->tstride) { pa_set_error("pa_step_validate: row %d needs %d pages, table rows hold %d", i, pages, L->tstride); return PA_ERR_INVALID; }
+        const int* row = buf + L->off_table + (size_t)i * L->tstride;
+        for (int j = 0; j < L->tstride; j++)
+            if (row[j] < 0 || row[j] >= mb) { pa_set_error("pa_step_validate: row %d page %d = %d outside the pool of %d pages", i, j, row[j], mb); return PA_ERR_INVALID; }
+        if (buf[L->off_cum_pages + i] != cum) { pa_set_error("pa_step_validate: page prefix sum of row %d", i); return PA_ERR_INVALID; }
+        cum += end > start ? (end + bs - 1) / bs - start / bs : 0;
+        if (buf[L->off_q_row0 + i] != qrow) { pa_set_error("pa_step_validate: query-row prefix sum of row %d", i); return PA_ERR_INVALID; }
+        const int nq = buf[L->off_q_row0 + i + 1] - qrow;
+        if (nq < 0 || nq > end + 1) { pa_set_error("pa_step_validate: row %d has %d query rows for %d cached tokens", i, nq, end); return PA_ERR_INVALID; }
+        qrow += nq;
+    }
+    if (buf[L->off_cum_pages + L->nseq] != cum || cum != L->total_pages) { pa_set_error("pa_step_validate: total pages"); return PA_ERR_INVALID; }
+    if (qrow != L->ntok) { pa_set_error("pa_step_validate: %d query rows, %d tokens", qrow, L->ntok); return PA_ERR_INVALID; }
+    for (int j = 0; j < L->ntok; j++) {
+        const int sl = buf[L->off_slot + j];
+        if (sl < 0 || sl >= mb * bs) { pa_set_error("pa_step_validate: slot %d of token %d outside the pool of %d rows", sl, j, mb * bs); return PA_ERR_INVALID; }
+    }
+    return PA_OK;
+}
+
 int pa_step_upload(pa_handle* h, void* stream) {
     if (!h || h->step.nseq < 1) { pa_set_error("pa_step_upload: no step"); return PA_ERR_INVALID; }
     if (h->host_only) { pa_set_error("pa_step_upload: host-only handle has no device"); return PA_ERR_NO_DEVICE; }
+    static int validate = -1;
+    if (validate < 0) { const char* e = getenv("PA_VALIDATE_STEP"); validate = (e && atoi(e) != 0) ? 1 : 0; }
+    if (validate) {
+        int rc = pa_step_validate(h);
+        if (rc != PA_OK) return rc;
+    }
     return pa_cu_step_upload(h, stream);
 }
 

@@ -100,6 +100,7 @@ def load():
         "pa_step_context_lens": (c_int_p, [vp, c_int_p]),
         "pa_step_block_table": (c_int_p, [vp, c_int_p, c_int_p]),
         "pa_step_upload": (C.c_int, [vp, vp]),
+        "pa_step_validate": (C.c_int, [vp]),
         "pa_append": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp]),
         "pa_decode": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),
         "pa_prefill": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]),

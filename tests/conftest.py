@@ -10,6 +10,10 @@ for p in (HERE, ROOT):
         sys.path.insert(0, p)
 
 
+# every step's tables are bounds-checked on upload while the tests run (pa_step_validate)
+os.environ.setdefault("PA_VALIDATE_STEP", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

@@ -131,3 +131,33 @@ def test_swapped_in_sequence_is_not_evicted_by_a_later_row_of_the_same_step():
         assert list(eng.context_lens()) == [9, 4]
     finally:
         eng.close()
+
+
+def test_step_validate_catches_tables_that_point_outside_the_pool():
+    """pa_step_validate (run by pa_step_upload under PA_VALIDATE_STEP=1, which the suite sets): every page index and
+    slot the kernels will use lies inside the pool, windows and prefix sums are consistent."""
+    import ctypes as C
+    eng = make(bs=4, blocks=8, seqs=3)
+    try:
+        assert eng.step_begin([0, 1], [6, 3]) == 0
+        assert eng.lib.pa_step_validate(eng.h) == 0
+        n, stride = C.c_int(), C.c_int()
+        tbl = eng.lib.pa_step_block_table(eng.h, C.byref(n), C.byref(stride))
+        old = tbl[1]
+        tbl[1] = 8                                   # one past the last page
+        assert eng.lib.pa_step_validate(eng.h) == pa.PA_ERR_INVALID and "outside the pool" in pa.last_error()
+        tbl[1] = old
+        nt = C.c_int()
+        slots = eng.lib.pa_step_slot_mapping(eng.h, C.byref(nt))
+        old = slots[0]
+        slots[0] = 8 * 4
+        assert eng.lib.pa_step_validate(eng.h) == pa.PA_ERR_INVALID and "slot" in pa.last_error()
+        slots[0] = old
+        ctx = eng.lib.pa_step_context_lens(eng.h, C.byref(n))
+        old = ctx[0]
+        ctx[0] = 4 * 4 * 4                           # more tokens than the table row has pages for
+        assert eng.lib.pa_step_validate(eng.h) == pa.PA_ERR_INVALID
+        ctx[0] = old
+        assert eng.lib.pa_step_validate(eng.h) == 0
+    finally:
+        eng.close()
