@@ -105,9 +105,16 @@ __device__ __forceinline__ void find_tile3(const Tc3Params& p, int tile_lin, int
     }
 }
 
-template <int HS, int BN, int NST, int SBUF, int OBUF>
+template <int HS, int BN, int NST, int SBUF, int OBUF, int NWG>
 struct Tc3Cfg {
-    static constexpr int kThreads = 384;       // three whole warpgroups (setmaxnreg works on warpgroups): softmax | splitter | producer, MMA issuer, two idle warps
+    // whole warpgroups (setmaxnreg works on warpgroups): NWG x softmax | splitter | producer, MMA issuer, two idle warps
+    static constexpr int kThreads = (NWG + 2) * 128;
+    // registers per thread after setmaxnreg: the launch gives 65536 / kThreads (168 at 384 threads, 128 at 512)
+    static constexpr int kRegSoftmax = NWG == 1 ? 232 : 184, kRegOther = NWG == 1 ? 96 : 72;
+    static_assert(NWG == 1 || NWG == 2, "one or two softmax warpgroups");
+    static_assert((NWG * kRegSoftmax + 2 * kRegOther) * 128 <= 65536, "register file");
+    static_assert(NWG == 1 || (SBUF == NWG), "with two softmax warpgroups each owns one S/P buffer");
+    static_assert((NWG - 1) * 128 * (HS + 2) * 4 <= NST * BN * HS * 4, "merge scratch must fit the K ring");
     static constexpr int kKVBytes = BN * HS * 4;
     static constexpr int kTileBytes = 4 * NST * kKVBytes;      // NST-deep rings of K, K_lo, V, V_lo tiles
     static constexpr int kNumBars = 6 * NST + 2 * SBUF + 2 * OBUF;
@@ -121,10 +128,10 @@ struct Tc3Cfg {
     static_assert(kSmem <= 227 * 1024, "shared memory");
 };
 
-template <int HS, int BN, int NST, int SBUF, int OBUF, bool EXPF>
-__global__ void __launch_bounds__(384, 1)
+template <int HS, int BN, int NST, int SBUF, int OBUF, int NWG, bool EXPF>
+__global__ void __launch_bounds__((NWG + 2) * 128, 1)
 pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const Tc3Params p) {
-    using Cfg = Tc3Cfg<HS, BN, NST, SBUF, OBUF>;
+    using Cfg = Tc3Cfg<HS, BN, NST, SBUF, OBUF, NWG>;
     constexpr int DB = HS / 32;                         // 32-column blocks per row
     constexpr uint32_t kIdescQK = instr_desc(kBM, BN, 0, 0);
     constexpr uint32_t kIdescPV = instr_desc(kBM, HS, 0, 1);
@@ -151,7 +158,7 @@ pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    constexpr int kProducerWarp = 8, kMmaWarp = 9;
+    constexpr int kSplitWarp0 = 4 * NWG, kProducerWarp = 4 * NWG + 4, kMmaWarp = 4 * NWG + 5;
 
     const int h = blockIdx.x / p.n_tiles;
     const int tile_lin = blockIdx.x - h * p.n_tiles;
@@ -201,7 +208,7 @@ pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     }
 
     // ---- Q tile -> TMEM: raw columns [0, HS) and lo columns [HS, 2 HS); thread = query row = TMEM lane.
-    // The two warpgroups share the columns (warpgroup g stores the 32-column blocks g, g+2, ...).
+    // The softmax and splitter warpgroups share the columns (warpgroup g stores the 32-column blocks g, g+2, ...).
     if (warp < 8 && n_kt > 0) {
         const int g = warp >> 2, wq = warp & 3;
         const int r = wq * 32 + lane;
@@ -230,8 +237,8 @@ pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     // Registers follow the roles: the kernel is compiled for 168 per thread (384 threads); the splitter and the
     // producer / issuer warpgroups hand most of theirs back and the softmax warpgroup -- a query row's running output
     // (hs floats) plus a key tile of scores per thread -- takes them (setmaxnreg).
-    if (warp >= 8) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (warp >= kProducerWarp) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::kRegOther));
       if (warp == kProducerWarp) {
         // ================================ TMA producer ========================================
         if (n_kt > 0) {
@@ -326,11 +333,11 @@ pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
             for (int it = max(0, n_kt - Cfg::kLag); it < n_kt; ++it) issue_pv(it);
         }
       }       // (warps 10 and 11 only complete the third warpgroup)
-    } else if (warp >= 4) {
+    } else if (warp >= kSplitWarp0) {
         // ============================== splitter warpgroup ====================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::kRegOther));
         // K -> (K_hi in place, K_lo beside it), V likewise: element-wise over the flat swizzled tile
-        const int t = tid - 128;
+        const int t = tid - kSplitWarp0 * 32;
         for (int it = 0; it < n_kt; ++it) {
             const int st = it % NST;
             const uint32_t par = (it / NST) & 1;
@@ -339,7 +346,7 @@ pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
                 mbar_wait(smem_u32(kv == 0 ? &k_full[st] : &v_full[st]), par);
                 float4* src = reinterpret_cast<float4*>((kv == 0 ? Ks : Vs) + st * Cfg::kKVBytes);
                 float4* dst = reinterpret_cast<float4*>((kv == 0 ? Kl : Vl) + st * Cfg::kKVBytes);
-#pragma unroll
+#pragma unroll 4
                 for (int i = 0; i < Cfg::kKVBytes / 16 / 128; ++i) {
                     const float4 v = src[t + i * 128];
                     const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
@@ -351,8 +358,11 @@ pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
             }
         }
     } else {
-        // ============================== softmax warpgroup =====================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        // ============================== softmax warpgroup(s) ===================================
+        // With two warpgroups, warpgroup g owns the key tiles g, g+2, ... with its own online-softmax state (m, l, o);
+        // the states are merged at the end, so the warpgroups never wait for each other.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::kRegSoftmax));
+        const int g = warp >> 2;                         // softmax warpgroup
         const int wq = warp & 3;                         // TMEM lane quarter of this warp
         const int r = wq * 32 + lane;                    // query row of the tile = TMEM lane
         const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
@@ -371,12 +381,12 @@ pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
             tc_fence_after();
             const uint32_t o_tmem = tmem_base + lane_off + Cfg::kO + ob * HS;
 #pragma unroll
-            for (int c = 0; c < HS; c += 32) {
-                float ov[32];
-                tmem_ld32(o_tmem + c, ov);
+            for (int c = 0; c < HS; c += 16) {
+                float ov[16];
+                tmem_ld16(o_tmem + c, ov);
                 tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha, ov[i]);
+                for (int i = 0; i < 16; ++i) o[c + i] = fmaf(o[c + i], alpha, ov[i]);
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&o_free[ob]));
@@ -422,17 +432,17 @@ pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
             const float neg_m = -m_new;
             float ps4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-            for (int c = 0; c < BN; c += 32) {
-                float ph[32], pl[32];
+            for (int c = 0; c < BN; c += 16) {               // 16 columns at a time: half the live registers of a 32-wide store
+                float ph[16], pl[16];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 16; ++i) {
                     const float e = EXPF ? expf(sv[c + i] - m_new) : ex2_approx(fmaf(sv[c + i], kscale, neg_m));   // masked keys: exp(-inf) = 0
                     ps4[i & 3] += e;
                     ph[i] = tf32_hi(e);
                     pl[i] = e - ph[i];
                 }
-                tmem_st32(s_tmem + c, ph);                      // P_hi
-                tmem_st32(s_tmem + BN + c, pl);                 // P_lo
+                tmem_st16(s_tmem + c, ph);                      // P_hi
+                tmem_st16(s_tmem + BN + c, pl);                 // P_lo
             }
             const float psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
             l_run = l_run * alpha + psum;
@@ -440,17 +450,43 @@ pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(smem_u32(&p_ready[sb]));
-            // the previous tile's P.V has had this tile's softmax to complete
-            if (it > 0) take_o(it - 1, alpha_pend);
+            // this warpgroup's previous tile's P.V has had this tile's softmax to complete
+            if (it >= NWG) take_o(it - NWG, alpha_pend);
             alpha_pend = alpha;
         };
-        for (int it = 0; it < n_kt; ++it) {
+        int last_mine = -1;
+        for (int it = g; it < n_kt; it += NWG) {
             const int g0 = k_begin + it * BN;
             if ((g0 < kv_start) || (g0 + BN > lim_first)) tile(std::true_type{}, it);
             else tile(std::false_type{}, it);
+            last_mine = it;
         }
-        if (n_kt > 0) take_o(n_kt - 1, alpha_pend);
-        if (r < rows && seq >= 0) {
+        if (last_mine >= 0) take_o(last_mine, alpha_pend);
+        if (NWG > 1) {
+            // merge the warpgroups' states: warpgroup 1 hands (o, m, l) of its rows to warpgroup 0 through the K ring
+            // (every MMA has completed: each warpgroup waited for its last P.V, and the tensor pipe runs in order)
+            asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
+            float* scratch = reinterpret_cast<float*>(Ks);               // [128][HS + 2]
+            if (g == 1) {
+                float* dst = scratch + r * (HS + 2);
+#pragma unroll
+                for (int i = 0; i < HS; ++i) dst[i] = o[i];
+                dst[HS] = m_run;
+                dst[HS + 1] = l_run;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NWG * 128) : "memory");
+            if (g == 0) {
+                const float* src = scratch + r * (HS + 2);
+                const float m1 = src[HS], l1 = src[HS + 1];
+                const float m = fmaxf(m_run, m1);
+                const float w0 = EXPF ? expf(m_run - m) : ex2_approx(m_run - m), w1 = EXPF ? expf(m1 - m) : ex2_approx(m1 - m);
+                l_run = l_run * w0 + l1 * w1;
+#pragma unroll
+                for (int i = 0; i < HS; ++i) o[i] = o[i] * w0 + src[i] * w1;
+                m_run = m;
+            }
+        }
+        if (g == 0 && r < rows && seq >= 0) {
             const float inv = (l_run == 0.0f) ? 0.0f : 1.0f / l_run;      // :213
             float* dst = p.out + (size_t)(row0 + j0 + r) * p.out_stride + h * HS;
 #pragma unroll
@@ -488,10 +524,10 @@ int make_pool_map3(CUtensorMap* map, float* pool, const pa_handle* h, CUtensorMa
     return PA_OK;
 }
 
-template <int HS, int BN, int NST, int SBUF, int OBUF, bool EXPF>
+template <int HS, int BN, int NST, int SBUF, int OBUF, int NWG, bool EXPF>
 int launch_tc3(const Tc3State* st, const Tc3Params& p, cudaStream_t s) {
-    using Cfg = Tc3Cfg<HS, BN, NST, SBUF, OBUF>;
-    auto fn = pa_prefill_tc3_kernel<HS, BN, NST, SBUF, OBUF, EXPF>;
+    using Cfg = Tc3Cfg<HS, BN, NST, SBUF, OBUF, NWG>;
+    auto fn = pa_prefill_tc3_kernel<HS, BN, NST, SBUF, OBUF, NWG, EXPF>;
     static std::atomic<unsigned long long> attr_done{0};       // per instantiation; one bit per device
     CU_CHECK(pa_optin_smem(attr_done, fn, (int)Cfg::kSmem));
     fn<<<(unsigned)((long long)p.n_tiles * p.NH), Cfg::kThreads, Cfg::kSmem, s>>>(st->tm_k, st->tm_v, p);
@@ -553,8 +589,15 @@ extern "C" int pa_cu_prefill_tc3(pa_handle* h, int layer, const float* q, int q_
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     static const bool expf_exact = getenv("PA_PREFILL_TC3_EXPF") && atoi(getenv("PA_PREFILL_TC3_EXPF")) != 0;
-    if (hs == 64) rc = expf_exact ? launch_tc3<64, 64, 3, 2, 2, true>(st, p, s) : launch_tc3<64, 64, 3, 2, 2, false>(st, p, s);      // TMEM 128 + 256 + 128 = 512 columns
-    else rc = expf_exact ? launch_tc3<128, 32, 3, 2, 1, true>(st, p, s) : launch_tc3<128, 32, 3, 2, 1, false>(st, p, s);            // TMEM 256 + 128 + 128 = 512 columns
+    // One softmax warpgroup.  A second one alternating key tiles (each with its own S/P and O buffers; head_dim 64 only:
+    // head_dim 128 has ONE O buffer in TMEM, which would serialise them) is built and tested
+    // (PA_PREFILL_TC3_WARPGROUPS=2) but measured SLOWER: 125 vs 133 TFLOP/s at 16 x 2048, 159 vs 166 at 16 x 4096 -- the
+    // softmax is not what bounds the kernel; the 48 N=64 MMA instructions per key tile are (a 128x64x8 tf32 instruction
+    // takes ~63 cycles, twice its ideal: measured in pa_gemm_tc.cu), and the extra warpgroup costs registers.
+    static const int nwg64 = getenv("PA_PREFILL_TC3_WARPGROUPS") ? atoi(getenv("PA_PREFILL_TC3_WARPGROUPS")) : 1;
+    if (hs == 64 && nwg64 == 2) rc = expf_exact ? launch_tc3<64, 64, 3, 2, 2, 2, true>(st, p, s) : launch_tc3<64, 64, 3, 2, 2, 2, false>(st, p, s);
+    else if (hs == 64) rc = expf_exact ? launch_tc3<64, 64, 3, 2, 2, 1, true>(st, p, s) : launch_tc3<64, 64, 3, 2, 2, 1, false>(st, p, s);      // TMEM 128 + 256 + 128 = 512 columns
+    else rc = expf_exact ? launch_tc3<128, 32, 3, 2, 1, 1, true>(st, p, s) : launch_tc3<128, 32, 3, 2, 1, 1, false>(st, p, s);                  // TMEM 256 + 128 + 128 = 512 columns
     if (rc == PA_OK) h->launches++;
     return rc;
 }
