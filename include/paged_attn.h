@@ -405,6 +405,7 @@ PA_API int pa_debug_timeline(pa_handle* h, unsigned long long* out, int max_ctas
 
 /* ---- thin CUDA plumbing for plain-C hosts (no cuda_runtime.h needed) ----------------------- */
 PA_API int pa_device_count(void);
+PA_API int pa_set_device(int device);                            /* current device of the calls below (handles switch by themselves) */
 PA_API void* pa_dev_alloc(size_t bytes);
 PA_API void pa_dev_free(void* p);
 PA_API void* pa_host_alloc(size_t bytes);                        /* pinned */

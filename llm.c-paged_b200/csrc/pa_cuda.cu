@@ -43,6 +43,13 @@ int pa_device_count(void) {
     return n;
 }
 
+/* the device the plumbing calls below (pa_dev_alloc, pa_memcpy_*, pa_stream_create, ...) act on: a host that drives
+ * several GPUs from one thread switches before it allocates on another one (handles switch by themselves) */
+int pa_set_device(int device) {
+    CU_CHECK(cudaSetDevice(device));
+    return PA_OK;
+}
+
 int pa_cu_init(pa_handle* h) {
     int n = pa_device_count();
     if (n <= 0) {

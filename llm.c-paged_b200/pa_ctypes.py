@@ -184,6 +184,7 @@ def load():
         "pa_tune_get": (C.c_int, [vp, C.c_int]),
         "pa_debug_timeline": (C.c_int, [vp, C.POINTER(C.c_ulonglong), C.c_int]),
         "pa_device_count": (C.c_int, []),
+        "pa_set_device": (C.c_int, [C.c_int]),
         "pa_dev_alloc": (vp, [C.c_size_t]),
         "pa_dev_free": (None, [vp]),
         "pa_host_alloc": (vp, [C.c_size_t]),

@@ -488,3 +488,49 @@ def test_group_of_one_gathers_through_the_library():
             ref.close(); eng.close()
             lib.pa_model_destroy(m)
             lib.pa_group_destroy(g)
+
+
+def test_group_gathers_tokens_and_logits_across_gpus():
+    """pa_group_create(n): ONE process, n GPUs, ncclCommInitAll; pa_group_gather_tokens / _gather_logits put every
+    rank's rows into every member's receive buffer, rank-major, stream-ordered on the members' streams.  Needs >= 2
+    GPUs (`gpurun --gpus 2`); the driver's 1-GPU box runs the group-of-one variant (a copy on the stream)."""
+    lib = pa.load()
+    n = min(lib.pa_device_count(), 8)
+    cfg = pa.PaConfig(16, 8, 4, 0, 1, 2, 64, 0, 4)
+    for world in sorted({1, n}):
+        g = C.c_void_p()
+        pa.check(lib.pa_group_create(C.byref(cfg), world, None, C.byref(g)), "group create")
+        send_t, recv_t, send_l, recv_l = [], [], [], []
+        try:
+            assert lib.pa_group_size(g) == world and lib.pa_group_local_count(g) == world
+            if world > 1:
+                assert lib.pa_nccl_version() >= 20000
+            n_tok, n_log = 5, 3 * 1001
+            toks = [np.arange(n_tok, dtype=np.int32) + 100 * (r + 1) for r in range(world)]
+            logs = [oa.normal((n_log,), seed=40 + r) for r in range(world)]
+            handles = [lib.pa_group_handle(g, i) for i in range(world)]
+            assert [lib.pa_device(h) for h in handles] == list(range(world))
+            # device buffers on each member's own GPU (pa_dev_alloc follows the current device)
+            for i in range(world):
+                pa.check(lib.pa_set_device(i), "set device")
+                send_t.append(pa.DevBuf.from_numpy(toks[i])); recv_t.append(pa.DevBuf(world * n_tok * 4))
+                send_l.append(pa.DevBuf.from_numpy(logs[i])); recv_l.append(pa.DevBuf(world * n_log * 4))
+            st = (C.c_void_p * world)(*[b.ptr for b in send_t]); rt = (C.c_void_p * world)(*[b.ptr for b in recv_t])
+            sl = (C.c_void_p * world)(*[b.ptr for b in send_l]); rl = (C.c_void_p * world)(*[b.ptr for b in recv_l])
+            for rep in range(3):
+                pa.check(lib.pa_group_gather_tokens(g, st, rt, n_tok), "gather tokens")
+                pa.check(lib.pa_group_gather_logits(g, sl, rl, n_log), "gather logits")
+            want_t, want_l = np.concatenate(toks), np.concatenate(logs)
+            for i in range(world):
+                pa.check(lib.pa_set_device(i), "set device")
+                pa.check(lib.pa_stream_sync(lib.pa_stream_of(handles[i])), "sync")
+                assert np.array_equal(recv_t[i].download((world * n_tok,), dtype=np.int32), want_t), (world, i)
+                assert np.array_equal(recv_l[i].download((world * n_log,)).view(np.uint32), want_l.view(np.uint32)), (world, i)
+            assert lib.pa_group_gather_tokens(g, st, rt, 0) == pa.PA_ERR_INVALID
+        finally:
+            for i in range(world):
+                lib.pa_set_device(i)
+                for b in (send_t[i:i + 1] + recv_t[i:i + 1] + send_l[i:i + 1] + recv_l[i:i + 1]):
+                    b.free()
+            lib.pa_set_device(0)
+            lib.pa_group_destroy(g)
