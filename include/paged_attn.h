@@ -392,7 +392,7 @@ typedef enum pa_tune_key {
     PA_TUNE_TC_KEY_TILE = 15,  /* tcgen05 prefill, head_dim 64: keys per tile, 0 auto (64), 64 or 128 */
     PA_TUNE_GEMM_PATH = 16,    /* projections: 0 auto (<= 4 rows: weight-streaming GEMV, else tcgen05 3xTF32, fp32-accurate), 1 fp32 SIMT, 2 tcgen05 3xTF32, 3 tcgen05 plain TF32 (reduced precision, own tolerance), 4 GEMV */
     PA_TUNE_GEMM_SPLIT_K = 17, /* tensor-core projections: CTAs per output tile splitting K. 0 auto; n > 0: n (<= 16, clamped to what is co-resident), partial tiles reduced through an L2 workspace; -2 / -4: a 2- / 4-CTA cluster reducing through distributed shared memory */
-    PA_TUNE_MODEL_PATH = 18,   /* pa_model_forward: 0 auto (<= 6 sequences of one new token: ONE persistent kernel for the whole step, else the chain of per-op kernels), 1 chain, 2 persistent kernel (fails when the step is outside its domain) */
+    PA_TUNE_MODEL_PATH = 18,   /* pa_model_forward: 0 auto (<= 6 sequences of one new token: ONE persistent kernel for the whole step, else the chain of per-op kernels), 1 chain, 2 persistent kernel, 3 one resident grid per layer between the attention launches (steps of <= 128 tokens; opt-in: measured slower than the chain); 2 and 3 fail when the step is outside their domain */
     PA_TUNE_MAX
 } pa_tune_key;
 PA_API int pa_tune_set(pa_handle* h, int key, int value);

@@ -590,6 +590,11 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 }  // namespace
 
+/* (rows, K) fp32 matrix -> tensor map with a 32-column x box_rows box, 128-byte swizzle (for pa_layer_fused.cu) */
+extern "C" int pa_cu_make_map_2d(void* map_out, const float* ptr, int rows, int K, int row_stride, int box_rows) {
+    return make_map(reinterpret_cast<CUtensorMap*>(map_out), ptr, rows, K, row_stride, box_rows);
+}
+
 /* out (M,N) = x (M,K) . w (N,K)^T + bias on the tensor cores; columns >= n_dense go to the page
  * slots (fused KV append) when pool_k is given.  terms = 3 (3xTF32, fp32-accurate) or 1 (TF32).
  * PA_ERR_UNSUPPORTED when the shape is outside the kernel's domain (caller falls back to SIMT). */

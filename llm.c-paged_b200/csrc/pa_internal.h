@@ -151,6 +151,14 @@ void pa_cu_gemm_stream_released(int device, void* stream);      /* frees the spl
 int pa_cu_linear(const float* x, int x_stride, const float* w, const float* bias, float* out, int out_stride,
                  int M, int N, int K, const float* residual, int res_stride, int act, int path, void* stream);
 
+/* ---- implemented in pa_layer_fused.cu: everything between two attention launches as ONE resident grid ------- */
+struct pa_fused_params;
+size_t pa_cu_layer_fused_smem(void);
+int pa_cu_layer_fused_max_tiles(void);
+int pa_cu_layer_fused_split(int N, int K, int sms, int* tiles_n);
+int pa_cu_layer_fused_launch(const struct pa_fused_params* p, int sms, int cooperative, void* stream);
+int pa_cu_make_map_2d(void* map_out, const float* ptr, int rows, int K, int row_stride, int box_rows);
+
 /* ---- implemented in pa_model_mega.cu: the whole decode step of a handful of sequences as ONE
  * persistent cooperative kernel (every op of gpt2_forward for one new token per sequence) ------- */
 #define PA_MEGA_MAX_SEQS 8

@@ -26,6 +26,7 @@
 #include "pa_internal.h"
 #include "pa_pdl.cuh"
 #include "pa_model_dev.cuh"
+#include "pa_layer_fused.cuh"
 
 #define CU_CHECK(call)                                                                         \
     do {                                                                                       \
@@ -59,6 +60,13 @@ struct pa_model {
     int* d_next_cur;                       // device: sampled tokens of the step in flight ...
     int* h_next_cur;                       // ... their pinned host copy ...
     int nseq_cur;                          // ... and how many (0: no step in flight)
+    // resident per-layer grid (pa_layer_fused.cu): tensor maps in device memory, split-K workspace, never-reset counters
+    CUtensorMap* fz_maps;                  // [3 + 4 L]: atty, ln, fch | per layer attprojw, fcw, fcprojw, qkvw
+    float4* fz_ws;
+    unsigned* fz_cnt;                      // [4 slots][max tiles] arrival counters | [1] grid barrier
+    unsigned fz_gen[4];                    // completed uses of each counter slot
+    unsigned fz_bar_gen;                   // grid-barrier generations completed
+    int fz_state;                          // 0 not set up, 1 ready, -1 unavailable (shape outside its domain / set-up failed)
 };
 
 namespace {
@@ -228,6 +236,99 @@ int mega_step(pa_model* m, int nseq, const int* tok, const int* pos, const float
     return rc;
 }
 
+// ---- the resident per-layer grid: set-up (once per model) and one launch -------------------------------------------
+enum { FZ_ATTY = 0, FZ_LN = 1, FZ_FCH = 2, FZ_W0 = 3 };      // map indices; per layer: +0 attprojw, +1 fcw, +2 fcprojw, +3 qkvw
+enum { FZ_SLOT_ATTPROJ = 0, FZ_SLOT_FC = 1, FZ_SLOT_FCPROJ = 2, FZ_SLOT_QKV = 3 };
+
+bool fused_domain(const pa_model* m, int ntok) {
+    const int C = m->C, sms = m->h->sm_count;
+    return ntok >= 1 && ntok <= 128 && (C % 64) == 0 && C <= 2048 && (4 * C) / 64 <= sms && sms <= pa_cu_layer_fused_max_tiles() &&
+           (size_t)m->h->smem_optin >= pa_cu_layer_fused_smem();
+}
+
+int fused_setup(pa_model* m) {
+    if (m->fz_state != 0) return m->fz_state > 0 ? PA_OK : PA_ERR_UNSUPPORTED;
+    m->fz_state = -1;
+    const int C = m->C, L = m->L, sms = m->h->sm_count;
+    const int rows = m->max_batch < 128 ? 128 : m->max_batch;      // (the activation buffers are at least this tall: see pa_model_create)
+    const int n_maps = FZ_W0 + 4 * L;
+    std::vector<CUtensorMap> maps(n_maps);
+    int rc = pa_cu_make_map_2d(&maps[FZ_ATTY], m->atty, m->max_batch, C, C, 128);
+    if (rc == PA_OK) rc = pa_cu_make_map_2d(&maps[FZ_LN], m->ln, m->max_batch, C, C, 128);
+    if (rc == PA_OK) rc = pa_cu_make_map_2d(&maps[FZ_FCH], m->fch, m->max_batch, 4 * C, 4 * C, 128);
+    for (int l = 0; l < L && rc == PA_OK; ++l) {
+        rc = pa_cu_make_map_2d(&maps[FZ_W0 + 4 * l + 0], m->attprojw + (size_t)l * C * C, C, C, C, 64);
+        if (rc == PA_OK) rc = pa_cu_make_map_2d(&maps[FZ_W0 + 4 * l + 1], m->fcw + (size_t)l * 4 * C * C, 4 * C, C, C, 64);
+        if (rc == PA_OK) rc = pa_cu_make_map_2d(&maps[FZ_W0 + 4 * l + 2], m->fcprojw + (size_t)l * 4 * C * C, C, 4 * C, 4 * C, 64);
+        if (rc == PA_OK) rc = pa_cu_make_map_2d(&maps[FZ_W0 + 4 * l + 3], m->qkvw + (size_t)l * 3 * C * C, 3 * C, C, C, 64);
+    }
+    (void)rows;
+    if (rc != PA_OK) return rc;
+    const size_t cnt_words = (size_t)4 * pa_cu_layer_fused_max_tiles() + 32;
+    cudaError_t e = cudaMalloc((void**)&m->fz_maps, (size_t)n_maps * sizeof(CUtensorMap));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->fz_ws, (size_t)sms * 16 * 128 * sizeof(float4));      // one 64-column partial tile per CTA
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->fz_cnt, cnt_words * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemcpy(m->fz_maps, maps.data(), (size_t)n_maps * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(m->fz_cnt, 0, cnt_words * sizeof(unsigned));
+    if (e != cudaSuccess) {
+        pa_set_error("fused layer grid: set-up failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return PA_ERR_NOMEM;
+    }
+    memset(m->fz_gen, 0, sizeof(m->fz_gen));
+    m->fz_bar_gen = 0;
+    m->fz_state = 1;
+    return PA_OK;
+}
+
+// one launch: [attproj, ln2, fc, fcproj] of layer l_post (when >= 0) followed by [ln1, QKV + KV append] of layer l_pre (when < L)
+int fused_launch(pa_model* m, int l_post, int l_pre, int ntok, cudaStream_t s) {
+    pa_handle* h = m->h;
+    const int C = m->C, sms = h->sm_count, mt = pa_cu_layer_fused_max_tiles();
+    pa_fused_params P;
+    memset(&P, 0, sizeof(P));
+    int n = 0;
+    auto proj = [&](int slot, int map_x, int map_w, const float* bias, float* out, int out_stride, int N, int K, int n_dense,
+                    const float* residual, int act) {
+        pa_fused_phase& ph = P.ph[n++];
+        ph.kind = 0;
+        ph.tm_x = m->fz_maps + map_x; ph.tm_w = m->fz_maps + map_w;
+        ph.bias = bias; ph.out = out; ph.out_stride = out_stride; ph.N = N; ph.K = K; ph.n_dense = n_dense;
+        ph.residual = residual; ph.res_stride = out_stride; ph.act = act;
+        ph.n_split = pa_cu_layer_fused_split(N, K, sms, &ph.tiles_n);
+        ph.slot = slot; ph.gen = m->fz_gen[slot]++;
+    };
+    auto lnorm = [&](const float* w, const float* b) {
+        pa_fused_phase& ph = P.ph[n++];
+        ph.kind = 1;
+        ph.ln_in = m->x; ph.ln_out = m->ln; ph.ln_w = w; ph.ln_b = b;
+    };
+    if (l_post >= 0) {
+        const int l = l_post;
+        proj(FZ_SLOT_ATTPROJ, FZ_ATTY, FZ_W0 + 4 * l + 0, m->attprojb + (size_t)l * C, m->x, C, C, C, C, m->x, 0);              // :716-717
+        lnorm(m->ln2w + (size_t)l * C, m->ln2b + (size_t)l * C);                                                               // :718
+        proj(FZ_SLOT_FC, FZ_LN, FZ_W0 + 4 * l + 1, m->fcb + (size_t)l * 4 * C, m->fch, 4 * C, 4 * C, C, 4 * C, nullptr, 1);     // :719-720
+        proj(FZ_SLOT_FCPROJ, FZ_FCH, FZ_W0 + 4 * l + 2, m->fcprojb + (size_t)l * C, m->x, C, C, 4 * C, C, m->x, 0);            // :721-722
+    }
+    if (l_pre < m->L) {
+        const int l = l_pre;
+        lnorm(m->ln1w + (size_t)l * C, m->ln1b + (size_t)l * C);                                                               // :703
+        proj(FZ_SLOT_QKV, FZ_LN, FZ_W0 + 4 * l + 3, m->qkvb + (size_t)l * 3 * C, m->q, C, 3 * C, C, C, nullptr, 0);             // :706 + add_to_cache :710
+        P.pool_k = h->pool_k + (size_t)l * h->layer_stride;
+        P.pool_v = h->pool_v + (size_t)l * h->layer_stride;
+        P.slots = h->d_step + h->step.off_slot;
+    }
+    P.n_phases = n; P.M = ntok; P.C = C;
+    P.ws = m->fz_ws; P.ws_cnt = m->fz_cnt; P.bar = m->fz_cnt + (size_t)4 * mt;
+    P.bar_gen = m->fz_bar_gen;
+    m->fz_bar_gen += (unsigned)(n - 1);
+    // the CTAs wait for each other: co-resident by construction (grid = SMs, one CTA per SM); cooperative (the driver checks
+    // it) whenever the chain's launch overlap is switched off anyway
+    const int rc = pa_cu_layer_fused_launch(&P, sms, !(pa_pdl_enabled && pa_pdl_gate), s);
+    if (rc == PA_OK) h->launches++;
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -334,6 +435,7 @@ void pa_model_destroy(pa_model* m) {
     if (!m) return;
     cudaFree(m->params); cudaFree(m->x); cudaFree(m->ln); cudaFree(m->q); cudaFree(m->atty); cudaFree(m->fch);
     cudaFree(m->logits); cudaFree(m->d_io); cudaFree(m->d_coins); cudaFree(m->mega_part); cudaFree(m->mega_bar);
+    cudaFree(m->fz_maps); cudaFree(m->fz_ws); cudaFree(m->fz_cnt);
     if (m->h_io) cudaFreeHost(m->h_io);
     if (m->h_coins) cudaFreeHost(m->h_coins);
     free(m);
@@ -435,7 +537,7 @@ static int model_forward_impl(pa_model* m, const int* seq_ids, const int* n_new,
     // A handful of sequences with one new token each: the whole step is ONE persistent kernel (pa_model_mega.cu)
     const int model_path = h->tune[PA_TUNE_MODEL_PATH];
     bool use_mega = false;
-    if (model_path != 1) {
+    if (model_path != 1 && model_path != 3) {
         const size_t mega_smem = (max_q == 1 && nseq <= (model_path == 2 ? PA_MEGA_MAX_SEQS : PA_MEGA_AUTO_SEQS)) ? pa_cu_model_mega_smem(nseq, C, h->cfg.head_dim, h->cfg.block_size) : 0;
         use_mega = mega_smem && (size_t)h->smem_optin >= mega_smem + 1024 && !(m->mega_refused && model_path != 2);
         if (!use_mega && model_path == 2) {
@@ -476,7 +578,27 @@ static int model_forward_impl(pa_model* m, const int* seq_ids, const int* n_new,
     const int path = h->tune[PA_TUNE_GEMM_PATH];
     const int ln_grid = ntok;                      // one CTA per row
     long launches = 1;
-    for (int l = 0; l < L; ++l) {
+    // model_path 3 (opt-in): everything between two attention launches as ONE resident grid (pa_layer_fused.cu), 2
+    // launches per layer instead of 7.  Measured SLOWER than the chain (cfg2: 1.675 vs 1.528 ms per step): with
+    // programmatic dependent launch the chain's launch overheads were already hidden, and a projection's ~8-10 us are
+    // its own latency chain (first TMA round trip, k-slabs at 0.4 us, split-K publish / poll / reduce), which a phase
+    // of the resident grid pays just the same, plus a grid barrier (profiles/r02_model_step.md).
+    bool use_fused = model_path == 3 && path == 0 && fused_domain(m, ntok);
+    if (use_fused && fused_setup(m) != PA_OK) use_fused = false;
+    if (model_path == 3 && !use_fused) {
+        pa_set_error("pa_model_forward: the resident per-layer grid takes steps of at most 128 tokens, C a multiple of 64 up to 2048, the automatic projection path");
+        pa_step_rollback(h);
+        return PA_ERR_UNSUPPORTED;
+    }
+    if (use_fused) {
+        rc = fused_launch(m, -1, 0, ntok, s);                                  // ln1 + QKV of layer 0
+        for (int l = 0; l < L && rc == PA_OK; ++l) {
+            rc = max_q == 1 ? pa_decode(h, l, m->q, C, m->atty, C, s) : pa_prefill(h, l, m->q, C, m->atty, C, s);
+            if (rc == PA_OK) rc = fused_launch(m, l, l + 1, ntok, s);         // the rest of layer l, ln1 + QKV of layer l + 1
+        }
+        if (rc != PA_OK) return rc;
+    }
+    for (int l = 0; l < L && !use_fused; ++l) {
         CU_CHECK(pa_launch_pdl(pa_layernorm_kernel, dim3(ln_grid), dim3(kLnThreads), 0, s, 1, m->ln, (const float*)m->x, m->ln1w + (size_t)l * C, m->ln1b + (size_t)l * C, ntok, C));
         rc = pa_qkv_append(h, l, m->ln, C, m->qkvw + (size_t)l * 3 * C * C, m->qkvb + (size_t)l * 3 * C, m->q, C, s);
         if (rc != PA_OK) return rc;

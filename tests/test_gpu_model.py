@@ -75,11 +75,14 @@ class OracleModel:
     (2, 3, 20, 77, 4, 0),          # C = 60: SIMT projections, generic attention kernel
     (2, 2, 64, 131, 16, 1),        # fp32 SIMT projections
 ])
-@pytest.mark.parametrize("model_path", [1, 0], ids=["per-op-chain", "auto"])
+@pytest.mark.parametrize("model_path", [1, 0, 3], ids=["per-op-chain", "auto", "resident-layer-grid"])
 def test_model_decode_steps_match_oracle(L, NH, hs, V, bs, gemm_path, model_path):
     """model_path auto: these 5-sequence steps run as ONE persistent kernel (pa_model_mega.cu) when
-    head_dim is 64/128, else (and with model_path 1) as the chain of per-op kernels."""
+    head_dim is 64/128, else (and with model_path 1) as the chain of per-op kernels; model_path 3: one resident
+    grid per layer between the attention launches (pa_layer_fused.cu)."""
     Cc, maxT, B = NH * hs, 96, 5
+    if model_path == 3 and (Cc % 64 or gemm_path != 0):
+        pytest.skip("resident per-layer grid: C a multiple of 64, automatic projection path")
     params = make_params(V, maxT, L, Cc, seed=300)
     eng = pa.PagedAttn(bs, 64, B, NH, hs, n_layers=L, device=0, max_batch_tokens=B)
     eng.tune(pa.PA_TUNE_GEMM_PATH, gemm_path)
@@ -99,6 +102,8 @@ def test_model_decode_steps_match_oracle(L, NH, hs, V, bs, gemm_path, model_path
             got_next = model.decode_step(active, tokens[active], coins)
             if model_path == 0 and hs in (64, 128):
                 assert eng.launches() - l0 == 1, "the small-batch step did not run as one persistent kernel"
+            if model_path == 3:
+                assert eng.launches() - l0 == 1 + (2 * L + 1) + 3, "embed + (L + 1 resident grids + L attention launches) + lnf, LM head, sampler"
             got = model.logits(len(active))
             want = orc.step(active, tokens[active], pos[active])
             err = np.abs(got.astype(np.float64) - want).max() / np.abs(want).max()
