@@ -287,7 +287,9 @@ void* pa_host_alloc(size_t bytes) {
     }
     return p;
 }
-void pa_host_free(void* p) { if (p) cudaFreeHost(p); }
+/* bumped whenever pinned memory goes away: remembered (host pointer -> device alias) pairs are only trusted within a generation */
+unsigned pa_host_free_generation = 0;
+void pa_host_free(void* p) { if (p) { ++pa_host_free_generation; cudaFreeHost(p); } }
 int pa_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
     CU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     if (!stream) CU_CHECK(cudaStreamSynchronize(0));

@@ -421,10 +421,8 @@ int pa_group_model_step_overlapped(pa_group* g, pa_model* const* models, const i
     // the PREVIOUS step's gather has had this whole step's queueing time (and its own step) to finish
     int got_prev = 0;
     if (rc == PA_OK) {
-        const int prev_pending = g->pending;
         got_prev = pa_group_gather_flush(g, gathered_prev);
         if (got_prev < 0) rc = got_prev;
-        (void)prev_pending;
     }
     for (int i = 0; i < n; ++i) {
         const int rw = pa_model_wait(models[i], next_local[i]);

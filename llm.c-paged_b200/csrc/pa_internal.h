@@ -125,6 +125,7 @@ int* pa_cu_step_host_buffer(pa_handle* h, size_t ints);
 int pa_cu_step_upload(pa_handle* h, void* stream);
 int pa_cu_is_device_ptr(const void* p);
 void pa_cu_host_pipe_release(pa_handle* h);
+extern unsigned pa_host_free_generation;      /* pa_cuda.cu: counts pa_host_free calls */
 /* rows [0, rows) of page src -> page dst, K and V, every layer; stream-ordered on the handle's stream, then synchronised */
 int pa_cu_copy_page_rows(pa_handle* h, int src_page, int dst_page, int rows);
 /* one page <-> host, K and V, every layer; host layout [layer][block_size*C] for K then the same for V */

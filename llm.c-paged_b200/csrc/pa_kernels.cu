@@ -1210,7 +1210,7 @@ struct HostPipe {            // streams and events of the staged host-buffer pip
     cudaEvent_t tick[kTickets][2] = {};
     long long next_ticket = 1;
     // pinned host pointer -> device alias, remembered (cudaPointerGetAttributes costs ~1 us per call)
-    struct Alias { const void* host = nullptr; void* dev = nullptr; bool pinned = false; };
+    struct Alias { const void* host = nullptr; void* dev = nullptr; bool pinned = false; unsigned gen = 0; };
     Alias alias[4];
     int alias_next = 0;
     // whole-step staging (pa_decode_step_host_layers_async): two sets of device buffers so that the input copy of
@@ -1229,9 +1229,10 @@ static HostPipe* host_pipe_get(pa_handle* h) {
 // pinned (page-locked) host memory and its address in the device's address space, or {false} for pageable memory
 static HostPipe::Alias host_alias(pa_handle* h, const void* p) {
     HostPipe* hp = host_pipe_get(h);
-    for (auto& a : hp->alias) if (a.host == p) return a;
+    for (auto& a : hp->alias) if (a.host == p && a.gen == pa_host_free_generation) return a;      // (a pa_host_free since then: ask again)
     HostPipe::Alias a;
     a.host = p;
+    a.gen = pa_host_free_generation;
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) { a.pinned = true; a.dev = attr.devicePointer; }
     cudaGetLastError();
