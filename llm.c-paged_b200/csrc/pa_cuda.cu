@@ -80,8 +80,14 @@ int pa_cu_init(pa_handle* h) {
 int pa_cu_alloc_pool(pa_handle* h) {
     CU_CHECK(cudaSetDevice(h->cfg.device));
     size_t bytes = (size_t)h->cfg.n_layers * h->layer_stride * sizeof(float);
-    cudaError_t e = cudaMalloc((void**)&h->pool_k, bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&h->pool_v, bytes);
+    /* Reference host code writes pages through KVBlock.keys / .values directly (block_manager_test.c:9-29).  For such
+     * callers a manager made by create_block_manager() can keep its pool in MANAGED memory (PA_COMPAT_HOST_PAGES=1): the
+     * same pointers are valid on the host and on the device (pages migrate on touch).  Everything else uses plain device
+     * memory -- the TMA / bulk-copy kernels want their pages resident in HBM. */
+    const char* hostp = getenv("PA_COMPAT_HOST_PAGES");
+    const bool managed = h->compat && hostp && atoi(hostp) != 0;
+    cudaError_t e = managed ? cudaMallocManaged((void**)&h->pool_k, bytes) : cudaMalloc((void**)&h->pool_k, bytes);
+    if (e == cudaSuccess) e = managed ? cudaMallocManaged((void**)&h->pool_v, bytes) : cudaMalloc((void**)&h->pool_v, bytes);
     if (e != cudaSuccess) {
         pa_set_error("KV pool: cudaMalloc of 2 x %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         cudaGetLastError();

@@ -52,6 +52,24 @@ if [ ! -f "$pat_bin" ] || [ "$HERE/build_dropin.sh" -nt "$pat_bin" ] || [ "$ROOT
         -Wl,-rpath,'$ORIGIN/../../llm.c-paged_b200' -lm -o "$pat_bin"
   echo "built $pat_bin"
 fi
+# ---- the reference's own unit test of the block manager (block_manager_test.c), as shipped and against the library:
+# the include becomes "paged_attn.h" (with PA_COMPAT_MACROS for its loops over BLOCK_SIZE) and the final free(manager)
+# becomes destroy_block_manager(manager) (the manager owns a device pool); run with PA_COMPAT_HOST_PAGES=1 because the
+# test writes and reads pages through KVBlock.keys / .values from the host.
+bt_ref="$OUT/block_manager_test_ref"
+bt_pat="$OUT/block_manager_test_patched"
+if [ ! -f "$bt_ref" ] || [ "$HERE/build_dropin.sh" -nt "$bt_ref" ]; then
+  ( cd "$REF" && gcc -O2 -w -x c block_manager_test.c -I"$REF" -o "$bt_ref" )
+  echo "built $bt_ref"
+fi
+if [ ! -f "$bt_pat" ] || [ "$HERE/build_dropin.sh" -nt "$bt_pat" ] || [ "$ROOT/include/paged_attn.h" -nt "$bt_pat" ] || [ "$lib" -nt "$bt_pat" ]; then
+  sed -e 's|^#include "block_manager.c"|#define PA_COMPAT_MACROS\n#include <stdlib.h>\n#include "paged_attn.h"|' \
+      -e 's|^\( *\)free(manager);|\1destroy_block_manager(manager);|' "$REF/block_manager_test.c" |
+    gcc -O2 -w -x c - -I"$ROOT/include" -L"$ROOT/llm.c-paged_b200" -lpaged_attn \
+        -Wl,-rpath,'$ORIGIN/../../llm.c-paged_b200' -o "$bt_pat"
+  echo "built $bt_pat"
+fi
+
 # what the patch removed / kept, for the record (stderr): the patched unit must not define the two functions
 n=$(instrument < "$REF/paged_infer.c" | patch_tu | grep -c '^void attention_paged(\|^void add_to_cache(' || true)
 [ "$n" = "0" ] || { echo "build_dropin.sh: the patch left $n definitions behind" >&2; exit 1; }

@@ -77,3 +77,27 @@ def test_patched_reference_main_generates_the_same_tokens_and_block_tables(tmp_p
     got16, state16, _ = run_main(PATCHED_BIN, str(tmp_path), env=env)
     assert got16 == want_tokens
     assert "Prompt 0 block count: 4" in state16 and "Block 3: filled 1" in state16, state16
+
+
+BT_REF = os.path.join(ge.ROOT, "oracle", "_ref", "block_manager_test_ref")
+BT_PATCHED = os.path.join(ge.ROOT, "oracle", "_ref", "block_manager_test_patched")
+
+
+def test_reference_block_manager_test_as_shipped():
+    if not os.path.exists(BT_REF):
+        pytest.skip("oracle/_ref/block_manager_test_ref not built (no /root/reference at build time)")
+    r = subprocess.run([BT_REF], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "All tests passed!" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_reference_block_manager_test_against_the_library():
+    """The reference's own block_manager_test.c (request_block, host writes and read-backs through KVBlock.keys /
+    .values, `filled`, free_blocks_for_prompt) compiled against paged_attn.h and linked with libpaged_attn.so: the
+    pool of a create_block_manager() manager lives in managed memory under PA_COMPAT_HOST_PAGES=1, so the reference's
+    host-side page accesses work on the very pointers the kernels use."""
+    if not os.path.exists(BT_PATCHED):
+        pytest.skip("oracle/_ref/block_manager_test_patched not built (no /root/reference at build time)")
+    env = dict(os.environ, PA_COMPAT_HOST_PAGES="1")
+    r = subprocess.run([BT_PATCHED], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and "All tests passed!" in r.stdout, r.stdout + r.stderr
