@@ -632,7 +632,9 @@ def run_workload(cx, wid, w, primary):
                 cx.barrier()
                 wall = time.perf_counter() - t0
                 return cx.allmax(max(lib.pa_event_elapsed_ms(e0, e1), 0.0)) / k, wall * 1e3 / k
-            k_e2e = max(5, min(steps, 50))
+            # its own step count (reported as e2e.steps): enough steps that filling and draining the one-step-ahead pipeline
+            # does not dominate, about 0.1 s of device time at most
+            k_e2e = int(max(10, min(100, 0.1 / max(ms_per_step * 1e-3, 1e-6))))
             for _ in range(3):
                 e2e_step()
             e2e_run(4, True)
