@@ -211,8 +211,11 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             if (chunk_start && ch >= 2) { mbar_wait(smem_u32(&chunk_free[cb]), ((ch >> 1) - 1) & 1); }
             mbar_wait(smem_u32(&split[st]), j & 1);
             tc_fence_after();
-            const uint32_t w_addr = smem_u32(base + st * Cfg::kStageBytes + Cfg::kXBytes);
-            const uint32_t wlo_addr = w_addr + Cfg::kWBytes;
+            // descriptor low words (address field + LBO) of the w and w_lo slabs, advanced by 2 (32 bytes) per k-step;
+            // the high word is constant: one uniform add per instruction instead of smem_desc()'s shift / mask / or chain
+            const uint32_t w_lo32 = smem_desc_lo(smem_u32(base + st * Cfg::kStageBytes + Cfg::kXBytes), 16);
+            const uint32_t wlo_lo32 = w_lo32 + (Cfg::kWBytes >> 4);
+            constexpr uint32_t w_hi32 = smem_desc_hi(1024, 2);
             const uint32_t a_raw = tmem_base + Cfg::kA + (s % kAStages) * Cfg::kACols;
             const uint32_t a_lo = a_raw + kBK;
             const uint32_t d_main = tmem_base + Cfg::kMain + cb * BN;
@@ -220,10 +223,10 @@ pa_gemm3x_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             if (leader) {
 #pragma unroll
                 for (int ks = 0; ks < kBK / 8; ++ks) {
-                    mma_tf32_ts(d_main, a_raw + ks * 8, smem_desc_k(w_addr + ks * 32), kIdesc, (chunk_start && ks == 0) ? 0u : 1u);
+                    mma_tf32_ts_lohi(d_main, a_raw + ks * 8, w_lo32 + ks * 2, w_hi32, kIdesc, (chunk_start && ks == 0) ? 0u : 1u);
                     if (p.terms == 3) {
-                        mma_tf32_ts(d_small, a_lo + ks * 8, smem_desc_k(w_addr + ks * 32), kIdesc, (s > 0 || ks > 0) ? 1u : 0u);
-                        mma_tf32_ts(d_small, a_raw + ks * 8, smem_desc_k(wlo_addr + ks * 32), kIdesc, 1u);
+                        mma_tf32_ts_lohi(d_small, a_lo + ks * 8, w_lo32 + ks * 2, w_hi32, kIdesc, (s > 0 || ks > 0) ? 1u : 0u);
+                        mma_tf32_ts_lohi(d_small, a_raw + ks * 8, wlo_lo32 + ks * 2, w_hi32, kIdesc, 1u);
                     }
                 }
                 tc_commit(smem_u32(&empty[st]));

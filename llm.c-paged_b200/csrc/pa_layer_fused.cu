@@ -223,8 +223,9 @@ pa_layer_fused_kernel(const pa_fused_params P) {
                     if (chunk_start && c >= 2) mbar_wait(smem_u32(&chunk_free[cb]), ((c >> 1) - 1) & 1);
                     mbar_wait(smem_u32(&split[st]), (g / kStages) & 1);
                     tc_fence_after();
-                    const uint32_t w_addr = smem_u32(base + st * kStageBytes + kXBytes);
-                    const uint32_t wlo_addr = w_addr + kWBytes;
+                    const uint32_t w_lo32 = smem_desc_lo(smem_u32(base + st * kStageBytes + kXBytes), 16);      // + 2 per k-step (pa_ptx.cuh)
+                    const uint32_t wlo_lo32 = w_lo32 + (kWBytes >> 4);
+                    constexpr uint32_t w_hi32 = smem_desc_hi(1024, 2);
                     const uint32_t a_raw = tmem_base + kA + (g % kAStages) * kACols;
                     const uint32_t a_lo = a_raw + kBK;
                     const uint32_t d_main = tmem_base + kMain + cb * kBN;
@@ -232,9 +233,9 @@ pa_layer_fused_kernel(const pa_fused_params P) {
                     if (leader) {
 #pragma unroll
                         for (int ks = 0; ks < kBK / 8; ++ks) {
-                            mma_tf32_ts(d_main, a_raw + ks * 8, smem_desc_k(w_addr + ks * 32), kIdesc, (chunk_start && ks == 0) ? 0u : 1u);
-                            mma_tf32_ts(d_small, a_lo + ks * 8, smem_desc_k(w_addr + ks * 32), kIdesc, (s > 0 || ks > 0) ? 1u : 0u);
-                            mma_tf32_ts(d_small, a_raw + ks * 8, smem_desc_k(wlo_addr + ks * 32), kIdesc, 1u);
+                            mma_tf32_ts_lohi(d_main, a_raw + ks * 8, w_lo32 + ks * 2, w_hi32, kIdesc, (chunk_start && ks == 0) ? 0u : 1u);
+                            mma_tf32_ts_lohi(d_small, a_lo + ks * 8, w_lo32 + ks * 2, w_hi32, kIdesc, (s > 0 || ks > 0) ? 1u : 0u);
+                            mma_tf32_ts_lohi(d_small, a_raw + ks * 8, wlo_lo32 + ks * 2, w_hi32, kIdesc, 1u);
                         }
                         tc_commit(smem_u32(&empty[st]));
                         if ((s % kChunk) == kChunk - 1 || s == n_slabs - 1) tc_commit(smem_u32(&chunk_done[cb]));

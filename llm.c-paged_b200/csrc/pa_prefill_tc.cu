@@ -258,14 +258,14 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
                 mbar_wait(smem_u32(&v_full[st]), (it / NST) & 1);
                 mbar_wait(smem_u32(&p_ready[sb]), (j / SBUF) & 1);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(Vs + st * Cfg::kKVBytes);
+                const uint32_t v_lo32 = smem_desc_lo(smem_u32(Vs + st * Cfg::kKVBytes), BN * 128);      // + 64 (1024 bytes) per k-step (pa_ptx.cuh)
+                constexpr uint32_t v_hi32 = smem_desc_hi(512, 1);
                 const uint32_t p_tmem = tmem_base + HS + sb * BN;
                 const uint32_t o_tmem = tmem_base + HS + NWG * SBUF * BN + b * HS;
                 if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < BN / 8; ++ks)          // 8 keys per instruction = two 4-row swizzle groups
-                        mma_tf32_ts(o_tmem, p_tmem + ks * 8, smem_desc(v_addr + ks * 1024, BN * 128, 512, 1), kIdescPV,
-                                    (j > 0 || ks > 0) ? 1u : 0u);
+                        mma_tf32_ts_lohi(o_tmem, p_tmem + ks * 8, v_lo32 + ks * 64, v_hi32, kIdescPV, (j > 0 || ks > 0) ? 1u : 0u);
                     tc_commit(smem_u32(&o_full[b]));
                     tc_commit(smem_u32(&v_empty[st]));
                 }
@@ -276,15 +276,16 @@ pa_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_cons
                 const int sb = b * SBUF + ((it / NWG) % SBUF);
                 mbar_wait(smem_u32(&k_full[st]), (it / NST) & 1);
                 tc_fence_after();
-                const uint32_t k_addr = smem_u32(Ks + st * Cfg::kKVBytes);
+                const uint32_t k_lo32 = smem_desc_lo(smem_u32(Ks + st * Cfg::kKVBytes), 16);
+                constexpr uint32_t k_hi32 = smem_desc_hi(1024, 2);
                 // the P.V that read this S/P buffer last was issued SBUF tiles of this warpgroup ago, before
                 // this instruction in program order: the tensor pipe executes them in order
                 const uint32_t s_tmem = tmem_base + HS + sb * BN;
                 if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < HS / 8; ++ks) {        // 8 floats (32 B) of the head dimension per instruction
-                        const uint32_t koff = (ks >> 2) * (BN * 128) + (ks & 3) * 32;
-                        mma_tf32_ts(s_tmem, tmem_base + ks * 8, smem_desc(k_addr + koff, 16, 1024), kIdescQK, ks > 0);
+                        const uint32_t koff = (ks >> 2) * (BN * 8) + (ks & 3) * 2;      // descriptor units (16 bytes)
+                        mma_tf32_ts_lohi(s_tmem, tmem_base + ks * 8, k_lo32 + koff, k_hi32, kIdescQK, ks > 0);
                     }
                     tc_commit(smem_u32(&s_full[sb]));
                     tc_commit(smem_u32(&k_empty[st]));

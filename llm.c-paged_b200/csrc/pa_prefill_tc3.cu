@@ -286,19 +286,21 @@ pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
                 mbar_wait(smem_u32(&p_ready[sb]), (it / SBUF) & 1);
                 if (it >= OBUF) mbar_wait(smem_u32(&o_free[ob]), (it / OBUF - 1) & 1);      // the tile that used this O buffer is in registers
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(Vs + st * Cfg::kKVBytes), vl_addr = smem_u32(Vl + st * Cfg::kKVBytes);
+                // descriptors: low word = address field (+ LBO), advanced by (byte offset >> 4) per instruction; high word constant
+                const uint32_t v_lo = smem_desc_lo(smem_u32(Vs + st * Cfg::kKVBytes), BN * 128), vl_lo = smem_desc_lo(smem_u32(Vl + st * Cfg::kKVBytes), BN * 128);
+                constexpr uint32_t v_hi = smem_desc_hi(512, 1);
                 const uint32_t p_tmem = tmem_base + Cfg::kSP + sb * 2 * BN, pl_tmem = p_tmem + BN;
                 const uint32_t o_tmem = tmem_base + Cfg::kO + ob * HS;
                 if (leader) {
                     // small products first (fresh accumulator), the leading one last
 #pragma unroll
-                    for (int ks = 0; ks < BN / 8; ++ks) {          // 8 keys per instruction = two 4-row swizzle groups
-                        mma_tf32_ts(o_tmem, pl_tmem + ks * 8, smem_desc(v_addr + ks * 1024, BN * 128, 512, 1), kIdescPV, ks > 0 ? 1u : 0u);
-                        mma_tf32_ts(o_tmem, p_tmem + ks * 8, smem_desc(vl_addr + ks * 1024, BN * 128, 512, 1), kIdescPV, 1u);
+                    for (int ks = 0; ks < BN / 8; ++ks) {          // 8 keys per instruction = two 4-row swizzle groups (1024 bytes)
+                        mma_tf32_ts_lohi(o_tmem, pl_tmem + ks * 8, v_lo + ks * 64, v_hi, kIdescPV, ks > 0 ? 1u : 0u);
+                        mma_tf32_ts_lohi(o_tmem, p_tmem + ks * 8, vl_lo + ks * 64, v_hi, kIdescPV, 1u);
                     }
 #pragma unroll
                     for (int ks = 0; ks < BN / 8; ++ks)
-                        mma_tf32_ts(o_tmem, p_tmem + ks * 8, smem_desc(v_addr + ks * 1024, BN * 128, 512, 1), kIdescPV, 1u);
+                        mma_tf32_ts_lohi(o_tmem, p_tmem + ks * 8, v_lo + ks * 64, v_hi, kIdescPV, 1u);
                     tc_commit(smem_u32(&o_full[ob]));
                     tc_commit(smem_u32(&v_empty[st]));
                 }
@@ -308,21 +310,24 @@ pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
                 const int st = it % NST, sb = it % SBUF;
                 mbar_wait(smem_u32(&k_split[st]), (it / NST) & 1);           // K landed and K_lo written
                 tc_fence_after();
-                const uint32_t k_addr = smem_u32(Ks + st * Cfg::kKVBytes), kl_addr = smem_u32(Kl + st * Cfg::kKVBytes);
+                const uint32_t k_lo = smem_desc_lo(smem_u32(Ks + st * Cfg::kKVBytes), 16), kl_lo = smem_desc_lo(smem_u32(Kl + st * Cfg::kKVBytes), 16);
+                constexpr uint32_t k_hi = smem_desc_hi(1024, 2);
                 // the P.V that read this S/P buffer last was issued SBUF tiles ago, before this instruction in
                 // program order: the tensor pipe executes them in order
                 const uint32_t s_tmem = tmem_base + Cfg::kSP + sb * 2 * BN;
                 if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < HS / 8; ++ks) {        // 8 floats (32 B) of the head dimension per instruction
-                        const uint32_t koff = (ks >> 2) * (BN * 128) + (ks & 3) * 32;
-                        mma_tf32_ts(s_tmem, tmem_base + Cfg::kQlo + ks * 8, smem_desc(k_addr + koff, 16, 1024), kIdescQK, ks > 0 ? 1u : 0u);
-                        mma_tf32_ts(s_tmem, tmem_base + Cfg::kQ + ks * 8, smem_desc(kl_addr + koff, 16, 1024), kIdescQK, 1u);
+                        constexpr int kBlk = BN * 128 / 16;      // a 32-column block, in descriptor units
+                        const uint32_t koff = (ks >> 2) * kBlk + (ks & 3) * 2;
+                        mma_tf32_ts_lohi(s_tmem, tmem_base + Cfg::kQlo + ks * 8, k_lo + koff, k_hi, kIdescQK, ks > 0 ? 1u : 0u);
+                        mma_tf32_ts_lohi(s_tmem, tmem_base + Cfg::kQ + ks * 8, kl_lo + koff, k_hi, kIdescQK, 1u);
                     }
 #pragma unroll
                     for (int ks = 0; ks < HS / 8; ++ks) {
-                        const uint32_t koff = (ks >> 2) * (BN * 128) + (ks & 3) * 32;
-                        mma_tf32_ts(s_tmem, tmem_base + Cfg::kQ + ks * 8, smem_desc(k_addr + koff, 16, 1024), kIdescQK, 1u);
+                        constexpr int kBlk = BN * 128 / 16;
+                        const uint32_t koff = (ks >> 2) * kBlk + (ks & 3) * 2;
+                        mma_tf32_ts_lohi(s_tmem, tmem_base + Cfg::kQ + ks * 8, k_lo + koff, k_hi, kIdescQK, 1u);
                     }
                     tc_commit(smem_u32(&s_full[sb]));
                     tc_commit(smem_u32(&k_empty[st]));

@@ -122,6 +122,28 @@ static __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_t
         "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// The same with the shared-memory descriptor handed over as its two 32-bit halves.  Only the address field (low 14 bits
+// of the low word, in 16-byte units) changes from one instruction of a tile to the next, so a caller builds
+// desc_lo(tile base) once and ADDS (byte offset >> 4) per instruction: one uniform-datapath add instead of the shift /
+// mask / or chain of smem_desc() -- the issuing lane was spending ~55 cycles per UTCHMMA on that chain (measured in
+// pa_prefill_tc3.cu: 24 instructions took 704 ns to issue while the tensor datapath was busy 46 % of the time).
+static __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t addr, uint32_t lbo_bytes) {
+    return ((addr & 0x3ffff) >> 4) | (((lbo_bytes >> 4) & 0x3fff) << 16);
+}
+static __host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+    return ((sbo_bytes >> 4) & 0x3fff) | (1u << 14) | (layout_type << 29);
+}
+static __device__ __forceinline__ void mma_tf32_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 bd;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 bd, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+        : "memory");
+}
 // 32 consecutive columns of this thread's TMEM lane (lane = 32 * (warp % 4) + lane id)
 static __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
