@@ -385,13 +385,27 @@ pa_prefill_tc3_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
             mbar_wait(smem_u32(&o_full[ob]), (it / OBUF) & 1);
             tc_fence_after();
             const uint32_t o_tmem = tmem_base + lane_off + Cfg::kO + ob * HS;
+            if (NWG == 1) {
+                // 64 columns per round trip (two loads in flight, ONE wait): the register budget of the single softmax
+                // warpgroup allows it, and four serialised TMEM round trips per tile were a tenth of the tile's time
 #pragma unroll
-            for (int c = 0; c < HS; c += 16) {
-                float ov[16];
-                tmem_ld16(o_tmem + c, ov);
-                tmem_wait_ld();
+                for (int c = 0; c < HS; c += 64) {
+                    float ov[64];
+                    tmem_ld32(o_tmem + c, ov);
+                    tmem_ld32(o_tmem + c + 32, ov + 32);
+                    tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) o[c + i] = fmaf(o[c + i], alpha, ov[i]);
+                    for (int i = 0; i < 64; ++i) o[c + i] = fmaf(o[c + i], alpha, ov[i]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < HS; c += 16) {
+                    float ov[16];
+                    tmem_ld16(o_tmem + c, ov);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[c + i] = fmaf(o[c + i], alpha, ov[i]);
+                }
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&o_free[ob]));
