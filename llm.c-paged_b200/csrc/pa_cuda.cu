@@ -196,6 +196,7 @@ int pa_cu_step_upload(pa_handle* h, void* stream) {
     CU_CHECK(cudaEventRecord(r->ev[r->cur], s));
     r->pending[r->cur] = true;
     h->step.uploaded = 1;
+    h->step_uploads++;
     return PA_OK;
 }
 

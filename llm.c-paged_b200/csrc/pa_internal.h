@@ -45,6 +45,7 @@ struct pa_handle {
     size_t d_step_cap_ints;
     void* step_ring;              /* opaque, owned by pa_cuda.cu */
     pa_step_layout step;
+    unsigned long step_uploads;   /* counts pa_step_upload calls: what was derived from the tables of one step is reused until it moves */
     int* step_seq_ids;            /* host [max_seqs] */
     int* step_n_new;              /* host [max_seqs] */
     int* step_pre_len;            /* host [max_seqs] context length of each sequence before the step being built */

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpaged_attn.so")
+# (PA_LIB_PATH: a developer hook -- A/B an alternative build of the same ABI on one box)
+LIB_PATH = os.environ.get("PA_LIB_PATH") or os.path.join(HERE, "libpaged_attn.so")
 
 c_int_p = C.POINTER(C.c_int)
 c_float_p = C.POINTER(C.c_float)

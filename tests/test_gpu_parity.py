@@ -621,6 +621,25 @@ def test_prefill_tcgen05_3xtf32_is_fp32_accurate(NH, hs, bs, before, n_new):
     print(f"tcgen05 3xtf32 prefill NH={NH} hs={hs} bs={bs}: max rel err {err:.2e}")
 
 
+def test_prefill_tcgen05_3xtf32_persistent_schedule():
+    """The kernel is persistent: one CTA per SM walks a host-built list of (sequence, q tile, head) units with nothing
+    draining in between (the next Q tile prefetched through the staging tile, the previous unit's rows stored after the
+    next unit's first key tile).  The cases above mostly give a CTA one unit; these give every CTA several: 40 ragged
+    sequences x 6 heads = 480+ units on 148 SMs, cached context and fragmented pages included; and a sliding window
+    that leaves whole q tiles without a visible key (zero rows, no key tile: every role must skip them alike)."""
+    rng = np.random.default_rng(5)
+    n_new = [int(x) for x in rng.integers(1, 300, 38)] + [700, 513]
+    before = [int(x) for x in rng.integers(0, 200, 38)] + [0, 90]
+    got, want = _run_prefill(6, 64, 16, before, n_new, 4, shuffle=True)
+    assert_close_tc3(got, want, "3xTF32 prefill, several units per CTA")
+    got, want = _run_prefill(2, 128, 16, [0, 40, 0] * 30, [200, 129, 260] * 30, 4, shuffle=True)
+    assert_close_tc3(got, want, "3xTF32 prefill, several units per CTA, head_dim 128")
+    # window start beyond the first q tile's last row: its rows, and rows 128..199 of the second tile, see nothing
+    got, want = _run_prefill(3, 64, 16, [0, 0], [300, 450], 4, kv_start=[200, 129])
+    assert (got[:200] == 0).all() and (got[300:300 + 129] == 0).all()
+    assert_close_tc3(got, want, "3xTF32 prefill, q tiles without keys")
+
+
 def test_prefill_tcgen05_3xtf32_window_large_logits_and_domain():
     got, want = _run_prefill(2, 64, 16, [150, 70], [90, 140], 4, kv_start=[37, 64])
     assert_close_tc3(got, want, "3xTF32 prefill, window")

@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--bn", type=int, default=0, help="tcgen05 path, head_dim 64: keys per tile (64/128)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--clocks", type=float, default=0.0, metavar="SECONDS",
+                    help="afterwards repeat the attention launch alone for this long and report SM clock / power under load (NVML)")
     ap.add_argument("--check", action="store_true", help="compare against the rows kernel (path 2) on the same inputs")
     args = ap.parse_args()
 
@@ -91,6 +93,42 @@ def main():
     line = {"tool": "prefill_bench", "shape": args.shape, "NH": NH, "hs": hs, "B": B, "T": T, "before": args.before,
             "bs": bs, "path": PATH_NAMES[args.path], "nwg": args.nwg, "bn": args.bn, "ms": t * 1e3, "tflops": flops / t / 1e12,
             "tokens_per_s": ntok / t, "ms_all": [round(x, 4) for x in ms]}
+    if args.clocks > 0:
+        # the step's attention launch back to back (no append: the cache is already in its post-step state for the
+        # last pass) while a thread samples NVML: what clock does the kernel actually run at?
+        import threading, time
+        import pynvml
+        pynvml.nvmlInit()
+        dev = pynvml.nvmlDeviceGetHandleByIndex(0)
+        samples, stop = [], threading.Event()
+
+        def sampler():
+            while not stop.is_set():
+                samples.append((pynvml.nvmlDeviceGetClockInfo(dev, pynvml.NVML_CLOCK_SM),
+                                pynvml.nvmlDeviceGetPowerUsage(dev) / 1000.0))
+                time.sleep(0.02)
+        assert eng.step_begin(list(range(B)), [T] * B) == 0, pa.last_error()
+        pa.check(eng.upload(), "upload")
+        pa.check(eng.append(0, d.ptr + C_ * 4, d.ptr + 2 * C_ * 4, 3 * C_), "append")
+        th = threading.Thread(target=sampler)
+        th.start()
+        t_end = time.time() + args.clocks
+        n_launch = 0
+        lib.pa_event_record(e0, stream)
+        while time.time() < t_end:
+            for _ in range(20):
+                pa.check(eng.prefill(0, d.ptr, 3 * C_, o.ptr, C_), "prefill")
+            n_launch += 20
+            eng.sync()
+        lib.pa_event_record(e1, stream)
+        eng.sync()
+        stop.set(); th.join()
+        pa.check(eng.step_rollback(), "rollback")
+        half = samples[len(samples) // 2:]               # (the first half: ramp)
+        ms_k = lib.pa_event_elapsed_ms(e0, e1) / n_launch
+        line["sustained"] = {"attention_ms": ms_k, "tflops": flops / (ms_k * 1e-3) / 1e12,
+                             "sm_mhz": float(np.median([x[0] for x in half])), "power_w": float(np.median([x[1] for x in half])),
+                             "sm_max_mhz": pynvml.nvmlDeviceGetMaxClockInfo(dev, pynvml.NVML_CLOCK_SM), "seconds": args.clocks}
     if args.check:
         got = o.download((ntok, C_))
         eng.tune(pa.PA_TUNE_PREFILL_PATH, 2)
