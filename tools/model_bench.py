@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--gemm-path", type=int, default=0)
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--prefill", type=int, default=0, help="instead of decode steps: prefill prompts of this many tokens for the B sequences in ONE step")
+    ap.add_argument("--replicas", type=int, default=1, help="EXPERIMENT: split the B sequences over this many engine + model pairs on the same GPU, "
+                    "each on its own stream, stepped concurrently (pa_model_forward_async on each, then pa_model_wait on each)")
     ap.add_argument("--model-path", type=int, default=0, help="0 auto, 1 chain of per-op kernels, 2 persistent step kernel")
     args = ap.parse_args()
     pa = ge.build(quiet=True)
@@ -73,6 +75,50 @@ def main():
         print(json.dumps({"tool": "model_bench", "mode": "prefill", "shape": args.shape, "B": B, "prompt": P, "layers": L,
                           "ms_per_step": dt * 1e3, "prompt_tokens_per_s": B * P / dt, "gemm_path": args.gemm_path}))
         model.close(); eng.close()
+        return
+    if args.replicas > 1:
+        import ctypes as C
+        eng.close()
+        R = args.replicas
+        Bp = B // R
+        V = 50257
+        engs, models = [], []
+        for r in range(R):
+            e = pa.PagedAttn(bs, Bp * pages + 8, Bp, NH, hs, n_layers=L, device=0, max_batch_tokens=Bp)
+            e.tune(pa.PA_TUNE_GEMM_PATH, args.gemm_path)
+            e.tune(pa.PA_TUNE_NO_PDL, 1 if args.no_pdl else 0)
+            e.tune(pa.PA_TUNE_MODEL_PATH, args.model_path)
+            pr = rng.permutation(Bp * pages + 8)
+            for s in range(Bp):
+                assert e.seq_adopt(s, pr[s * pages: s * pages + (ctx - 1 + bs - 1) // bs], ctx - 1) == 0, pa.last_error()
+            engs.append(e)
+            models.append(pa.Model(e, max(1024, ctx + 8), V, params=None, seed=1, max_batch=Bp))
+        seq = np.arange(Bp, dtype=np.int32)
+        ones = np.ones(Bp, dtype=np.int32)
+        tok = rng.integers(0, V, size=Bp).astype(np.int32)
+        coins = rng.random(Bp).astype(np.float32)
+        nxt = np.zeros(Bp, dtype=np.int32)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+
+        def rstep():
+            for m in models:
+                pa.check(lib.pa_model_forward_async(m.m, ip(seq), ip(ones), ip(tok), coins.ctypes.data, Bp), "forward_async")
+            for m in models:
+                pa.check(lib.pa_model_wait(m.m, ip(nxt)), "wait")
+            for e in engs:
+                pa.check(e.step_rollback(), "rollback")
+        for _ in range(3):
+            rstep()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rstep()
+        dt = (time.perf_counter() - t0) / args.steps
+        print(json.dumps({"tool": "model_bench", "mode": "replicas", "replicas": R, "shape": args.shape, "B": B, "ctx": ctx, "layers": L,
+                          "ms_per_step": dt * 1e3, "tokens_per_s": Bp * R / dt}))
+        for m in models:
+            m.close()
+        for e in engs:
+            e.close()
         return
     for s in range(B):
         assert eng.seq_adopt(s, perm[s * pages: s * pages + (ctx - 1 + bs - 1) // bs], ctx - 1) == 0, pa.last_error()
