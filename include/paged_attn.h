@@ -186,7 +186,8 @@ PA_API int pa_decode_append(pa_handle* h, int layer, const float* q, const float
                             float* out, int out_stride, void* stream);
 /* Causal rows: the n_new[i] new tokens of each sequence are the queries (packed in step order);
  * row j of sequence i attends [kv_start, ctx_before + j].  fp32 accuracy (1e-5) on every automatic path: tensor
- * cores with the 3xTF32 split where the step is large enough, fp32 SIMT otherwise (PA_TUNE_PREFILL_PATH). */
+ * cores with the 3xTF32 split wherever the kernel's domain allows (head_dim 64 / 128, pages of 8..64 resp. 8..32
+ * tokens), fp32 SIMT otherwise (PA_TUNE_PREFILL_PATH). */
 PA_API int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream);
 
 /* QKV projection of the step's new tokens with the KV append fused into its epilogue
@@ -387,7 +388,7 @@ typedef enum pa_tune_key {
     PA_TUNE_LAST_HPG = 10,     /* read-only: heads per tile, ring stages and CTAs of the last stream-decode launch */
     PA_TUNE_LAST_STAGES = 11,  /*            (0 when the last decode ran on the generic kernel) */
     PA_TUNE_LAST_GRID = 12,
-    PA_TUNE_PREFILL_PATH = 13, /* 0 auto (tcgen05 3xTF32 for steps of >= 256 query rows with >= 32 per sequence, else tiled fp32 SIMT: both within 1e-5), 1 tiled fp32 SIMT, 2 generic rows kernel, 3 tcgen05 plain TF32 (opt-in, own tolerance 5e-3), 4 tcgen05 3xTF32 (fp32-accurate; fails outside its domain) */
+    PA_TUNE_PREFILL_PATH = 13, /* 0 auto (tcgen05 3xTF32 wherever its domain allows -- head_dim 64/128, pages of 8..64 resp. 8..32 tokens -- else tiled fp32 SIMT: both within 1e-5), 1 tiled fp32 SIMT, 2 generic rows kernel, 3 tcgen05 plain TF32 (opt-in, own tolerance 5e-3), 4 tcgen05 3xTF32 (fp32-accurate; fails outside its domain) */
     PA_TUNE_TC_WARPGROUPS = 14,/* tcgen05 prefill: softmax warpgroups per CTA, 0 auto, 1 or 2 */
     PA_TUNE_TC_KEY_TILE = 15,  /* tcgen05 prefill, head_dim 64: keys per tile, 0 auto (64), 64 or 128 */
     PA_TUNE_GEMM_PATH = 16,    /* projections: 0 auto (<= 4 rows: weight-streaming GEMV, else tcgen05 3xTF32, fp32-accurate), 1 fp32 SIMT, 2 tcgen05 3xTF32, 3 tcgen05 plain TF32 (reduced precision, own tolerance), 4 GEMV */

@@ -1181,10 +1181,13 @@ int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out
             pa_set_error("pa_prefill: tcgen05 kernel needs head_dim 64/128, block_size 8..128 (power of two), 16-byte aligned rows");
         return rc;
     }
-    // fp32-accurate tensor-core kernel (tcgen05 3xTF32, tolerance 1e-5): forced with 4; chosen by itself (0) when the
-    // step has enough query rows for 128-row tiles to pay (measured crossover against the tiled SIMT kernel)
-    static const int tc3_min_rows = getenv("PA_PREFILL_TC3_MIN_ROWS") ? atoi(getenv("PA_PREFILL_TC3_MIN_ROWS")) : 256;
-    if (path == 4 || (path == 0 && h->step.ntok >= tc3_min_rows && h->step.max_q >= 32)) {
+    // fp32-accurate tensor-core kernel (tcgen05 3xTF32, tolerance 1e-5): forced with 4, and the automatic choice (0)
+    // wherever its domain allows.  Since it became persistent there is no crossover left against the tiled SIMT kernel:
+    // it is as fast at 1 x 16 rows and 1.6-2.7 x faster from 16 x 128 on, and 4-6 x on few rows over a long cache
+    // (64 x 4 rows on 1024 cached tokens: 0.165 vs 0.891 ms; profiles/r02_prefill.md).  PA_PREFILL_TC3_MIN_ROWS
+    // restores a threshold.
+    static const int tc3_min_rows = getenv("PA_PREFILL_TC3_MIN_ROWS") ? atoi(getenv("PA_PREFILL_TC3_MIN_ROWS")) : 1;
+    if (path == 4 || (path == 0 && h->step.ntok >= tc3_min_rows)) {
         rc = pa_cu_prefill_tc3(h, layer, q, q_stride, out, out_stride, (void*)s);
         if (rc != PA_ERR_UNSUPPORTED) return rc;
         if (path == 4) {

@@ -653,11 +653,18 @@ def test_prefill_tcgen05_3xtf32_window_large_logits_and_domain():
         _run_prefill(2, 64, 4, [0], [40], 4)
     with pytest.raises(pa.PagedAttnError):          # head_dim 128: pages above 32 tokens exceed the 32-key tile
         _run_prefill(1, 128, 64, [0], [129], 4)
-    # the automatic choice (path 0) takes it for large steps and the SIMT kernel for small ones: same answers
+    # the automatic choice (path 0) is this kernel wherever its domain allows, small steps included, and the SIMT
+    # kernels outside it (pages of 4 tokens; head_dim 5): same answers
     big, want_big = _run_prefill(2, 64, 16, [0, 10], [300, 200], 0)
     assert_close_tc3(big, want_big, "auto, large step")
     small, want_small = _run_prefill(2, 64, 16, [0, 10], [20, 9], 0)
-    assert_close(small, want_small, "auto, small step")
+    assert_close_tc3(small, want_small, "auto, small step")
+    few, want_few = _run_prefill(12, 64, 16, [1000] * 20, [4] * 20, 0, shuffle=True)     # few rows on a long cache
+    assert_close_tc3(few, want_few, "auto, 4 rows on 1000 cached")
+    tiny_pages, want_tp = _run_prefill(2, 64, 4, [0, 10], [40, 9], 0)
+    assert_close(tiny_pages, want_tp, "auto, pages of 4 tokens (SIMT)")
+    odd, want_odd = _run_prefill(2, 5, 2, [3], [17], 0)
+    assert_close(odd, want_odd, "auto, head_dim 5 (rows kernel)")
 
 
 def test_prefill_tcgen05_window_and_unsupported_shapes():
