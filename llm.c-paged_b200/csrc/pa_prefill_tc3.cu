@@ -15,15 +15,20 @@
  *     exp2 domain (2^-22 relative; PA_PREFILL_TC3_EXPF=1 switches to expf as the reference writes it).
  * Measured against the oracle: see tests/test_gpu_parity.py (prefill cases, path 4) and profiles/r02_prefill.md.
  *
- * One CTA per (head, sequence, tile of 128 query rows) = one TMEM lane per query row; 12 warps (three warpgroups):
+ * PERSISTENT: one CTA per SM walks its column of a host-built schedule of units (sequence, tile of 128 query rows =
+ * TMEM lanes, head) -- see build_schedule() -- and nothing drains between units (see the kernel's comment).
+ * 12 warps (three warpgroups):
  *   warps 0-3   softmax warpgroup: thread = query row.  Reads its row of S (tcgen05.ld), online softmax, writes
- *               P and P_lo back into TMEM as the A operands of P.V (tcgen05.st), and folds the PREVIOUS tile's
- *               P.V result into its register accumulator while the tensor core works on the current one
+ *               P and P_lo back into TMEM as the A operands of P.V (tcgen05.st), folds the PREVIOUS tile's
+ *               P.V result into its register accumulator while the tensor core works on the current one, and
+ *               stores a finished unit's rows (after the next unit's first key tile)
  *   warps 4-7   splitter warpgroup: K_lo / V_lo tiles next to the raw ones the TMA delivered (element-wise over
- *               the flat swizzled buffers: same layout, other base address)
+ *               the flat swizzled buffers: same layout, other base address); the next unit's Q tile: prefetched
+ *               into the staging tile (cp.async), split and moved to TMEM at the unit boundary
  *   warp 8      TMA producer (+ TMEM allocation): one tensor-map box per page and 32-column block
  *   warp 9      MMA issuer (one elected lane): S = Q.K^T (A = Q, Q_lo from TMEM; B = K, K_lo from shared memory,
  *               K-major SW128) and O_tile = P.V (A = P, P_lo from TMEM; B = V, V_lo MN-major SW128/32B atoms)
+ * Shared memory: 3-deep rings of K, K_lo, V, V_lo (192 KB) + the 32 KB Q / O staging tile.
  * TMEM columns: Q hs | Q_lo hs | SBUF x (S/P BN | P_lo BN) | OBUF x O_tile hs  <= 512.
  */
 #include <cuda.h>
