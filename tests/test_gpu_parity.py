@@ -2,6 +2,7 @@
 is the CPU oracle (pinned to the compiled reference by test_oracle_pinned.py) and, where the
 reference itself was built (oracle/_ref), the reference's own attention_paged."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -638,6 +639,66 @@ def test_prefill_tcgen05_3xtf32_persistent_schedule():
     got, want = _run_prefill(3, 64, 16, [0, 0], [300, 450], 4, kv_start=[200, 129])
     assert (got[:200] == 0).all() and (got[300:300 + 129] == 0).all()
     assert_close_tc3(got, want, "3xTF32 prefill, q tiles without keys")
+
+
+def _prefill_two_paths(NH, hs, bs, before, n_new, kv_start, seed, paths=(4, 2)):
+    """The same step through two kernels on ONE engine (the step is rolled back in between): outputs of both."""
+    Cc = NH * hs
+    sc = Scenario(NH, hs, bs, before, seed=seed, extra_blocks=sum((n + bs - 1) // bs + 1 for n in n_new) + 8,
+                  max_batch_tokens=sum(n_new), shuffle=True)
+    try:
+        eng = sc.eng
+        ntok = sum(n_new)
+        qkv = oa.normal((ntok, 3 * Cc), seed=seed + 1)
+        d = pa.DevBuf.from_numpy(qkv)
+        o = pa.DevBuf(ntok * Cc * 4)
+        outs = []
+        for path in paths:
+            eng.tune(pa.PA_TUNE_PREFILL_PATH, path)
+            assert eng.step_begin(sc.seq_ids, n_new) == 0, pa.last_error()
+            if kv_start is not None:
+                assert eng.step_set_kv_start(kv_start) == 0, pa.last_error()
+            pa.check(eng.upload(), "upload")
+            pa.check(eng.lib.pa_memset(o.ptr, 0xff, ntok * Cc * 4, None), "memset")   # NaN canary
+            pa.check(eng.append(0, d.ptr + Cc * 4, d.ptr + 2 * Cc * 4, 3 * Cc), "append")
+            pa.check(eng.prefill(0, d.ptr, 3 * Cc, o.ptr, Cc), "prefill")
+            eng.sync()
+            outs.append(o.download((ntok, Cc)))
+            pa.check(eng.step_rollback(), "rollback")
+        d.free(); o.free()
+        return outs
+    finally:
+        sc.close()
+
+
+@pytest.mark.timeout(300)
+def test_prefill_tcgen05_3xtf32_random_ragged_steps_match_rows_kernel():
+    """Fuzz of the persistent kernel's scheduling (units per CTA, unit boundaries, q tiles without keys, one-tile
+    units, partial q tiles, both head dims, every page size of its domain, sliding windows) against the generic rows
+    kernel, which the cases above pin to the oracle: 30 seeded random steps, same tolerance as against the oracle."""
+    rng = np.random.default_rng(int(os.environ.get("PA_FUZZ_SEED", "2024")))
+    for case in range(int(os.environ.get("PA_FUZZ_CASES", "30"))):
+        hs = int(rng.choice([64, 128]))
+        bs = int(rng.choice([8, 16, 32, 64] if hs == 64 else [8, 16, 32]))
+        NH = int(rng.integers(1, 7))
+        B = int(rng.integers(1, 25))
+        shape = rng.integers(0, 3)
+        if shape == 0:      # many short sequences
+            n_new = [int(x) for x in rng.integers(1, 140, B)]
+            before = [int(x) for x in rng.integers(0, 100, B)]
+        elif shape == 1:    # few rows on longer caches (the verify step of speculative decoding)
+            n_new = [int(x) for x in rng.integers(1, 9, B)]
+            before = [int(x) for x in rng.integers(0, 900, B)]
+        else:               # a few long prompts
+            B = min(B, 4)
+            n_new = [int(x) for x in rng.integers(100, 700, B)]
+            before = [int(x) for x in rng.integers(0, 300, B)]
+        kv_start = None
+        if rng.random() < 0.4:        # windows; some start beyond what the first rows may see (rows without keys)
+            kv_start = [int(rng.integers(0, before[i] + n_new[i])) for i in range(B)]
+        got, want = _prefill_two_paths(NH, hs, bs, before, n_new, kv_start, seed=100 + case)
+        assert np.isfinite(want).all()
+        assert_close_tc3(got, want, f"case {case}: NH={NH} hs={hs} bs={bs} B={B} n_new={n_new[:6]} before={before[:6]} kv_start={None if kv_start is None else kv_start[:6]}")
 
 
 def test_prefill_tcgen05_3xtf32_window_large_logits_and_domain():
