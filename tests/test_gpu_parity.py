@@ -701,6 +701,111 @@ def test_prefill_tcgen05_3xtf32_random_ragged_steps_match_rows_kernel():
         assert_close_tc3(got, want, f"case {case}: NH={NH} hs={hs} bs={bs} B={B} n_new={n_new[:6]} before={before[:6]} kv_start={None if kv_start is None else kv_start[:6]}")
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("name,NH,hs,B,T,before", [
+    ("headline-16x2048", 12, 64, 16, 2048, 0),                 # bench.py's prefill shape
+    ("cfg5-chunk-on-30000-cached", 32, 128, 2, 2048, 30000),   # a 2048-token chunk of the 32k prompts, head_dim 128
+])
+def test_prefill_full_size_properties(name, NH, hs, B, T, before):
+    """The persistent 3xTF32 prefill at the sizes bench.py times, through properties that need no CPU pass over 10^11
+    products: (1) with every V row equal to one vector c, every output row is c (the weights sum to one; all rows, all
+    heads: masking and normalisation); (2) the last row of every sequence equals what the DECODE kernel computes for
+    that query over the same cache (two independent kernels, one of them pinned to the oracle at this size by
+    test_baseline_full_size_decode_parity_and_properties); (3) causality, bit-exact: other K/V in the last 100 tokens of
+    every sequence leaves all earlier rows' outputs unchanged; (4) the run is deterministic."""
+    lib = pa.load()
+    bs = 16
+    Cc = NH * hs
+    pages = (before + T + bs - 1) // bs + 1
+    eng = pa.PagedAttn(bs, B * pages + 8, B, NH, hs, n_layers=1, device=0, max_batch_tokens=B * T)
+    try:
+        stream = lib.pa_stream_of(eng.h)
+        rng = np.random.default_rng(11)
+        perm = rng.permutation(B * pages + 8)
+        nb = (before + bs - 1) // bs
+        pool_floats = (B * pages + 8) * bs * Cc
+        pa.check(lib.pa_fill_normal(eng.pool_k(0), pool_floats, 1.0, 0.0, 501, stream), "fill")
+        pa.check(lib.pa_fill_normal(eng.pool_v(0), pool_floats, 1.0, 0.0, 502, stream), "fill")
+        for s_ in range(B):
+            if before:
+                assert eng.seq_adopt(s_, perm[s_ * pages: s_ * pages + nb], before) == 0, pa.last_error()
+        ntok = B * T
+        d_in, d_o = pa.DevBuf(ntok * 3 * Cc * 4), pa.DevBuf(ntok * Cc * 4)
+        pa.check(lib.pa_fill_normal(d_in.ptr, ntok * 3 * Cc, 1.0, 0.0, 503, stream), "fill")
+        seq_ids = np.arange(B, dtype=np.int32)
+        eng.tune(pa.PA_TUNE_PREFILL_PATH, 4)
+
+        def run_step(keep=False):
+            assert eng.step_begin(seq_ids, [T] * B) == 0, pa.last_error()
+            pa.check(eng.upload(), "upload")
+            pa.check(lib.pa_memset(d_o.ptr, 0xff, ntok * Cc * 4, None), "memset")
+            pa.check(eng.append(0, d_in.ptr + Cc * 4, d_in.ptr + 2 * Cc * 4, 3 * Cc), "append")
+            pa.check(eng.prefill(0, d_in.ptr, 3 * Cc, d_o.ptr, Cc), "prefill")
+            eng.sync()
+            out = d_o.download((ntok, Cc))
+            if not keep:
+                pa.check(eng.step_rollback(), "rollback")
+            return out
+
+        base = run_step()
+        assert np.isfinite(base).all()
+        assert np.array_equal(base, run_step()), "not deterministic"                                  # (4)
+
+        # (3) other K/V in the last 100 tokens of every sequence: rows before them unchanged, bit for bit
+        tail = oa.normal((100, 3 * Cc), seed=77)
+        tail[:, :Cc] = 0.0
+        saved = []
+        for s_ in range(B):
+            off = ((s_ * T + T - 100) * 3 * Cc) * 4
+            row = d_in.download((100, 3 * Cc), offset_bytes=off)
+            saved.append(row)
+            mod = row.copy()
+            mod[:, Cc:] = tail[:, Cc:]                           # K and V columns only: the queries stay
+            pa.check(lib.pa_memcpy_h2d(d_in.ptr + off, mod.ctypes.data, mod.nbytes, None), "h2d")
+        changed = run_step()
+        for s_ in range(B):
+            assert np.array_equal(changed[s_ * T: s_ * T + T - 100], base[s_ * T: s_ * T + T - 100]), f"sequence {s_}: a future token changed a past row"
+            assert not np.array_equal(changed[s_ * T + T - 100: (s_ + 1) * T], base[s_ * T + T - 100: (s_ + 1) * T])
+            pa.check(lib.pa_memcpy_h2d(d_in.ptr + ((s_ * T + T - 100) * 3 * Cc) * 4, saved[s_].ctypes.data, saved[s_].nbytes, None), "h2d")
+
+        # (2) last rows against the decode kernel over the same cache (the step stays appended)
+        full = run_step(keep=True)
+        assert np.array_equal(full, base)
+        q_last = np.stack([d_in.download((1, 3 * Cc), offset_bytes=((s_ * T + T - 1) * 3 * Cc) * 4)[0, :Cc] for s_ in range(B)])
+        d_q, d_dec = pa.DevBuf.from_numpy(np.ascontiguousarray(q_last)), pa.DevBuf(B * Cc * 4)
+        assert eng.step_begin_readonly(seq_ids) == 0, pa.last_error()
+        pa.check(eng.upload(), "upload")
+        pa.check(eng.decode(0, d_q.ptr, Cc, d_dec.ptr, Cc), "decode")
+        eng.sync()
+        dec = d_dec.download((B, Cc))
+        err = assert_close_tc3(full[T - 1::T], dec, f"{name}: last prefill rows vs the decode kernel")
+        print(f"{name}: last prefill rows vs decode kernel, max rel err {err:.2e}")
+        d_q.free(); d_dec.free()
+        for s_ in range(B):
+            eng.seq_free(s_)
+
+        # (1) constant V rows (cache and new tokens): every output row is that vector
+        c = oa.normal((1, Cc), seed=5)[0]
+        vrows = np.ascontiguousarray(np.broadcast_to(c, (4096, Cc)))
+        for r0 in range(0, (B * pages + 8) * bs, 4096):
+            n = min(4096, (B * pages + 8) * bs - r0)
+            pa.check(lib.pa_memcpy_h2d(eng.pool_v(0) + r0 * Cc * 4, vrows.ctypes.data, n * Cc * 4, None), "h2d")
+        chunk = d_in.download((T, 3 * Cc), offset_bytes=0)
+        for s_ in range(B):
+            if before:
+                assert eng.seq_adopt(s_, perm[s_ * pages: s_ * pages + nb], before) == 0, pa.last_error()
+            blk = d_in.download((T, 3 * Cc), offset_bytes=(s_ * T * 3 * Cc) * 4) if s_ else chunk
+            blk[:, 2 * Cc:] = c
+            pa.check(lib.pa_memcpy_h2d(d_in.ptr + (s_ * T * 3 * Cc) * 4, blk.ctypes.data, blk.nbytes, None), "h2d")
+        const = run_step()
+        scale = np.abs(c).max()
+        dev = np.abs(const.astype(np.float64) - c.astype(np.float64)).max() / scale
+        assert dev <= 1e-5, f"{name}: constant-V rows deviate by {dev:.2e} of max|c|"
+        d_in.free(); d_o.free()
+    finally:
+        eng.close()
+
+
 def test_prefill_tcgen05_3xtf32_window_large_logits_and_domain():
     got, want = _run_prefill(2, 64, 16, [150, 70], [90, 140], 4, kv_start=[37, 64])
     assert_close_tc3(got, want, "3xTF32 prefill, window")
