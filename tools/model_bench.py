@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--prefill", type=int, default=0, help="instead of decode steps: prefill prompts of this many tokens for the B sequences in ONE step")
     ap.add_argument("--replicas", type=int, default=1, help="EXPERIMENT: split the B sequences over this many engine + model pairs on the same GPU, "
                     "each on its own stream, stepped concurrently (pa_model_forward_async on each, then pa_model_wait on each)")
+    ap.add_argument("--attn-grid", type=int, default=0, help="with --replicas: CTAs of the decode attention launch (PA_TUNE_GRID)")
     ap.add_argument("--model-path", type=int, default=0, help="0 auto, 1 chain of per-op kernels, 2 persistent step kernel")
     args = ap.parse_args()
     pa = ge.build(quiet=True)
@@ -88,6 +89,7 @@ def main():
             e.tune(pa.PA_TUNE_GEMM_PATH, args.gemm_path)
             e.tune(pa.PA_TUNE_NO_PDL, 1 if args.no_pdl else 0)
             e.tune(pa.PA_TUNE_MODEL_PATH, args.model_path)
+            e.tune(pa.PA_TUNE_GRID, args.attn_grid)
             pr = rng.permutation(Bp * pages + 8)
             for s in range(Bp):
                 assert e.seq_adopt(s, pr[s * pages: s * pages + (ctx - 1 + bs - 1) // bs], ctx - 1) == 0, pa.last_error()
