@@ -71,7 +71,7 @@ struct Tc3Params {
     const int* table;
     const int2* units;      // the schedule: [n_rows][gridDim.x], CTA c's j-th unit at [j][c]; x = sequence (-1: none), y = q tile | head << 16
     unsigned long long* dbg;   // optional timeline (PA_PREFILL_TC3_TIMELINE=1)
-    int B, C, NH, bs, tstride, q_stride, out_stride;
+    int bs, tstride, q_stride, out_stride;
     int n_rows, layer;
     float scale;
     float sl2;              // scale * log2(e)
@@ -856,7 +856,7 @@ extern "C" int pa_cu_prefill_tc3(pa_handle* h, int layer, const float* q, int q_
     p.table = h->d_step + L.off_table;
     p.units = st->d_units;
     p.dbg = nullptr;
-    p.B = L.nseq; p.C = h->C; p.NH = h->cfg.n_heads; p.bs = bs;
+    p.bs = bs;
     p.tstride = L.tstride; p.q_stride = q_stride; p.out_stride = out_stride;
     p.n_rows = st->sched_rows;
     p.layer = layer;
