@@ -189,6 +189,13 @@ PA_API int pa_decode_append(pa_handle* h, int layer, const float* q, const float
  * cores with the 3xTF32 split wherever the kernel's domain allows (head_dim 64 / 128, pages of 8..64 resp. 8..32
  * tokens), fp32 SIMT otherwise (PA_TUNE_PREFILL_PATH). */
 PA_API int pa_prefill(pa_handle* h, int layer, const float* q, int q_stride, float* out, int out_stride, void* stream);
+/* The work list of the persistent tensor-core prefill kernel for the step being built (host only, no GPU needed;
+ * what pa_prefill uploads once per step): one CTA per column, `n_ctas` columns (at most `max_ctas`, 0 = the device's
+ * SM count, 148 without a device), `rows` units per column; units[row * n_ctas + cta] = { sequence index in the step
+ * (-1: none), q tile | head << 16 }; a q tile is 128 query rows, key_tile = 64 keys at head_dim 64, 32 at 128.
+ * `units` may be NULL to ask for the sizes only; cap = its capacity in entries.  Exposed for tests and tools: every
+ * (sequence, q tile, head) must appear exactly once, and the columns' work (key tiles) must balance. */
+PA_API int pa_prefill_schedule(pa_handle* h, int key_tile, int max_ctas, int* units, size_t cap, int* n_ctas, int* rows);
 
 /* QKV projection of the step's new tokens with the KV append fused into its epilogue
  * (matmul_cached + add_to_cache in one kernel): x (ntok, C) rows in step order, w (3C, C), bias (3C)

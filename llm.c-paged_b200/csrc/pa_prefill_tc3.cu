@@ -691,9 +691,12 @@ int make_pool_map3(CUtensorMap* map, float* pool, const pa_handle* h, CUtensorMa
 // head, q tile) -- heads OUTSIDE the q tiles; and the list is dealt boustrophedon.  Balance stays >= 0.97 of ideal on
 // the shapes of profiles/r02_prefill.md, a ragged batch included.  Laid out [row][cta]: a CTA reads its column.
 constexpr int kBuckets = 8;
-int build_schedule(pa_handle* h, Tc3State* st, int BN, cudaStream_t s) {
+// (pure host code: no CUDA call, so that the CPU test suite can check it; `flat` NULL = sizes only)
+int make_schedule(const pa_handle* h, int BN, int max_ctas, int2* flat, size_t cap, int* grid_out, int* rows_out) {
     const pa_step_layout& L = h->step;
     const int NH = h->cfg.n_heads;
+    *grid_out = 0; *rows_out = 0;
+    if (!h->h_step || L.nseq < 1) return PA_OK;
     const int* qr = h->h_step + L.off_q_row0;
     const int* ke = h->h_step + L.off_kv_end;
     const int* ks = h->h_step + L.off_kv_start;
@@ -710,8 +713,6 @@ int build_schedule(pa_handle* h, Tc3State* st, int BN, cudaStream_t s) {
         }
     }
     const long long n_units = (long long)tiles.size() * NH;
-    st->sched_grid = 0; st->sched_rows = 0;
-    st->sched_uploads = h->step_uploads; st->sched_bn = BN;
     if (n_units == 0) return PA_OK;
     int max_kt = 1;
     for (const Tile& t : tiles) max_kt = std::max(max_kt, t.n_kt);
@@ -721,21 +722,11 @@ int build_schedule(pa_handle* h, Tc3State* st, int BN, cudaStream_t s) {
         if (ba != bb) return ba > bb;
         if (a.seq != b.seq) return a.seq < b.seq;
         return a.qt > b.qt; });
-    const int grid = (int)std::min<long long>(n_units, std::max(1, h->sm_count));
+    const int grid = (int)std::min<long long>(n_units, std::max(1, max_ctas));
     const size_t rows = (size_t)((n_units + grid - 1) / grid), n = rows * grid;
-    if (st->units_cap < n) {
-        CU_CHECK(cudaStreamSynchronize(s));            // (rare: nothing may still read the old list)
-        if (st->d_units) cudaFree(st->d_units);
-        if (st->h_units) cudaFreeHost(st->h_units);
-        st->d_units = nullptr; st->h_units = nullptr; st->units_cap = 0;
-        const size_t cap = n + n / 2 + 1024;
-        CU_CHECK(cudaMalloc((void**)&st->d_units, cap * sizeof(int2)));
-        CU_CHECK(cudaMallocHost((void**)&st->h_units, cap * sizeof(int2)));
-        st->units_cap = cap;
-    }
-    if (!st->copied) CU_CHECK(cudaEventCreateWithFlags(&st->copied, cudaEventDisableTiming));
-    else CU_CHECK(cudaEventSynchronize(st->copied));          // the previous step's copy has left the pinned buffer (long ago)
-    int2* flat = st->h_units;
+    *grid_out = grid; *rows_out = (int)rows;
+    if (!flat) return PA_OK;
+    if (cap < n) { pa_set_error("pa_prefill_schedule: %zu entries needed, room for %zu", n, cap); return PA_ERR_INVALID; }
     size_t k = 0;
     for (size_t i0 = 0; i0 < tiles.size();) {
         size_t i1 = i0 + 1;                            // a run of one sequence's q tiles of one class
@@ -751,9 +742,34 @@ int build_schedule(pa_handle* h, Tc3State* st, int BN, cudaStream_t s) {
         const size_t row = k / grid, pos = k % grid;
         flat[row * grid + ((row & 1) ? grid - 1 - pos : pos)] = make_int2(-1, 0);
     }
-    CU_CHECK(cudaMemcpyAsync(st->d_units, flat, n * sizeof(int2), cudaMemcpyHostToDevice, s));
+    return PA_OK;
+}
+
+// build the step's schedule and send it to the device (once per uploaded step)
+int build_schedule(pa_handle* h, Tc3State* st, int BN, cudaStream_t s) {
+    st->sched_grid = 0; st->sched_rows = 0;
+    st->sched_uploads = h->step_uploads; st->sched_bn = BN;
+    int grid = 0, rows = 0;
+    int rc = make_schedule(h, BN, h->sm_count, nullptr, 0, &grid, &rows);
+    if (rc != PA_OK || grid == 0) return rc;
+    const size_t n = (size_t)rows * grid;
+    if (st->units_cap < n) {
+        CU_CHECK(cudaStreamSynchronize(s));            // (rare: nothing may still read the old list)
+        if (st->d_units) cudaFree(st->d_units);
+        if (st->h_units) cudaFreeHost(st->h_units);
+        st->d_units = nullptr; st->h_units = nullptr; st->units_cap = 0;
+        const size_t cap = n + n / 2 + 1024;
+        CU_CHECK(cudaMalloc((void**)&st->d_units, cap * sizeof(int2)));
+        CU_CHECK(cudaMallocHost((void**)&st->h_units, cap * sizeof(int2)));
+        st->units_cap = cap;
+    }
+    if (!st->copied) CU_CHECK(cudaEventCreateWithFlags(&st->copied, cudaEventDisableTiming));
+    else CU_CHECK(cudaEventSynchronize(st->copied));          // the previous step's copy has left the pinned buffer (long ago)
+    rc = make_schedule(h, BN, h->sm_count, st->h_units, st->units_cap, &grid, &rows);
+    if (rc != PA_OK) return rc;
+    CU_CHECK(cudaMemcpyAsync(st->d_units, st->h_units, n * sizeof(int2), cudaMemcpyHostToDevice, s));
     CU_CHECK(cudaEventRecord(st->copied, s));
-    st->sched_grid = grid; st->sched_rows = (int)rows;
+    st->sched_grid = grid; st->sched_rows = rows;
     return PA_OK;
 }
 
@@ -805,6 +821,13 @@ int launch_tc3(const Tc3State* st, const Tc3Params& p, cudaStream_t s) {
 bool aligned16_3(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
+
+extern "C" PA_API int pa_prefill_schedule(pa_handle* h, int key_tile, int max_ctas, int* units, size_t cap, int* n_ctas, int* rows) {
+    if (!h || !n_ctas || !rows || !(key_tile == 32 || key_tile == 64)) { pa_set_error("pa_prefill_schedule: bad arguments"); return PA_ERR_INVALID; }
+    if (h->step.nseq < 1) { pa_set_error("pa_prefill_schedule: no step (pa_step_begin)"); return PA_ERR_INVALID; }
+    if (max_ctas <= 0) max_ctas = h->sm_count > 0 ? h->sm_count : 148;
+    return make_schedule(h, key_tile, max_ctas, reinterpret_cast<int2*>(units), cap, n_ctas, rows);
+}
 
 extern "C" void pa_cu_prefill_tc3_release(pa_handle* h) {
     Tc3State* st = (Tc3State*)h->tc3_state;

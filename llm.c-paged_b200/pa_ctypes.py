@@ -117,6 +117,7 @@ def load():
         "pa_model_destroy": (None, [vp]),
         "pa_model_decode_step": (C.c_int, [vp, c_int_p, c_int_p, vp, C.c_int, c_int_p]),
         "pa_model_forward": (C.c_int, [vp, c_int_p, c_int_p, c_int_p, vp, C.c_int, c_int_p]),
+        "pa_prefill_schedule": (C.c_int, [vp, C.c_int, C.c_int, c_int_p, C.c_size_t, c_int_p, c_int_p]),
         "pa_model_forward_async": (C.c_int, [vp, c_int_p, c_int_p, c_int_p, vp, C.c_int]),
         "pa_model_wait": (C.c_int, [vp, c_int_p]),
         "pa_model_next_tokens_dev": (vp, [vp]),
